@@ -1,0 +1,215 @@
+// g3 (scan + key emission) and g5 (tile offsets): integer / bitwise HBM-bound kernels.
+// Compiled with -fmad=false like projection.cu because tile_rect() must reproduce the tile
+// rectangle the projection kernel counted.
+#include "egs_common.cuh"
+#include "egs_math.cuh"
+
+namespace egs {
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive scan int32 -> int64.  Three small launches (block sums, scan of block sums, apply):
+// 12 B/element of traffic, launch-latency class at the sizes of this path (N <= a few million).
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;                         // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;  // 2048 per block
+
+__device__ __forceinline__ int64_t warp_inclusive_scan(int64_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int64_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+// inclusive scan over the block; returns this thread's inclusive prefix and the block total
+__device__ __forceinline__ int64_t block_inclusive_scan(int64_t v, int64_t* smem /*[33]*/, int64_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t inc = warp_inclusive_scan(v, lane);
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int64_t w = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0;
+    int64_t wi = warp_inclusive_scan(w, lane);
+    smem[lane] = wi - w;  // exclusive prefix of warp totals
+    if (lane == 31) smem[32] = wi;
+  }
+  __syncthreads();
+  inc += smem[warp];
+  total = smem[32];
+  __syncthreads();
+  return inc;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                                        int64_t* __restrict__ block_sums) {
+  __shared__ int64_t smem[33];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile;
+  int64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    int64_t j = base + (int64_t)i * kScanThreads + threadIdx.x;
+    if (j < n) s += in[j];
+  }
+  int64_t total;
+  block_inclusive_scan(s, smem, total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the block sums in place, grand total to *total
+__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int64_t* __restrict__ block_sums, int64_t nblocks,
+                                                                   int64_t* __restrict__ total_out) {
+  __shared__ int64_t smem[33];
+  int64_t carry = 0;
+  for (int64_t base = 0; base < nblocks; base += kScanThreads) {
+    int64_t j = base + threadIdx.x;
+    int64_t v = (j < nblocks) ? block_sums[j] : 0;
+    int64_t total;
+    int64_t inc = block_inclusive_scan(v, smem, total);
+    if (j < nblocks) block_sums[j] = carry + inc - v;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                                   const int64_t* __restrict__ block_sums,
+                                                                   int64_t* __restrict__ out) {
+  __shared__ int64_t smem[33];
+  // blocked arrangement: thread t owns items [t*kScanItems, (t+1)*kScanItems) of the tile
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int32_t v[kScanItems];
+  int64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    s += v[i];
+  }
+  int64_t total;
+  int64_t inc = block_inclusive_scan(s, smem, total);
+  int64_t run = block_sums[blockIdx.x] + inc - s;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += v[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Key emission: one thread per (camera, Gaussian); a visible Gaussian writes its tile rectangle
+// row-major at its scanned offset.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEmitThreads = 256;
+
+__global__ void __launch_bounds__(kEmitThreads) isect_emit_kernel(
+    int C, int N, const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
+    const float* __restrict__ depths, const int64_t* __restrict__ cum_excl, float tile_size, int tile_w, int tile_h,
+    int tile_n_bits, int64_t n_isects, int64_t* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids) {
+  const int64_t idx = (int64_t)blockIdx.x * kEmitThreads + threadIdx.x;
+  if (idx >= (int64_t)C * N) return;
+  const int32_t r = radii[idx];
+  if (r <= 0) return;
+  const float2 m = means2d[idx];
+  int32_t x0, y0, x1, y1;
+  tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+  const int64_t cam = idx / N;
+  const uint64_t hi = (uint64_t)cam << tile_n_bits;
+  const uint64_t depth_bits = (uint64_t)__float_as_uint(depths[idx]);
+  int64_t out = cum_excl[idx];
+  for (int32_t y = y0; y < y1; ++y) {
+    for (int32_t x = x0; x < x1; ++x) {
+      if (out < n_isects) {  // guards against a caller passing a short buffer
+        uint64_t tile = (uint64_t)(y * tile_w + x);
+        isect_ids[out] = (int64_t)(((hi | tile) << 32) | depth_bits);
+        flatten_ids[out] = (int32_t)idx;
+      }
+      ++out;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile offsets from the sorted keys.
+// ------------------------------------------------------------------------------------------------
+constexpr int kOffThreads = 256;
+
+__global__ void __launch_bounds__(kOffThreads) isect_offset_encode_kernel(int64_t n_isects,
+                                                                          const int64_t* __restrict__ ids,
+                                                                          int n_tiles, int tile_n_bits, int64_t n_slots,
+                                                                          int32_t* __restrict__ offsets) {
+  const int64_t i = (int64_t)blockIdx.x * kOffThreads + threadIdx.x;
+  if (i >= n_isects) return;
+  const uint64_t tile_mask = (1ull << tile_n_bits) - 1ull;
+  const uint64_t hi = (uint64_t)ids[i] >> 32;
+  const int64_t cur = (int64_t)(hi >> tile_n_bits) * n_tiles + (int64_t)(hi & tile_mask);
+  if (i == 0) {
+    for (int64_t t = 0; t <= cur && t < n_slots; ++t) offsets[t] = 0;
+  } else {
+    const uint64_t hp = (uint64_t)ids[i - 1] >> 32;
+    const int64_t prev = (int64_t)(hp >> tile_n_bits) * n_tiles + (int64_t)(hp & tile_mask);
+    for (int64_t t = prev + 1; t <= cur && t < n_slots; ++t) offsets[t] = (int32_t)i;
+  }
+  if (i == n_isects - 1) {
+    for (int64_t t = cur + 1; t < n_slots; ++t) offsets[t] = (int32_t)n_isects;
+  }
+}
+
+}  // namespace egs
+
+using namespace egs;
+
+extern "C" int64_t egs_exclusive_scan_workspace_bytes(int64_t n) {
+  if (n < 0) return 0;
+  return (ceil_div(n > 0 ? n : 1, kScanTile) + 1) * (int64_t)sizeof(int64_t);
+}
+
+extern "C" int egs_exclusive_scan(int64_t n, const int32_t* in, int64_t* out, int64_t* total, void* workspace,
+                                  int64_t workspace_bytes, egs_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EGS_REQUIRE(n >= 0, "exclusive_scan: n=%lld < 0", (long long)n);
+  if (n == 0) {
+    EGS_CUDA(cudaMemsetAsync(total, 0, sizeof(int64_t), stream));
+    return 0;
+  }
+  if (workspace_bytes < egs_exclusive_scan_workspace_bytes(n))
+    return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "exclusive_scan: workspace %lld < %lld bytes", (long long)workspace_bytes,
+                (long long)egs_exclusive_scan_workspace_bytes(n));
+  const int64_t nblocks = ceil_div(n, kScanTile);
+  EGS_REQUIRE(nblocks <= 0x7fffffff, "exclusive_scan: n too large");
+  int64_t* block_sums = reinterpret_cast<int64_t*>(workspace);
+  scan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(in, n, block_sums);
+  scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, total);
+  scan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(in, n, block_sums, out);
+  return check_launch("exclusive_scan");
+}
+
+extern "C" int egs_isect_emit(int32_t C, int32_t N, const float* means2d, const int32_t* radii, const float* depths,
+                              const int64_t* cum_tiles_excl, int32_t tile_size, int32_t tile_width,
+                              int32_t tile_height, int32_t tile_n_bits, int64_t n_isects, int64_t* isect_ids,
+                              int32_t* flatten_ids, egs_stream_t stream) {
+  EGS_REQUIRE(C >= 0 && N >= 0, "isect_emit: negative sizes");
+  EGS_REQUIRE((int64_t)C * N < 0x7fffffffLL, "isect_emit: C*N=%lld does not fit the int32 flatten id", (long long)C * N);
+  EGS_REQUIRE(tile_n_bits >= 1 && tile_n_bits <= 30, "isect_emit: tile_n_bits=%d out of range", tile_n_bits);
+  if ((int64_t)C * N == 0 || n_isects == 0) return 0;
+  const int64_t nblocks = ceil_div((int64_t)C * N, kEmitThreads);
+  isect_emit_kernel<<<(unsigned)nblocks, kEmitThreads, 0, (cudaStream_t)stream>>>(
+      C, N, reinterpret_cast<const float2*>(means2d), radii, depths, cum_tiles_excl, (float)tile_size, tile_width,
+      tile_height, tile_n_bits, n_isects, isect_ids, flatten_ids);
+  return check_launch("isect_emit_kernel");
+}
+
+extern "C" int egs_isect_offset_encode(int64_t n_isects, const int64_t* isect_ids_sorted, int32_t C, int32_t n_tiles,
+                                       int32_t tile_n_bits, int32_t* offsets, egs_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EGS_REQUIRE(n_isects >= 0 && n_isects < 0x7fffffffLL, "isect_offset_encode: n_isects=%lld out of int32 range", (long long)n_isects);
+  const int64_t n_slots = (int64_t)C * n_tiles;
+  if (n_slots == 0) return 0;
+  if (n_isects == 0) {
+    EGS_CUDA(cudaMemsetAsync(offsets, 0, n_slots * sizeof(int32_t), stream));
+    return 0;
+  }
+  isect_offset_encode_kernel<<<(unsigned)ceil_div(n_isects, kOffThreads), kOffThreads, 0, stream>>>(
+      n_isects, isect_ids_sorted, n_tiles, tile_n_bits, n_slots, offsets);
+  return check_launch("isect_offset_encode_kernel");
+}

@@ -1,0 +1,264 @@
+// g1 + g2 (+ tile count of g3) forward, and g8 + g9 backward: per-Gaussian streaming kernels.
+//
+// Both are HBM-bound (68 B/Gaussian projection + 204 B/visible Gaussian SH forward;
+// 108 + 408 B backward), one thread per Gaussian, so the arithmetic is free and is written in the
+// oracle's canonical fp32 order (this file is compiled with -fmad=false) to make radii, tile counts,
+// means2d and depth bits bit-identical to the oracle.
+#include "egs_common.cuh"
+#include "egs_math.cuh"
+
+namespace egs {
+
+constexpr int kProjThreads = 256;
+
+struct ProjFwdParams {
+  int C, N, K, sh_degree, colors_per_camera;
+  const float *means, *quats, *scales, *opacities, *sh, *viewmats, *Ks;
+  float width, height, eps2d, near_plane, far_plane, radius_clip, tile_size;
+  int tile_w, tile_h;
+  int32_t* radii;
+  float *means2d, *depths, *conics, *colors;
+  int32_t* tiles_per_gauss;
+  float4* splats;
+};
+
+// Load the first `nfloats` floats of a per-Gaussian coefficient block into registers.
+// VEC4: the block start is 16-byte aligned (K*3 % 4 == 0) -> 128-bit loads.
+template <bool VEC4>
+__device__ __forceinline__ void load_coeffs(const float* __restrict__ base, int nfloats, float (&c)[48]) {
+  if (VEC4) {
+    const float4* b4 = reinterpret_cast<const float4*>(base);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      if (i * 4 < nfloats) {
+        float4 v = __ldg(b4 + i);
+        c[i * 4 + 0] = v.x; c[i * 4 + 1] = v.y; c[i * 4 + 2] = v.z; c[i * 4 + 3] = v.w;
+      } else {
+        c[i * 4 + 0] = 0.f; c[i * 4 + 1] = 0.f; c[i * 4 + 2] = 0.f; c[i * 4 + 3] = 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 48; ++i) c[i] = (i < nfloats) ? __ldg(base + i) : 0.f;
+  }
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(kProjThreads) projection_fwd_kernel(const ProjFwdParams p) {
+  __shared__ Camera cam;
+  const int c = blockIdx.y;
+  if (threadIdx.x == 0) load_camera(p.viewmats + (size_t)c * 16, p.Ks + (size_t)c * 9, cam);
+  __syncthreads();
+  const int n = blockIdx.x * kProjThreads + threadIdx.x;
+  if (n >= p.N) return;
+  const size_t idx = (size_t)c * p.N + n;
+
+  float mean[3], quat[4], scale[3];
+  mean[0] = __ldg(p.means + 3 * (size_t)n + 0);
+  mean[1] = __ldg(p.means + 3 * (size_t)n + 1);
+  mean[2] = __ldg(p.means + 3 * (size_t)n + 2);
+  float4 q4 = __ldg(reinterpret_cast<const float4*>(p.quats) + n);
+  quat[0] = q4.x; quat[1] = q4.y; quat[2] = q4.z; quat[3] = q4.w;
+  scale[0] = __ldg(p.scales + 3 * (size_t)n + 0);
+  scale[1] = __ldg(p.scales + 3 * (size_t)n + 1);
+  scale[2] = __ldg(p.scales + 3 * (size_t)n + 2);
+
+  ProjState st;
+  ProjOut o;
+  const bool vis = project_fwd(mean, quat, scale, cam, p.width, p.height, p.eps2d, p.near_plane, p.far_plane,
+                               p.radius_clip, st, o);
+  int32_t ntiles = 0;
+  float rgb[3] = {0.f, 0.f, 0.f};
+  if (vis) {
+    int32_t x0, y0, x1, y1;
+    tile_rect(o.m2x, o.m2y, o.radius, p.tile_size, p.tile_w, p.tile_h, x0, y0, x1, y1);
+    ntiles = (x1 - x0) * (y1 - y0);
+    if (p.sh_degree >= 0) {
+      const int nb = (p.sh_degree + 1) * (p.sh_degree + 1);
+      float co[48];
+      load_coeffs<VEC4>(p.sh + (size_t)n * p.K * 3, nb * 3, co);
+      sh_color_fwd(p.sh_degree, mean, cam, co, rgb);
+    } else {
+      const float* cp = p.sh + (p.colors_per_camera ? idx : (size_t)n) * 3;
+      rgb[0] = __ldg(cp + 0); rgb[1] = __ldg(cp + 1); rgb[2] = __ldg(cp + 2);
+    }
+    const float opac = __ldg(p.opacities + n);
+    float4* s = p.splats + idx * 3;
+    s[0] = make_float4(o.m2x, o.m2y, o.ca, o.cb);
+    s[1] = make_float4(o.cc, opac, rgb[0], rgb[1]);
+    s[2] = make_float4(rgb[2], o.depth, 0.f, 0.f);
+  }
+  p.radii[idx] = o.radius;
+  p.tiles_per_gauss[idx] = ntiles;
+  reinterpret_cast<float2*>(p.means2d)[idx] = make_float2(o.m2x, o.m2y);
+  p.depths[idx] = o.depth;
+  p.conics[idx * 3 + 0] = o.ca; p.conics[idx * 3 + 1] = o.cb; p.conics[idx * 3 + 2] = o.cc;
+  p.colors[idx * 3 + 0] = rgb[0]; p.colors[idx * 3 + 1] = rgb[1]; p.colors[idx * 3 + 2] = rgb[2];
+}
+
+struct ProjBwdParams {
+  int C, N, K, sh_degree, colors_per_camera;
+  const float *means, *quats, *scales, *sh, *viewmats, *Ks;
+  float width, height, eps2d;
+  const int32_t* radii;
+  const float* colors;
+  const float4* v_splats;
+  const float* v_means2d_extra;
+  float *v_means, *v_quats, *v_scales, *v_opacities, *v_sh;
+};
+
+constexpr int kProjBwdThreads = 128;
+constexpr int kMaxCamerasSmem = 64;
+
+// One thread per Gaussian, looping over cameras: gradients summed over cameras stay in registers,
+// so there are no atomics for any C.  Every output element is written exactly once (zeros for culled
+// Gaussians and inactive SH bands), so the caller does not have to clear the gradient buffers.
+template <bool VEC4>
+__global__ void __launch_bounds__(kProjBwdThreads) projection_bwd_kernel(const ProjBwdParams p) {
+  __shared__ Camera cams[kMaxCamerasSmem];
+  for (int c = threadIdx.x; c < p.C && c < kMaxCamerasSmem; c += kProjBwdThreads)
+    load_camera(p.viewmats + (size_t)c * 16, p.Ks + (size_t)c * 9, cams[c]);
+  __syncthreads();
+  const int n = blockIdx.x * kProjBwdThreads + threadIdx.x;
+  if (n >= p.N) return;
+
+  float mean[3], quat[4], scale[3];
+  mean[0] = __ldg(p.means + 3 * (size_t)n + 0);
+  mean[1] = __ldg(p.means + 3 * (size_t)n + 1);
+  mean[2] = __ldg(p.means + 3 * (size_t)n + 2);
+  float4 q4 = __ldg(reinterpret_cast<const float4*>(p.quats) + n);
+  quat[0] = q4.x; quat[1] = q4.y; quat[2] = q4.z; quat[3] = q4.w;
+  scale[0] = __ldg(p.scales + 3 * (size_t)n + 0);
+  scale[1] = __ldg(p.scales + 3 * (size_t)n + 1);
+  scale[2] = __ldg(p.scales + 3 * (size_t)n + 2);
+
+  const bool has_sh = p.sh_degree >= 0;
+  const int nb = has_sh ? (p.sh_degree + 1) * (p.sh_degree + 1) : 0;
+  float v_mean[3] = {0.f, 0.f, 0.f}, v_quat[4] = {0.f, 0.f, 0.f, 0.f}, v_scale[3] = {0.f, 0.f, 0.f};
+  float v_opac = 0.f;
+  float vco[48];
+#pragma unroll
+  for (int i = 0; i < 48; ++i) vco[i] = 0.f;
+  float co[48];
+  bool co_loaded = false;
+  float v_rgb_sum[3] = {0.f, 0.f, 0.f};
+
+  for (int c = 0; c < p.C; ++c) {
+    const size_t idx = (size_t)c * p.N + n;
+    const bool vis = p.radii[idx] > 0;
+    float v_rgb[3] = {0.f, 0.f, 0.f};
+    if (vis) {
+      Camera cam_local;
+      const Camera* cam = &cams[c < kMaxCamerasSmem ? c : 0];
+      if (c >= kMaxCamerasSmem) { load_camera(p.viewmats + (size_t)c * 16, p.Ks + (size_t)c * 9, cam_local); cam = &cam_local; }
+      const float4 g0 = p.v_splats[idx * 3 + 0];
+      const float4 g1 = p.v_splats[idx * 3 + 1];
+      const float4 g2 = p.v_splats[idx * 3 + 2];
+      float v_m2x = g0.x, v_m2y = g0.y;
+      if (p.v_means2d_extra != nullptr) {
+        v_m2x += p.v_means2d_extra[idx * 2 + 0];
+        v_m2y += p.v_means2d_extra[idx * 2 + 1];
+      }
+      ProjState st;
+      ProjOut o;
+      project_fwd(mean, quat, scale, *cam, p.width, p.height, p.eps2d, 0.f, INFINITY, -1.f, st, o);
+      // (culling thresholds are irrelevant here: visibility was decided by the forward pass; the
+      //  off-screen test cannot fire differently because it only depends on the same values.)
+      if (o.radius > 0) project_bwd(st, scale, *cam, v_m2x, v_m2y, 0.f, g0.z, g0.w, g1.x, o, v_mean, v_quat, v_scale);
+      v_opac += g1.y;
+      v_rgb[0] = g1.z; v_rgb[1] = g1.w; v_rgb[2] = g2.x;
+      if (has_sh) {
+        if (!co_loaded) { load_coeffs<VEC4>(p.sh + (size_t)n * p.K * 3, nb * 3, co); co_loaded = true; }
+        const float* col = p.colors + idx * 3;
+        const float rgb_stored[3] = {col[0], col[1], col[2]};
+        sh_color_bwd(p.sh_degree, mean, *cam, co, rgb_stored, v_rgb, vco, v_mean);
+      } else {
+        v_rgb_sum[0] += v_rgb[0]; v_rgb_sum[1] += v_rgb[1]; v_rgb_sum[2] += v_rgb[2];
+      }
+    }
+    if (!has_sh && p.colors_per_camera) {
+      p.v_sh[idx * 3 + 0] = v_rgb[0]; p.v_sh[idx * 3 + 1] = v_rgb[1]; p.v_sh[idx * 3 + 2] = v_rgb[2];
+    }
+  }
+
+  p.v_means[3 * (size_t)n + 0] = v_mean[0]; p.v_means[3 * (size_t)n + 1] = v_mean[1]; p.v_means[3 * (size_t)n + 2] = v_mean[2];
+  reinterpret_cast<float4*>(p.v_quats)[n] = make_float4(v_quat[0], v_quat[1], v_quat[2], v_quat[3]);
+  p.v_scales[3 * (size_t)n + 0] = v_scale[0]; p.v_scales[3 * (size_t)n + 1] = v_scale[1]; p.v_scales[3 * (size_t)n + 2] = v_scale[2];
+  p.v_opacities[n] = v_opac;
+  if (has_sh) {
+    float* out = p.v_sh + (size_t)n * p.K * 3;
+    const int total = p.K * 3;
+    if (VEC4) {
+      float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll
+      for (int i = 0; i < 12; ++i)
+        if (i * 4 < total) o4[i] = make_float4(vco[4 * i + 0], vco[4 * i + 1], vco[4 * i + 2], vco[4 * i + 3]);
+      for (int i = 48; i < total; ++i) out[i] = 0.f;  // K > 16: bands this kernel never activates
+    } else {
+#pragma unroll
+      for (int i = 0; i < 48; ++i)
+        if (i < total) out[i] = vco[i];
+      for (int i = 48; i < total; ++i) out[i] = 0.f;
+    }
+  } else if (!p.colors_per_camera) {
+    p.v_sh[3 * (size_t)n + 0] = v_rgb_sum[0]; p.v_sh[3 * (size_t)n + 1] = v_rgb_sum[1]; p.v_sh[3 * (size_t)n + 2] = v_rgb_sum[2];
+  }
+}
+
+}  // namespace egs
+
+using namespace egs;
+
+extern "C" int egs_projection_fwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                                  const float* opacities, const float* sh_coeffs, int32_t K, int32_t sh_degree,
+                                  int32_t colors_per_camera, const float* viewmats, const float* Ks, int32_t width,
+                                  int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
+                                  int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii,
+                                  float* means2d, float* depths, float* conics, float* colors,
+                                  int32_t* tiles_per_gauss, float* splats, egs_stream_t stream) {
+  EGS_REQUIRE(C >= 0 && N >= 0, "projection_fwd: negative sizes C=%d N=%d", C, N);
+  EGS_REQUIRE(C <= 65535, "projection_fwd: C=%d exceeds 65535 cameras per call", C);
+  EGS_REQUIRE(width >= 1 && height >= 1, "projection_fwd: width/height must be >= 1 (got %d x %d)", width, height);
+  EGS_REQUIRE(tile_size >= 1 && (tile_size & (tile_size - 1)) == 0, "projection_fwd: tile_size must be a power of two");
+  EGS_REQUIRE(sh_degree <= 3, "projection_fwd: sh_degree %d > 3 is not supported", sh_degree);
+  EGS_REQUIRE(sh_degree < 0 || K >= (sh_degree + 1) * (sh_degree + 1), "projection_fwd: K=%d too small for sh_degree=%d", K, sh_degree);
+  if (C == 0 || N == 0) return 0;
+  ProjFwdParams p;
+  p.C = C; p.N = N; p.K = K; p.sh_degree = sh_degree; p.colors_per_camera = colors_per_camera;
+  p.means = means; p.quats = quats; p.scales = scales; p.opacities = opacities; p.sh = sh_coeffs;
+  p.viewmats = viewmats; p.Ks = Ks;
+  p.width = (float)width; p.height = (float)height; p.eps2d = eps2d; p.near_plane = near_plane;
+  p.far_plane = far_plane; p.radius_clip = radius_clip; p.tile_size = (float)tile_size;
+  p.tile_w = tile_width; p.tile_h = tile_height;
+  p.radii = radii; p.means2d = means2d; p.depths = depths; p.conics = conics; p.colors = colors;
+  p.tiles_per_gauss = tiles_per_gauss; p.splats = reinterpret_cast<float4*>(splats);
+  dim3 grid((unsigned)ceil_div(N, kProjThreads), (unsigned)C);
+  const bool vec4 = sh_degree >= 0 && (K * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(sh_coeffs) % 16 == 0);
+  if (vec4) projection_fwd_kernel<true><<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(p);
+  else      projection_fwd_kernel<false><<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("projection_fwd_kernel");
+}
+
+extern "C" int egs_projection_bwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                                  const float* sh_coeffs, int32_t K, int32_t sh_degree, int32_t colors_per_camera,
+                                  const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
+                                  const int32_t* radii, const float* colors, const float* v_splats,
+                                  const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
+                                  float* v_opacities, float* v_sh_coeffs, egs_stream_t stream) {
+  EGS_REQUIRE(C >= 0 && N >= 0, "projection_bwd: negative sizes C=%d N=%d", C, N);
+  EGS_REQUIRE(sh_degree <= 3, "projection_bwd: sh_degree %d > 3 is not supported", sh_degree);
+  if (N == 0) return 0;
+  ProjBwdParams p;
+  p.C = C; p.N = N; p.K = K; p.sh_degree = sh_degree; p.colors_per_camera = colors_per_camera;
+  p.means = means; p.quats = quats; p.scales = scales; p.sh = sh_coeffs; p.viewmats = viewmats; p.Ks = Ks;
+  p.width = (float)width; p.height = (float)height; p.eps2d = eps2d;
+  p.radii = radii; p.colors = colors; p.v_splats = reinterpret_cast<const float4*>(v_splats);
+  p.v_means2d_extra = v_means2d_extra;
+  p.v_means = v_means; p.v_quats = v_quats; p.v_scales = v_scales; p.v_opacities = v_opacities; p.v_sh = v_sh_coeffs;
+  const bool vec4 = sh_degree >= 0 && (K * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(sh_coeffs) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(v_sh_coeffs) % 16 == 0);
+  unsigned grid = (unsigned)ceil_div(N, kProjBwdThreads);
+  if (vec4) projection_bwd_kernel<true><<<grid, kProjBwdThreads, 0, (cudaStream_t)stream>>>(p);
+  else      projection_bwd_kernel<false><<<grid, kProjBwdThreads, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("projection_bwd_kernel");
+}

@@ -1,0 +1,292 @@
+// g4: hand-written onesweep radix sort of (u64 key, u32 value) pairs — stable, LSD, 8-bit digits,
+// decoupled look-back (takes the place of cub::DeviceRadixSort::SortPairs in gsplat's isect_tiles).
+//
+// Launch sequence for P = ceil(end_bit / 8) passes over n pairs:
+//   1 memset   : histograms, dynamic tile counters and look-back status words
+//   1 histogram: reads the keys once (8 B/pair) and builds all P digit histograms
+//   1 scan     : exclusive scan of each 256-bin histogram -> global digit bases
+//   P passes   : each reads 12 B/pair and writes 12 B/pair; a tile of 4096 pairs is ranked in
+//                shared memory (warp-level match_any multisplit, stable), its per-digit counts are
+//                chained to the preceding tiles with decoupled look-back, and the tile is written
+//                out digit-run by digit-run so stores are coalesced.
+// HBM traffic: 8 + 24*P bytes per pair = 152 B at P = 6.  Integer work only.
+#include "egs_common.cuh"
+
+namespace egs {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kMaxPasses = 8;
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortItems = 16;                          // pairs per thread
+constexpr int kSortTile = kSortThreads * kSortItems;    // 4096 pairs per tile
+constexpr int kWarpSpan = 32 * kSortItems;              // 512 consecutive pairs per warp
+
+constexpr uint32_t kFlagAggregate = 1u << 30;
+constexpr uint32_t kFlagPrefix = 2u << 30;
+constexpr uint32_t kValueMask = (1u << 30) - 1u;
+
+struct SortWorkspace {
+  uint32_t* hist;      // [kMaxPasses][256]  digit counts, then exclusive digit bases
+  uint32_t* counters;  // [kMaxPasses]       dynamic tile ids
+  uint32_t* status;    // [passes][ntiles][256]
+};
+
+__host__ __device__ inline int64_t sort_ntiles(int64_t n) { return (n + kSortTile - 1) / kSortTile; }
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- histogram of every digit position in one read of the keys -----------------------------------
+constexpr int kHistThreads = 256;
+constexpr int kHistItems = 16;
+
+__global__ void __launch_bounds__(kHistThreads) radix_histogram_kernel(const uint64_t* __restrict__ keys, int64_t n,
+                                                                        int passes, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kMaxPasses * kRadix];
+  for (int i = threadIdx.x; i < passes * kRadix; i += kHistThreads) sh[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * kHistThreads;
+  const int64_t n_round = ((n + 31) / 32) * 32;  // keep whole warps in the loop for match_any
+  for (int64_t i = (int64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n_round; i += stride) {
+    const bool valid = i < n;
+    const uint64_t key = valid ? keys[i] : 0ull;
+    for (int p = 0; p < passes; ++p) {
+      const uint32_t d = (uint32_t)(key >> (p * kRadixBits)) & (kRadix - 1);
+      const uint32_t m = __match_any_sync(0xffffffffu, d | (valid ? 0u : 0x100u));
+      // the lowest lane of every group of equal digits adds the group size
+      if (valid && (m & ((1u << lane) - 1u)) == 0u) atomicAdd(&sh[p * kRadix + d], (uint32_t)__popc(m));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * kRadix; i += kHistThreads) {
+    const uint32_t v = sh[i];
+    if (v) atomicAdd(&hist[i], v);
+  }
+}
+
+// one block per pass: counts -> exclusive bases, in place
+__global__ void __launch_bounds__(kRadix) radix_scan_hist_kernel(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t warp_tot[kRadix / 32];
+  uint32_t* h = hist + (size_t)blockIdx.x * kRadix;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t v = h[threadIdx.x];
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w = 0; w < warp; ++w) base += warp_tot[w];
+  h[threadIdx.x] = base + inc - v;
+}
+
+// ---- one onesweep pass ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(
+    const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ digit_base /*[256]*/,
+    uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ status /*[ntiles][256]*/) {
+  __shared__ __align__(16) uint64_t s_keys[kSortTile];        // 32 KB, reused for the values
+  __shared__ uint32_t s_warp_hist[kSortWarps][kRadix];        // 8 KB
+  __shared__ uint32_t s_digit_start[kRadix];                  // first slot of each digit inside the tile
+  __shared__ uint32_t s_dst_base[kRadix];                     // global base - digit_start (mod 2^32)
+  __shared__ uint32_t s_warp_tot[kSortWarps];
+  __shared__ uint32_t s_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // dynamic tile id: a tile only waits on tiles that have already started (no look-back deadlock)
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+#pragma unroll
+  for (int i = 0; i < kSortWarps; ++i) s_warp_hist[i][tid] = 0;  // tid < 256 == kRadix
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int64_t tile_base = (int64_t)tile * kSortTile;
+  const int tile_count = (int)min((int64_t)kSortTile, n - tile_base);
+
+  // (a) load, warp-striped: item i of lane l in warp w is element w*512 + i*32 + l of the tile
+  uint64_t key[kSortItems];
+  uint32_t val[kSortItems];
+  const int warp_off = warp * kWarpSpan + lane;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int local = warp_off + i * 32;
+    const bool valid = local < tile_count;
+    key[i] = valid ? keys_in[tile_base + local] : ~0ull;
+    val[i] = valid ? vals_in[tile_base + local] : 0u;
+  }
+
+  // (b) stable rank of every item among the items of its warp with the same digit
+  uint32_t rank[kSortItems];
+  uint32_t* wh = s_warp_hist[warp];
+  const uint32_t lanemask_lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const bool valid = (warp_off + i * 32) < tile_count;
+    const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
+    const uint32_t m = __match_any_sync(0xffffffffu, d | (valid ? 0u : 0x100u));
+    const uint32_t before = __popc(m & lanemask_lt);
+    const uint32_t prev = wh[d];
+    __syncwarp();
+    if (valid && before == 0) wh[d] = prev + (uint32_t)__popc(m);
+    __syncwarp();
+    rank[i] = prev + before;
+  }
+  __syncthreads();
+
+  // (c) thread d owns digit d: exclusive prefix over the warps, tile total
+  uint32_t count = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) {
+    const uint32_t t = s_warp_hist[w][tid];
+    s_warp_hist[w][tid] = count;
+    count += t;
+  }
+  // publish the tile aggregate (or the inclusive prefix for tile 0) as early as possible
+  uint32_t* my_status = status + (size_t)tile * kRadix + tid;
+  st_volatile_u32(my_status, (tile == 0 ? kFlagPrefix : kFlagAggregate) | count);
+
+  // (d) exclusive scan of the digit counts across the 256 threads -> slot of each digit in the tile
+  uint32_t inc = count;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp_tot[warp] = inc;
+  __syncthreads();
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) wbase += (w < warp) ? s_warp_tot[w] : 0u;
+  const uint32_t digit_start = wbase + inc - count;
+  s_digit_start[tid] = digit_start;
+  __syncthreads();
+
+  // (e) scatter the keys into tile-sorted order in shared memory
+  uint32_t pos[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
+    pos[i] = s_digit_start[d] + wh[d] + rank[i];
+    if ((warp_off + i * 32) < tile_count) s_keys[pos[i]] = key[i];
+  }
+
+  // (f) decoupled look-back for digit tid
+  uint32_t excl = 0;
+  if (tile > 0) {
+    int64_t j = (int64_t)tile - 1;
+    while (true) {
+      const uint32_t* ps = status + (size_t)j * kRadix + tid;
+      uint32_t v;
+      do { v = ld_volatile_u32(ps); } while ((v >> 30) == 0u);
+      excl += v & kValueMask;
+      if ((v & kFlagPrefix) != 0u || j == 0) break;
+      --j;
+    }
+    st_volatile_u32(my_status, kFlagPrefix | ((excl + count) & kValueMask));
+  }
+  s_dst_base[tid] = digit_base[tid] + excl - digit_start;
+  __syncthreads();
+
+  // (g) write the keys out; consecutive slots of one digit go to consecutive addresses
+  uint32_t dst[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int p = tid + i * kSortThreads;
+    if (p < tile_count) {
+      const uint64_t k = s_keys[p];
+      const uint32_t d = (uint32_t)(k >> shift) & (kRadix - 1);
+      dst[i] = s_dst_base[d] + (uint32_t)p;
+      keys_out[dst[i]] = k;
+    }
+  }
+  __syncthreads();
+
+  // (h) the values take the same route through the (reused) shared buffer
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys);
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i)
+    if ((warp_off + i * 32) < tile_count) s_vals[pos[i]] = val[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int p = tid + i * kSortThreads;
+    if (p < tile_count) vals_out[dst[i]] = s_vals[p];
+  }
+}
+
+static int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, int passes, SortWorkspace& w, int64_t& clear_bytes) {
+  const int64_t ntiles = sort_ntiles(n);
+  const int64_t hist_b = (int64_t)kMaxPasses * kRadix * 4;
+  const int64_t cnt_b = 256;  // kMaxPasses counters, padded
+  const int64_t status_b = (int64_t)passes * ntiles * kRadix * 4;
+  clear_bytes = hist_b + cnt_b + status_b;
+  if (ws == nullptr) return 0;
+  if (ws_bytes < clear_bytes) return -1;
+  char* base = reinterpret_cast<char*>(ws);
+  w.hist = reinterpret_cast<uint32_t*>(base);
+  w.counters = reinterpret_cast<uint32_t*>(base + hist_b);
+  w.status = reinterpret_cast<uint32_t*>(base + hist_b + cnt_b);
+  return 0;
+}
+
+}  // namespace egs
+
+using namespace egs;
+
+extern "C" int64_t egs_radix_sort_workspace_bytes(int64_t n, int32_t end_bit) {
+  if (n < 0 || end_bit < 0) return 0;
+  int passes = (end_bit + kRadixBits - 1) / kRadixBits;
+  if (passes > kMaxPasses) passes = kMaxPasses;
+  SortWorkspace w;
+  int64_t bytes = 0;
+  carve_workspace(nullptr, 0, n, passes, w, bytes);
+  return bytes;
+}
+
+extern "C" int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
+                                            uint32_t* vals_b, int32_t end_bit, void* workspace,
+                                            int64_t workspace_bytes, int32_t* host_result_in_b,
+                                            egs_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EGS_REQUIRE(n >= 0, "radix_sort: n=%lld < 0", (long long)n);
+  EGS_REQUIRE(n < (1ll << 30), "radix_sort: n=%lld exceeds the 2^30 pairs the look-back words can count", (long long)n);
+  EGS_REQUIRE(end_bit >= 0 && end_bit <= 64, "radix_sort: end_bit=%d out of [0,64]", end_bit);
+  const int passes = (end_bit + kRadixBits - 1) / kRadixBits;
+  if (host_result_in_b) *host_result_in_b = (passes & 1);
+  if (n == 0 || passes == 0) {
+    if (host_result_in_b) *host_result_in_b = 0;
+    return 0;
+  }
+  SortWorkspace w;
+  int64_t clear_bytes = 0;
+  if (carve_workspace(workspace, workspace_bytes, n, passes, w, clear_bytes) != 0 || workspace == nullptr)
+    return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "radix_sort: workspace %lld < %lld bytes", (long long)workspace_bytes,
+                (long long)clear_bytes);
+  EGS_CUDA(cudaMemsetAsync(workspace, 0, clear_bytes, stream));
+  const int64_t ntiles = sort_ntiles(n);
+  int64_t hist_blocks = ceil_div(n, (int64_t)kHistThreads * kHistItems);
+  if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
+  radix_histogram_kernel<<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, passes, w.hist);
+  radix_scan_hist_kernel<<<passes, kRadix, 0, stream>>>(w.hist);
+  uint64_t* kin = keys_a; uint32_t* vin = vals_a;
+  uint64_t* kout = keys_b; uint32_t* vout = vals_b;
+  for (int p = 0; p < passes; ++p) {
+    radix_onesweep_kernel<<<(unsigned)ntiles, kSortThreads, 0, stream>>>(
+        kin, vin, kout, vout, n, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
+        w.status + (size_t)p * ntiles * kRadix);
+    uint64_t* tk = kin; kin = kout; kout = tk;
+    uint32_t* tv = vin; vin = vout; vout = tv;
+  }
+  return check_launch("radix_sort_pairs");
+}

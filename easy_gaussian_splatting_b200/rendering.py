@@ -1,0 +1,203 @@
+"""Drop-in for ``gsplat.rendering.rasterization`` — the one call the reference makes into its
+rasterizer (/root/reference/model/gaussian.py:8 import, :353-367 call site).
+
+Same Python signature, same outputs: ``(render_colors[C,H,W,3], render_alphas[C,H,W,1], meta)``
+with ``meta["radii"]`` int32 ``[C,N]`` (> 0 iff visible) and ``meta["means2d"]`` fp32 ``[C,N,2]`` which,
+after ``backward()`` with ``absgrad=True``, carries the attribute ``.absgrad`` ``[C,N,2]`` that
+``GaussianModel.update_statistics`` reads (/root/reference/model/gaussian.py:188-197).
+
+The host side is PyTorch (allocation, autograd wiring, streams) over the C-ABI library in
+``include/egs_raster.h``; every stage is a hand-written sm_100a kernel and there is no CPU path.
+
+One autograd node covers the whole pipeline so the backward pass stays fused:
+``rasterize_bwd`` accumulates packed 48-byte gradient records that the fused SH+projection
+backward consumes directly (no unpacking pass, no per-stage autograd nodes).
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import stages
+
+__all__ = ["rasterization"]
+
+
+class _Rasterization(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg):
+        width, height, sh_degree = cfg["width"], cfg["height"], cfg["sh_degree"]
+        C, N = viewmats.shape[0], means.shape[0]
+        proj = stages.projection_fwd(means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree,
+                                     eps2d=cfg["eps2d"], near_plane=cfg["near_plane"], far_plane=cfg["far_plane"],
+                                     radius_clip=cfg["radius_clip"])
+        tw, th = stages.tile_grid(width, height)
+        tiles_per_gauss, isect_ids, flatten_ids = stages.isect_tiles(
+            proj["means2d"], proj["radii"], proj["depths"], stages.TILE_SIZE, tw, th, sort=True,
+            tiles_per_gauss=proj["tiles_per_gauss"])
+        isect_offsets = stages.isect_offset_encode(isect_ids, C, tw, th)
+        render_colors, render_alphas, last_ids = stages.rasterize_fwd(
+            proj["splats"], isect_offsets, flatten_ids, backgrounds, width, height)
+
+        means2d = proj["means2d"]
+        ctx.cfg = cfg
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(means, quats, scales, colors, viewmats, Ks, backgrounds, proj["radii"], proj["colors"],
+                              proj["splats"], isect_offsets, flatten_ids, render_alphas, last_ids)
+        nondiff = (proj["radii"], proj["depths"], proj["conics"], proj["colors"], tiles_per_gauss, isect_ids,
+                   flatten_ids, isect_offsets, last_ids)
+        ctx.mark_non_differentiable(*nondiff)
+        return (render_colors, render_alphas, means2d) + nondiff
+
+    @staticmethod
+    def backward(ctx, v_colors, v_alphas, v_means2d, *_unused):
+        (means, quats, scales, colors, viewmats, Ks, backgrounds, radii, colors_rgb, splats, isect_offsets,
+         flatten_ids, render_alphas, last_ids) = ctx.saved_tensors
+        cfg = ctx.cfg
+        width, height = cfg["width"], cfg["height"]
+        C = viewmats.shape[0]
+        if v_colors is None:
+            v_colors = torch.zeros(C, height, width, 3, dtype=torch.float32, device=means.device)
+        if v_alphas is None:
+            v_alphas = torch.zeros(C, height, width, 1, dtype=torch.float32, device=means.device)
+        v_splats = stages.rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height,
+                                        render_alphas, last_ids, v_colors, v_alphas)
+        if cfg["absgrad"]:
+            ref = getattr(ctx, "means2d_ref", None)
+            target = ref() if ref is not None else None
+            if target is not None:
+                # same contract as gsplat: attribute tagging on the tensor object handed out in meta
+                target.absgrad = v_splats[..., 9:11].contiguous()
+        v_means, v_quats, v_scales, v_opac, v_cols = stages.projection_bwd(
+            means, quats, scales, colors, viewmats, Ks, width, height, cfg["sh_degree"], cfg["eps2d"], radii,
+            colors_rgb, v_splats, v_means2d)
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[7]:
+            v_bg = ((1.0 - render_alphas) * v_colors).sum(dim=(1, 2))
+        return v_means, v_quats, v_scales, v_opac, v_cols, None, None, v_bg, None
+
+
+def _check_inputs(means, quats, scales, opacities, colors, viewmats, Ks, sh_degree, backgrounds):
+    N = means.shape[0]
+    C = viewmats.shape[0]
+    if means.shape != (N, 3):
+        raise ValueError(f"means must be [N,3], got {tuple(means.shape)}")
+    if quats.shape != (N, 4):
+        raise ValueError(f"quats must be [N,4], got {tuple(quats.shape)}")
+    if scales.shape != (N, 3):
+        raise ValueError(f"scales must be [N,3], got {tuple(scales.shape)}")
+    if opacities.shape != (N,):
+        raise ValueError(f"opacities must be [N], got {tuple(opacities.shape)}")
+    if viewmats.shape != (C, 4, 4):
+        raise ValueError(f"viewmats must be [C,4,4], got {tuple(viewmats.shape)}")
+    if Ks.shape != (C, 3, 3):
+        raise ValueError(f"Ks must be [C,3,3], got {tuple(Ks.shape)}")
+    if sh_degree is None:
+        ok = (colors.dim() == 2 and colors.shape == (N, 3)) or (colors.dim() == 3 and colors.shape == (C, N, 3))
+        if not ok:
+            if colors.dim() in (2, 3) and colors.shape[-1] != 3:
+                raise NotImplementedError("only 3 colour channels are implemented (the reference renders RGB)")
+            raise ValueError(f"colors must be [N,3] or [C,N,3] when sh_degree is None, got {tuple(colors.shape)}")
+    else:
+        if colors.dim() == 4:
+            raise NotImplementedError("per-camera SH coefficients [C,N,K,3] are not implemented")
+        if not (colors.dim() == 3 and colors.shape[0] == N and colors.shape[2] == 3):
+            raise ValueError(f"colors must be [N,K,3] SH coefficients, got {tuple(colors.shape)}")
+        if not 0 <= sh_degree <= 3:
+            raise NotImplementedError(f"sh_degree={sh_degree}: degrees 0..3 are implemented (the reference uses <= 3)")
+        if (sh_degree + 1) ** 2 > colors.shape[1]:
+            raise ValueError(f"sh_degree={sh_degree} needs K >= {(sh_degree + 1) ** 2}, got K={colors.shape[1]}")
+    if backgrounds is not None and backgrounds.shape != (C, 3):
+        raise ValueError(f"backgrounds must be [C,3], got {tuple(backgrounds.shape)}")
+    for name, t in (("means", means), ("quats", quats), ("scales", scales), ("opacities", opacities),
+                    ("colors", colors), ("viewmats", viewmats), ("Ks", Ks), ("backgrounds", backgrounds)):
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} is on {t.device}: this rasterizer is CUDA-only and has no CPU fallback")
+        if t.device != means.device:
+            raise RuntimeError(f"{name} is on {t.device} but means is on {means.device}")
+        if t.dtype != torch.float32:
+            raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if C * N >= 2 ** 31:
+        raise ValueError("C*N must fit an int32 flatten id")
+
+
+def rasterization(
+    means: Tensor,  # [N, 3]
+    quats: Tensor,  # [N, 4] wxyz, need not be normalised
+    scales: Tensor,  # [N, 3]
+    opacities: Tensor,  # [N]
+    colors: Tensor,  # [N, K, 3] SH coefficients (sh_degree given) or [N, 3] / [C, N, 3]
+    viewmats: Tensor,  # [C, 4, 4] world -> camera
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    sh_degree: Optional[int] = None,
+    packed: bool = True,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: str = "RGB",
+    sparse_grad: bool = False,
+    absgrad: bool = False,
+    rasterize_mode: str = "classic",
+    channel_chunk: int = 32,
+) -> Tuple[Tensor, Tensor, Dict]:
+    """See module docstring.  The combination the reference uses — SH colours, ``packed=False``,
+    ``absgrad=True``, one camera, a [1,3] background — and C > 1 are implemented; modes the
+    reference never requests raise ``NotImplementedError`` instead of silently approximating."""
+    if render_mode != "RGB":
+        raise NotImplementedError(f"render_mode={render_mode!r}: only 'RGB' is implemented (the reference's mode)")
+    if rasterize_mode != "classic":
+        raise NotImplementedError(f"rasterize_mode={rasterize_mode!r}: only 'classic' is implemented")
+    if sparse_grad:
+        raise NotImplementedError("sparse_grad=True is not implemented")
+    if packed:
+        raise NotImplementedError("packed=True is not implemented; the reference calls with packed=False "
+                                  "(model/gaussian.py:366) and results do not depend on it")
+    if tile_size != stages.TILE_SIZE:
+        raise NotImplementedError(f"tile_size={tile_size}: the blending kernels are specialised for 16")
+    width, height = int(width), int(height)
+    if width < 1 or height < 1:
+        raise ValueError(f"width and height must be >= 1, got {width} x {height}")
+    _check_inputs(means, quats, scales, opacities, colors, viewmats, Ks, sh_degree, backgrounds)
+    if viewmats.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("gradients w.r.t. viewmats are not implemented (the reference never asks for them)")
+    C = viewmats.shape[0]
+    cfg = dict(width=width, height=height, sh_degree=sh_degree, eps2d=float(eps2d), near_plane=float(near_plane),
+               far_plane=float(far_plane), radius_clip=float(radius_clip), absgrad=bool(absgrad))
+    outs = _Rasterization.apply(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg)
+    (render_colors, render_alphas, means2d, radii, depths, conics, colors_rgb, tiles_per_gauss, isect_ids,
+     flatten_ids, isect_offsets, _last_ids) = outs
+    if absgrad and render_colors.grad_fn is not None:
+        # the backward node tags .absgrad on exactly this tensor object (weak: no reference cycle)
+        render_colors.grad_fn.means2d_ref = weakref.ref(means2d)
+    tw, th = stages.tile_grid(width, height)
+    meta = {
+        "camera_ids": None,
+        "gaussian_ids": None,
+        "radii": radii,
+        "means2d": means2d,
+        "depths": depths,
+        "conics": conics,
+        "opacities": opacities[None].expand(C, -1),
+        "colors": colors_rgb,
+        "tile_width": tw,
+        "tile_height": th,
+        "tiles_per_gauss": tiles_per_gauss,
+        "isect_ids": isect_ids,
+        "flatten_ids": flatten_ids,
+        "isect_offsets": isect_offsets,
+        "width": width,
+        "height": height,
+        "tile_size": tile_size,
+        "n_cameras": C,
+    }
+    return render_colors, render_alphas, meta

@@ -1,0 +1,261 @@
+"""Per-stage operators over the C-ABI (tensor in -> tensor out, no autograd).
+
+Names and argument meaning mirror the gsplat-1.0.0 operators that sit behind the reference's
+``rasterization`` call (/root/reference/model/gaussian.py:353-367): projection (+SH),
+``isect_tiles``, ``isect_offset_encode``, ``rasterize_to_pixels`` fwd/bwd.  All tensors must be CUDA,
+fp32/int32/int64 and are made contiguous here; every launch goes to the current stream of the
+tensors' device (viewer threads never call ``set_device``, SURVEY.md §3.3, so the device is pinned
+around each call).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+SPLAT_FLOATS = 12
+TILE_SIZE = 16
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32c(t: Tensor, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: this rasterizer has no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def tile_grid(width: int, height: int, tile_size: int = TILE_SIZE) -> Tuple[int, int]:
+    return math.ceil(width / tile_size), math.ceil(height / tile_size)
+
+
+def tile_n_bits(tile_width: int, tile_height: int) -> int:
+    return int(math.floor(math.log2(tile_width * tile_height))) + 1
+
+
+def camera_n_bits(C: int) -> int:
+    return int(math.floor(math.log2(C))) + 1 if C > 1 else 0
+
+
+def projection_fwd(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, colors: Tensor,
+                   viewmats: Tensor, Ks: Tensor, width: int, height: int, sh_degree: Optional[int],
+                   eps2d: float = 0.3, near_plane: float = 0.01, far_plane: float = 1e10,
+                   radius_clip: float = 0.0, tile_size: int = TILE_SIZE) -> Dict[str, Tensor]:
+    """g1+g2+count(g3).  colors: [N,K,3] SH coefficients when sh_degree is not None, else [N,3]/[C,N,3]."""
+    lib = _lib.load()
+    means, quats, scales = _f32c(means, "means"), _f32c(quats, "quats"), _f32c(scales, "scales")
+    opacities, colors = _f32c(opacities, "opacities"), _f32c(colors, "colors")
+    viewmats, Ks = _f32c(viewmats, "viewmats"), _f32c(Ks, "Ks")
+    dev = means.device
+    N, C = means.shape[0], viewmats.shape[0]
+    if sh_degree is None:
+        K, deg, per_cam = 1, -1, int(colors.dim() == 3)
+    else:
+        K, deg, per_cam = colors.shape[-2], int(sh_degree), 0
+    tw, th = tile_grid(width, height, tile_size)
+    out = {
+        "radii": torch.empty(C, N, dtype=torch.int32, device=dev),
+        "means2d": torch.empty(C, N, 2, dtype=torch.float32, device=dev),
+        "depths": torch.empty(C, N, dtype=torch.float32, device=dev),
+        "conics": torch.empty(C, N, 3, dtype=torch.float32, device=dev),
+        "colors": torch.empty(C, N, 3, dtype=torch.float32, device=dev),
+        "tiles_per_gauss": torch.empty(C, N, dtype=torch.int32, device=dev),
+        "splats": torch.empty(C, N, SPLAT_FLOATS, dtype=torch.float32, device=dev),
+    }
+    with torch.cuda.device(dev):
+        rc = lib.egs_projection_fwd(C, N, _ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(colors),
+                                    K, deg, per_cam, _ptr(viewmats), _ptr(Ks), int(width), int(height),
+                                    float(eps2d), float(near_plane), float(far_plane), float(radius_clip),
+                                    int(tile_size), tw, th, _ptr(out["radii"]), _ptr(out["means2d"]),
+                                    _ptr(out["depths"]), _ptr(out["conics"]), _ptr(out["colors"]),
+                                    _ptr(out["tiles_per_gauss"]), _ptr(out["splats"]), _stream(dev))
+    _lib.check(rc, "egs_projection_fwd")
+    return out
+
+
+def projection_bwd(means: Tensor, quats: Tensor, scales: Tensor, colors: Tensor, viewmats: Tensor, Ks: Tensor,
+                   width: int, height: int, sh_degree: Optional[int], eps2d: float, radii: Tensor,
+                   colors_rgb: Tensor, v_splats: Tensor, v_means2d_extra: Optional[Tensor] = None):
+    """g8+g9. -> v_means[N,3], v_quats[N,4], v_scales[N,3], v_opacities[N], v_colors (shape of colors)."""
+    lib = _lib.load()
+    dev = means.device
+    N, C = means.shape[0], viewmats.shape[0]
+    if sh_degree is None:
+        K, deg, per_cam = 1, -1, int(colors.dim() == 3)
+    else:
+        K, deg, per_cam = colors.shape[-2], int(sh_degree), 0
+    v_means = torch.empty_like(means)
+    v_quats = torch.empty_like(quats)
+    v_scales = torch.empty_like(scales)
+    v_opac = torch.empty(N, dtype=torch.float32, device=dev)
+    v_colors = torch.empty_like(colors)
+    if v_means2d_extra is not None:
+        v_means2d_extra = _f32c(v_means2d_extra, "v_means2d")
+    with torch.cuda.device(dev):
+        rc = lib.egs_projection_bwd(C, N, _ptr(means), _ptr(quats), _ptr(scales), _ptr(colors), K, deg, per_cam,
+                                    _ptr(viewmats), _ptr(Ks), int(width), int(height), float(eps2d), _ptr(radii),
+                                    _ptr(colors_rgb), _ptr(v_splats), _ptr(v_means2d_extra), _ptr(v_means),
+                                    _ptr(v_quats), _ptr(v_scales), _ptr(v_opac), _ptr(v_colors), _stream(dev))
+    _lib.check(rc, "egs_projection_bwd")
+    return v_means, v_quats, v_scales, v_opac, v_colors
+
+
+def exclusive_scan(counts: Tensor) -> Tuple[Tensor, Tensor]:
+    """int32[n] -> (exclusive prefix int64[n], total int64[1]) — device side, no sync."""
+    lib = _lib.load()
+    flat = counts.reshape(-1).contiguous()
+    n, dev = flat.numel(), flat.device
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    ws_bytes = lib.egs_exclusive_scan_workspace_bytes(n)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.egs_exclusive_scan(n, _ptr(flat), _ptr(out), _ptr(total), _ptr(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "egs_exclusive_scan")
+    return out, total
+
+
+def radix_sort_pairs(keys: Tensor, vals: Tensor, end_bit: int) -> Tuple[Tensor, Tensor]:
+    """Stable ascending sort of (int64 key, int32 value) pairs on key bits [0, end_bit).
+    The inputs are used as one side of the ping-pong and are clobbered."""
+    lib = _lib.load()
+    n, dev = keys.numel(), keys.device
+    if n == 0:
+        return keys, vals
+    keys_b, vals_b = torch.empty_like(keys), torch.empty_like(vals)
+    ws_bytes = lib.egs_radix_sort_workspace_bytes(n, end_bit)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    in_b = ctypes.c_int32(0)
+    with torch.cuda.device(dev):
+        rc = lib.egs_radix_sort_pairs_u64_u32(n, _ptr(keys), _ptr(vals), _ptr(keys_b), _ptr(vals_b), int(end_bit),
+                                              _ptr(ws), ws_bytes, ctypes.byref(in_b), _stream(dev))
+    _lib.check(rc, "egs_radix_sort_pairs_u64_u32")
+    return (keys_b, vals_b) if in_b.value else (keys, vals)
+
+
+def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
+                sort: bool = True, tiles_per_gauss: Optional[Tensor] = None,
+                n_isects: Optional[int] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """g3+g4 -> tiles_per_gauss[C,N] i32, isect_ids[n] i64, flatten_ids[n] i32 (sorted when sort=True).
+
+    When ``tiles_per_gauss`` is not given it is recomputed with torch from (means2d, radii) the same
+    way the projection kernel counts (exact: divisions by the power-of-two tile size)."""
+    lib = _lib.load()
+    means2d, depths = _f32c(means2d, "means2d"), _f32c(depths, "depths")
+    radii = radii.contiguous()
+    C, N = radii.shape
+    dev = radii.device
+    if tiles_per_gauss is None:
+        ts = float(tile_size)
+        r = radii.to(torch.float32) / ts
+        tx, ty = means2d[..., 0] / ts, means2d[..., 1] / ts
+        x0 = torch.floor(tx - r).clamp(0, tile_width)
+        x1 = torch.ceil(tx + r).clamp(0, tile_width)
+        y0 = torch.floor(ty - r).clamp(0, tile_height)
+        y1 = torch.ceil(ty + r).clamp(0, tile_height)
+        tiles_per_gauss = torch.where(radii > 0, (x1 - x0) * (y1 - y0), torch.zeros_like(x0)).to(torch.int32)
+    cum, total = exclusive_scan(tiles_per_gauss)
+    if n_isects is None:
+        n_isects = int(total.item())  # the one host sync of the forward pass
+    ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+    flat = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    nbits = tile_n_bits(tile_width, tile_height)
+    with torch.cuda.device(dev):
+        rc = lib.egs_isect_emit(C, N, _ptr(means2d), _ptr(radii), _ptr(depths), _ptr(cum), int(tile_size),
+                                tile_width, tile_height, nbits, n_isects, _ptr(ids), _ptr(flat), _stream(dev))
+    _lib.check(rc, "egs_isect_emit")
+    if sort and n_isects > 0:
+        ids, flat = radix_sort_pairs(ids, flat, 32 + nbits + camera_n_bits(C))
+    return tiles_per_gauss, ids, flat
+
+
+def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height: int) -> Tensor:
+    """g5 -> offsets[C, tile_height, tile_width] int32."""
+    lib = _lib.load()
+    dev = isect_ids.device
+    offs = torch.empty(C, tile_height, tile_width, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.egs_isect_offset_encode(isect_ids.numel(), _ptr(isect_ids), C, tile_width * tile_height,
+                                         tile_n_bits(tile_width, tile_height), _ptr(offs), _stream(dev))
+    _lib.check(rc, "egs_isect_offset_encode")
+    return offs
+
+
+def pack_splats(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, depths: Optional[Tensor] = None) -> Tensor:
+    """Builds the packed 48-byte splat records [C,N,12] from separate tensors (stage-level tests)."""
+    C, N = means2d.shape[:2]
+    z = torch.zeros(C, N, 1, dtype=torch.float32, device=means2d.device)
+    d = z if depths is None else depths[..., None]
+    return torch.cat([means2d, conics, opacities[..., None], colors, d, z, z], -1).contiguous()
+
+
+def rasterize_fwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],
+                  width: int, height: int, count_pairs: bool = False):
+    """g6 -> render_colors[C,H,W,3], render_alphas[C,H,W,1], last_ids[C,H,W] (, (P_eval, P_acc) tensor)."""
+    lib = _lib.load()
+    dev = splats.device
+    C, N = splats.shape[:2]
+    th, tw = isect_offsets.shape[1:]
+    colors = torch.empty(C, height, width, 3, dtype=torch.float32, device=dev)
+    alphas = torch.empty(C, height, width, 1, dtype=torch.float32, device=dev)
+    last = torch.empty(C, height, width, dtype=torch.int32, device=dev)
+    bg = None if backgrounds is None else _f32c(backgrounds, "backgrounds")
+    args = [C, N, flatten_ids.numel(), _ptr(splats), _ptr(isect_offsets), _ptr(flatten_ids), _ptr(bg), int(width),
+            int(height), tw, th, _ptr(colors), _ptr(alphas), _ptr(last)]
+    with torch.cuda.device(dev):
+        if count_pairs:
+            counters = torch.zeros(2, dtype=torch.int64, device=dev)
+            rc = lib.egs_rasterize_fwd_count(*args, _ptr(counters), _stream(dev))
+        else:
+            rc = lib.egs_rasterize_fwd(*args, _stream(dev))
+    _lib.check(rc, "egs_rasterize_fwd")
+    return (colors, alphas, last, counters) if count_pairs else (colors, alphas, last)
+
+
+def rasterize_bwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],
+                  width: int, height: int, render_alphas: Tensor, last_ids: Tensor, v_render_colors: Tensor,
+                  v_render_alphas: Tensor) -> Tensor:
+    """g7 -> packed gradient records v_splats[C,N,12] (layout in include/egs_raster.h)."""
+    lib = _lib.load()
+    dev = splats.device
+    C, N = splats.shape[:2]
+    th, tw = isect_offsets.shape[1:]
+    v_splats = torch.zeros(C, N, SPLAT_FLOATS, dtype=torch.float32, device=dev)
+    bg = None if backgrounds is None else _f32c(backgrounds, "backgrounds")
+    v_c, v_a = _f32c(v_render_colors, "v_render_colors"), _f32c(v_render_alphas, "v_render_alphas")
+    with torch.cuda.device(dev):
+        rc = lib.egs_rasterize_bwd(C, N, flatten_ids.numel(), _ptr(splats), _ptr(isect_offsets), _ptr(flatten_ids),
+                                   _ptr(bg), int(width), int(height), tw, th, _ptr(render_alphas), _ptr(last_ids),
+                                   _ptr(v_c), _ptr(v_a), _ptr(v_splats), _stream(dev))
+    _lib.check(rc, "egs_rasterize_bwd")
+    return v_splats
+
+
+def densify_stats_update(max_radii: Tensor, grad_norm_accum: Tensor, collecting_counts: Tensor, radii: Tensor,
+                         absgrad: Tensor, width: int, height: int) -> None:
+    """§8f-1: in-place, sync-free equivalent of GaussianModel.update_statistics
+    (/root/reference/model/gaussian.py:188-197) for all C views of a call."""
+    lib = _lib.load()
+    dev = radii.device
+    C, N = radii.shape
+    absgrad = _f32c(absgrad, "absgrad")
+    for t, nm in ((max_radii, "max_radii"), (grad_norm_accum, "grad_norm_accum"), (collecting_counts, "collecting_counts")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == N):
+            raise ValueError(f"{nm} must be a contiguous float32 CUDA tensor of N={N} elements")
+    with torch.cuda.device(dev):
+        rc = lib.egs_densify_stats_update(C, N, _ptr(radii.contiguous()), _ptr(absgrad), float(max(height, width)),
+                                          _ptr(max_radii), _ptr(grad_norm_accum), _ptr(collecting_counts), _stream(dev))
+    _lib.check(rc, "egs_densify_stats_update")

@@ -1,0 +1,150 @@
+/*
+ * egs_raster.h — C ABI of the B200-native differentiable Gaussian rasterizer.
+ *
+ * This is the drop-in boundary for the ONE hot path of li199603/easy_gaussian_splatting:
+ * the call `gsplat.rendering.rasterization(...)` at /root/reference/model/gaussian.py:353-367
+ * (import at model/gaussian.py:8).  The reference has no FFI of its own — it is pure Python and
+ * reaches CUDA through the third-party `gsplat` package — so every entry point below cites the
+ * gsplat-1.0.0 operator whose role it takes behind that call (SURVEY.md §2.1 / §8a rows g1–g9)
+ * and, where one exists, the reference line that consumes the result.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all pointers are DEVICE pointers unless named `host_*`;
+ *   - all arrays are dense, row-major, fp32 / int32 / int64 as named;
+ *   - the library never allocates, frees or caches device memory and keeps no device state;
+ *     work buffers are passed in (`*_workspace_bytes` tells how large);
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and re-entrant;
+ *   - return value: 0 on success, otherwise a negative egs_status or a positive cudaError_t;
+ *     `egs_last_error_string()` (thread local) explains the last failure.  Nothing throws.
+ */
+#ifndef EGS_RASTER_H_
+#define EGS_RASTER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGS_ABI_VERSION 1
+
+typedef void* egs_stream_t; /* cudaStream_t */
+
+enum egs_status {
+  EGS_OK = 0,
+  EGS_ERR_INVALID_ARGUMENT = -1,
+  EGS_ERR_WORKSPACE_TOO_SMALL = -2,
+  EGS_ERR_UNSUPPORTED = -3,
+};
+
+/* Number of floats in one packed splat record / one packed gradient record (48 bytes, 16B aligned).
+ * splat record : {x, y, conic_a, conic_b | conic_c, opacity, r, g | b, depth, 0, 0}
+ * grad  record : {v_x, v_y, v_conic_a, v_conic_b | v_conic_c, v_opacity, v_r, v_g | v_b, |v_x|, |v_y|, 0} */
+#define EGS_SPLAT_FLOATS 12
+
+int egs_abi_version(void);
+const char* egs_last_error_string(void);
+
+/* ---- g1 + g2 (+ the count half of g3): fused projection, SH colour, tile count ---------------
+ * Replaces gsplat `fully_fused_projection` fwd, `spherical_harmonics` fwd, the Python glue
+ * `dirs = means - inverse(viewmats)[:3,3]`, `clamp_min(rgb + 0.5, 0)` and the first launch of
+ * `isect_tiles`, all reached from model/gaussian.py:353-367.
+ *   means[N,3] quats[N,4](wxyz, unnormalised) scales[N,3] opacities[N]
+ *   sh_coeffs: sh_degree >= 0 → [N,K,3] SH coefficients (K >= (sh_degree+1)^2, sh_degree <= 3);
+ *              sh_degree <  0 → colours used as they are, [N,3] (colors_per_camera = 0)
+ *              or [C,N,3] (colors_per_camera = 1)
+ *   viewmats[C,4,4] Ks[C,3,3]
+ * outputs (culled entries are zero-filled, radii == 0):
+ *   radii[C,N] i32, means2d[C,N,2], depths[C,N], conics[C,N,3], colors[C,N,3],
+ *   tiles_per_gauss[C,N] i32, splats[C,N,12] packed records (only visible entries are written). */
+int egs_projection_fwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                       const float* opacities, const float* sh_coeffs, int32_t K, int32_t sh_degree,
+                       int32_t colors_per_camera, const float* viewmats, const float* Ks, int32_t width,
+                       int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
+                       int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii,
+                       float* means2d, float* depths, float* conics, float* colors, int32_t* tiles_per_gauss,
+                       float* splats, egs_stream_t stream);
+
+/* ---- g8 + g9: fused SH backward + projection backward ------------------------------------------
+ * Replaces gsplat `spherical_harmonics` bwd and `fully_fused_projection` bwd (summed over cameras).
+ *   v_splats[C,N,12]: packed gradient records produced by egs_rasterize_bwd
+ *   v_means2d_extra[C,N,2] (nullable): user gradient that arrived on meta["means2d"] itself
+ * outputs (dense, written for every Gaussian): v_means[N,3], v_quats[N,4], v_scales[N,3],
+ *   v_opacities[N], v_sh_coeffs (same shape as sh_coeffs; inactive bands and culled entries are 0). */
+int egs_projection_bwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                       const float* sh_coeffs, int32_t K, int32_t sh_degree, int32_t colors_per_camera,
+                       const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
+                       const int32_t* radii, const float* colors, const float* v_splats,
+                       const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
+                       float* v_opacities, float* v_sh_coeffs, egs_stream_t stream);
+
+/* ---- g3: exclusive scan of tiles_per_gauss, then key emission -------------------------------------
+ * Replaces `torch.cumsum` + the second launch of gsplat `isect_tiles`.
+ * egs_exclusive_scan: out[i] = sum_{j<i} in[j] (int64), *total = sum of all (device int64). */
+int64_t egs_exclusive_scan_workspace_bytes(int64_t n);
+int egs_exclusive_scan(int64_t n, const int32_t* in, int64_t* out, int64_t* total, void* workspace,
+                       int64_t workspace_bytes, egs_stream_t stream);
+
+/* key = cam << (32 + tile_n_bits) | tile << 32 | bits(depth);  value = c*N + n.
+ * Emission order: flat (c,n) order, tiles row-major inside a Gaussian. */
+int egs_isect_emit(int32_t C, int32_t N, const float* means2d, const int32_t* radii, const float* depths,
+                   const int64_t* cum_tiles_excl, int32_t tile_size, int32_t tile_width, int32_t tile_height,
+                   int32_t tile_n_bits, int64_t n_isects, int64_t* isect_ids, int32_t* flatten_ids,
+                   egs_stream_t stream);
+
+/* ---- g4: stable LSD onesweep radix sort of (u64 key, u32 value) pairs ----------------------------
+ * Replaces `cub::DeviceRadixSort::SortPairs` inside gsplat `isect_tiles`.  Sorts on key bits
+ * [0, end_bit) in ceil(end_bit / 8) passes, ping-ponging between (keys_a, vals_a) and
+ * (keys_b, vals_b); input is taken from the `a` buffers.  Returns in *result_in_b (HOST int)
+ * whether the sorted data ended in the `b` buffers. */
+int64_t egs_radix_sort_workspace_bytes(int64_t n, int32_t end_bit);
+int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
+                                 uint32_t* vals_b, int32_t end_bit, void* workspace, int64_t workspace_bytes,
+                                 int32_t* host_result_in_b, egs_stream_t stream);
+
+/* ---- g5: tile offsets -------------------------------------------------------------------------------
+ * Replaces gsplat `isect_offset_encode`.  offsets[C*n_tiles] i32 (fully written, also for n = 0). */
+int egs_isect_offset_encode(int64_t n_isects, const int64_t* isect_ids_sorted, int32_t C, int32_t n_tiles,
+                            int32_t tile_n_bits, int32_t* offsets, egs_stream_t stream);
+
+/* ---- g6: alpha blending forward ----------------------------------------------------------------------
+ * Replaces gsplat `rasterize_to_pixels` fwd (3 colour channels, tile_size 16).
+ *   backgrounds[C,3] nullable.  outputs: render_colors[C,H,W,3], render_alphas[C,H,W,1],
+ *   last_ids[C,H,W] i32 (index into the sorted intersection list of the last blended Gaussian). */
+int egs_rasterize_fwd(int32_t C, int32_t N, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
+                      const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
+                      int32_t tile_width, int32_t tile_height, float* render_colors, float* render_alphas,
+                      int32_t* last_ids, egs_stream_t stream);
+
+/* Instrumented variant used only by bench.py / tests for the roofline model: additionally adds the
+ * number of evaluated and accepted (pixel, Gaussian) pairs (P_eval, P_acc of SURVEY.md §8d) to
+ * pair_counters[0..1] (device uint64, zeroed by the caller). */
+int egs_rasterize_fwd_count(int32_t C, int32_t N, int64_t n_isects, const float* splats,
+                            const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
+                            int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
+                            float* render_colors, float* render_alphas, int32_t* last_ids,
+                            uint64_t* pair_counters, egs_stream_t stream);
+
+/* ---- g7: alpha blending backward ----------------------------------------------------------------------
+ * Replaces gsplat `rasterize_to_pixels` bwd incl. absgrad (model/gaussian.py:191 reads it).
+ * v_splats[C,N,12] must be zero-filled by the caller; gradients are accumulated with
+ * warp-reduced global reductions. */
+int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
+                      const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
+                      int32_t tile_width, int32_t tile_height, const float* render_alphas,
+                      const int32_t* last_ids, const float* v_render_colors, const float* v_render_alphas,
+                      float* v_splats, egs_stream_t stream);
+
+/* ---- §8f-1: fused, sync-free densification statistics (C-aware) ----------------------------------------
+ * Replaces GaussianModel.update_statistics, /root/reference/model/gaussian.py:188-197, applied once
+ * per camera: visible = radii > 0; max_radii = max(max_radii, radii / max_hw);
+ * grad_norm_accum += |absgrad|_2 * max_hw; collecting_counts += 1.
+ *   radii[C,N] i32, absgrad[C,N,2] (the tensor tagged on meta["means2d"].absgrad), stats [N] f32. */
+int egs_densify_stats_update(int32_t C, int32_t N, const int32_t* radii, const float* absgrad, float max_hw,
+                             float* max_radii, float* grad_norm_accum, float* collecting_counts,
+                             egs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGS_RASTER_H_ */
