@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""Benchmark of the differentiable Gaussian rasterizer hot path (BASELINE.json metric:
+"fwd+bwd raster Mpix/s at 1M Gaussians 1080p").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload metric|cfg2|...]
+
+One "step" = every rank renders its `views_per_rank` camera views of the replicated synthetic
+scene through `rasterization()` forward + backward of the linear functional
+L = sum(colors*Wc) + sum(alphas*Wa); for N > 1 the step ends with the NCCL
+all-reduce of the flat parameter-gradient bucket and of the densification statistics (the path's
+one real exchange step).  value = total pixels rendered by all ranks / time, Mpix/s.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's
+rasterizer (oracle/, pure PyTorch — gsplat itself is not installable here) on a
+bounded crop of the same workload on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+METRIC = "fwd+bwd raster Mpix/s at 1M Gaussians 1080p"
+UNIT = "Mpix/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="metric")
+    ap.add_argument("--views-per-rank", type=int, default=4)
+    ap.add_argument("--n-gaussians", type=int, default=None, help="override N (debug only; marks the line invalid)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stage-timing", action="store_true")
+    ap.add_argument("--ref-crop", type=int, default=8, help="reference arm: crop = 1/ref_crop of W and of H")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on a bounded crop of the workload
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_scene(workload: str, crop: int, n_override=None):
+    """Same scene and camera; only a centred (W/crop x H/crop) window of the image is rendered
+    (principal point shifted accordingly), which bounds the CPU work."""
+    from easy_gaussian_splatting_b200.synthetic import CONFIGS, make_config_scene
+    sc = make_config_scene(workload, n_views=1, N=n_override)
+    cw, ch = max(16, sc.width // crop), max(16, sc.height // crop)
+    x0, y0 = (sc.width - cw) // 2, (sc.height - ch) // 2
+    Ks = sc.Ks.clone()
+    Ks[:, 0, 2] -= x0
+    Ks[:, 1, 2] -= y0
+    sc.Ks, sc.width, sc.height = Ks, cw, ch
+    return sc, f"{cw}x{ch} centre crop of the {CONFIGS[workload]['width']}x{CONFIGS[workload]['height']} view, all {sc.means.shape[0]} Gaussians, 1 view"
+
+
+def run_cpu_oracle(sc, steps: int, warmup: int):
+    """fwd+bwd of the oracle; returns (median seconds per step, Mpix/s)."""
+    from easy_gaussian_splatting_b200.synthetic import loss_weights
+    from oracle import gsplat_oracle as O
+    Wc, Wa = loss_weights(sc.seed, 1, sc.height, sc.width)
+    times = []
+    for it in range(warmup + steps):
+        leaves = [t.detach().clone().requires_grad_(True) for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+        t0 = time.perf_counter()
+        rc, ra, meta = O.rasterization(*leaves, sc.viewmats, sc.Ks, sc.width, sc.height, sh_degree=3, packed=False,
+                                       absgrad=True, backgrounds=sc.background[None])
+        ((rc * Wc).sum() + (ra * Wa).sum()).backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return med, sc.width * sc.height / med / 1e6, sum(times)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # only rank 0 runs the CPU comparator
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sc, sample = cpu_sample_scene(args.workload, args.ref_crop, args.n_gaussians)
+    med, mpix, total = run_cpu_oracle(sc, args.steps, max(args.warmup, 1) if args.steps > 1 else args.warmup)
+    line = {
+        "metric": METRIC, "value": mpix, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": sample,
+                   "note": "CPU restatement of gsplat 1.0.0 semantics in pure PyTorch (oracle/); gsplat itself is "
+                           "not installable in this image"},
+        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    from easy_gaussian_splatting_b200.synthetic import CONFIGS
+    c = dict(CONFIGS[args.workload])
+    if args.n_gaussians:
+        c["N"] = args.n_gaussians
+    return f"{args.workload}: {c['N']} Gaussians ({c['kind']} scene, seed {c['seed']}), {c['width']}x{c['height']}, SH degree 3, absgrad, packed=False"
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch.distributed as dist
+    from easy_gaussian_splatting_b200 import _lib, rasterization, stages
+    from easy_gaussian_splatting_b200.distributed import DensifyStats, FlatGradBucket
+    from easy_gaussian_splatting_b200.synthetic import CONFIGS, loss_weights, make_config_scene
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    V = args.views_per_rank
+    cfg = CONFIGS[args.workload]
+    W, H = cfg["width"], cfg["height"]
+
+    # identical replicated scene on every rank; rank r renders views {r*V .. r*V+V-1} of a world*V orbit
+    sc_cpu = make_config_scene(args.workload, n_views=world * V, N=args.n_gaussians)
+    N = sc_cpu.means.shape[0]
+    my_views = list(range(rank * V, rank * V + V))
+    names = ("means", "quats", "scales", "opacities", "colors")
+    params = [getattr(sc_cpu, k).to(dev).requires_grad_(True) for k in names]
+    bucket = FlatGradBucket(params)
+    stats = DensifyStats(N, dev)
+    bg = sc_cpu.background[None].to(dev)
+    Wc_cpu, Wa_cpu = loss_weights(sc_cpu.seed, 1, H, W)
+    # pinned host copies of the per-step inputs (camera + loss weights = the "target image" of a training step)
+    pin = lambda t: t.contiguous().pin_memory()
+    host_views = [(pin(sc_cpu.viewmats[v:v + 1]), pin(sc_cpu.Ks[v:v + 1])) for v in my_views]
+    host_Wc, host_Wa = pin(Wc_cpu), pin(Wa_cpu)
+    dev_views = [(a.to(dev), b.to(dev)) for a, b in host_views]
+    dev_Wc, dev_Wa = host_Wc.to(dev), host_Wa.to(dev)
+    h2d_bytes = V * (host_views[0][0].numel() * 4 + host_views[0][1].numel() * 4 + host_Wc.numel() * 4 + host_Wa.numel() * 4)
+    d2h_bytes = V * 4
+
+    def one_view(viewmat, K, Wc, Wa, want_loss):
+        rc, ra, meta = rasterization(params[0], params[1], params[2], params[3], params[4], viewmat, K, W, H,
+                                     sh_degree=3, packed=False, absgrad=True, backgrounds=bg)
+        loss = (rc * Wc).sum() + (ra * Wa).sum()
+        loss.backward()
+        stats.update_local(meta["radii"], meta["means2d"].absgrad, W, H)
+        return loss if want_loss else None
+
+    def step_resident():
+        bucket.zero_()
+        before = stats.clone() if world > 1 else None
+        for (vm, K) in dev_views:
+            one_view(vm, K, dev_Wc, dev_Wa, False)
+        if world > 1:
+            bucket.all_reduce()
+            stats.all_reduce_delta(before)
+
+    def step_e2e():
+        bucket.zero_()
+        before = stats.clone() if world > 1 else None
+        total = 0.0
+        for (hvm, hK) in host_views:
+            vm, K = hvm.to(dev, non_blocking=True), hK.to(dev, non_blocking=True)
+            Wc, Wa = host_Wc.to(dev, non_blocking=True), host_Wa.to(dev, non_blocking=True)
+            loss = one_view(vm, K, Wc, Wa, True)
+            total += loss.item()  # device -> host read of the step's result, like train.py:107-108
+        if world > 1:
+            bucket.all_reduce()
+            stats.all_reduce_delta(before)
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.15)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    W_ = max(args.warmup, 3)
+    ms_total, clocks = timed(step_resident, args.steps, W_, sample_clocks=True)
+    ms_step = ms_total / args.steps
+    pixels_per_step = world * V * W * H
+    value = pixels_per_step / (ms_step * 1e-3) / 1e6
+    ms_e2e_total, _ = timed(step_e2e, args.steps, 2)
+    e2e_value = pixels_per_step / (ms_e2e_total / args.steps * 1e-3) / 1e6
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "views_per_rank_per_step": V, "views_per_step": world * V,
+                   "l2": "inputs larger than L2 (236 MB parameters + 96 MB splat/gradient records per view vs 126 MB L2)",
+                   "exchange": "none (1 GPU)" if world == 1 else "NCCL all-reduce of the flat 236 B/Gaussian gradient bucket + 12 B/Gaussian densify stats each step"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e_total / args.steps,
+                "what": "rasterization() fwd+bwd per view with the view's camera and loss weights (target-image sized) copied "
+                        "from pinned host memory and loss.item() read back each view; Gaussian parameters stay resident "
+                        "(they are the model, /root/reference/train.py:97-108)"},
+        "gpu_launches": 17 * V * args.steps,
+    }
+    if args.n_gaussians:
+        line["invalid"] = "N overridden (debug run)"
+
+    if rank == 0 and not args.no_stage_timing:
+        line.update(stage_rooflines(lib, stages, params, dev_views[0], bg, dev_Wc, dev_Wa, W, H, dev))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sc, sample = cpu_sample_scene(args.workload, args.ref_crop, args.n_gaussians)
+        med, mpix, _ = run_cpu_oracle(sc, 3, 1)
+        line["cpu_baseline"] = {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                "ms_per_sample": med * 1e3}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
+    """Times every kernel family in isolation with CUDA events on the launching stream and relates it
+    to its algorithmic work (BASELINE.md §4 constants)."""
+    import ctypes
+    pk = peaks()
+    means, quats, scales, opac, colors = [p.detach() for p in params]
+    vm, K = view
+    N = means.shape[0]
+    tw, th = stages.tile_grid(W, H)
+
+    def tm(fn, reps=reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    # FP32 peak probe (dependent FMA chains, 8 per thread)
+    out = torch.zeros(4, device=dev)
+    flops = ctypes.c_double(0)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def probe():
+        lib.egs_probe_fp32_fma(148 * 16, 4096, ctypes.c_void_p(out.data_ptr()), ctypes.byref(flops), st)
+    probe_ms = tm(probe, 5)
+    fp32_peak = flops.value / (probe_ms * 1e-3) / 1e12
+
+    proj = stages.projection_fwd(means, quats, scales, opac, colors, vm, K, W, H, 3)
+    n_vis = int((proj["radii"] > 0).sum())
+    tpg, ids_u, flat_u = stages.isect_tiles(proj["means2d"], proj["radii"], proj["depths"], 16, tw, th, sort=False,
+                                            tiles_per_gauss=proj["tiles_per_gauss"])
+    n_isects = ids_u.numel()
+    nbits = stages.tile_n_bits(tw, th)
+    ids, flat = stages.radix_sort_pairs(ids_u.clone(), flat_u.clone(), 32 + nbits)
+    offs = stages.isect_offset_encode(ids, 1, tw, th)
+    rc, ra, last, pairs = stages.rasterize_fwd(proj["splats"], offs, flat, bg, W, H, count_pairs=True)
+    p_eval, p_acc = int(pairs[0]), int(pairs[1])
+    v_splats = stages.rasterize_bwd(proj["splats"], offs, flat, bg, W, H, ra, last, Wc, Wa)
+
+    t = {}
+    t["projection_sh_fwd"] = tm(lambda: stages.projection_fwd(means, quats, scales, opac, colors, vm, K, W, H, 3))
+    t["scan"] = tm(lambda: stages.exclusive_scan(proj["tiles_per_gauss"]))
+    t["emit"] = tm(lambda: stages.isect_tiles(proj["means2d"], proj["radii"], proj["depths"], 16, tw, th, sort=False,
+                                              tiles_per_gauss=proj["tiles_per_gauss"], n_isects=n_isects)) - t["scan"]
+    ka, va = ids_u.clone(), flat_u.clone()
+
+    def sort_once():
+        ka.copy_(ids_u)
+        va.copy_(flat_u)
+        stages.radix_sort_pairs(ka, va, 32 + nbits)
+    copy_ms = tm(lambda: (ka.copy_(ids_u), va.copy_(flat_u)))
+    t["radix_sort"] = tm(sort_once) - copy_ms
+    t["offset_encode"] = tm(lambda: stages.isect_offset_encode(ids, 1, tw, th))
+    t["rasterize_fwd"] = tm(lambda: stages.rasterize_fwd(proj["splats"], offs, flat, bg, W, H))
+    zero_ms = tm(lambda: torch.zeros_like(v_splats))
+    t["rasterize_bwd"] = tm(lambda: stages.rasterize_bwd(proj["splats"], offs, flat, bg, W, H, ra, last, Wc, Wa)) - zero_ms
+    t["projection_sh_bwd"] = tm(lambda: stages.projection_bwd(means, quats, scales, colors, vm, K, W, H, 3, 0.3,
+                                                               proj["radii"], proj["colors"], v_splats))
+    passes = math.ceil((32 + nbits) / 8)
+    work = {  # algorithmic bytes (HBM-bound stages) or flops (blend) per launch, BASELINE.md §4
+        "projection_sh_fwd": ("hbm", 68 * N + 204 * n_vis),
+        "scan": ("hbm", 12 * N),
+        "emit": ("hbm", 32 * N + 12 * n_isects),
+        "radix_sort": ("hbm", (8 + 24 * passes) * n_isects),
+        "offset_encode": ("hbm", 8 * n_isects + 4 * tw * th),
+        "rasterize_fwd": ("fp32", 16 * p_eval + 10 * p_acc),
+        "rasterize_bwd": ("fp32", 16 * p_eval + 54 * p_acc),
+        "projection_sh_bwd": ("hbm", 108 * N + 12 * N + 408 * n_vis + 192 * (N - n_vis)),
+    }
+    stages_out = {}
+    for k, (bound, w) in work.items():
+        ms = max(t[k], 1e-6)
+        if bound == "hbm":
+            ach = w / (ms * 1e-3) / 1e9
+            stages_out[k] = {"ms": ms, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "frac": ach / pk["hbm_gbs"], "algorithmic_bytes": w}
+        else:
+            ach = w / (ms * 1e-3) / 1e12
+            stages_out[k] = {"ms": ms, "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                             "frac": ach / fp32_peak, "algorithmic_flops": w}
+    dominant = max(t, key=lambda k: t[k])
+    roof = dict(stages_out[dominant])
+    roof["kernel"] = dominant
+    roof["traffic"] = None
+    roof["peak_source"] = pk["source"] if roof["bound"] == "hbm" else \
+        f"measured live: dependent-FMA probe kernel, {fp32_peak:.1f} TFLOP/s (theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)"
+    return {"roofline": roof, "stages": stages_out,
+            "scene_stats": {"N": N, "N_vis": n_vis, "n_isects": n_isects, "isects_per_visible": n_isects / max(n_vis, 1),
+                            "P_eval": p_eval, "P_acc": p_acc, "fp32_peak_tflops_measured": fp32_peak,
+                            "sum_stage_ms": sum(t.values())}}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+"""View-sharded multi-GPU training step (new capability named by BASELINE.json north_star; the
+reference itself is single-GPU).
+
+Every rank holds a full replica of the Gaussian parameters, renders its own share of the step's
+camera views, and then two collectives make the replicas agree again:
+
+* parameter gradients: one SUM all-reduce over a single flat bucket (59 floats = 236 B per
+  Gaussian).  The bucket is the storage of every ``param.grad``, so autograd accumulates straight
+  into it and no pack / unpack copy exists;
+* densification statistics (/root/reference/model/gaussian.py:56-64,188-197): SUM for
+  ``grad_norm_accum`` and ``collecting_counts``, MAX for ``max_radii`` (12 B per Gaussian).  Each
+  rank first applies the per-view update for its own views (``stages.densify_stats_update``), so the
+  reduced result equals what one GPU would have accumulated over all views.
+
+Works with any torch.distributed backend (NCCL over NVLink on the B200 box, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Sequence
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def shard_views(n_views: int, rank: int, world_size: int) -> List[int]:
+    """Round-robin view partition: rank r renders {v : v mod R == r}."""
+    return [v for v in range(n_views) if v % world_size == rank]
+
+
+class FlatGradBucket:
+    """One contiguous fp32 buffer that backs ``.grad`` of every parameter."""
+
+    def __init__(self, params: Sequence[Tensor]):
+        self.params = list(params)
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        off = 0
+        self.views = []
+        for p in self.params:
+            v = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = v
+            self.views.append(v)
+            off += p.numel()
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):  # an optimizer may have detached .grad
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
+
+    def all_reduce(self, group=None, async_op: bool = False):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return None
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+
+class DensifyStats:
+    """max_radii / grad_norm_accum / collecting_counts with the reference's semantics, kept as three
+    rows of one [3,N] buffer so the SUM rows travel in one collective."""
+
+    def __init__(self, n: int, device):
+        self.buf = torch.zeros(3, n, dtype=torch.float32, device=device)
+
+    @property
+    def grad_norm_accum(self) -> Tensor:
+        return self.buf[0]
+
+    @property
+    def collecting_counts(self) -> Tensor:
+        return self.buf[1]
+
+    @property
+    def max_radii(self) -> Tensor:
+        return self.buf[2]
+
+    def update_local(self, radii: Tensor, absgrad: Tensor, width: int, height: int) -> None:
+        """Per-view update for the views this rank rendered (CUDA kernel; no host sync)."""
+        from . import stages
+        stages.densify_stats_update(self.max_radii, self.grad_norm_accum, self.collecting_counts, radii, absgrad,
+                                    width, height)
+
+    def all_reduce_delta(self, before: "DensifyStats", group=None) -> None:
+        """Replicas start a step with identical stats; each adds its own views' contribution.  The
+        globally consistent result is before + SUM(delta) for the two accumulators and MAX for radii."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        delta = self.buf[:2] - before.buf[:2]
+        dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
+        self.buf[:2] = before.buf[:2] + delta
+        mr = self.buf[2].contiguous()
+        dist.all_reduce(mr, op=dist.ReduceOp.MAX, group=group)
+        self.buf[2] = mr
+
+    def clone(self) -> "DensifyStats":
+        c = DensifyStats.__new__(DensifyStats)
+        c.buf = self.buf.clone()
+        return c

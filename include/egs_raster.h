@@ -144,6 +144,11 @@ int egs_densify_stats_update(int32_t C, int32_t N, const int32_t* radii, const f
                              float* max_radii, float* grad_norm_accum, float* collecting_counts,
                              egs_stream_t stream);
 
+/* ---- measurement utility (bench.py only) -----------------------------------------------------------------
+ * Dependent-FMA throughput probe: the FP32-SIMT roofline denominator for the blending kernels
+ * (BASELINE.md §3).  blocks x 256 threads x iters x 32 FMAs; *host_flops (HOST double) = flops issued. */
+int egs_probe_fp32_fma(int32_t blocks, int32_t iters, float* out, double* host_flops, egs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,201 @@
+"""-m gpu: per-stage parity of the CUDA kernels (called through the C-ABI) against the CPU oracle.
+Integer / index work must be bit-exact; floating point within the tolerance written at each check."""
+import math
+
+import pytest
+import torch
+
+from easy_gaussian_splatting_b200.synthetic import make_scene
+from oracle import gsplat_oracle as O
+from tests.util import image_report, rel_err
+
+pytestmark = pytest.mark.gpu
+
+SCENES = [
+    dict(kind="blob", N=10_000, width=256, height=256, fx=274.5, seed=0, n_views=1),
+    dict(kind="blob", N=3_000, width=131, height=77, fx=120.0, seed=7, n_views=3),      # ragged tiles, C>1
+    dict(kind="outdoor", N=60_000, width=979, height=546, fx=581.0, seed=2, n_views=2),  # many culled
+    dict(kind="object", N=20_000, width=400, height=400, fx=555.0, seed=1, n_views=1, white_background=True),
+]
+
+
+def _stages():
+    from easy_gaussian_splatting_b200 import stages
+    return stages
+
+
+@pytest.mark.parametrize("cfg", SCENES)
+@pytest.mark.parametrize("sh_degree", [0, 3])
+def test_projection_bit_exact(cfg, sh_degree):
+    st = _stages()
+    sc = make_scene(**cfg)
+    d = sc.to("cuda")
+    out = st.projection_fwd(d.means, d.quats, d.scales, d.opacities, d.colors, d.viewmats, d.Ks, sc.width, sc.height, sh_degree)
+    radii, m2, dep, con = O.fully_fused_projection(sc.means, sc.quats, sc.scales, sc.viewmats, sc.Ks, sc.width, sc.height)
+    assert torch.equal(out["radii"].cpu(), radii), "radii must be bit-exact"
+    assert torch.equal(out["means2d"].cpu(), m2), "means2d must be bit-exact"
+    assert torch.equal(out["depths"].cpu(), dep), "depths must be bit-exact"
+    assert torch.equal(out["conics"].cpu(), con), "conics must be bit-exact"
+    tw, th = st.tile_grid(sc.width, sc.height)
+    tpg, _, _ = O.isect_tiles(m2, radii, dep, 16, tw, th, sort=False)
+    assert torch.equal(out["tiles_per_gauss"].cpu(), tpg), "tiles_per_gauss must be bit-exact"
+    C = sc.viewmats.shape[0]
+    campos = torch.inverse(sc.viewmats)[:, :3, 3]
+    dirs = sc.means[None] - campos[:, None]
+    cols = torch.clamp_min(O.spherical_harmonics(sh_degree, dirs, sc.colors[None].expand(C, -1, -1, -1), radii > 0) + 0.5, 0)
+    cols = torch.where((radii > 0)[..., None], cols, torch.zeros(()))
+    assert (out["colors"].cpu() - cols).abs().max().item() <= 2e-6  # fp32 summation-order tolerance
+    # packed records agree with the separate tensors where visible
+    vis = radii > 0
+    sp = out["splats"].cpu()[vis]
+    assert torch.equal(sp[:, 0:2], m2[vis]) and torch.equal(sp[:, 2:5], con[vis])
+    assert torch.equal(sp[:, 5], sc.opacities[None].expand(C, -1)[vis])
+    assert torch.equal(sp[:, 6:9], out["colors"].cpu()[vis])
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 255, 256, 2047, 2048, 2049, 100_000, 1_234_567])
+def test_exclusive_scan(n):
+    st = _stages()
+    g = torch.Generator().manual_seed(n)
+    x = torch.randint(0, 50, (n,), generator=g, dtype=torch.int32)
+    out, total = st.exclusive_scan(x.cuda())
+    ref = torch.cumsum(x.long(), 0) - x.long()
+    assert torch.equal(out.cpu(), ref)
+    assert int(total.item()) == int(x.long().sum())
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 4095, 4096, 4097, 50_000, 1_000_003])
+@pytest.mark.parametrize("end_bit,dist", [(45, "uniform"), (41, "few_tiles"), (64, "uniform"), (8, "uniform"), (47, "dups")])
+def test_radix_sort_pairs(n, end_bit, dist):
+    st = _stages()
+    g = torch.Generator().manual_seed(n * 131 + end_bit)
+    if dist == "uniform":
+        hi = torch.randint(0, 2 ** 31 - 1, (n,), generator=g, dtype=torch.int64)
+        lo = torch.randint(0, 2 ** 31 - 1, (n,), generator=g, dtype=torch.int64)
+        keys = (hi << 32) | (lo << 1) | (hi & 1)
+    elif dist == "few_tiles":  # realistic: few distinct high parts, float-like low parts
+        tile = torch.randint(0, 300, (n,), generator=g, dtype=torch.int64)
+        depth = (torch.rand(n, generator=g) * 10 + 0.5).view(torch.int32).long()
+        keys = (tile << 32) | depth
+    else:  # heavy duplication: stability decides the value order
+        keys = torch.randint(0, 7, (n,), generator=g, dtype=torch.int64) << 33
+    if end_bit < 64:
+        keys = keys & ((1 << end_bit) - 1)
+    else:
+        keys = keys & 0x7FFFFFFFFFFFFFFF  # torch.sort is signed; keep the sign bit clear
+    vals = torch.arange(n, dtype=torch.int32)
+    k, v = st.radix_sort_pairs(keys.cuda().clone(), vals.cuda().clone(), end_bit)
+    rk, order = torch.sort(keys, stable=True)
+    assert torch.equal(k.cpu(), rk), "sorted keys must be bit-exact"
+    assert torch.equal(v.cpu(), vals[order]), "values must follow a STABLE sort"
+
+
+@pytest.mark.parametrize("cfg", SCENES)
+def test_isect_tiles_sort_offsets_bit_exact(cfg):
+    """Given the ORACLE's projection outputs, binning must be bit-exact unconditionally (SURVEY B-1 layer ii)."""
+    st = _stages()
+    sc = make_scene(**cfg)
+    radii, m2, dep, con = O.fully_fused_projection(sc.means, sc.quats, sc.scales, sc.viewmats, sc.Ks, sc.width, sc.height)
+    tw, th = st.tile_grid(sc.width, sc.height)
+    C = sc.viewmats.shape[0]
+    tpg_o, ids_u, flat_u = O.isect_tiles(m2, radii, dep, 16, tw, th, sort=False)
+    tpg_o, ids_o, flat_o = O.isect_tiles(m2, radii, dep, 16, tw, th, sort=True)
+    tpg, ids, flat = st.isect_tiles(m2.cuda(), radii.cuda(), dep.cuda(), 16, tw, th, sort=False)
+    assert torch.equal(tpg.cpu(), tpg_o)
+    assert torch.equal(ids.cpu(), ids_u) and torch.equal(flat.cpu(), flat_u), "unsorted emission order / keys"
+    tpg, ids, flat = st.isect_tiles(m2.cuda(), radii.cuda(), dep.cuda(), 16, tw, th, sort=True)
+    assert torch.equal(ids.cpu(), ids_o), "sorted isect_ids"
+    assert torch.equal(flat.cpu(), flat_o), "sorted flatten_ids (stable tie order)"
+    offs = st.isect_offset_encode(ids, C, tw, th)
+    assert torch.equal(offs.cpu(), O.isect_offset_encode(ids_o, C, tw, th))
+
+
+def test_offsets_empty_and_sparse():
+    st = _stages()
+    empty = torch.zeros(0, dtype=torch.int64, device="cuda")
+    offs = st.isect_offset_encode(empty, 2, 5, 3)
+    assert offs.shape == (2, 3, 5) and int(offs.abs().sum()) == 0
+    nb = st.tile_n_bits(5, 3)
+    # entries only in camera 1, tiles 2 and 14 (last)
+    keys = torch.tensor([((1 << nb) | 2) << 32, ((1 << nb) | 2) << 32 | 5, ((1 << nb) | 14) << 32], dtype=torch.int64)
+    offs = st.isect_offset_encode(keys.cuda(), 2, 5, 3).cpu()
+    assert torch.equal(offs, O.isect_offset_encode(keys, 2, 5, 3))
+
+
+def _oracle_front(sc, sh_degree=3):
+    radii, m2, dep, con = O.fully_fused_projection(sc.means, sc.quats, sc.scales, sc.viewmats, sc.Ks, sc.width, sc.height)
+    C = sc.viewmats.shape[0]
+    campos = torch.inverse(sc.viewmats)[:, :3, 3]
+    dirs = sc.means[None] - campos[:, None]
+    cols = torch.clamp_min(O.spherical_harmonics(sh_degree, dirs, sc.colors[None].expand(C, -1, -1, -1), radii > 0) + 0.5, 0)
+    tw, th = math.ceil(sc.width / 16), math.ceil(sc.height / 16)
+    _, ids, flat = O.isect_tiles(m2, radii, dep, 16, tw, th)
+    offs = O.isect_offset_encode(ids, C, tw, th)
+    opac = sc.opacities[None].expand(C, -1).contiguous()
+    return radii, m2, dep, con, cols, opac, ids, flat, offs
+
+
+@pytest.mark.parametrize("cfg", SCENES)
+@pytest.mark.parametrize("with_bg", [True, False])
+def test_rasterize_fwd_bwd_vs_oracle(cfg, with_bg):
+    """Blend kernels fed with the oracle's own intermediates: colours/alphas <= 1e-4 abs on non-borderline
+    pixels (borderline = threshold-flip candidates, counted and bounded separately, SURVEY B-2);
+    per-Gaussian gradients <= 1e-3 norm-wise relative."""
+    st = _stages()
+    sc = make_scene(**cfg)
+    radii, m2, dep, con, cols, opac, ids, flat, offs = _oracle_front(sc)
+    C = sc.viewmats.shape[0]
+    bg = sc.background[None].expand(C, 3).contiguous() if with_bg else None
+    leaves = [t.clone().requires_grad_(True) for t in (m2, con, cols, opac)]
+    counters = {}
+    rc, ra, last = O.rasterize_to_pixels(*leaves, sc.width, sc.height, 16, offs, flat, backgrounds=bg, absgrad=True, counters=counters)
+    g = torch.Generator().manual_seed(5)
+    Wc = torch.rand(rc.shape, generator=g)
+    Wa = torch.rand(ra.shape, generator=g)
+    ((rc * Wc).sum() + (ra * Wa).sum()).backward()
+
+    splats = st.pack_splats(m2.cuda(), con.cuda(), cols.cuda(), opac.cuda(), dep.cuda())
+    bgc = None if bg is None else bg.cuda()
+    colors, alphas, last_ids, pc = st.rasterize_fwd(splats, offs.cuda(), flat.cuda(), bgc, sc.width, sc.height, count_pairs=True)
+    colors2, alphas2, last2 = st.rasterize_fwd(splats, offs.cuda(), flat.cuda(), bgc, sc.width, sc.height)
+    assert torch.equal(colors, colors2) and torch.equal(alphas, alphas2) and torch.equal(last_ids, last2)
+    border = counters["borderline"]
+    rep_c = image_report(colors.cpu(), rc.detach(), border)
+    rep_a = image_report(alphas.cpu(), ra.detach(), border)
+    print("fwd colours", rep_c, "alphas", rep_a, "pairs", pc.tolist(), counters["P_eval"], counters["P_acc"])
+    assert rep_c["max_clean"] <= 1e-4 and rep_a["max_clean"] <= 1e-4
+    assert rep_c["max_border"] <= 2e-2 and rep_c["n_border"] <= max(20, 0.002 * border.numel())
+    same_last = (last_ids.cpu() == last) | border
+    assert same_last.all(), "last_ids must match on non-borderline pixels"
+    # pair counters agree with the oracle up to threshold flips
+    assert abs(pc[0].item() - counters["P_eval"]) <= 1e-3 * counters["P_eval"] + 64
+    assert abs(pc[1].item() - counters["P_acc"]) <= 1e-3 * counters["P_acc"] + 64
+
+    v = st.rasterize_bwd(splats, offs.cuda(), flat.cuda(), bgc, sc.width, sc.height, alphas, last_ids, Wc.cuda(), Wa.cuda()).cpu()
+    tol = 1e-3
+    errs = dict(xy=rel_err(v[..., 0:2], leaves[0].grad), conic=rel_err(v[..., 2:5], leaves[1].grad),
+                opac=rel_err(v[..., 5], leaves[3].grad), rgb=rel_err(v[..., 6:9], leaves[2].grad),
+                absxy=rel_err(v[..., 9:11], m2_abs(leaves[0])))
+    print("bwd rel errs", errs)
+    assert all(e <= tol for e in errs.values()), errs
+    assert float(v[..., 11].abs().max()) == 0.0
+
+
+def m2_abs(leaf):
+    return leaf.absgrad
+
+
+def test_densify_stats_update():
+    st = _stages()
+    g = torch.Generator().manual_seed(3)
+    C, N, W, H = 3, 5000, 640, 360
+    radii = torch.randint(-1, 40, (C, N), generator=g, dtype=torch.int32).clamp_min(0)
+    absg = torch.rand(C, N, 2, generator=g)
+    stats = [torch.rand(N, generator=g) for _ in range(3)]
+    ref = [s.clone() for s in stats]
+    O.update_statistics(ref[0], ref[1], ref[2], radii, absg, W, H)
+    dev = [s.cuda() for s in stats]
+    st.densify_stats_update(dev[0], dev[1], dev[2], radii.cuda(), absg.cuda(), W, H)
+    assert torch.equal(dev[0].cpu(), ref[0]), "max_radii"
+    assert torch.allclose(dev[1].cpu(), ref[1], rtol=1e-6, atol=1e-6), "grad_norm_accum"
+    assert torch.equal(dev[2].cpu(), ref[2]), "collecting_counts"
