@@ -2,24 +2,31 @@
 // rasterize_to_pixels fwd/bwd).  FP32 SIMT + MUFU bound; no dense contraction, so
 // no tensor cores.
 //
-// One CTA per 16x16 pixel tile, one pixel per thread, each warp owning a compact 8x4 pixel block
-// (more coherent accept / terminate decisions than two 16-pixel rows).  The tile's depth-sorted
-// Gaussians are staged through shared memory in batches of 256 packed 48-byte splat records with
-// cp.async (LDGSTS, three 16-byte copies per record, double buffered, with the flatten ids of the
-// batch after next prefetched into registers), so the gather latency of batch b+1 hides behind the
-// blending of batch b.
+// One CTA per 16x16 pixel tile.  A thread owns a PXW x PYH block of pixels (default 2x2: 64 threads,
+// two warps, each warp a compact 16x8 pixel region): the per-Gaussian shared-memory reads, the loop
+// overhead, the separable parts of the quadratic form and — in the backward pass — the warp
+// reduction are amortised over 4 pixels, and the 4 independent pixel chains give the scheduler ILP.
+// The tile's depth-sorted Gaussians are staged through shared memory in batches of 128/256 packed
+// 48-byte splat records with cp.async (LDGSTS, three 16-byte copies per record, double buffered,
+// flatten ids of the batch after next prefetched into registers), so the gather latency of batch
+// b+1 hides behind the blending of batch b.
 //
-// Backward: per-pixel back-to-front replay; the 11 per-Gaussian partial gradients of a warp are
-// combined with a 16-slot shuffle reduce-scatter (16 SHFL instead of the 55 of a per-value
-// butterfly), after which 11 lanes issue one coalesced RED.ADD.F32 into the packed 48-byte gradient
-// record of the Gaussian.
+// All loops over a batch are WARP-UNIFORM (finished pixels are predicated off, a vote at the top of
+// the body is the reconvergence point).  A per-lane break/continue lets the lanes of a warp drift
+// apart under independent thread scheduling: measured with ncu on the first version of the forward
+// kernel, 1.9 active threads per instruction and a 20x slowdown (profiles/r1a_*).
+//
+// Backward: per-pixel back-to-front replay; the 11 per-Gaussian partial gradients are first summed
+// over the thread's own pixels in registers, then combined across the warp with a 16-slot shuffle
+// reduce-scatter (16 SHFL instead of the 55 of a per-value butterfly), after which 11 lanes issue one
+// coalesced RED.ADD.F32 into the packed 48-byte gradient record of the Gaussian.
+#include <stdlib.h>
+
 #include "egs_common.cuh"
 
 namespace egs {
 
 constexpr int kTileSize = 16;
-constexpr int kBlendThreads = kTileSize * kTileSize;  // 256
-constexpr int kBatch = kBlendThreads;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.999f;
 constexpr float kTMin = 1e-4f;
@@ -28,29 +35,49 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-struct TileCoord {
-  int cam, tile_id, px, py;
-  bool inside;
+// exp(-sigma) as one FMUL + MUFU.EX2 (flush-to-zero: anything that small is rejected as alpha < 1/255)
+__device__ __forceinline__ float fast_exp_neg(float sigma) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(sigma * -1.4426950408889634f));
+  return e;
+}
+
+// Thread <-> pixel mapping of one tile.
+template <int PXW, int PYH>
+struct TileMap {
+  static constexpr int NP = PXW * PYH;            // pixels per thread
+  static constexpr int TX = kTileSize / PXW;      // thread grid
+  static constexpr int TY = kTileSize / PYH;
+  static constexpr int NT = TX * TY;              // threads per CTA
+  static constexpr int NW = NT / 32;              // warps per CTA
+  static constexpr int WPR = TX / 8;              // a warp spans 8 x 4 threads
+  // splat records staged per batch: small CTAs use small batches so that shared memory (2 buffers x
+  // 48 B x BATCH) does not cap the number of resident CTAs below what registers allow
+  static constexpr int BATCH = NT >= 256 ? 256 : 128;
+  static constexpr int RPT = BATCH / NT;          // records staged per thread per batch
+  static_assert(TX % 8 == 0 && TY % 4 == 0, "unsupported pixel block");
+};
+
+struct TileRange {
+  int cam, tile_id, x0, y0;  // x0,y0: first pixel of this thread's block
   int range_start, range_end;
 };
 
-__device__ __forceinline__ TileCoord tile_setup(int width, int height, int tile_w, int tile_h, int64_t n_isects,
+template <class M>
+__device__ __forceinline__ TileRange tile_setup(int tile_w, int tile_h, int64_t n_isects,
                                                 const int32_t* __restrict__ tile_offsets, int n_tiles_total) {
-  TileCoord tc;
+  TileRange tc;
   tc.cam = blockIdx.z;
   tc.tile_id = (tc.cam * tile_h + blockIdx.y) * tile_w + blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  tc.px = blockIdx.x * kTileSize + (warp & 1) * 8 + (lane & 7);
-  tc.py = blockIdx.y * kTileSize + (warp >> 1) * 4 + (lane >> 3);
-  tc.inside = tc.px < width && tc.py < height;
+  const int qx = (warp % M::WPR) * 8 + (lane & 7);
+  const int qy = (warp / M::WPR) * 4 + (lane >> 3);
+  tc.x0 = blockIdx.x * kTileSize + qx * (kTileSize / M::TX);
+  tc.y0 = blockIdx.y * kTileSize + qy * (kTileSize / M::TY);
   tc.range_start = tile_offsets[tc.tile_id];
   tc.range_end = (tc.tile_id == n_tiles_total - 1) ? (int)n_isects : tile_offsets[tc.tile_id + 1];
   return tc;
@@ -59,92 +86,133 @@ __device__ __forceinline__ TileCoord tile_setup(int width, int height, int tile_
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlendThreads) rasterize_fwd_kernel(
+template <int PXW, int PYH, bool COUNT>
+__global__ void __launch_bounds__(TileMap<PXW, PYH>::NT) rasterize_fwd_kernel(
     int64_t n_isects, const float4* __restrict__ splats, const int32_t* __restrict__ tile_offsets,
     const int32_t* __restrict__ flatten_ids, const float* __restrict__ backgrounds, int width, int height, int tile_w,
     int tile_h, int n_tiles_total, float* __restrict__ render_colors, float* __restrict__ render_alphas,
     int32_t* __restrict__ last_ids, unsigned long long* __restrict__ pair_counters) {
+  using M = TileMap<PXW, PYH>;
+  constexpr int NP = M::NP, NT = M::NT, RPT = M::RPT, kBatch = M::BATCH;
   __shared__ __align__(16) float4 sb[2][kBatch * 3];
   const int tid = threadIdx.x;
-  const TileCoord tc = tile_setup(width, height, tile_w, tile_h, n_isects, tile_offsets, n_tiles_total);
-  const float px = (float)tc.px + 0.5f, py = (float)tc.py + 0.5f;
-  const int range = tc.range_end - tc.range_start;
-  const int nb = (range + kBatch - 1) / kBatch;
+  const TileRange tc = tile_setup<M>(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total);
+  const int nb = (tc.range_end - tc.range_start + kBatch - 1) / kBatch;
 
-  float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f;
-  int last = 0;
-  bool done = !tc.inside;
+  float pxf[PXW], pyf[PYH];
+#pragma unroll
+  for (int i = 0; i < PXW; ++i) pxf[i] = (float)(tc.x0 + i) + 0.5f;
+#pragma unroll
+  for (int i = 0; i < PYH; ++i) pyf[i] = (float)(tc.y0 + i) + 0.5f;
+  float T[NP], cr[NP], cg[NP], cb[NP];
+  int last[NP];
+  bool done[NP];
+  bool all_done = true;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T[j] = 1.0f; cr[j] = 0.f; cg[j] = 0.f; cb[j] = 0.f; last[j] = 0;
+    done[j] = !((tc.x0 + j % PXW) < width && (tc.y0 + j / PXW) < height);
+    all_done = all_done && done[j];
+  }
   unsigned int n_eval = 0, n_acc = 0;
 
-  auto load_id = [&](int b) -> int {
-    const int idx = tc.range_start + b * kBatch + tid;
-    return (b < nb && idx < tc.range_end) ? __ldg(flatten_ids + idx) : -1;
+  auto load_ids = [&](int b, int (&ids)[RPT]) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int idx = tc.range_start + b * kBatch + r * NT + tid;
+      ids[r] = (b < nb && idx < tc.range_end) ? __ldg(flatten_ids + idx) : -1;
+    }
   };
-  auto issue = [&](int buf, int id) {
-    if (id >= 0) {
-      const float4* src = splats + (size_t)id * 3;
-      float4* dst = &sb[buf][tid * 3];
-      cp_async16(dst + 0, src + 0);
-      cp_async16(dst + 1, src + 1);
-      cp_async16(dst + 2, src + 2);
+  auto issue = [&](int buf, const int (&ids)[RPT]) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      if (ids[r] >= 0) {
+        const float4* src = splats + (size_t)ids[r] * 3;
+        float4* dst = &sb[buf][(r * NT + tid) * 3];
+        cp_async16(dst + 0, src + 0);
+        cp_async16(dst + 1, src + 1);
+        cp_async16(dst + 2, src + 2);
+      }
     }
     cp_async_commit();
   };
 
   if (nb > 0) {
-    issue(0, load_id(0));
-    int id_next = load_id(1);
+    int ids[RPT];
+    load_ids(0, ids);
+    issue(0, ids);
+    load_ids(1, ids);
     for (int b = 0; b < nb; ++b) {
       if (b + 1 < nb) {
-        issue((b + 1) & 1, id_next);
-        id_next = load_id(b + 2);
+        issue((b + 1) & 1, ids);
+        load_ids(b + 2, ids);
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
       }
-      // barrier (makes batch b visible to everyone) + vote: stop when every pixel is finished
-      if (__syncthreads_and(done)) break;
+      // barrier (makes batch b visible to everyone) + vote: stop when every pixel of the tile is finished
+      if (__syncthreads_and(all_done)) break;
       const int batch_start = tc.range_start + b * kBatch;
       const int batch_size = min(kBatch, tc.range_end - batch_start);
       const float4* s = sb[b & 1];
-      for (int t = 0; t < batch_size && !done; ++t) {
+      for (int t = 0; t < batch_size; ++t) {
+        if (__all_sync(0xffffffffu, all_done)) break;  // warp-uniform exit + reconvergence point
         const float4 g0 = s[t * 3 + 0];  // x, y, conic_a, conic_b
         const float4 g1 = s[t * 3 + 1];  // conic_c, opacity, r, g
-        const float dx = g0.x - px, dy = g0.y - py;
-        const float sigma = 0.5f * (g0.z * dx * dx + g1.x * dy * dy) + g0.w * dx * dy;
-        const float alpha = fminf(kAlphaMax, g1.y * __expf(-sigma));
-        if (COUNT) ++n_eval;
-        if (sigma < 0.f || alpha < kAlphaMin) continue;
-        const float next_T = T * (1.0f - alpha);
-        if (next_T <= kTMin) { done = true; break; }
-        const float w = alpha * T;
-        cr += g1.z * w;
-        cg += g1.w * w;
-        cb += s[t * 3 + 2].x * w;
-        last = batch_start + t;
-        T = next_T;
-        if (COUNT) ++n_acc;
+        const float cbl = s[t * 3 + 2].x;
+        const float ha = 0.5f * g0.z, hc = 0.5f * g1.x;
+        float dx[PXW], hax[PXW], bx[PXW], dy[PYH], hcy[PYH];
+#pragma unroll
+        for (int i = 0; i < PXW; ++i) { dx[i] = g0.x - pxf[i]; hax[i] = ha * dx[i] * dx[i]; bx[i] = g0.w * dx[i]; }
+#pragma unroll
+        for (int i = 0; i < PYH; ++i) { dy[i] = g0.y - pyf[i]; hcy[i] = hc * dy[i] * dy[i]; }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const float sigma = fmaf(bx[j % PXW], dy[j / PXW], hax[j % PXW] + hcy[j / PXW]);
+          const float alpha = fminf(kAlphaMax, g1.y * fast_exp_neg(sigma));
+          if (COUNT && !done[j]) ++n_eval;
+          const bool acc = !done[j] && sigma >= 0.f && alpha >= kAlphaMin;
+          if (acc) {
+            const float next_T = T[j] * (1.0f - alpha);
+            if (next_T <= kTMin) {
+              done[j] = true;
+            } else {
+              const float w = alpha * T[j];
+              cr[j] = fmaf(g1.z, w, cr[j]);
+              cg[j] = fmaf(g1.w, w, cg[j]);
+              cb[j] = fmaf(cbl, w, cb[j]);
+              last[j] = batch_start + t;
+              T[j] = next_T;
+              if (COUNT) ++n_acc;
+            }
+          }
+        }
+        all_done = true;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) all_done = all_done && done[j];
       }
       __syncthreads();  // everyone is done with buffer b&1 before batch b+2 overwrites it
     }
     cp_async_wait<0>();
   }
 
-  if (tc.inside) {
-    const size_t pix = ((size_t)tc.cam * height + tc.py) * width + tc.px;
-    if (backgrounds != nullptr) {
-      const float* bg = backgrounds + tc.cam * 3;
-      cr += T * bg[0]; cg += T * bg[1]; cb += T * bg[2];
+  float bgr = 0.f, bgg = 0.f, bgb = 0.f;
+  if (backgrounds != nullptr) {
+    bgr = backgrounds[tc.cam * 3 + 0]; bgg = backgrounds[tc.cam * 3 + 1]; bgb = backgrounds[tc.cam * 3 + 2];
+  }
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const int x = tc.x0 + j % PXW, y = tc.y0 + j / PXW;
+    if (x < width && y < height) {
+      const size_t pix = ((size_t)tc.cam * height + y) * width + x;
+      render_colors[pix * 3 + 0] = fmaf(T[j], bgr, cr[j]);
+      render_colors[pix * 3 + 1] = fmaf(T[j], bgg, cg[j]);
+      render_colors[pix * 3 + 2] = fmaf(T[j], bgb, cb[j]);
+      render_alphas[pix] = 1.0f - T[j];
+      last_ids[pix] = last[j];
     }
-    render_colors[pix * 3 + 0] = cr;
-    render_colors[pix * 3 + 1] = cg;
-    render_colors[pix * 3 + 2] = cb;
-    render_alphas[pix] = 1.0f - T;
-    last_ids[pix] = last;
   }
   if (COUNT) {
-    // warp-reduce, then one atomic pair per warp
     for (int d = 16; d > 0; d >>= 1) {
       n_eval += __shfl_xor_sync(0xffffffffu, n_eval, d);
       n_acc += __shfl_xor_sync(0xffffffffu, n_acc, d);
@@ -190,71 +258,97 @@ __device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane)
   return r;
 }
 
-__global__ void __launch_bounds__(kBlendThreads) rasterize_bwd_kernel(
+template <int PXW, int PYH>
+__global__ void __launch_bounds__(TileMap<PXW, PYH>::NT) rasterize_bwd_kernel(
     int64_t n_isects, const float4* __restrict__ splats, const int32_t* __restrict__ tile_offsets,
     const int32_t* __restrict__ flatten_ids, const float* __restrict__ backgrounds, int width, int height, int tile_w,
     int tile_h, int n_tiles_total, const float* __restrict__ render_alphas, const int32_t* __restrict__ last_ids,
     const float* __restrict__ v_render_colors, const float* __restrict__ v_render_alphas,
     float* __restrict__ v_splats) {
+  using M = TileMap<PXW, PYH>;
+  constexpr int NP = M::NP, NT = M::NT, RPT = M::RPT, NW = M::NW, kBatch = M::BATCH;
   __shared__ __align__(16) float4 sb[2][kBatch * 3];
   __shared__ int s_id[2][kBatch];
-  __shared__ int s_warp_last[kBlendThreads / 32];
+  __shared__ int s_warp_last[NW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const TileCoord tc = tile_setup(width, height, tile_w, tile_h, n_isects, tile_offsets, n_tiles_total);
+  const TileRange tc = tile_setup<M>(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total);
   if (tc.range_end <= tc.range_start) return;  // uniform for the block
-  const float px = (float)tc.px + 0.5f, py = (float)tc.py + 0.5f;
 
-  float T_final = 1.f, vcr = 0.f, vcg = 0.f, vcb = 0.f, va = 0.f;
-  int bin_final = -1;  // pixels outside the image never match any index
-  if (tc.inside) {
-    const size_t pix = ((size_t)tc.cam * height + tc.py) * width + tc.px;
-    T_final = 1.0f - render_alphas[pix];
-    bin_final = last_ids[pix];
-    vcr = v_render_colors[pix * 3 + 0];
-    vcg = v_render_colors[pix * 3 + 1];
-    vcb = v_render_colors[pix * 3 + 2];
-    va = v_render_alphas[pix];
-  }
-  float bg_dot = 0.f;
+  float pxf[PXW], pyf[PYH];
+#pragma unroll
+  for (int i = 0; i < PXW; ++i) pxf[i] = (float)(tc.x0 + i) + 0.5f;
+#pragma unroll
+  for (int i = 0; i < PYH; ++i) pyf[i] = (float)(tc.y0 + i) + 0.5f;
+
+  // per-pixel replay state.  bdot = sum over the Gaussians behind of fac * (rgb . v_colour), which is all
+  // the backward pass needs of the colour accumulated behind; tfv = T_final * (v_alpha_out - bg . v_colour).
+  float T[NP], bdot[NP], vcr[NP], vcg[NP], vcb[NP], tfv[NP];
+  int bin_final[NP];
+  int my_last = -1;
+  float bgr = 0.f, bgg = 0.f, bgb = 0.f;
   if (backgrounds != nullptr) {
-    const float* bg = backgrounds + tc.cam * 3;
-    bg_dot = bg[0] * vcr + bg[1] * vcg + bg[2] * vcb;
+    bgr = backgrounds[tc.cam * 3 + 0]; bgg = backgrounds[tc.cam * 3 + 1]; bgb = backgrounds[tc.cam * 3 + 2];
   }
-  float T = T_final, br = 0.f, bgc = 0.f, bb = 0.f;  // running T and colour accumulated behind
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const int x = tc.x0 + j % PXW, y = tc.y0 + j / PXW;
+    T[j] = 1.f; bdot[j] = 0.f; vcr[j] = 0.f; vcg[j] = 0.f; vcb[j] = 0.f; tfv[j] = 0.f;
+    bin_final[j] = -1;  // pixels outside the image never match any index
+    if (x < width && y < height) {
+      const size_t pix = ((size_t)tc.cam * height + y) * width + x;
+      const float T_final = 1.0f - render_alphas[pix];
+      T[j] = T_final;
+      bin_final[j] = last_ids[pix];
+      vcr[j] = v_render_colors[pix * 3 + 0];
+      vcg[j] = v_render_colors[pix * 3 + 1];
+      vcb[j] = v_render_colors[pix * 3 + 2];
+      tfv[j] = T_final * (v_render_alphas[pix] - (bgr * vcr[j] + bgg * vcg[j] + bgb * vcb[j]));
+    }
+    my_last = max(my_last, bin_final[j]);
+  }
 
-  const int warp_last = __reduce_max_sync(0xffffffffu, bin_final);
+  const int warp_last = __reduce_max_sync(0xffffffffu, my_last);
   if (lane == 0) s_warp_last[warp] = warp_last;
   __syncthreads();
   int block_last = s_warp_last[0];
 #pragma unroll
-  for (int w = 1; w < kBlendThreads / 32; ++w) block_last = max(block_last, s_warp_last[w]);
+  for (int w = 1; w < NW; ++w) block_last = max(block_last, s_warp_last[w]);
   // nothing behind the last blended Gaussian of any pixel of the tile can receive gradient
   const int end_idx = min(tc.range_end - 1, block_last);
   if (end_idx < tc.range_start) return;
   const int nb = (end_idx - tc.range_start + 1 + kBatch - 1) / kBatch;
 
-  auto load_id = [&](int b) -> int {
-    const int idx = end_idx - b * kBatch - tid;
-    return (b < nb && idx >= tc.range_start) ? __ldg(flatten_ids + idx) : -1;
-  };
-  auto issue = [&](int buf, int id) {
-    if (id >= 0) {
-      const float4* src = splats + (size_t)id * 3;
-      float4* dst = &sb[buf][tid * 3];
-      cp_async16(dst + 0, src + 0);
-      cp_async16(dst + 1, src + 1);
-      cp_async16(dst + 2, src + 2);
+  auto load_ids = [&](int b, int (&ids)[RPT]) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int idx = end_idx - b * kBatch - (r * NT + tid);
+      ids[r] = (b < nb && idx >= tc.range_start) ? __ldg(flatten_ids + idx) : -1;
     }
-    s_id[buf][tid] = id;
+  };
+  auto issue = [&](int buf, const int (&ids)[RPT]) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int slot = r * NT + tid;
+      if (ids[r] >= 0) {
+        const float4* src = splats + (size_t)ids[r] * 3;
+        float4* dst = &sb[buf][slot * 3];
+        cp_async16(dst + 0, src + 0);
+        cp_async16(dst + 1, src + 1);
+        cp_async16(dst + 2, src + 2);
+      }
+      s_id[buf][slot] = ids[r];
+    }
     cp_async_commit();
   };
 
-  issue(0, load_id(0));
-  int id_next = load_id(1);
+  int ids[RPT];
+  load_ids(0, ids);
+  issue(0, ids);
+  load_ids(1, ids);
   for (int b = 0; b < nb; ++b) {
     if (b + 1 < nb) {
-      issue((b + 1) & 1, id_next);
-      id_next = load_id(b + 2);
+      issue((b + 1) & 1, ids);
+      load_ids(b + 2, ids);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -263,50 +357,66 @@ __global__ void __launch_bounds__(kBlendThreads) rasterize_bwd_kernel(
     const int batch_end = end_idx - b * kBatch;  // sorted index held in slot 0 (the one furthest back)
     const int batch_size = min(kBatch, batch_end + 1 - tc.range_start);
     const float4* s = sb[b & 1];
-    const int* ids = s_id[b & 1];
-    for (int t = max(0, batch_end - warp_last); t < batch_size; ++t) {
-      bool valid = (batch_end - t) <= bin_final;
-      float4 g0, g1;
-      float dx = 0.f, dy = 0.f, vis = 0.f, alpha = 0.f;
-      if (valid) {
-        g0 = s[t * 3 + 0];
-        g1 = s[t * 3 + 1];
-        dx = g0.x - px; dy = g0.y - py;
-        const float sigma = 0.5f * (g0.z * dx * dx + g1.x * dy * dy) + g0.w * dx * dy;
-        vis = __expf(-sigma);
-        alpha = fminf(kAlphaMax, g1.y * vis);
-        if (sigma < 0.f || alpha < kAlphaMin) valid = false;
+    const int* sid = s_id[b & 1];
+    for (int t = max(0, batch_end - warp_last); t < batch_size; ++t) {  // warp-uniform bounds
+      const int idx = batch_end - t;
+      const float4 g0 = s[t * 3 + 0];  // x, y, conic_a, conic_b
+      const float4 g1 = s[t * 3 + 1];  // conic_c, opacity, r, g
+      const float ha = 0.5f * g0.z, hc = 0.5f * g1.x;
+      float dx[PXW], hax[PXW], bx[PXW], dy[PYH], hcy[PYH];
+#pragma unroll
+      for (int i = 0; i < PXW; ++i) { dx[i] = g0.x - pxf[i]; hax[i] = ha * dx[i] * dx[i]; bx[i] = g0.w * dx[i]; }
+#pragma unroll
+      for (int i = 0; i < PYH; ++i) { dy[i] = g0.y - pyf[i]; hcy[i] = hc * dy[i] * dy[i]; }
+      float vis[NP], alpha[NP];
+      bool valid[NP];
+      bool any_valid = false;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const float sigma = fmaf(bx[j % PXW], dy[j / PXW], hax[j % PXW] + hcy[j / PXW]);
+        vis[j] = fast_exp_neg(sigma);
+        alpha[j] = fminf(kAlphaMax, g1.y * vis[j]);
+        valid[j] = idx <= bin_final[j] && sigma >= 0.f && alpha[j] >= kAlphaMin;
+        any_valid = any_valid || valid[j];
       }
-      if (!__any_sync(0xffffffffu, valid)) continue;
+      if (!__any_sync(0xffffffffu, any_valid)) continue;  // warp-uniform
+      const float cbl = s[t * 3 + 2].x;
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = 0.f;
-      if (valid) {
-        const float cb_ = s[t * 3 + 2].x;
-        const float ra = __fdividef(1.0f, 1.0f - alpha);
-        T *= ra;
-        const float fac = alpha * T;
-        v[6] = fac * vcr; v[7] = fac * vcg; v[8] = fac * vcb;
-        float v_alpha = (g1.z * T - br * ra) * vcr + (g1.w * T - bgc * ra) * vcg + (cb_ * T - bb * ra) * vcb;
-        v_alpha += T_final * ra * va;
-        v_alpha -= T_final * ra * bg_dot;
-        const float ov = g1.y * vis;
-        if (ov <= kAlphaMax) {
-          const float v_sigma = -ov * v_alpha;
-          v[2] = 0.5f * v_sigma * dx * dx;
-          v[3] = v_sigma * dx * dy;
-          v[4] = 0.5f * v_sigma * dy * dy;
-          v[0] = v_sigma * (g0.z * dx + g0.w * dy);
-          v[1] = v_sigma * (g0.w * dx + g1.x * dy);
-          v[9] = fabsf(v[0]);
-          v[10] = fabsf(v[1]);
-          v[5] = vis * v_alpha;
+      for (int k = 0; k < 16; ++k) v[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        if (valid[j]) {
+          const float ddx = dx[j % PXW], ddy = dy[j / PXW];
+          const float ra = __fdividef(1.0f, 1.0f - alpha[j]);
+          T[j] *= ra;  // transmittance in front of this Gaussian
+          const float fac = alpha[j] * T[j];
+          v[6] = fmaf(fac, vcr[j], v[6]);
+          v[7] = fmaf(fac, vcg[j], v[7]);
+          v[8] = fmaf(fac, vcb[j], v[8]);
+          const float cdot = g1.z * vcr[j] + g1.w * vcg[j] + cbl * vcb[j];
+          const float v_alpha = T[j] * cdot - ra * (bdot[j] - tfv[j]);
+          bdot[j] = fmaf(cdot, fac, bdot[j]);
+          const float ov = g1.y * vis[j];
+          if (ov <= kAlphaMax) {
+            const float v_sigma = -ov * v_alpha;
+            const float sx = v_sigma * ddx, sy = v_sigma * ddy;
+            v[2] = fmaf(0.5f * sx, ddx, v[2]);
+            v[3] = fmaf(sx, ddy, v[3]);
+            v[4] = fmaf(0.5f * sy, ddy, v[4]);
+            const float gx = g0.z * sx + g0.w * sy;
+            const float gy = g0.w * sx + g1.x * sy;
+            v[0] += gx;
+            v[1] += gy;
+            v[9] += fabsf(gx);
+            v[10] += fabsf(gy);
+            v[5] = fmaf(vis[j], v_alpha, v[5]);
+          }
         }
-        br += g1.z * fac; bgc += g1.w * fac; bb += cb_ * fac;
       }
       const float total = warp_reduce_scatter16(v, lane);
       const int slot = lane >> 1;
-      if ((lane & 1) == 0 && slot < 11) atomicAdd(v_splats + (size_t)ids[t] * EGS_SPLAT_FLOATS + slot, total);
+      if ((lane & 1) == 0 && slot < 11) atomicAdd(v_splats + (size_t)sid[t] * EGS_SPLAT_FLOATS + slot, total);
     }
     __syncthreads();
   }
@@ -328,6 +438,40 @@ static int check_raster_args(const char* who, int32_t C, int64_t n_isects, int32
   return 0;
 }
 
+// Pixel-block variant: 22 = 2x2 pixels per thread (default), 21 = 2x1, 11 = 1x1.  The environment
+// variable EGS_BLEND_VARIANT exists for tuning runs only.
+static int blend_variant() {
+  static int v = [] {
+    const char* e = getenv("EGS_BLEND_VARIANT");
+    int x = e ? atoi(e) : 22;
+    return (x == 11 || x == 21 || x == 22) ? x : 22;
+  }();
+  return v;
+}
+
+template <bool COUNT>
+static int launch_fwd(int32_t C, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
+                      const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
+                      int32_t tile_width, int32_t tile_height, float* render_colors, float* render_alphas,
+                      int32_t* last_ids, uint64_t* pair_counters, egs_stream_t stream) {
+  dim3 grid(tile_width, tile_height, C);
+  const float4* sp = reinterpret_cast<const float4*>(splats);
+  unsigned long long* pc = reinterpret_cast<unsigned long long*>(pair_counters);
+  const int nt = C * tile_width * tile_height;
+  cudaStream_t st = (cudaStream_t)stream;
+#define EGS_LAUNCH_FWD(PX, PY)                                                                                    \
+  rasterize_fwd_kernel<PX, PY, COUNT><<<grid, TileMap<PX, PY>::NT, 0, st>>>(                                       \
+      n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, nt,           \
+      render_colors, render_alphas, last_ids, pc)
+  switch (blend_variant()) {
+    case 11: EGS_LAUNCH_FWD(1, 1); break;
+    case 21: EGS_LAUNCH_FWD(2, 1); break;
+    default: EGS_LAUNCH_FWD(2, 2); break;
+  }
+#undef EGS_LAUNCH_FWD
+  return check_launch("rasterize_fwd_kernel");
+}
+
 extern "C" int egs_rasterize_fwd(int32_t C, int32_t N, int64_t n_isects, const float* splats,
                                  const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
                                  int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
@@ -335,11 +479,8 @@ extern "C" int egs_rasterize_fwd(int32_t C, int32_t N, int64_t n_isects, const f
   (void)N;
   if (int rc = check_raster_args("rasterize_fwd", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (C == 0) return 0;
-  dim3 grid(tile_width, tile_height, C);
-  rasterize_fwd_kernel<false><<<grid, kBlendThreads, 0, (cudaStream_t)stream>>>(
-      n_isects, reinterpret_cast<const float4*>(splats), tile_offsets, flatten_ids, backgrounds, width, height,
-      tile_width, tile_height, C * tile_width * tile_height, render_colors, render_alphas, last_ids, nullptr);
-  return check_launch("rasterize_fwd_kernel");
+  return launch_fwd<false>(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width,
+                           tile_height, render_colors, render_alphas, last_ids, nullptr, stream);
 }
 
 // Instrumented variant for the roofline model: also accumulates P_eval and P_acc
@@ -352,12 +493,8 @@ extern "C" int egs_rasterize_fwd_count(int32_t C, int32_t N, int64_t n_isects, c
   (void)N;
   if (int rc = check_raster_args("rasterize_fwd_count", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (C == 0) return 0;
-  dim3 grid(tile_width, tile_height, C);
-  rasterize_fwd_kernel<true><<<grid, kBlendThreads, 0, (cudaStream_t)stream>>>(
-      n_isects, reinterpret_cast<const float4*>(splats), tile_offsets, flatten_ids, backgrounds, width, height,
-      tile_width, tile_height, C * tile_width * tile_height, render_colors, render_alphas, last_ids,
-      reinterpret_cast<unsigned long long*>(pair_counters));
-  return check_launch("rasterize_fwd_kernel<count>");
+  return launch_fwd<true>(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width,
+                          tile_height, render_colors, render_alphas, last_ids, pair_counters, stream);
 }
 
 extern "C" int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const float* splats,
@@ -369,9 +506,18 @@ extern "C" int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const f
   if (int rc = check_raster_args("rasterize_bwd", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (C == 0 || n_isects == 0) return 0;
   dim3 grid(tile_width, tile_height, C);
-  rasterize_bwd_kernel<<<grid, kBlendThreads, 0, (cudaStream_t)stream>>>(
-      n_isects, reinterpret_cast<const float4*>(splats), tile_offsets, flatten_ids, backgrounds, width, height,
-      tile_width, tile_height, C * tile_width * tile_height, render_alphas, last_ids, v_render_colors,
-      v_render_alphas, v_splats);
+  const float4* sp = reinterpret_cast<const float4*>(splats);
+  const int nt = C * tile_width * tile_height;
+  cudaStream_t st = (cudaStream_t)stream;
+#define EGS_LAUNCH_BWD(PX, PY)                                                                                   \
+  rasterize_bwd_kernel<PX, PY><<<grid, TileMap<PX, PY>::NT, 0, st>>>(                                             \
+      n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, nt,          \
+      render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats)
+  switch (blend_variant()) {
+    case 11: EGS_LAUNCH_BWD(1, 1); break;
+    case 21: EGS_LAUNCH_BWD(2, 1); break;
+    default: EGS_LAUNCH_BWD(2, 2); break;
+  }
+#undef EGS_LAUNCH_BWD
   return check_launch("rasterize_bwd_kernel");
 }
