@@ -46,6 +46,20 @@ __device__ __forceinline__ float fast_exp_neg(float sigma) {
   return e;
 }
 
+// ex2 of an argument that is already scaled by -log2(e)
+__device__ __forceinline__ float fast_ex2(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+// Stops ptxas from re-deriving a loop-invariant value inside the loop (it otherwise rematerialises
+// the pixel-centre coordinates with I2FP + FADD in every iteration to save two registers).
+__device__ __forceinline__ float opaque(float x) {
+  asm volatile("" : "+f"(x));
+  return x;
+}
+constexpr float kNegLog2e = -1.4426950408889634f;
+
 // Thread <-> pixel mapping of one tile.
 template <int PXW, int PYH>
 struct TileMap {
@@ -65,6 +79,7 @@ struct TileMap {
 struct TileRange {
   int cam, tile_id, x0, y0;  // x0,y0: first pixel of this thread's block
   int range_start, range_end;
+  float wx_lo, wx_hi, wy_lo, wy_hi;  // pixel-centre rectangle covered by this thread's WARP
 };
 
 template <class M>
@@ -80,6 +95,11 @@ __device__ __forceinline__ TileRange tile_setup(int tile_w, int tile_h, int64_t 
   tc.y0 = blockIdx.y * kTileSize + qy * (kTileSize / M::TY);
   tc.range_start = tile_offsets[tc.tile_id];
   tc.range_end = (tc.tile_id == n_tiles_total - 1) ? (int)n_isects : tile_offsets[tc.tile_id + 1];
+  constexpr int PXW = kTileSize / M::TX, PYH = kTileSize / M::TY;
+  tc.wx_lo = (float)(blockIdx.x * kTileSize + (warp % M::WPR) * 8 * PXW) + 0.5f;
+  tc.wx_hi = tc.wx_lo + (float)(8 * PXW - 1);
+  tc.wy_lo = (float)(blockIdx.y * kTileSize + (warp / M::WPR) * 4 * PYH) + 0.5f;
+  tc.wy_hi = tc.wy_lo + (float)(4 * PYH - 1);
   return tc;
 }
 
@@ -101,18 +121,20 @@ __global__ void __launch_bounds__(TileMap<PXW, PYH>::NT) rasterize_fwd_kernel(
 
   float pxf[PXW], pyf[PYH];
 #pragma unroll
-  for (int i = 0; i < PXW; ++i) pxf[i] = (float)(tc.x0 + i) + 0.5f;
+  for (int i = 0; i < PXW; ++i) pxf[i] = opaque((float)(tc.x0 + i) + 0.5f);
 #pragma unroll
-  for (int i = 0; i < PYH; ++i) pyf[i] = (float)(tc.y0 + i) + 0.5f;
+  for (int i = 0; i < PYH; ++i) pyf[i] = opaque((float)(tc.y0 + i) + 0.5f);
+  // T[j] > 0: transmittance of a live pixel; T[j] < 0: pixel finished, |T[j]| is its final transmittance
+  // (the "done" flag lives in the sign bit, so liveness is one more FSETP in the accept test).
+  const float wx_lo = opaque(tc.wx_lo), wx_hi = opaque(tc.wx_hi), wy_lo = opaque(tc.wy_lo), wy_hi = opaque(tc.wy_hi);
   float T[NP], cr[NP], cg[NP], cb[NP];
   int last[NP];
-  bool done[NP];
   bool all_done = true;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    T[j] = 1.0f; cr[j] = 0.f; cg[j] = 0.f; cb[j] = 0.f; last[j] = 0;
-    done[j] = !((tc.x0 + j % PXW) < width && (tc.y0 + j / PXW) < height);
-    all_done = all_done && done[j];
+    const bool inside = (tc.x0 + j % PXW) < width && (tc.y0 + j / PXW) < height;
+    T[j] = inside ? 1.0f : -1.0f; cr[j] = 0.f; cg[j] = 0.f; cb[j] = 0.f; last[j] = 0;
+    all_done = all_done && !inside;
   }
   unsigned int n_eval = 0, n_acc = 0;
 
@@ -158,24 +180,38 @@ __global__ void __launch_bounds__(TileMap<PXW, PYH>::NT) rasterize_fwd_kernel(
       for (int t = 0; t < batch_size; ++t) {
         if (__all_sync(0xffffffffu, all_done)) break;  // warp-uniform exit + reconvergence point
         const float4 g0 = s[t * 3 + 0];  // x, y, conic_a, conic_b
+        const float4 g2 = s[t * 3 + 2];  // b, depth, r_eff^2, -
+        {
+          // warp-uniform skip: the warp's pixel rectangle lies outside the circle in which alpha >= 1/255
+          const float ex = fmaxf(fmaxf(wx_lo - g0.x, g0.x - wx_hi), 0.f);
+          const float ey = fmaxf(fmaxf(wy_lo - g0.y, g0.y - wy_hi), 0.f);
+          if (fmaf(ex, ex, ey * ey) > g2.z) {
+            if (COUNT) {
+#pragma unroll
+              for (int j = 0; j < NP; ++j) n_eval += (T[j] > 0.f) ? 1u : 0u;
+            }
+            continue;
+          }
+        }
         const float4 g1 = s[t * 3 + 1];  // conic_c, opacity, r, g
-        const float cbl = s[t * 3 + 2].x;
-        const float ha = 0.5f * g0.z, hc = 0.5f * g1.x;
-        float dx[PXW], hax[PXW], bx[PXW], dy[PYH], hcy[PYH];
+        const float cbl = g2.x;
+        // q(dx,dy) = -log2(e) * sigma, separable parts shared by the rows / columns of the pixel block
+        const float la = (0.5f * kNegLog2e) * g0.z, lc = (0.5f * kNegLog2e) * g1.x, lb = kNegLog2e * g0.w;
+        float qx[PXW], bx[PXW], dy[PYH], qy[PYH];
 #pragma unroll
-        for (int i = 0; i < PXW; ++i) { dx[i] = g0.x - pxf[i]; hax[i] = ha * dx[i] * dx[i]; bx[i] = g0.w * dx[i]; }
+        for (int i = 0; i < PXW; ++i) { const float dx = g0.x - pxf[i]; qx[i] = la * dx * dx; bx[i] = lb * dx; }
 #pragma unroll
-        for (int i = 0; i < PYH; ++i) { dy[i] = g0.y - pyf[i]; hcy[i] = hc * dy[i] * dy[i]; }
+        for (int i = 0; i < PYH; ++i) { dy[i] = g0.y - pyf[i]; qy[i] = lc * dy[i] * dy[i]; }
+        float tmax = -1.0f;
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
-          const float sigma = fmaf(bx[j % PXW], dy[j / PXW], hax[j % PXW] + hcy[j / PXW]);
-          const float alpha = fminf(kAlphaMax, g1.y * fast_exp_neg(sigma));
-          if (COUNT && !done[j]) ++n_eval;
-          const bool acc = !done[j] && sigma >= 0.f && alpha >= kAlphaMin;
-          if (acc) {
+          const float q = fmaf(bx[j % PXW], dy[j / PXW], qx[j % PXW] + qy[j / PXW]);
+          const float alpha = fminf(kAlphaMax, g1.y * fast_ex2(q));
+          if (COUNT && T[j] > 0.f) ++n_eval;
+          if (T[j] > 0.f && q <= 0.f && alpha >= kAlphaMin) {  // sigma >= 0  <=>  q <= 0
             const float next_T = T[j] * (1.0f - alpha);
             if (next_T <= kTMin) {
-              done[j] = true;
+              T[j] = -T[j];  // finished: this Gaussian is not blended
             } else {
               const float w = alpha * T[j];
               cr[j] = fmaf(g1.z, w, cr[j]);
@@ -186,10 +222,9 @@ __global__ void __launch_bounds__(TileMap<PXW, PYH>::NT) rasterize_fwd_kernel(
               if (COUNT) ++n_acc;
             }
           }
+          tmax = fmaxf(tmax, T[j]);
         }
-        all_done = true;
-#pragma unroll
-        for (int j = 0; j < NP; ++j) all_done = all_done && done[j];
+        all_done = !(tmax > 0.f);
       }
       __syncthreads();  // everyone is done with buffer b&1 before batch b+2 overwrites it
     }
@@ -205,10 +240,11 @@ __global__ void __launch_bounds__(TileMap<PXW, PYH>::NT) rasterize_fwd_kernel(
     const int x = tc.x0 + j % PXW, y = tc.y0 + j / PXW;
     if (x < width && y < height) {
       const size_t pix = ((size_t)tc.cam * height + y) * width + x;
-      render_colors[pix * 3 + 0] = fmaf(T[j], bgr, cr[j]);
-      render_colors[pix * 3 + 1] = fmaf(T[j], bgg, cg[j]);
-      render_colors[pix * 3 + 2] = fmaf(T[j], bgb, cb[j]);
-      render_alphas[pix] = 1.0f - T[j];
+      const float Tf = fabsf(T[j]);
+      render_colors[pix * 3 + 0] = fmaf(Tf, bgr, cr[j]);
+      render_colors[pix * 3 + 1] = fmaf(Tf, bgg, cg[j]);
+      render_colors[pix * 3 + 2] = fmaf(Tf, bgb, cb[j]);
+      render_alphas[pix] = 1.0f - Tf;
       last_ids[pix] = last[j];
     }
   }
@@ -276,10 +312,11 @@ __global__ void __launch_bounds__(TileMap<PXW, PYH>::NT) rasterize_bwd_kernel(
 
   float pxf[PXW], pyf[PYH];
 #pragma unroll
-  for (int i = 0; i < PXW; ++i) pxf[i] = (float)(tc.x0 + i) + 0.5f;
+  for (int i = 0; i < PXW; ++i) pxf[i] = opaque((float)(tc.x0 + i) + 0.5f);
 #pragma unroll
-  for (int i = 0; i < PYH; ++i) pyf[i] = (float)(tc.y0 + i) + 0.5f;
+  for (int i = 0; i < PYH; ++i) pyf[i] = opaque((float)(tc.y0 + i) + 0.5f);
 
+  const float wx_lo = opaque(tc.wx_lo), wx_hi = opaque(tc.wx_hi), wy_lo = opaque(tc.wy_lo), wy_hi = opaque(tc.wy_hi);
   // per-pixel replay state.  bdot = sum over the Gaussians behind of fac * (rgb . v_colour), which is all
   // the backward pass needs of the colour accumulated behind; tfv = T_final * (v_alpha_out - bg . v_colour).
   float T[NP], bdot[NP], vcr[NP], vcg[NP], vcb[NP], tfv[NP];
@@ -361,26 +398,35 @@ __global__ void __launch_bounds__(TileMap<PXW, PYH>::NT) rasterize_bwd_kernel(
     for (int t = max(0, batch_end - warp_last); t < batch_size; ++t) {  // warp-uniform bounds
       const int idx = batch_end - t;
       const float4 g0 = s[t * 3 + 0];  // x, y, conic_a, conic_b
+      const float4 g2 = s[t * 3 + 2];  // b, depth, r_eff^2, -
+      {
+        // warp-uniform skip (same test as the forward pass)
+        const float ex = fmaxf(fmaxf(wx_lo - g0.x, g0.x - wx_hi), 0.f);
+        const float ey = fmaxf(fmaxf(wy_lo - g0.y, g0.y - wy_hi), 0.f);
+        if (fmaf(ex, ex, ey * ey) > g2.z) continue;
+      }
       const float4 g1 = s[t * 3 + 1];  // conic_c, opacity, r, g
-      const float ha = 0.5f * g0.z, hc = 0.5f * g1.x;
-      float dx[PXW], hax[PXW], bx[PXW], dy[PYH], hcy[PYH];
+      const float la = (0.5f * kNegLog2e) * g0.z, lc = (0.5f * kNegLog2e) * g1.x, lb = kNegLog2e * g0.w;
+      float dx[PXW], qx[PXW], bx[PXW], dy[PYH], qy[PYH];
 #pragma unroll
-      for (int i = 0; i < PXW; ++i) { dx[i] = g0.x - pxf[i]; hax[i] = ha * dx[i] * dx[i]; bx[i] = g0.w * dx[i]; }
+      for (int i = 0; i < PXW; ++i) { dx[i] = g0.x - pxf[i]; qx[i] = la * dx[i] * dx[i]; bx[i] = lb * dx[i]; }
 #pragma unroll
-      for (int i = 0; i < PYH; ++i) { dy[i] = g0.y - pyf[i]; hcy[i] = hc * dy[i] * dy[i]; }
-      float vis[NP], alpha[NP];
+      for (int i = 0; i < PYH; ++i) { dy[i] = g0.y - pyf[i]; qy[i] = lc * dy[i] * dy[i]; }
+      float ov[NP];  // opacity * exp(-sigma), before the 0.999 clamp
       bool valid[NP];
       bool any_valid = false;
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
-        const float sigma = fmaf(bx[j % PXW], dy[j / PXW], hax[j % PXW] + hcy[j / PXW]);
-        vis[j] = fast_exp_neg(sigma);
-        alpha[j] = fminf(kAlphaMax, g1.y * vis[j]);
-        valid[j] = idx <= bin_final[j] && sigma >= 0.f && alpha[j] >= kAlphaMin;
+        const float q = fmaf(bx[j % PXW], dy[j / PXW], qx[j % PXW] + qy[j / PXW]);  // -log2(e) * sigma
+        ov[j] = g1.y * fast_ex2(q);
+        valid[j] = idx <= bin_final[j] && q <= 0.f && ov[j] >= kAlphaMin;  // min(.999, ov) >= 1/255 <=> ov >= 1/255
         any_valid = any_valid || valid[j];
       }
       if (!__any_sync(0xffffffffu, any_valid)) continue;  // warp-uniform
-      const float cbl = s[t * 3 + 2].x;
+      const float cbl = g2.x;
+      const float inv_o = __fdividef(1.0f, g1.y);
+      // v[2], v[3], v[4] accumulate sx*dx, sx*dy, sy*dy (the 0.5 of the conic gradient is applied once, after
+      // the warp reduction); v[5] accumulates ov * v_alpha (the 1/opacity is applied after the reduction).
       float v[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) v[k] = 0.f;
@@ -388,32 +434,33 @@ __global__ void __launch_bounds__(TileMap<PXW, PYH>::NT) rasterize_bwd_kernel(
       for (int j = 0; j < NP; ++j) {
         if (valid[j]) {
           const float ddx = dx[j % PXW], ddy = dy[j / PXW];
-          const float ra = __fdividef(1.0f, 1.0f - alpha[j]);
+          const float alpha = fminf(kAlphaMax, ov[j]);
+          const float ra = __fdividef(1.0f, 1.0f - alpha);
           T[j] *= ra;  // transmittance in front of this Gaussian
-          const float fac = alpha[j] * T[j];
+          const float fac = alpha * T[j];
           v[6] = fmaf(fac, vcr[j], v[6]);
           v[7] = fmaf(fac, vcg[j], v[7]);
           v[8] = fmaf(fac, vcb[j], v[8]);
-          const float cdot = g1.z * vcr[j] + g1.w * vcg[j] + cbl * vcb[j];
-          const float v_alpha = T[j] * cdot - ra * (bdot[j] - tfv[j]);
+          const float cdot = fmaf(cbl, vcb[j], fmaf(g1.w, vcg[j], g1.z * vcr[j]));
+          const float v_alpha = fmaf(T[j], cdot, -ra * (bdot[j] - tfv[j]));
           bdot[j] = fmaf(cdot, fac, bdot[j]);
-          const float ov = g1.y * vis[j];
-          if (ov <= kAlphaMax) {
-            const float v_sigma = -ov * v_alpha;
-            const float sx = v_sigma * ddx, sy = v_sigma * ddy;
-            v[2] = fmaf(0.5f * sx, ddx, v[2]);
+          if (ov[j] <= kAlphaMax) {  // the clamp was inactive: alpha depends on sigma and opacity
+            const float w = ov[j] * v_alpha;  // = opacity * d(alpha)/d(opacity) * v_alpha = -v_sigma
+            const float sx = -w * ddx, sy = -w * ddy;
+            v[2] = fmaf(sx, ddx, v[2]);
             v[3] = fmaf(sx, ddy, v[3]);
-            v[4] = fmaf(0.5f * sy, ddy, v[4]);
-            const float gx = g0.z * sx + g0.w * sy;
-            const float gy = g0.w * sx + g1.x * sy;
+            v[4] = fmaf(sy, ddy, v[4]);
+            const float gx = fmaf(g0.w, sy, g0.z * sx);
+            const float gy = fmaf(g1.x, sy, g0.w * sx);
             v[0] += gx;
             v[1] += gy;
             v[9] += fabsf(gx);
             v[10] += fabsf(gy);
-            v[5] = fmaf(vis[j], v_alpha, v[5]);
+            v[5] += w;
           }
         }
       }
+      v[2] *= 0.5f; v[4] *= 0.5f; v[5] *= inv_o;
       const float total = warp_reduce_scatter16(v, lane);
       const int slot = lane >> 1;
       if ((lane & 1) == 0 && slot < 11) atomicAdd(v_splats + (size_t)sid[t] * EGS_SPLAT_FLOATS + slot, total);
@@ -438,13 +485,13 @@ static int check_raster_args(const char* who, int32_t C, int64_t n_isects, int32
   return 0;
 }
 
-// Pixel-block variant: 22 = 2x2 pixels per thread (default), 21 = 2x1, 11 = 1x1.  The environment
+// Pixel-block variant: 22 = 2x2 pixels per thread (default), 24 = 2x4 (one warp per tile), 21 = 2x1, 11 = 1x1.  The environment
 // variable EGS_BLEND_VARIANT exists for tuning runs only.
 static int blend_variant() {
   static int v = [] {
     const char* e = getenv("EGS_BLEND_VARIANT");
     int x = e ? atoi(e) : 22;
-    return (x == 11 || x == 21 || x == 22) ? x : 22;
+    return (x == 11 || x == 21 || x == 22 || x == 24) ? x : 22;
   }();
   return v;
 }
@@ -466,6 +513,7 @@ static int launch_fwd(int32_t C, int64_t n_isects, const float* splats, const in
   switch (blend_variant()) {
     case 11: EGS_LAUNCH_FWD(1, 1); break;
     case 21: EGS_LAUNCH_FWD(2, 1); break;
+    case 24: EGS_LAUNCH_FWD(2, 4); break;
     default: EGS_LAUNCH_FWD(2, 2); break;
   }
 #undef EGS_LAUNCH_FWD
@@ -516,6 +564,7 @@ extern "C" int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const f
   switch (blend_variant()) {
     case 11: EGS_LAUNCH_BWD(1, 1); break;
     case 21: EGS_LAUNCH_BWD(2, 1); break;
+    case 24: EGS_LAUNCH_BWD(2, 4); break;
     default: EGS_LAUNCH_BWD(2, 2); break;
   }
 #undef EGS_LAUNCH_BWD

@@ -88,6 +88,7 @@ struct ProjState {
 
 struct ProjOut {
   float m2x, m2y, depth, ca, cb, cc;
+  float lambda_max;           // largest eigenvalue of the blurred 2D covariance (clamped like the radius)
   int32_t radius;             // 0 = culled
 };
 
@@ -95,7 +96,7 @@ struct ProjOut {
 EGS_HD bool project_fwd(const float mean[3], const float quat[4], const float scale[3], const Camera& cam,
                         float width, float height, float eps2d, float near_plane, float far_plane,
                         float radius_clip, ProjState& st, ProjOut& o) {
-  o.m2x = 0.f; o.m2y = 0.f; o.depth = 0.f; o.ca = 0.f; o.cb = 0.f; o.cc = 0.f; o.radius = 0;
+  o.m2x = 0.f; o.m2y = 0.f; o.depth = 0.f; o.ca = 0.f; o.cb = 0.f; o.cc = 0.f; o.radius = 0; o.lambda_max = 0.f;
   quat_to_rotmat(quat, st.R, st.qn, st.inv_norm);
   const float* R = st.R;
   float* M = st.M;
@@ -172,8 +173,19 @@ EGS_HD bool project_fwd(const float mean[3], const float quat[4], const float sc
   o.cb = -(b * inv_det);
   o.cc = a * inv_det;
   o.m2x = m2x; o.m2y = m2y; o.depth = z;
+  o.lambda_max = v1;
   o.radius = (int32_t)fminf(radius, 2147483520.0f);
   return true;
+}
+
+// Squared radius (pixels^2) outside of which alpha = min(.999, o exp(-sigma)) < 1/255 is guaranteed:
+// sigma >= 0.5 |d|^2 / lambda_max, so alpha >= 1/255 needs |d|^2 <= 2 ln(255 o) lambda_max.  The blending
+// kernels skip a Gaussian for a whole warp when the warp's pixel rectangle lies outside this circle.
+// A 2 % + 0.01 px^2 margin keeps the test conservative under fp32 rounding of sigma.  Negative = never visible.
+EGS_HD float effective_radius2(float opacity, float lambda_max) {
+  const float t = 255.0f * opacity;
+  if (!(t > 1.0f)) return -1.0f;
+  return 2.0f * logf(t) * lambda_max * 1.02f + 0.01f;
 }
 
 // Tile rectangle of a visible Gaussian: min inclusive, max exclusive.

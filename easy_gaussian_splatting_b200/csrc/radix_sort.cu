@@ -10,6 +10,8 @@
 //                chained to the preceding tiles with decoupled look-back, and the tile is written
 //                out digit-run by digit-run so stores are coalesced.
 // HBM traffic: 8 + 24*P bytes per pair = 152 B at P = 6.  Integer work only.
+#include <stdlib.h>
+
 #include "egs_common.cuh"
 
 namespace egs {
@@ -23,6 +25,7 @@ constexpr int kSortItems = 16;                          // pairs per thread
 constexpr int kSortTile = kSortThreads * kSortItems;    // 4096 pairs per tile
 constexpr int kWarpSpan = 32 * kSortItems;              // 512 consecutive pairs per warp
 
+constexpr int kLookWindow = 8;
 constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagPrefix = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1u;
@@ -50,20 +53,53 @@ constexpr int kHistItems = 16;
 
 __global__ void __launch_bounds__(kHistThreads) radix_histogram_kernel(const uint64_t* __restrict__ keys, int64_t n,
                                                                         int passes, uint32_t* __restrict__ hist) {
+  // Each thread walks kHistItems CONSECUTIVE keys and combines runs of equal digits in a register before
+  // touching shared memory.  The keys of this path come out of isect_emit in runs that share the depth
+  // word and most of the tile id (one Gaussian = one run), so almost every shared-memory atomic
+  // is saved and the hot-bin serialisation of a plain atomic histogram disappears.
   __shared__ uint32_t sh[kMaxPasses * kRadix];
   for (int i = threadIdx.x; i < passes * kRadix; i += kHistThreads) sh[i] = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t stride = (int64_t)gridDim.x * kHistThreads;
-  const int64_t n_round = ((n + 31) / 32) * 32;  // keep whole warps in the loop for match_any
-  for (int64_t i = (int64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n_round; i += stride) {
-    const bool valid = i < n;
-    const uint64_t key = valid ? keys[i] : 0ull;
+  const int64_t chunk = (int64_t)kHistThreads * kHistItems;
+  for (int64_t base = (int64_t)blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
+    const int64_t first = base + (int64_t)threadIdx.x * kHistItems;
+    uint64_t k[kHistItems];
+    int cnt = 0;
+    if (first + kHistItems <= n) {
+      const ulonglong2* p2 = reinterpret_cast<const ulonglong2*>(keys + first);  // first % 16 keys == 0: 16B aligned
+#pragma unroll
+      for (int i = 0; i < kHistItems / 2; ++i) {
+        const ulonglong2 v = __ldg(p2 + i);
+        k[2 * i] = v.x;
+        k[2 * i + 1] = v.y;
+      }
+      cnt = kHistItems;
+    } else {
+#pragma unroll
+      for (int i = 0; i < kHistItems; ++i) {
+        if (first + i < n) { k[i] = keys[first + i]; cnt = i + 1; }
+        else k[i] = 0;
+      }
+    }
+    if (cnt == 0) continue;
     for (int p = 0; p < passes; ++p) {
-      const uint32_t d = (uint32_t)(key >> (p * kRadixBits)) & (kRadix - 1);
-      const uint32_t m = __match_any_sync(0xffffffffu, d | (valid ? 0u : 0x100u));
-      // the lowest lane of every group of equal digits adds the group size
-      if (valid && (m & ((1u << lane) - 1u)) == 0u) atomicAdd(&sh[p * kRadix + d], (uint32_t)__popc(m));
+      const int shift = p * kRadixBits;
+      uint32_t run_d = (uint32_t)(k[0] >> shift) & (kRadix - 1);
+      uint32_t run_n = 1;
+#pragma unroll
+      for (int i = 1; i < kHistItems; ++i) {
+        if (i < cnt) {
+          const uint32_t d = (uint32_t)(k[i] >> shift) & (kRadix - 1);
+          if (d == run_d) {
+            ++run_n;
+          } else {
+            atomicAdd(&sh[p * kRadix + run_d], run_n);
+            run_d = d;
+            run_n = 1;
+          }
+        }
+      }
+      atomicAdd(&sh[p * kRadix + run_d], run_n);
     }
   }
   __syncthreads();
@@ -93,42 +129,51 @@ __global__ void __launch_bounds__(kRadix) radix_scan_hist_kernel(uint32_t* __res
 }
 
 // ---- one onesweep pass ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(
+// Dynamic shared memory layout of one tile (59.4 KB -> 3 resident CTAs per SM):
+struct SortSmem {
+  uint64_t keys[kSortTile];                 // 32 KB  tile-sorted keys
+  uint32_t vals[kSortTile];                 // 16 KB  tile-sorted values
+  uint32_t warp_hist[kSortWarps][kRadix];   //  8 KB  per-warp digit counts, then per-warp exclusive offsets
+  uint32_t digit_start[kRadix];             // first slot of each digit inside the tile
+  uint32_t dst_base[kRadix];                // global base - digit_start (mod 2^32)
+  uint32_t warp_tot[kSortWarps];
+  uint32_t tile;
+};
+
+// Register budget: the 16 keys (32 registers) are only live until they are scattered into shared memory;
+// ranks / slots are packed two per register; the values are loaded after the keys have left, and the
+// global destination of a slot is recomputed from the key's digit instead of being kept.  That keeps
+// the kernel at <= 64 registers with every global load of a phase in flight at once.
+template <int MINB>
+__global__ void __launch_bounds__(kSortThreads, MINB) radix_onesweep_kernel(
     const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ digit_base /*[256]*/,
     uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ status /*[ntiles][256]*/) {
-  __shared__ __align__(16) uint64_t s_keys[kSortTile];        // 32 KB, reused for the values
-  __shared__ uint32_t s_warp_hist[kSortWarps][kRadix];        // 8 KB
-  __shared__ uint32_t s_digit_start[kRadix];                  // first slot of each digit inside the tile
-  __shared__ uint32_t s_dst_base[kRadix];                     // global base - digit_start (mod 2^32)
-  __shared__ uint32_t s_warp_tot[kSortWarps];
-  __shared__ uint32_t s_tile;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // dynamic tile id: a tile only waits on tiles that have already started (no look-back deadlock)
-  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  if (tid == 0) sm.tile = atomicAdd(tile_counter, 1u);
 #pragma unroll
-  for (int i = 0; i < kSortWarps; ++i) s_warp_hist[i][tid] = 0;  // tid < 256 == kRadix
+  for (int i = 0; i < kSortWarps; ++i) sm.warp_hist[i][tid] = 0;  // tid < 256 == kRadix
   __syncthreads();
-  const uint32_t tile = s_tile;
+  const uint32_t tile = sm.tile;
   const int64_t tile_base = (int64_t)tile * kSortTile;
   const int tile_count = (int)min((int64_t)kSortTile, n - tile_base);
 
   // (a) load, warp-striped: item i of lane l in warp w is element w*512 + i*32 + l of the tile
   uint64_t key[kSortItems];
-  uint32_t val[kSortItems];
   const int warp_off = warp * kWarpSpan + lane;
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const int local = warp_off + i * 32;
-    const bool valid = local < tile_count;
-    key[i] = valid ? keys_in[tile_base + local] : ~0ull;
-    val[i] = valid ? vals_in[tile_base + local] : 0u;
+    key[i] = (local < tile_count) ? keys_in[tile_base + local] : ~0ull;
   }
 
-  // (b) stable rank of every item among the items of its warp with the same digit
-  uint32_t rank[kSortItems];
-  uint32_t* wh = s_warp_hist[warp];
+  // (b) stable rank of every item among the items of its warp with the same digit (two ranks per register)
+  uint32_t packed[kSortItems / 2];
+  uint32_t* wh = sm.warp_hist[warp];
   const uint32_t lanemask_lt = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
@@ -140,7 +185,9 @@ __global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(
     __syncwarp();
     if (valid && before == 0) wh[d] = prev + (uint32_t)__popc(m);
     __syncwarp();
-    rank[i] = prev + before;
+    const uint32_t rank = prev + before;
+    if (i & 1) packed[i / 2] |= rank << 16;
+    else packed[i / 2] = rank;
   }
   __syncthreads();
 
@@ -148,8 +195,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(
   uint32_t count = 0;
 #pragma unroll
   for (int w = 0; w < kSortWarps; ++w) {
-    const uint32_t t = s_warp_hist[w][tid];
-    s_warp_hist[w][tid] = count;
+    const uint32_t t = sm.warp_hist[w][tid];
+    sm.warp_hist[w][tid] = count;
     count += t;
   }
   // publish the tile aggregate (or the inclusive prefix for tile 0) as early as possible
@@ -163,65 +210,78 @@ __global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(
     uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
     if (lane >= d) inc += t;
   }
-  if (lane == 31) s_warp_tot[warp] = inc;
+  if (lane == 31) sm.warp_tot[warp] = inc;
   __syncthreads();
   uint32_t wbase = 0;
 #pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) wbase += (w < warp) ? s_warp_tot[w] : 0u;
+  for (int w = 0; w < kSortWarps; ++w) wbase += (w < warp) ? sm.warp_tot[w] : 0u;
   const uint32_t digit_start = wbase + inc - count;
-  s_digit_start[tid] = digit_start;
+  sm.digit_start[tid] = digit_start;
   __syncthreads();
 
-  // (e) scatter the keys into tile-sorted order in shared memory
-  uint32_t pos[kSortItems];
+  // (e) scatter the keys into tile-sorted order in shared memory; keep the slots (packed)
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
-    pos[i] = s_digit_start[d] + wh[d] + rank[i];
-    if ((warp_off + i * 32) < tile_count) s_keys[pos[i]] = key[i];
+    const uint32_t rank = (i & 1) ? (packed[i / 2] >> 16) : (packed[i / 2] & 0xffffu);
+    const uint32_t pos = sm.digit_start[d] + wh[d] + rank;
+    if ((warp_off + i * 32) < tile_count) sm.keys[pos] = key[i];
+    if (i & 1) packed[i / 2] = (packed[i / 2] & 0xffffu) | (pos << 16);
+    else packed[i / 2] = (packed[i / 2] & 0xffff0000u) | pos;
   }
 
-  // (f) decoupled look-back for digit tid
+  // the values can start travelling now (their registers are the ones the keys just released)
+  uint32_t val[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int local = warp_off + i * 32;
+    val[i] = (local < tile_count) ? vals_in[tile_base + local] : 0u;
+  }
+
+  // (f) decoupled look-back for digit tid.  kLookWindow predecessors are polled with independent loads per
+  // round (one L2 latency per round instead of one per predecessor), then consumed in order.
   uint32_t excl = 0;
   if (tile > 0) {
     int64_t j = (int64_t)tile - 1;
-    while (true) {
-      const uint32_t* ps = status + (size_t)j * kRadix + tid;
-      uint32_t v;
-      do { v = ld_volatile_u32(ps); } while ((v >> 30) == 0u);
-      excl += v & kValueMask;
-      if ((v & kFlagPrefix) != 0u || j == 0) break;
-      --j;
+    bool finished = false;
+    while (!finished) {
+      uint32_t v[kLookWindow];
+#pragma unroll
+      for (int w = 0; w < kLookWindow; ++w)
+        v[w] = (j - w >= 0) ? ld_volatile_u32(status + (size_t)(j - w) * kRadix + tid) : kFlagPrefix;
+#pragma unroll
+      for (int w = 0; w < kLookWindow; ++w) {
+        if (!finished) {
+          if ((v[w] >> 30) == 0u) break;  // predecessor has not published yet: poll again from it
+          excl += v[w] & kValueMask;
+          --j;
+          if ((v[w] & kFlagPrefix) != 0u) finished = true;
+        }
+      }
     }
     st_volatile_u32(my_status, kFlagPrefix | ((excl + count) & kValueMask));
   }
-  s_dst_base[tid] = digit_base[tid] + excl - digit_start;
+  sm.dst_base[tid] = digit_base[tid] + excl - digit_start;
+
+  // (g) values into tile-sorted order
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint32_t pos = (i & 1) ? (packed[i / 2] >> 16) : (packed[i / 2] & 0xffffu);
+    if ((warp_off + i * 32) < tile_count) sm.vals[pos] = val[i];
+  }
   __syncthreads();
 
-  // (g) write the keys out; consecutive slots of one digit go to consecutive addresses
-  uint32_t dst[kSortItems];
+  // (h) write out; consecutive slots of one digit go to consecutive addresses
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const int p = tid + i * kSortThreads;
     if (p < tile_count) {
-      const uint64_t k = s_keys[p];
+      const uint64_t k = sm.keys[p];
       const uint32_t d = (uint32_t)(k >> shift) & (kRadix - 1);
-      dst[i] = s_dst_base[d] + (uint32_t)p;
-      keys_out[dst[i]] = k;
+      const uint32_t dst = sm.dst_base[d] + (uint32_t)p;
+      keys_out[dst] = k;
+      vals_out[dst] = sm.vals[p];
     }
-  }
-  __syncthreads();
-
-  // (h) the values take the same route through the (reused) shared buffer
-  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys);
-#pragma unroll
-  for (int i = 0; i < kSortItems; ++i)
-    if ((warp_off + i * 32) < tile_count) s_vals[pos[i]] = val[i];
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    const int p = tid + i * kSortThreads;
-    if (p < tile_count) vals_out[dst[i]] = s_vals[p];
   }
 }
 
@@ -262,6 +322,8 @@ extern "C" int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_
   EGS_REQUIRE(n >= 0, "radix_sort: n=%lld < 0", (long long)n);
   EGS_REQUIRE(n < (1ll << 30), "radix_sort: n=%lld exceeds the 2^30 pairs the look-back words can count", (long long)n);
   EGS_REQUIRE(end_bit >= 0 && end_bit <= 64, "radix_sort: end_bit=%d out of [0,64]", end_bit);
+  EGS_REQUIRE(reinterpret_cast<uintptr_t>(keys_a) % 16 == 0 && reinterpret_cast<uintptr_t>(keys_b) % 16 == 0,
+              "radix_sort: key buffers must be 16-byte aligned");
   const int passes = (end_bit + kRadixBits - 1) / kRadixBits;
   if (host_result_in_b) *host_result_in_b = (passes & 1);
   if (n == 0 || passes == 0) {
@@ -273,6 +335,18 @@ extern "C" int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_
   if (carve_workspace(workspace, workspace_bytes, n, passes, w, clear_bytes) != 0 || workspace == nullptr)
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "radix_sort: workspace %lld < %lld bytes", (long long)workspace_bytes,
                 (long long)clear_bytes);
+  static const int minb = [] {  // tuning knob (resident CTAs per SM the kernel is compiled for)
+    const char* e = getenv("EGS_SORT_MINBLOCKS");
+    const int v = e ? atoi(e) : 3;
+    return (v == 2) ? 2 : 3;
+  }();
+  static const cudaError_t attr_rc = [] {
+    cudaError_t a = cudaFuncSetAttribute(radix_onesweep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+    cudaError_t b = cudaFuncSetAttribute(radix_onesweep_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+    return a != cudaSuccess ? a : b;
+  }();
+  if (attr_rc != cudaSuccess) return fail((int)attr_rc, "radix_sort: cannot opt in to %d bytes of shared memory: %s",
+                                          (int)sizeof(SortSmem), cudaGetErrorString(attr_rc));
   EGS_CUDA(cudaMemsetAsync(workspace, 0, clear_bytes, stream));
   const int64_t ntiles = sort_ntiles(n);
   int64_t hist_blocks = ceil_div(n, (int64_t)kHistThreads * kHistItems);
@@ -282,9 +356,14 @@ extern "C" int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_
   uint64_t* kin = keys_a; uint32_t* vin = vals_a;
   uint64_t* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < passes; ++p) {
-    radix_onesweep_kernel<<<(unsigned)ntiles, kSortThreads, 0, stream>>>(
-        kin, vin, kout, vout, n, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
-        w.status + (size_t)p * ntiles * kRadix);
+    if (minb == 2)
+      radix_onesweep_kernel<2><<<(unsigned)ntiles, kSortThreads, sizeof(SortSmem), stream>>>(
+          kin, vin, kout, vout, n, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
+          w.status + (size_t)p * ntiles * kRadix);
+    else
+      radix_onesweep_kernel<3><<<(unsigned)ntiles, kSortThreads, sizeof(SortSmem), stream>>>(
+          kin, vin, kout, vout, n, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
+          w.status + (size_t)p * ntiles * kRadix);
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }

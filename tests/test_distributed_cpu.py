@@ -1,0 +1,110 @@
+"""CPU tests (gloo, world_size 2) of the view-sharded step's host logic: the flat gradient bucket and the
+densify-statistics exchange must reproduce what a single process accumulates over all views."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from easy_gaussian_splatting_b200.distributed import DensifyStats, FlatGradBucket, shard_views
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_view(v, shapes, N):
+    """Deterministic per-view 'gradients' and statistics, standing in for one rasterization fwd+bwd."""
+    g = torch.Generator().manual_seed(1000 + v)
+    grads = [torch.randn(*s, generator=g) for s in shapes]
+    radii = torch.randint(0, 20, (1, N), generator=g, dtype=torch.int32)
+    absgrad = torch.rand(1, N, 2, generator=g)
+    return grads, radii, absgrad
+
+
+def _stats_update_cpu(stats, radii, absgrad, W, H):
+    # same per-view semantics as the CUDA kernel / gaussian.py:188-197 (CPU tensors in this test)
+    max_hw = max(W, H)
+    r = radii[0].float() / max_hw
+    vis = r > 0
+    stats.max_radii[vis] = torch.max(stats.max_radii[vis], r[vis])
+    stats.grad_norm_accum[vis] += absgrad[0].norm(dim=-1)[vis] * max_hw
+    stats.collecting_counts[vis] += 1
+
+
+SHAPES = [(50, 3), (50, 4), (50, 3), (50,), (50, 16, 3)]
+N_VIEWS, N, W, H = 6, 50, 640, 480
+
+
+def _worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = [torch.zeros(*s, requires_grad=True) for s in SHAPES]
+    bucket = FlatGradBucket(params)
+    stats = DensifyStats(N, "cpu")
+    stats.buf[0] = 1.0  # pre-existing accumulations, identical on all replicas
+    before = stats.clone()
+    bucket.zero_()
+    for v in shard_views(N_VIEWS, rank, world):
+        grads, radii, absgrad = _fake_view(v, SHAPES, N)
+        for p, g in zip(params, grads):
+            p.grad += g  # autograd accumulates in place into the bucket views
+        _stats_update_cpu(stats, radii, absgrad, W, H)
+    bucket.all_reduce()
+    stats.all_reduce_delta(before)
+    out_q.put((rank, bucket.flat.clone(), stats.buf.clone(), [p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, bucket.views)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_view_sharded_exchange_matches_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference over all views
+    params = [torch.zeros(*s, requires_grad=True) for s in SHAPES]
+    bucket = FlatGradBucket(params)
+    stats = DensifyStats(N, "cpu")
+    stats.buf[0] = 1.0
+    for v in range(N_VIEWS):
+        grads, radii, absgrad = _fake_view(v, SHAPES, N)
+        for p, g in zip(params, grads):
+            p.grad += g
+        _stats_update_cpu(stats, radii, absgrad, W, H)
+    for rank, flat, sbuf, aliased in results:
+        assert all(aliased), "param.grad must alias the flat bucket (no pack/unpack copies)"
+        assert torch.allclose(flat, bucket.flat, atol=1e-5), f"rank {rank} gradients"
+        assert torch.allclose(sbuf[:2], stats.buf[:2], atol=1e-4), f"rank {rank} SUM statistics"
+        assert torch.equal(sbuf[2], stats.buf[2]), f"rank {rank} MAX statistics"
+    assert torch.equal(results[0][1], results[1][1]), "replicas must end bit-identical"
+
+
+def test_shard_views_partition():
+    for world in (1, 2, 4, 8):
+        allv = sorted(v for r in range(world) for v in shard_views(64, r, world))
+        assert allv == list(range(64))
+        assert all(len(shard_views(64, r, world)) == 64 // world for r in range(world))
+
+
+def test_flat_bucket_survives_optimizer_zero_grad():
+    params = [torch.zeros(4, 3, requires_grad=True), torch.zeros(4, requires_grad=True)]
+    bucket = FlatGradBucket(params)
+    opt = torch.optim.Adam(params, lr=0.1)
+    (params[0].sum() + params[1].sum()).backward()
+    assert float(bucket.flat.sum()) == 16.0
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    bucket.zero_()
+    assert all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, bucket.views))
