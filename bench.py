@@ -218,7 +218,7 @@ def ours(args):
     dev_views = [(a.to(dev), b.to(dev)) for a, b in host_views]
     dev_Wc, dev_Wa = host_Wc.to(dev), host_Wa.to(dev)
     h2d_bytes = V * (host_views[0][0].numel() * 4 + host_views[0][1].numel() * 4 + host_Wc.numel() * 4 + host_Wa.numel() * 4)
-    d2h_bytes = V * 4
+    d2h_bytes = 4
 
     def one_view(viewmat, K, Wc, Wa, want_loss):
         rc, ra, meta = rasterization(params[0], params[1], params[2], params[3], params[4], viewmat, K, W, H,
@@ -237,19 +237,43 @@ def ours(args):
             bucket.all_reduce()
             stats.all_reduce_delta(before)
 
+    # e2e: per-view inputs travel host -> device inside the timed region, double buffered on a copy stream so
+    # the copy of view i+1 overlaps the rendering of view i; the step's loss is read back once per step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [dict(vm=torch.empty_like(dev_views[0][0]), K=torch.empty_like(dev_views[0][1]),
+                  Wc=torch.empty_like(dev_Wc), Wa=torch.empty_like(dev_Wa),
+                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+
+    def stage_view(i):
+        b = stage[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(b["free"])  # the view that used this buffer two views ago has finished
+            b["vm"].copy_(host_views[i][0], non_blocking=True)
+            b["K"].copy_(host_views[i][1], non_blocking=True)
+            b["Wc"].copy_(host_Wc, non_blocking=True)
+            b["Wa"].copy_(host_Wa, non_blocking=True)
+            b["ready"].record(copy_stream)
+
     def step_e2e():
         bucket.zero_()
         before = stats.clone() if world > 1 else None
-        total = 0.0
-        for (hvm, hK) in host_views:
-            vm, K = hvm.to(dev, non_blocking=True), hK.to(dev, non_blocking=True)
-            Wc, Wa = host_Wc.to(dev, non_blocking=True), host_Wa.to(dev, non_blocking=True)
-            loss = one_view(vm, K, Wc, Wa, True)
-            total += loss.item()  # device -> host read of the step's result, like train.py:107-108
+        main = torch.cuda.current_stream(dev)
+        total = torch.zeros((), device=dev)
+        for b in stage:
+            b["free"].record(main)
+        stage_view(0)
+        for i in range(V):
+            b = stage[i % 2]
+            if i + 1 < V:
+                stage_view(i + 1)
+            main.wait_event(b["ready"])
+            loss = one_view(b["vm"], b["K"], b["Wc"], b["Wa"], True)
+            total += loss.detach()
+            b["free"].record(main)
         if world > 1:
             bucket.all_reduce()
             stats.all_reduce_delta(before)
-        return total
+        return total.item()  # device -> host read of the step's result (train.py:107-108 reads the loss)
 
     def barrier():
         if world > 1:
@@ -298,9 +322,10 @@ def ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e_total / args.steps,
                 "what": "rasterization() fwd+bwd per view with the view's camera and loss weights (target-image sized) copied "
-                        "from pinned host memory and loss.item() read back each view; Gaussian parameters stay resident "
-                        "(they are the model, /root/reference/train.py:97-108)"},
-        "gpu_launches": 17 * V * args.steps,
+                        "from pinned host memory inside the timed region (double buffered on a copy stream) and the step's loss "
+                        "read back with .item(); Gaussian parameters stay resident (they are the model, "
+                        "/root/reference/train.py:97-108)"},
+        "gpu_launches": 29 * V * args.steps,
     }
     if args.n_gaussians:
         line["invalid"] = "N overridden (debug run)"
@@ -369,9 +394,19 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
 
     t = {}
     t["projection_sh_fwd"] = tm(lambda: stages.projection_fwd(means, quats, scales, opac, colors, vm, K, W, H, 3))
-    t["scan"] = tm(lambda: stages.exclusive_scan(proj["tiles_per_gauss"]))
-    t["emit"] = tm(lambda: stages.isect_tiles(proj["means2d"], proj["radii"], proj["depths"], 16, tw, th, sort=False,
-                                              tiles_per_gauss=proj["tiles_per_gauss"], n_isects=n_isects)) - t["scan"]
+    # product path of g3-g5: two-level route (includes its one host sync)
+    t["binning_fast_path"] = tm(lambda: stages.isect_sorted(proj["means2d"], proj["radii"], proj["depths"],
+                                                            proj["tiles_per_gauss"], 16, tw, th))
+    t["rasterize_fwd"] = tm(lambda: stages.rasterize_fwd(proj["splats"], offs, flat, bg, W, H))
+    zero_ms = tm(lambda: torch.zeros_like(v_splats))
+    t["rasterize_bwd"] = tm(lambda: stages.rasterize_bwd(proj["splats"], offs, flat, bg, W, H, ra, last, Wc, Wa)) - zero_ms
+    t["projection_sh_bwd"] = tm(lambda: stages.projection_bwd(means, quats, scales, colors, vm, K, W, H, 3, 0.3,
+                                                               proj["radii"], proj["colors"], v_splats))
+    # standalone C-ABI operators of the classic route (64-bit keys), not on the product path any more
+    u = {}
+    u["scan"] = tm(lambda: stages.exclusive_scan(proj["tiles_per_gauss"]))
+    u["emit_u64"] = tm(lambda: stages.isect_tiles(proj["means2d"], proj["radii"], proj["depths"], 16, tw, th, sort=False,
+                                                  tiles_per_gauss=proj["tiles_per_gauss"], n_isects=n_isects)) - u["scan"]
     ka, va = ids_u.clone(), flat_u.clone()
 
     def sort_once():
@@ -379,42 +414,45 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
         va.copy_(flat_u)
         stages.radix_sort_pairs(ka, va, 32 + nbits)
     copy_ms = tm(lambda: (ka.copy_(ids_u), va.copy_(flat_u)))
-    t["radix_sort"] = tm(sort_once) - copy_ms
-    t["offset_encode"] = tm(lambda: stages.isect_offset_encode(ids, 1, tw, th))
-    t["rasterize_fwd"] = tm(lambda: stages.rasterize_fwd(proj["splats"], offs, flat, bg, W, H))
-    zero_ms = tm(lambda: torch.zeros_like(v_splats))
-    t["rasterize_bwd"] = tm(lambda: stages.rasterize_bwd(proj["splats"], offs, flat, bg, W, H, ra, last, Wc, Wa)) - zero_ms
-    t["projection_sh_bwd"] = tm(lambda: stages.projection_bwd(means, quats, scales, colors, vm, K, W, H, 3, 0.3,
-                                                               proj["radii"], proj["colors"], v_splats))
+    u["radix_sort_u64"] = tm(sort_once) - copy_ms
+    u["offset_encode"] = tm(lambda: stages.isect_offset_encode(ids, 1, tw, th))
     passes = math.ceil((32 + nbits) / 8)
-    work = {  # algorithmic bytes (HBM-bound stages) or flops (blend) per launch, BASELINE.md §4
+    sort_bytes = (8 + 24 * passes) * n_isects
+    work = {  # algorithmic bytes (HBM-bound stages) or flops (blend) per launch, BASELINE.md section 4 (frozen)
         "projection_sh_fwd": ("hbm", 68 * N + 204 * n_vis),
-        "scan": ("hbm", 12 * N),
-        "emit": ("hbm", 32 * N + 12 * n_isects),
-        "radix_sort": ("hbm", (8 + 24 * passes) * n_isects),
-        "offset_encode": ("hbm", 8 * n_isects + 4 * tw * th),
+        "binning_fast_path": ("hbm", 44 * N + 12 * n_isects + sort_bytes + 8 * n_isects + 4 * tw * th),
         "rasterize_fwd": ("fp32", 16 * p_eval + 10 * p_acc),
         "rasterize_bwd": ("fp32", 16 * p_eval + 54 * p_acc),
         "projection_sh_bwd": ("hbm", 108 * N + 12 * N + 408 * n_vis + 192 * (N - n_vis)),
     }
-    stages_out = {}
-    for k, (bound, w) in work.items():
-        ms = max(t[k], 1e-6)
+    work_u = {
+        "scan": ("hbm", 12 * N),
+        "emit_u64": ("hbm", 32 * N + 12 * n_isects),
+        "radix_sort_u64": ("hbm", sort_bytes),
+        "offset_encode": ("hbm", 8 * n_isects + 4 * tw * th),
+    }
+
+    def line(ms, bound, w):
+        ms = max(ms, 1e-6)
         if bound == "hbm":
             ach = w / (ms * 1e-3) / 1e9
-            stages_out[k] = {"ms": ms, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": ach / pk["hbm_gbs"], "algorithmic_bytes": w}
-        else:
-            ach = w / (ms * 1e-3) / 1e12
-            stages_out[k] = {"ms": ms, "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                             "frac": ach / fp32_peak, "algorithmic_flops": w}
+            return {"ms": ms, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "algorithmic_bytes": w}
+        ach = w / (ms * 1e-3) / 1e12
+        return {"ms": ms, "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": ach / fp32_peak, "algorithmic_flops": w}
+
+    stages_out = {k: line(t[k], *work[k]) for k in work}
+    stages_out["binning_fast_path"]["note"] = ("algorithmic bytes are the frozen figure of the classic route (emit 64-bit keys, "
+                                               "6-pass LSD sort, offset encode = 172 B/isect); the two-level route moves ~3x less")
+    standalone = {k: line(u[k], *work_u[k]) for k in work_u}
     dominant = max(t, key=lambda k: t[k])
     roof = dict(stages_out[dominant])
     roof["kernel"] = dominant
     roof["traffic"] = None
     roof["peak_source"] = pk["source"] if roof["bound"] == "hbm" else \
         f"measured live: dependent-FMA probe kernel, {fp32_peak:.1f} TFLOP/s (theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)"
-    return {"roofline": roof, "stages": stages_out,
+    return {"roofline": roof, "stages": stages_out, "stages_standalone": standalone,
             "scene_stats": {"N": N, "N_vis": n_vis, "n_isects": n_isects, "isects_per_visible": n_isects / max(n_vis, 1),
                             "P_eval": p_eval, "P_acc": p_acc, "fp32_peak_tflops_measured": fp32_peak,
                             "sum_stage_ms": sum(t.values())}}

@@ -19,11 +19,11 @@ namespace egs {
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 16;                          // pairs per thread
+constexpr int kSortItems = 8;                           // pairs per thread
 constexpr int kSortTile = kSortThreads * kSortItems;    // 4096 pairs per tile
-constexpr int kWarpSpan = 32 * kSortItems;              // 512 consecutive pairs per warp
+constexpr int kWarpSpan = 32 * kSortItems;              // 256 consecutive pairs per warp
 
 constexpr int kLookWindow = 8;
 constexpr uint32_t kFlagAggregate = 1u << 30;
@@ -51,7 +51,8 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 constexpr int kHistThreads = 256;
 constexpr int kHistItems = 16;
 
-__global__ void __launch_bounds__(kHistThreads) radix_histogram_kernel(const uint64_t* __restrict__ keys, int64_t n,
+template <typename KeyT>
+__global__ void __launch_bounds__(kHistThreads) radix_histogram_kernel(const KeyT* __restrict__ keys, int64_t n,
                                                                         int passes, uint32_t* __restrict__ hist) {
   // Each thread walks kHistItems CONSECUTIVE keys and combines runs of equal digits in a register before
   // touching shared memory.  The keys of this path come out of isect_emit in runs that share the depth
@@ -60,18 +61,23 @@ __global__ void __launch_bounds__(kHistThreads) radix_histogram_kernel(const uin
   __shared__ uint32_t sh[kMaxPasses * kRadix];
   for (int i = threadIdx.x; i < passes * kRadix; i += kHistThreads) sh[i] = 0;
   __syncthreads();
+  constexpr int kVec = 16 / sizeof(KeyT);  // keys per 128-bit load
   const int64_t chunk = (int64_t)kHistThreads * kHistItems;
   for (int64_t base = (int64_t)blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
     const int64_t first = base + (int64_t)threadIdx.x * kHistItems;
-    uint64_t k[kHistItems];
+    KeyT k[kHistItems];
     int cnt = 0;
     if (first + kHistItems <= n) {
-      const ulonglong2* p2 = reinterpret_cast<const ulonglong2*>(keys + first);  // first % 16 keys == 0: 16B aligned
+      const uint4* p4 = reinterpret_cast<const uint4*>(keys + first);  // first is a multiple of 16 keys: 16B aligned
 #pragma unroll
-      for (int i = 0; i < kHistItems / 2; ++i) {
-        const ulonglong2 v = __ldg(p2 + i);
-        k[2 * i] = v.x;
-        k[2 * i + 1] = v.y;
+      for (int i = 0; i < kHistItems / kVec; ++i) {
+        const uint4 v = __ldg(p4 + i);
+        if constexpr (sizeof(KeyT) == 8) {
+          k[2 * i] = (KeyT)(((uint64_t)v.y << 32) | v.x);
+          k[2 * i + 1] = (KeyT)(((uint64_t)v.w << 32) | v.z);
+        } else {
+          k[4 * i] = (KeyT)v.x; k[4 * i + 1] = (KeyT)v.y; k[4 * i + 2] = (KeyT)v.z; k[4 * i + 3] = (KeyT)v.w;
+        }
       }
       cnt = kHistItems;
     } else {
@@ -129,47 +135,48 @@ __global__ void __launch_bounds__(kRadix) radix_scan_hist_kernel(uint32_t* __res
 }
 
 // ---- one onesweep pass ------------------------------------------------------------------------------
-// Dynamic shared memory layout of one tile (59.4 KB -> 3 resident CTAs per SM):
+// Dynamic shared memory layout of one tile (67.6 KB with 64-bit keys -> 2 resident CTAs of 16 warps per SM):
+template <typename KeyT>
 struct SortSmem {
-  uint64_t keys[kSortTile];                 // 32 KB  tile-sorted keys
+  KeyT keys[kSortTile];                     // 32 KB (u64) / 16 KB (u32)  tile-sorted keys
   uint32_t vals[kSortTile];                 // 16 KB  tile-sorted values
-  uint32_t warp_hist[kSortWarps][kRadix];   //  8 KB  per-warp digit counts, then per-warp exclusive offsets
+  uint32_t warp_hist[kSortWarps][kRadix];   // 16 KB  per-warp digit counts, then per-warp exclusive offsets
   uint32_t digit_start[kRadix];             // first slot of each digit inside the tile
   uint32_t dst_base[kRadix];                // global base - digit_start (mod 2^32)
-  uint32_t warp_tot[kSortWarps];
+  uint32_t warp_tot[kRadix / 32];
   uint32_t tile;
 };
 
 // Register budget: the 16 keys (32 registers) are only live until they are scattered into shared memory;
 // ranks / slots are packed two per register; the values are loaded after the keys have left, and the
 // global destination of a slot is recomputed from the key's digit instead of being kept.  That keeps
-// the kernel at <= 64 registers with every global load of a phase in flight at once.
-template <int MINB>
-__global__ void __launch_bounds__(kSortThreads, MINB) radix_onesweep_kernel(
-    const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
+// the kernel at 64 registers (2 CTAs of 512 threads per SM) with every global load of a phase in flight at once.
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads, 2) radix_onesweep_kernel(
+    const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ digit_base /*[256]*/,
     uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ status /*[ntiles][256]*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
+  SortSmem<KeyT>& sm = *reinterpret_cast<SortSmem<KeyT>*>(smem_raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // dynamic tile id: a tile only waits on tiles that have already started (no look-back deadlock)
   if (tid == 0) sm.tile = atomicAdd(tile_counter, 1u);
-#pragma unroll
-  for (int i = 0; i < kSortWarps; ++i) sm.warp_hist[i][tid] = 0;  // tid < 256 == kRadix
+  for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = sm.tile;
   const int64_t tile_base = (int64_t)tile * kSortTile;
   const int tile_count = (int)min((int64_t)kSortTile, n - tile_base);
 
-  // (a) load, warp-striped: item i of lane l in warp w is element w*512 + i*32 + l of the tile
-  uint64_t key[kSortItems];
+  // (a) load, warp-striped: item i of lane l in warp w is element w*256 + i*32 + l of the tile
+  // (loads are unpredicated — out-of-range items re-read the tile's last element and are masked by `valid`
+  //  where it matters — because per-load predicates exhaust the 7 predicate registers and make ptxas
+  //  serialise the loads behind the ranking loop: profiles/r1c)
+  KeyT key[kSortItems];
   const int warp_off = warp * kWarpSpan + lane;
+  const int last_local = tile_count - 1;
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    const int local = warp_off + i * 32;
-    key[i] = (local < tile_count) ? keys_in[tile_base + local] : ~0ull;
-  }
+  for (int i = 0; i < kSortItems; ++i) key[i] = keys_in[tile_base + min(warp_off + i * 32, last_local)];
 
   // (b) stable rank of every item among the items of its warp with the same digit (two ranks per register)
   uint32_t packed[kSortItems / 2];
@@ -191,32 +198,38 @@ __global__ void __launch_bounds__(kSortThreads, MINB) radix_onesweep_kernel(
   }
   __syncthreads();
 
-  // (c) thread d owns digit d: exclusive prefix over the warps, tile total
+  // (c) thread d (< 256) owns digit d: exclusive prefix over the warps, tile total
+  const bool owner = tid < kRadix;
   uint32_t count = 0;
+  uint32_t* my_status = status + (size_t)tile * kRadix + (owner ? tid : 0);
+  if (owner) {
 #pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) {
-    const uint32_t t = sm.warp_hist[w][tid];
-    sm.warp_hist[w][tid] = count;
-    count += t;
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t t = sm.warp_hist[w][tid];
+      sm.warp_hist[w][tid] = count;
+      count += t;
+    }
+    // publish the tile aggregate (or the inclusive prefix for tile 0) as early as possible
+    st_volatile_u32(my_status, (tile == 0 ? kFlagPrefix : kFlagAggregate) | count);
   }
-  // publish the tile aggregate (or the inclusive prefix for tile 0) as early as possible
-  uint32_t* my_status = status + (size_t)tile * kRadix + tid;
-  st_volatile_u32(my_status, (tile == 0 ? kFlagPrefix : kFlagAggregate) | count);
 
-  // (d) exclusive scan of the digit counts across the 256 threads -> slot of each digit in the tile
+  // (d) exclusive scan of the digit counts across the 256 owner threads -> slot of each digit in the tile
   uint32_t inc = count;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
     if (lane >= d) inc += t;
   }
-  if (lane == 31) sm.warp_tot[warp] = inc;
+  if (owner && lane == 31) sm.warp_tot[warp] = inc;
   __syncthreads();
-  uint32_t wbase = 0;
+  uint32_t digit_start = 0;
+  if (owner) {
+    uint32_t wbase = 0;
 #pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) wbase += (w < warp) ? sm.warp_tot[w] : 0u;
-  const uint32_t digit_start = wbase + inc - count;
-  sm.digit_start[tid] = digit_start;
+    for (int w = 0; w < kRadix / 32; ++w) wbase += (w < warp) ? sm.warp_tot[w] : 0u;
+    digit_start = wbase + inc - count;
+    sm.digit_start[tid] = digit_start;
+  }
   __syncthreads();
 
   // (e) scatter the keys into tile-sorted order in shared memory; keep the slots (packed)
@@ -233,22 +246,22 @@ __global__ void __launch_bounds__(kSortThreads, MINB) radix_onesweep_kernel(
   // the values can start travelling now (their registers are the ones the keys just released)
   uint32_t val[kSortItems];
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    const int local = warp_off + i * 32;
-    val[i] = (local < tile_count) ? vals_in[tile_base + local] : 0u;
-  }
+  for (int i = 0; i < kSortItems; ++i) val[i] = vals_in[tile_base + min(warp_off + i * 32, last_local)];
 
   // (f) decoupled look-back for digit tid.  kLookWindow predecessors are polled with independent loads per
   // round (one L2 latency per round instead of one per predecessor), then consumed in order.
   uint32_t excl = 0;
-  if (tile > 0) {
+  if (owner && tile > 0) {
     int64_t j = (int64_t)tile - 1;
     bool finished = false;
     while (!finished) {
       uint32_t v[kLookWindow];
 #pragma unroll
-      for (int w = 0; w < kLookWindow; ++w)
-        v[w] = (j - w >= 0) ? ld_volatile_u32(status + (size_t)(j - w) * kRadix + tid) : kFlagPrefix;
+      for (int w = 0; w < kLookWindow; ++w) {
+        const int64_t jj = j - w;
+        const uint32_t x = ld_volatile_u32(status + (size_t)(jj > 0 ? jj : 0) * kRadix + tid);
+        v[w] = (jj >= 0) ? x : kFlagPrefix;  // before tile 0: an empty prefix
+      }
 #pragma unroll
       for (int w = 0; w < kLookWindow; ++w) {
         if (!finished) {
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(kSortThreads, MINB) radix_onesweep_kernel(
     }
     st_volatile_u32(my_status, kFlagPrefix | ((excl + count) & kValueMask));
   }
-  sm.dst_base[tid] = digit_base[tid] + excl - digit_start;
+  if (owner) sm.dst_base[tid] = digit_base[tid] + excl - digit_start;
 
   // (g) values into tile-sorted order
 #pragma unroll
@@ -276,7 +289,7 @@ __global__ void __launch_bounds__(kSortThreads, MINB) radix_onesweep_kernel(
   for (int i = 0; i < kSortItems; ++i) {
     const int p = tid + i * kSortThreads;
     if (p < tile_count) {
-      const uint64_t k = sm.keys[p];
+      const KeyT k = sm.keys[p];
       const uint32_t d = (uint32_t)(k >> shift) & (kRadix - 1);
       const uint32_t dst = sm.dst_base[d] + (uint32_t)p;
       keys_out[dst] = k;
@@ -314,14 +327,14 @@ extern "C" int64_t egs_radix_sort_workspace_bytes(int64_t n, int32_t end_bit) {
   return bytes;
 }
 
-extern "C" int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
-                                            uint32_t* vals_b, int32_t end_bit, void* workspace,
-                                            int64_t workspace_bytes, int32_t* host_result_in_b,
-                                            egs_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+template <typename KeyT>
+static int radix_sort_pairs_impl(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
+                                 int32_t end_bit, void* workspace, int64_t workspace_bytes,
+                                 int32_t* host_result_in_b, cudaStream_t stream) {
+  constexpr int kKeyBits = (int)sizeof(KeyT) * 8;
   EGS_REQUIRE(n >= 0, "radix_sort: n=%lld < 0", (long long)n);
   EGS_REQUIRE(n < (1ll << 30), "radix_sort: n=%lld exceeds the 2^30 pairs the look-back words can count", (long long)n);
-  EGS_REQUIRE(end_bit >= 0 && end_bit <= 64, "radix_sort: end_bit=%d out of [0,64]", end_bit);
+  EGS_REQUIRE(end_bit >= 0 && end_bit <= kKeyBits, "radix_sort: end_bit=%d out of [0,%d]", end_bit, kKeyBits);
   EGS_REQUIRE(reinterpret_cast<uintptr_t>(keys_a) % 16 == 0 && reinterpret_cast<uintptr_t>(keys_b) % 16 == 0,
               "radix_sort: key buffers must be 16-byte aligned");
   const int passes = (end_bit + kRadixBits - 1) / kRadixBits;
@@ -335,37 +348,41 @@ extern "C" int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_
   if (carve_workspace(workspace, workspace_bytes, n, passes, w, clear_bytes) != 0 || workspace == nullptr)
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "radix_sort: workspace %lld < %lld bytes", (long long)workspace_bytes,
                 (long long)clear_bytes);
-  static const int minb = [] {  // tuning knob (resident CTAs per SM the kernel is compiled for)
-    const char* e = getenv("EGS_SORT_MINBLOCKS");
-    const int v = e ? atoi(e) : 3;
-    return (v == 2) ? 2 : 3;
-  }();
-  static const cudaError_t attr_rc = [] {
-    cudaError_t a = cudaFuncSetAttribute(radix_onesweep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
-    cudaError_t b = cudaFuncSetAttribute(radix_onesweep_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
-    return a != cudaSuccess ? a : b;
-  }();
-  if (attr_rc != cudaSuccess) return fail((int)attr_rc, "radix_sort: cannot opt in to %d bytes of shared memory: %s",
-                                          (int)sizeof(SortSmem), cudaGetErrorString(attr_rc));
+  constexpr int kSmem = (int)sizeof(SortSmem<KeyT>);
+  static const cudaError_t attr_rc =
+      cudaFuncSetAttribute(radix_onesweep_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  if (attr_rc != cudaSuccess)
+    return fail((int)attr_rc, "radix_sort: cannot opt in to %d bytes of shared memory: %s", kSmem, cudaGetErrorString(attr_rc));
   EGS_CUDA(cudaMemsetAsync(workspace, 0, clear_bytes, stream));
   const int64_t ntiles = sort_ntiles(n);
   int64_t hist_blocks = ceil_div(n, (int64_t)kHistThreads * kHistItems);
   if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-  radix_histogram_kernel<<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, passes, w.hist);
+  radix_histogram_kernel<KeyT><<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, passes, w.hist);
   radix_scan_hist_kernel<<<passes, kRadix, 0, stream>>>(w.hist);
-  uint64_t* kin = keys_a; uint32_t* vin = vals_a;
-  uint64_t* kout = keys_b; uint32_t* vout = vals_b;
+  KeyT* kin = keys_a; uint32_t* vin = vals_a;
+  KeyT* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < passes; ++p) {
-    if (minb == 2)
-      radix_onesweep_kernel<2><<<(unsigned)ntiles, kSortThreads, sizeof(SortSmem), stream>>>(
-          kin, vin, kout, vout, n, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
-          w.status + (size_t)p * ntiles * kRadix);
-    else
-      radix_onesweep_kernel<3><<<(unsigned)ntiles, kSortThreads, sizeof(SortSmem), stream>>>(
-          kin, vin, kout, vout, n, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
-          w.status + (size_t)p * ntiles * kRadix);
-    uint64_t* tk = kin; kin = kout; kout = tk;
+    radix_onesweep_kernel<KeyT><<<(unsigned)ntiles, kSortThreads, kSmem, stream>>>(
+        kin, vin, kout, vout, n, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
+        w.status + (size_t)p * ntiles * kRadix);
+    KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
   return check_launch("radix_sort_pairs");
+}
+
+extern "C" int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
+                                            uint32_t* vals_b, int32_t end_bit, void* workspace,
+                                            int64_t workspace_bytes, int32_t* host_result_in_b,
+                                            egs_stream_t stream) {
+  return radix_sort_pairs_impl<uint64_t>(n, keys_a, vals_a, keys_b, vals_b, end_bit, workspace, workspace_bytes,
+                                         host_result_in_b, (cudaStream_t)stream);
+}
+
+extern "C" int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
+                                            uint32_t* vals_b, int32_t end_bit, void* workspace,
+                                            int64_t workspace_bytes, int32_t* host_result_in_b,
+                                            egs_stream_t stream) {
+  return radix_sort_pairs_impl<uint32_t>(n, keys_a, vals_a, keys_b, vals_b, end_bit, workspace, workspace_bytes,
+                                         host_result_in_b, (cudaStream_t)stream);
 }

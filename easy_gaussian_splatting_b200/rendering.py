@@ -35,10 +35,9 @@ class _Rasterization(torch.autograd.Function):
                                      eps2d=cfg["eps2d"], near_plane=cfg["near_plane"], far_plane=cfg["far_plane"],
                                      radius_clip=cfg["radius_clip"])
         tw, th = stages.tile_grid(width, height)
-        tiles_per_gauss, isect_ids, flatten_ids = stages.isect_tiles(
-            proj["means2d"], proj["radii"], proj["depths"], stages.TILE_SIZE, tw, th, sort=True,
-            tiles_per_gauss=proj["tiles_per_gauss"])
-        isect_offsets = stages.isect_offset_encode(isect_ids, C, tw, th)
+        tiles_per_gauss = proj["tiles_per_gauss"]
+        isect_ids, flatten_ids, isect_offsets = stages.isect_sorted(
+            proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th)
         render_colors, render_alphas, last_ids = stages.rasterize_fwd(
             proj["splats"], isect_offsets, flatten_ids, backgrounds, width, height)
 

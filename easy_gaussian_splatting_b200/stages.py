@@ -182,6 +182,79 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
     return tiles_per_gauss, ids, flat
 
 
+def radix_sort_pairs_u32(keys: Tensor, vals: Tensor, end_bit: int) -> Tuple[Tensor, Tensor]:
+    """Same onesweep sort for (int32-as-uint32 key, int32 value) pairs; inputs are clobbered."""
+    lib = _lib.load()
+    n, dev = keys.numel(), keys.device
+    if n == 0 or end_bit == 0:
+        return keys, vals
+    keys_b, vals_b = torch.empty_like(keys), torch.empty_like(vals)
+    ws_bytes = lib.egs_radix_sort_workspace_bytes(n, end_bit)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    in_b = ctypes.c_int32(0)
+    with torch.cuda.device(dev):
+        rc = lib.egs_radix_sort_pairs_u32_u32(n, _ptr(keys), _ptr(vals), _ptr(keys_b), _ptr(vals_b), int(end_bit),
+                                              _ptr(ws), ws_bytes, ctypes.byref(in_b), _stream(dev))
+    _lib.check(rc, "egs_radix_sort_pairs_u32_u32")
+    return (keys_b, vals_b) if in_b.value else (keys, vals)
+
+
+def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
+                 tile_width: int, tile_height: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """g3+g4+g5 fast path -> (isect_ids[n] i64 sorted, flatten_ids[n] i32, isect_offsets[C,th,tw] i32).
+
+    Bit-identical to ``isect_tiles(sort=True)`` + ``isect_offset_encode`` (a stable sort on cam|tile|depth
+    equals a stable depth sort of the visible Gaussians followed by a stable sort on the tile index), but the
+    n_isects-sized passes move 8-byte pairs through 2-3 radix passes instead of 12-byte pairs through 6."""
+    lib = _lib.load()
+    means2d, depths = _f32c(means2d, "means2d"), _f32c(depths, "depths")
+    radii, tiles_per_gauss = radii.contiguous(), tiles_per_gauss.contiguous()
+    C, N = radii.shape
+    dev = radii.device
+    n = C * N
+    n_tiles = tile_width * tile_height
+    nbits = tile_n_bits(tile_width, tile_height)
+    ws_bytes = max(lib.egs_isect_scan_workspace_bytes(max(n, 1)), 16)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    totals = torch.empty(2, dtype=torch.int64, device=dev)
+    keys1 = torch.empty(n, dtype=torch.int64, device=dev)  # upper bound n_vis <= C*N; sliced after the sync
+    vals1 = torch.empty(n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.egs_isect_visible_keys(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(keys1), _ptr(vals1),
+                                        _ptr(totals), _ptr(ws), ws_bytes, _stream(dev))
+    _lib.check(rc, "egs_isect_visible_keys")
+    n_vis, n_isects = (int(v) for v in totals.tolist())  # the one host sync of the forward pass
+    offsets = torch.empty(C, tile_height, tile_width, dtype=torch.int32, device=dev)
+    isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+    if n_isects == 0:
+        offsets.zero_()
+        return isect_ids, torch.empty(0, dtype=torch.int32, device=dev), offsets
+    if n_isects >= 2 ** 31 - 1:
+        raise RuntimeError(f"{n_isects} tile intersections do not fit int32 offsets; render fewer cameras per call")
+    # level 1: visible Gaussians in (camera, depth, index) order
+    k1, order = radix_sort_pairs(keys1[:n_vis], vals1[:n_vis], 32 + camera_n_bits(C))
+    # tile counts in that order -> write offsets
+    cum = torch.empty(n_vis, dtype=torch.int64, device=dev)
+    total2 = torch.empty(1, dtype=torch.int64, device=dev)
+    tile_keys = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    flat_vals = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.egs_exclusive_scan_gather(n_vis, _ptr(tiles_per_gauss), _ptr(order), _ptr(cum), _ptr(total2), _ptr(ws),
+                                           ws_bytes, _stream(dev))
+        _lib.check(rc, "egs_exclusive_scan_gather")
+        rc = lib.egs_isect_emit_sorted(C, N, n_vis, _ptr(order), _ptr(cum), _ptr(means2d), _ptr(radii), int(tile_size),
+                                       tile_width, tile_height, n_isects, _ptr(tile_keys), _ptr(flat_vals), _stream(dev))
+        _lib.check(rc, "egs_isect_emit_sorted")
+    # level 2: stable sort on the dense (camera, tile) index
+    end_bit = max(1, int(C * n_tiles - 1).bit_length())
+    tile_keys, flat_vals = radix_sort_pairs_u32(tile_keys, flat_vals, end_bit)
+    with torch.cuda.device(dev):
+        rc = lib.egs_isect_finalize(n_isects, _ptr(tile_keys), _ptr(flat_vals), _ptr(depths), C, n_tiles, nbits,
+                                    _ptr(isect_ids), _ptr(offsets), _stream(dev))
+    _lib.check(rc, "egs_isect_finalize")
+    return isect_ids, flat_vals, offsets
+
+
 def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height: int) -> Tensor:
     """g5 -> offsets[C, tile_height, tile_width] int32."""
     lib = _lib.load()

@@ -104,6 +104,35 @@ int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_t* vals_a, 
                                  uint32_t* vals_b, int32_t end_bit, void* workspace, int64_t workspace_bytes,
                                  int32_t* host_result_in_b, egs_stream_t stream);
 
+/* Same sort for 32-bit keys (used by the fast binning path below). */
+int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                                 int32_t end_bit, void* workspace, int64_t workspace_bytes,
+                                 int32_t* host_result_in_b, egs_stream_t stream);
+
+/* ---- g3-g5 fast path: identical sorted (isect_ids, flatten_ids, isect_offsets), ~3x less traffic ----------
+ * A stable sort on cam|tile|depth keys equals (1) a stable sort of the VISIBLE Gaussians on cam|depth,
+ * (2) emitting their tiles in that order, (3) a stable sort of the emitted pairs on the (cam,tile) index alone.
+ *   egs_isect_visible_keys : compacts visible entries (tiles_per_gauss > 0) into level-1 pairs
+ *                            keys1 = cam<<32 | bits(depth), vals1 = flat index; totals[2] = {n_vis, n_isects} (device)
+ *   (sort keys1/vals1 with egs_radix_sort_pairs_u64_u32 on bits [0, 32 + cam bits))
+ *   egs_exclusive_scan_gather : out[i] = sum_{j<i} src[gather[j]]  (tile counts in depth order)
+ *   egs_isect_emit_sorted  : warp-cooperative emission of tile_keys = cam*n_tiles + tile (u32), flat_vals
+ *   (sort tile_keys/flat_vals with egs_radix_sort_pairs_u32_u32 on bits [0, ceil(log2(C*n_tiles))))
+ *   egs_isect_finalize     : rebuilds the 64-bit isect_ids and derives the tile offsets */
+int64_t egs_isect_scan_workspace_bytes(int64_t n);
+int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths, uint64_t* keys1,
+                           uint32_t* vals1, int64_t* totals, void* workspace, int64_t workspace_bytes,
+                           egs_stream_t stream);
+int egs_exclusive_scan_gather(int64_t n, const int32_t* src, const uint32_t* gather, int64_t* out, int64_t* total,
+                              void* workspace, int64_t workspace_bytes, egs_stream_t stream);
+int egs_isect_emit_sorted(int32_t C, int32_t N, int64_t n_vis, const uint32_t* order, const int64_t* cum_excl,
+                          const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_width,
+                          int32_t tile_height, int64_t n_isects, uint32_t* tile_keys, uint32_t* flat_vals,
+                          egs_stream_t stream);
+int egs_isect_finalize(int64_t n_isects, const uint32_t* tile_keys_sorted, const uint32_t* flat_sorted,
+                       const float* depths, int32_t C, int32_t n_tiles, int32_t tile_n_bits, int64_t* isect_ids,
+                       int32_t* offsets, egs_stream_t stream);
+
 /* ---- g5: tile offsets -------------------------------------------------------------------------------
  * Replaces gsplat `isect_offset_encode`.  offsets[C*n_tiles] i32 (fully written, also for n = 0). */
 int egs_isect_offset_encode(int64_t n_isects, const int64_t* isect_ids_sorted, int32_t C, int32_t n_tiles,

@@ -110,6 +110,54 @@ def test_isect_tiles_sort_offsets_bit_exact(cfg):
     assert torch.equal(offs.cpu(), O.isect_offset_encode(ids_o, C, tw, th))
 
 
+@pytest.mark.parametrize("cfg", SCENES)
+def test_isect_fast_path_bit_exact(cfg):
+    """Two-level route (depth sort of visible Gaussians, then stable tile sort) == 64-bit key sort, bit for bit."""
+    st = _stages()
+    sc = make_scene(**cfg)
+    radii, m2, dep, con = O.fully_fused_projection(sc.means, sc.quats, sc.scales, sc.viewmats, sc.Ks, sc.width, sc.height)
+    tw, th = st.tile_grid(sc.width, sc.height)
+    C = sc.viewmats.shape[0]
+    tpg_o, ids_o, flat_o = O.isect_tiles(m2, radii, dep, 16, tw, th, sort=True)
+    ids, flat, offs = st.isect_sorted(m2.cuda(), radii.cuda(), dep.cuda(), tpg_o.cuda(), 16, tw, th)
+    assert torch.equal(ids.cpu(), ids_o), "sorted isect_ids"
+    assert torch.equal(flat.cpu(), flat_o), "sorted flatten_ids (stable tie order)"
+    assert torch.equal(offs.cpu(), O.isect_offset_encode(ids_o, C, tw, th))
+
+
+def test_isect_fast_path_depth_ties_and_empty():
+    st = _stages()
+    # many Gaussians at exactly the same depth and overlapping tiles: the tie order must be the flat index
+    N, W, H = 3000, 96, 64
+    g = torch.Generator().manual_seed(0)
+    m2 = torch.rand(1, N, 2, generator=g) * torch.tensor([W, H])
+    radii = torch.randint(0, 12, (1, N), generator=g, dtype=torch.int32)
+    dep = torch.full((1, N), 2.5)
+    dep[0, ::7] = 1.25
+    tw, th = st.tile_grid(W, H)
+    tpg_o, ids_o, flat_o = O.isect_tiles(m2, radii, dep, 16, tw, th, sort=True)
+    ids, flat, offs = st.isect_sorted(m2.cuda(), radii.cuda(), dep.cuda(), tpg_o.cuda(), 16, tw, th)
+    assert torch.equal(ids.cpu(), ids_o) and torch.equal(flat.cpu(), flat_o)
+    assert torch.equal(offs.cpu(), O.isect_offset_encode(ids_o, 1, tw, th))
+    z = torch.zeros(2, 10, dtype=torch.int32, device="cuda")
+    ids, flat, offs = st.isect_sorted(torch.zeros(2, 10, 2, device="cuda"), z, torch.zeros(2, 10, device="cuda"), z, 16, 3, 2)
+    assert ids.numel() == 0 and flat.numel() == 0 and int(offs.abs().sum()) == 0 and offs.shape == (2, 2, 3)
+
+
+@pytest.mark.parametrize("n", [1, 33, 4096, 4097, 300_001])
+@pytest.mark.parametrize("end_bit", [1, 13, 19, 32])
+def test_radix_sort_pairs_u32(n, end_bit):
+    st = _stages()
+    g = torch.Generator().manual_seed(n + end_bit)
+    keys = torch.randint(0, 2 ** 31 - 1, (n,), generator=g, dtype=torch.int64)
+    if end_bit < 32:
+        keys = keys & ((1 << end_bit) - 1)
+    vals = torch.arange(n, dtype=torch.int32)
+    k, v = st.radix_sort_pairs_u32(keys.to(torch.int32).cuda(), vals.cuda().clone(), end_bit)
+    rk, order = torch.sort(keys, stable=True)
+    assert torch.equal(k.cpu().long(), rk) and torch.equal(v.cpu(), vals[order])
+
+
 def test_offsets_empty_and_sparse():
     st = _stages()
     empty = torch.zeros(0, dtype=torch.int64, device="cuda")
