@@ -6,7 +6,7 @@
 //   1 histogram: reads the keys once (8 B/pair) and builds all P digit histograms
 //   1 scan     : exclusive scan of each 256-bin histogram -> global digit bases
 //   P passes   : each reads 12 B/pair and writes 12 B/pair; a tile of 4096 pairs is ranked in
-//                shared memory (warp-level match_any multisplit, stable), its per-digit counts are
+//                shared memory (warp-level ballot multisplit, stable), its per-digit counts are
 //                chained to the preceding tiles with decoupled look-back, and the tile is written
 //                out digit-run by digit-run so stores are coalesced.
 // HBM traffic: 8 + 24*P bytes per pair = 152 B at P = 6.  Integer work only.
@@ -21,9 +21,7 @@ constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
 constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 8;                           // pairs per thread
-constexpr int kSortTile = kSortThreads * kSortItems;    // 4096 pairs per tile
-constexpr int kWarpSpan = 32 * kSortItems;              // 256 consecutive pairs per warp
+// pairs per thread is a template parameter ITEMS (8 or 16): tile = 512 * ITEMS pairs
 
 constexpr int kLookWindow = 8;
 constexpr uint32_t kFlagAggregate = 1u << 30;
@@ -36,7 +34,7 @@ struct SortWorkspace {
   uint32_t* status;    // [passes][ntiles][256]
 };
 
-__host__ __device__ inline int64_t sort_ntiles(int64_t n) { return (n + kSortTile - 1) / kSortTile; }
+__host__ __device__ inline int64_t sort_ntiles(int64_t n, int items) { const int64_t t = (int64_t)kSortThreads * items; return (n + t - 1) / t; }
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   uint32_t v;
@@ -136,8 +134,9 @@ __global__ void __launch_bounds__(kRadix) radix_scan_hist_kernel(uint32_t* __res
 
 // ---- one onesweep pass ------------------------------------------------------------------------------
 // Dynamic shared memory layout of one tile (67.6 KB with 64-bit keys -> 2 resident CTAs of 16 warps per SM):
-template <typename KeyT>
+template <typename KeyT, int ITEMS>
 struct SortSmem {
+  static constexpr int kSortTile = kSortThreads * ITEMS;
   KeyT keys[kSortTile];                     // 32 KB (u64) / 16 KB (u32)  tile-sorted keys
   uint32_t vals[kSortTile];                 // 16 KB  tile-sorted values
   uint32_t warp_hist[kSortWarps][kRadix];   // 16 KB  per-warp digit counts, then per-warp exclusive offsets
@@ -151,13 +150,14 @@ struct SortSmem {
 // ranks / slots are packed two per register; the values are loaded after the keys have left, and the
 // global destination of a slot is recomputed from the key's digit instead of being kept.  That keeps
 // the kernel at 64 registers (2 CTAs of 512 threads per SM) with every global load of a phase in flight at once.
-template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads, 2) radix_onesweep_kernel(
+template <typename KeyT, int ITEMS>
+__global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 : 2) radix_onesweep_kernel(
     const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ digit_base /*[256]*/,
     uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ status /*[ntiles][256]*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SortSmem<KeyT>& sm = *reinterpret_cast<SortSmem<KeyT>*>(smem_raw);
+  constexpr int kSortItems = ITEMS, kSortTile = kSortThreads * ITEMS, kWarpSpan = 32 * ITEMS;
+  SortSmem<KeyT, ITEMS>& sm = *reinterpret_cast<SortSmem<KeyT, ITEMS>*>(smem_raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // dynamic tile id: a tile only waits on tiles that have already started (no look-back deadlock)
@@ -186,7 +186,16 @@ __global__ void __launch_bounds__(kSortThreads, 2) radix_onesweep_kernel(
   for (int i = 0; i < kSortItems; ++i) {
     const bool valid = (warp_off + i * 32) < tile_count;
     const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
-    const uint32_t m = __match_any_sync(0xffffffffu, d | (valid ? 0u : 0x100u));
+    // lanes holding the same digit: 8 ballots (one per digit bit) instead of match.any, whose cost grows with
+    // the number of distinct values in the warp (ncu r1e: short-scoreboard stalls of 10-14 warps per issue on
+    // high-entropy digits)
+    uint32_t m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < kRadixBits; ++b) {
+      const uint32_t bit = (d >> b) & 1u;
+      const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+      m &= bit ? bal : ~bal;
+    }
     const uint32_t before = __popc(m & lanemask_lt);
     const uint32_t prev = wh[d];
     __syncwarp();
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) radix_onesweep_kernel(
 }
 
 static int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, int passes, SortWorkspace& w, int64_t& clear_bytes) {
-  const int64_t ntiles = sort_ntiles(n);
+  const int64_t ntiles = sort_ntiles(n, 8);  // sized for the smallest tile (most tiles)
   const int64_t hist_b = (int64_t)kMaxPasses * kRadix * 4;
   const int64_t cnt_b = 256;  // kMaxPasses counters, padded
   const int64_t status_b = (int64_t)passes * ntiles * kRadix * 4;
@@ -327,6 +336,10 @@ extern "C" int64_t egs_radix_sort_workspace_bytes(int64_t n, int32_t end_bit) {
   return bytes;
 }
 
+template <typename KeyT, int ITEMS>
+static int run_passes(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int passes,
+                      const SortWorkspace& w, cudaStream_t stream);
+
 template <typename KeyT>
 static int radix_sort_pairs_impl(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
                                  int32_t end_bit, void* workspace, int64_t workspace_bytes,
@@ -348,23 +361,36 @@ static int radix_sort_pairs_impl(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT
   if (carve_workspace(workspace, workspace_bytes, n, passes, w, clear_bytes) != 0 || workspace == nullptr)
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "radix_sort: workspace %lld < %lld bytes", (long long)workspace_bytes,
                 (long long)clear_bytes);
-  constexpr int kSmem = (int)sizeof(SortSmem<KeyT>);
-  static const cudaError_t attr_rc =
-      cudaFuncSetAttribute(radix_onesweep_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-  if (attr_rc != cudaSuccess)
-    return fail((int)attr_rc, "radix_sort: cannot opt in to %d bytes of shared memory: %s", kSmem, cudaGetErrorString(attr_rc));
   EGS_CUDA(cudaMemsetAsync(workspace, 0, clear_bytes, stream));
-  const int64_t ntiles = sort_ntiles(n);
   int64_t hist_blocks = ceil_div(n, (int64_t)kHistThreads * kHistItems);
   if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
   radix_histogram_kernel<KeyT><<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, passes, w.hist);
   radix_scan_hist_kernel<<<passes, kRadix, 0, stream>>>(w.hist);
+  static const int items = [] {  // tuning knob: pairs per thread (tile = 512 * items)
+    const char* e = getenv("EGS_SORT_ITEMS");
+    const int v = e ? atoi(e) : 8;
+    return (v == 16) ? 16 : 8;
+  }();
+  if (items == 16) return run_passes<KeyT, 16>(n, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
+  return run_passes<KeyT, 8>(n, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
+}
+
+template <typename KeyT, int ITEMS>
+static int run_passes(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int passes,
+                      const SortWorkspace& w, cudaStream_t stream) {
+  constexpr int kSmem = (int)sizeof(SortSmem<KeyT, ITEMS>);
+  static const cudaError_t attr_rc =
+      cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  if (attr_rc != cudaSuccess)
+    return fail((int)attr_rc, "radix_sort: cannot opt in to %d bytes of shared memory: %s", kSmem, cudaGetErrorString(attr_rc));
+  const int64_t ntiles = sort_ntiles(n, ITEMS);
+  const int64_t status_stride = sort_ntiles(n, 8) * kRadix;  // workspace was carved for the smallest tile
   KeyT* kin = keys_a; uint32_t* vin = vals_a;
   KeyT* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < passes; ++p) {
-    radix_onesweep_kernel<KeyT><<<(unsigned)ntiles, kSortThreads, kSmem, stream>>>(
+    radix_onesweep_kernel<KeyT, ITEMS><<<(unsigned)ntiles, kSortThreads, kSmem, stream>>>(
         kin, vin, kout, vout, n, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
-        w.status + (size_t)p * ntiles * kRadix);
+        w.status + (size_t)p * status_stride);
     KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
