@@ -178,14 +178,14 @@ EGS_HD bool project_fwd(const float mean[3], const float quat[4], const float sc
   return true;
 }
 
-// Squared radius (pixels^2) outside of which alpha = min(.999, o exp(-sigma)) < 1/255 is guaranteed:
-// sigma >= 0.5 |d|^2 / lambda_max, so alpha >= 1/255 needs |d|^2 <= 2 ln(255 o) lambda_max.  The blending
-// kernels skip a Gaussian for a whole warp when the warp's pixel rectangle lies outside this circle.
-// A 2 % + 0.01 px^2 margin keeps the test conservative under fp32 rounding of sigma.  Negative = never visible.
-EGS_HD float effective_radius2(float opacity, float lambda_max) {
+// Largest sigma at which alpha = min(.999, o exp(-sigma)) can still reach 1/255: ln(255 o), with a small
+// margin that keeps every use of it conservative under fp32 rounding.  <= 0 means never visible.  The
+// blending kernels drop a Gaussian for a whole warp when the minimum of sigma over the warp's pixel
+// rectangle exceeds this value.
+EGS_HD float sigma_cutoff(float opacity) {
   const float t = 255.0f * opacity;
   if (!(t > 1.0f)) return -1.0f;
-  return 2.0f * logf(t) * lambda_max * 1.02f + 0.01f;
+  return logf(t) * 1.0001f + 1e-4f;
 }
 
 // Tile rectangle of a visible Gaussian: min inclusive, max exclusive.

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kProjThreads) projection_fwd_kernel(const Proj
     float4* s = p.splats + idx * 3;
     s[0] = make_float4(o.m2x, o.m2y, o.ca, o.cb);
     s[1] = make_float4(o.cc, opac, rgb[0], rgb[1]);
-    s[2] = make_float4(rgb[2], o.depth, effective_radius2(opac, o.lambda_max), 0.f);
+    s[2] = make_float4(rgb[2], o.depth, 0.f, sigma_cutoff(opac));
   }
   p.radii[idx] = o.radius;
   p.tiles_per_gauss[idx] = ntiles;

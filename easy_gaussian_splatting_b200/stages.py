@@ -272,8 +272,8 @@ def pack_splats(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tens
     C, N = means2d.shape[:2]
     z = torch.zeros(C, N, 1, dtype=torch.float32, device=means2d.device)
     d = z if depths is None else depths[..., None]
-    reff2 = torch.full_like(z, float("inf"))  # no warp-level skip: every pair is evaluated
-    return torch.cat([means2d, conics, opacities[..., None], colors, d, reff2, z], -1).contiguous()
+    cut = torch.full_like(z, float("inf"))  # sigma_cut = +inf: no warp-level culling, every pair is evaluated
+    return torch.cat([means2d, conics, opacities[..., None], colors, d, z, cut], -1).contiguous()
 
 
 def rasterize_fwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],

@@ -38,9 +38,10 @@ enum egs_status {
 };
 
 /* Number of floats in one packed splat record / one packed gradient record (48 bytes, 16B aligned).
- * splat record : {x, y, conic_a, conic_b | conic_c, opacity, r, g | b, depth, r_eff^2, 0}
- *                r_eff^2 = squared pixel radius beyond which alpha < 1/255 is guaranteed (+inf disables the
- *                warp-level skip it enables; negative = never visible)
+ * splat record : {x, y, conic_a, conic_b | conic_c, opacity, r, g | b, depth, 0, sigma_cut}
+ *                sigma_cut = ln(255 * opacity) (+ margin): the largest sigma at which alpha can reach 1/255.  The
+ *                blending kernels drop a Gaussian for a warp when min sigma over the warp's pixels exceeds it
+ *                (+inf disables that culling; <= 0 = never visible)
  * grad  record : {v_x, v_y, v_conic_a, v_conic_b | v_conic_c, v_opacity, v_r, v_g | v_b, |v_x|, |v_y|, 0} */
 #define EGS_SPLAT_FLOATS 12
 
