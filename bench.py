@@ -396,7 +396,7 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     t["projection_sh_fwd"] = tm(lambda: stages.projection_fwd(means, quats, scales, opac, colors, vm, K, W, H, 3))
     # product path of g3-g5: two-level route (includes its one host sync)
     t["binning_fast_path"] = tm(lambda: stages.isect_sorted(proj["means2d"], proj["radii"], proj["depths"],
-                                                            proj["tiles_per_gauss"], 16, tw, th))
+                                                            proj["tiles_per_gauss"], 16, tw, th, materialize_ids=False))
     t["rasterize_fwd"] = tm(lambda: stages.rasterize_fwd(proj["splats"], offs, flat, bg, W, H))
     zero_ms = tm(lambda: torch.zeros_like(v_splats))
     t["rasterize_bwd"] = tm(lambda: stages.rasterize_bwd(proj["splats"], offs, flat, bg, W, H, ra, last, Wc, Wa)) - zero_ms

@@ -336,9 +336,12 @@ __global__ void __launch_bounds__(kOffThreads) isect_finalize_kernel(int64_t n_i
   const int64_t i = (int64_t)blockIdx.x * kOffThreads + threadIdx.x;
   if (i >= n_isects) return;
   const int64_t cur = tile_keys[i];
-  const uint64_t cam = (uint64_t)(cur / n_tiles), tile = (uint64_t)(cur % n_tiles);
-  const uint64_t depth_bits = (uint64_t)__float_as_uint(depths[flat_vals[i]]);
-  isect_ids[i] = (int64_t)(((((cam << tile_n_bits) | tile)) << 32) | depth_bits);
+  if (isect_ids != nullptr) {
+    const uint64_t cam = (uint64_t)(cur / n_tiles), tile = (uint64_t)(cur % n_tiles);
+    const uint64_t depth_bits = (uint64_t)__float_as_uint(depths[flat_vals[i]]);
+    isect_ids[i] = (int64_t)(((((cam << tile_n_bits) | tile)) << 32) | depth_bits);
+  }
+  if (offsets == nullptr) return;
   if (i == 0) {
     for (int64_t t = 0; t <= cur && t < n_slots; ++t) offsets[t] = 0;
   } else {
@@ -477,7 +480,7 @@ extern "C" int egs_isect_finalize(int64_t n_isects, const uint32_t* tile_keys_so
   const int64_t n_slots = (int64_t)C * n_tiles;
   if (n_slots == 0) return 0;
   if (n_isects == 0) {
-    EGS_CUDA(cudaMemsetAsync(offsets, 0, n_slots * sizeof(int32_t), stream));
+    if (offsets != nullptr) EGS_CUDA(cudaMemsetAsync(offsets, 0, n_slots * sizeof(int32_t), stream));
     return 0;
   }
   isect_finalize_kernel<<<(unsigned)ceil_div(n_isects, kOffThreads), kOffThreads, 0, stream>>>(

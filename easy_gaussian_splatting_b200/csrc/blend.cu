@@ -54,6 +54,13 @@ __device__ __forceinline__ float fast_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
   return e;
 }
+// 1/x as a single MUFU.RCP (the operands here are never denormal: 1 - alpha >= 1e-3, opacity >= 1/255, conic
+// diagonals of visible splats; the fast-division intrinsic would add 4 range-fixup instructions around it)
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // Stops ptxas from re-deriving a loop-invariant value inside the loop (it otherwise rematerialises
 // the pixel-centre coordinates with I2FP + FADD in every iteration to save two registers).
 __device__ __forceinline__ float opaque(float x) {
@@ -99,7 +106,7 @@ __device__ __forceinline__ bool splat_touches_rect(const float4 g0, const float4
   const float a = g0.z, b = g0.w, c = g1.x;
   const float dxl = rx_lo - g0.x, dxh = rx_hi - g0.x, dyl = ry_lo - g0.y, dyh = ry_hi - g0.y;
   if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return true;  // centre inside
-  const float nb_c = -b * __fdividef(1.0f, c), nb_a = -b * __fdividef(1.0f, a);
+  const float nb_c = -b * fast_rcp(c), nb_a = -b * fast_rcp(a);
   float best;
   {
     const float dy = fminf(fmaxf(nb_c * dxl, dyl), dyh);
@@ -438,7 +445,7 @@ __global__ void __launch_bounds__(kBlendThreads) rasterize_bwd_kernel(
       }
       if (!__any_sync(0xffffffffu, any_valid)) continue;  // warp-uniform
       const float cbl = s[cur * 3 + 2].x;
-      const float inv_o = __fdividef(1.0f, g1.y);
+      const float inv_o = fast_rcp(g1.y);
       // v[2], v[3], v[4] accumulate sx*dx, sx*dy, sy*dy (the 0.5 of the conic gradient is applied once, after
       // the per-lane sum); v[5] accumulates ov * v_alpha (the 1/opacity is applied after the per-lane sum).
       float v[16];
@@ -449,7 +456,7 @@ __global__ void __launch_bounds__(kBlendThreads) rasterize_bwd_kernel(
         if (valid[j]) {
           const float ddx = dx[j & 1], ddy = dy[j >> 1];
           const float alpha = fminf(kAlphaMax, ov[j]);
-          const float ra = __fdividef(1.0f, 1.0f - alpha);
+          const float ra = fast_rcp(1.0f - alpha);
           T[j] *= ra;  // transmittance in front of this Gaussian
           const float fac = alpha * T[j];
           v[6] = fmaf(fac, vcr[j], v[6]);

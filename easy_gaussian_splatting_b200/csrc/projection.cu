@@ -205,6 +205,159 @@ __global__ void __launch_bounds__(kProjBwdThreads) projection_bwd_kernel(const P
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Backward, K = 16 SH coefficients (the reference's layout): the 192-byte coefficient rows and the
+// 192-byte gradient rows of a warp's 32 Gaussians are contiguous in HBM, so they travel through a
+// shared-memory tile with fully coalesced 512-byte warp transactions instead of 32 strided 16-byte
+// accesses per instruction; rows of Gaussians that no camera sees are not read.  Keeping the rows in
+// shared memory also takes the 96 coefficient / gradient registers out of the thread (224 -> ~110),
+// which triples the number of resident warps.  Row stride 52 floats makes the per-thread float4
+// accesses of a quarter warp conflict free.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowFloats = 48;   // K * 3
+constexpr int kRowStride = 52;
+constexpr int kPB2Threads = 128;
+constexpr int kPB2Warps = kPB2Threads / 32;
+
+__global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const ProjBwdParams p) {
+  extern __shared__ __align__(16) float smem_pb[];
+  __shared__ Camera cams[kMaxCamerasSmem];
+  for (int c = threadIdx.x; c < p.C && c < kMaxCamerasSmem; c += kPB2Threads)
+    load_camera(p.viewmats + (size_t)c * 16, p.Ks + (size_t)c * 9, cams[c]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* co_tile = smem_pb + (size_t)warp * 32 * kRowStride;                       // coefficients
+  float* vc_tile = smem_pb + (size_t)(kPB2Warps + warp) * 32 * kRowStride;         // gradient accumulation
+  const int n_base = blockIdx.x * kPB2Threads + warp * 32;
+  const int n = n_base + lane;
+  const bool in_range = n < p.N;
+  const int nb = (p.sh_degree + 1) * (p.sh_degree + 1);
+
+  // which of this warp's Gaussians does any camera see?
+  bool seen = false;
+  if (in_range)
+    for (int c = 0; c < p.C; ++c) seen = seen || (p.radii[(size_t)c * p.N + n] > 0);
+  const uint32_t seen_mask = __ballot_sync(0xffffffffu, seen);
+
+  // phase 1: coalesced load of the coefficient rows that are needed; zero the gradient rows
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.sh) + (size_t)n_base * (kRowFloats / 4);
+#pragma unroll
+    for (int i = 0; i < kRowFloats / 4; ++i) {
+      const int f = i * 32 + lane;           // float4 index inside the warp's 32 x 12 block
+      const int row = f / 12, c4 = f - row * 12;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.sh_degree >= 1 && ((seen_mask >> row) & 1u)) v = __ldg(src + f);
+      *reinterpret_cast<float4*>(co_tile + row * kRowStride + c4 * 4) = v;
+      *reinterpret_cast<float4*>(vc_tile + row * kRowStride + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncwarp();
+
+  // phase 2: thread-private work on its own Gaussian / its own two rows
+  float v_mean[3] = {0.f, 0.f, 0.f}, v_quat[4] = {0.f, 0.f, 0.f, 0.f}, v_scale[3] = {0.f, 0.f, 0.f};
+  float v_opac = 0.f;
+  if (seen) {
+    float mean[3], quat[4], scale[3];
+    mean[0] = __ldg(p.means + 3 * (size_t)n + 0);
+    mean[1] = __ldg(p.means + 3 * (size_t)n + 1);
+    mean[2] = __ldg(p.means + 3 * (size_t)n + 2);
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(p.quats) + n);
+    quat[0] = q4.x; quat[1] = q4.y; quat[2] = q4.z; quat[3] = q4.w;
+    scale[0] = __ldg(p.scales + 3 * (size_t)n + 0);
+    scale[1] = __ldg(p.scales + 3 * (size_t)n + 1);
+    scale[2] = __ldg(p.scales + 3 * (size_t)n + 2);
+    const float* co = co_tile + lane * kRowStride;
+    float* vc = vc_tile + lane * kRowStride;
+    for (int c = 0; c < p.C; ++c) {
+      const size_t idx = (size_t)c * p.N + n;
+      if (!(p.radii[idx] > 0)) continue;
+      Camera cam_local;
+      const Camera* cam = &cams[c < kMaxCamerasSmem ? c : 0];
+      if (c >= kMaxCamerasSmem) { load_camera(p.viewmats + (size_t)c * 16, p.Ks + (size_t)c * 9, cam_local); cam = &cam_local; }
+      const float4 g0 = p.v_splats[idx * 3 + 0];
+      const float4 g1 = p.v_splats[idx * 3 + 1];
+      const float4 g2 = p.v_splats[idx * 3 + 2];
+      float v_m2x = g0.x, v_m2y = g0.y;
+      if (p.v_means2d_extra != nullptr) {
+        v_m2x += p.v_means2d_extra[idx * 2 + 0];
+        v_m2y += p.v_means2d_extra[idx * 2 + 1];
+      }
+      {
+        ProjState st;
+        ProjOut o;
+        project_fwd(mean, quat, scale, *cam, p.width, p.height, p.eps2d, 0.f, INFINITY, -1.f, st, o);
+        if (o.radius > 0) project_bwd(st, scale, *cam, v_m2x, v_m2y, 0.f, g0.z, g0.w, g1.x, o, v_mean, v_quat, v_scale);
+      }
+      v_opac += g1.y;
+      // SH: rgb = max(sum + 0.5, 0) -> gradient passes where the stored colour is > 0
+      const float* col = p.colors + idx * 3;
+      const float vr = (col[0] > 0.f) ? g1.z : 0.f, vg = (col[1] > 0.f) ? g1.w : 0.f, vb = (col[2] > 0.f) ? g2.x : 0.f;
+      const float dx = mean[0] - cam->campos[0], dy = mean[1] - cam->campos[1], dz = mean[2] - cam->campos[2];
+      const float inorm = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+      const float x = dx * inorm, y = dy * inorm, z = dz * inorm;
+      float Y[16], g[16];
+      sh_basis(p.sh_degree, x, y, z, Y);
+      // rows are walked 4 bands (= 12 floats = 3 float4) at a time
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float cf[12], out[12];
+        if (p.sh_degree >= 1) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(co + j * 12 + q * 4);
+            cf[q * 4 + 0] = t.x; cf[q * 4 + 1] = t.y; cf[q * 4 + 2] = t.z; cf[q * 4 + 3] = t.w;
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = j * 4 + kk;
+          const bool act = k < nb;
+          g[k] = (act && p.sh_degree >= 1) ? (cf[3 * kk + 0] * vr + cf[3 * kk + 1] * vg + cf[3 * kk + 2] * vb) : 0.f;
+          const float yk = act ? Y[k] : 0.f;
+          out[3 * kk + 0] = yk * vr; out[3 * kk + 1] = yk * vg; out[3 * kk + 2] = yk * vb;
+        }
+        if (j * 4 < nb) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            float4* dst = reinterpret_cast<float4*>(vc + j * 12 + q * 4);
+            float4 acc = *dst;
+            acc.x += out[q * 4 + 0]; acc.y += out[q * 4 + 1]; acc.z += out[q * 4 + 2]; acc.w += out[q * 4 + 3];
+            *dst = acc;
+          }
+        }
+      }
+      if (p.sh_degree >= 1) {
+        float vx, vy, vz;
+        sh_basis_vjp(p.sh_degree, x, y, z, g, vx, vy, vz);
+        const float dp = vx * x + vy * y + vz * z;
+        v_mean[0] += (vx - dp * x) * inorm;
+        v_mean[1] += (vy - dp * y) * inorm;
+        v_mean[2] += (vz - dp * z) * inorm;
+      }
+    }
+  }
+  __syncwarp();
+
+  // phase 3: coalesced store of the gradient rows; small per-Gaussian outputs directly
+  {
+    float4* dst = reinterpret_cast<float4*>(p.v_sh) + (size_t)n_base * (kRowFloats / 4);
+#pragma unroll
+    for (int i = 0; i < kRowFloats / 4; ++i) {
+      const int f = i * 32 + lane;
+      const int row = f / 12, c4 = f - row * 12;
+      if (n_base + row < p.N) dst[f] = *reinterpret_cast<const float4*>(vc_tile + row * kRowStride + c4 * 4);
+    }
+  }
+  if (in_range) {
+    p.v_means[3 * (size_t)n + 0] = v_mean[0]; p.v_means[3 * (size_t)n + 1] = v_mean[1]; p.v_means[3 * (size_t)n + 2] = v_mean[2];
+    reinterpret_cast<float4*>(p.v_quats)[n] = make_float4(v_quat[0], v_quat[1], v_quat[2], v_quat[3]);
+    p.v_scales[3 * (size_t)n + 0] = v_scale[0]; p.v_scales[3 * (size_t)n + 1] = v_scale[1]; p.v_scales[3 * (size_t)n + 2] = v_scale[2];
+    p.v_opacities[n] = v_opac;
+  }
+}
+
 }  // namespace egs
 
 using namespace egs;
@@ -257,6 +410,15 @@ extern "C" int egs_projection_bwd(int32_t C, int32_t N, const float* means, cons
   p.v_means = v_means; p.v_quats = v_quats; p.v_scales = v_scales; p.v_opacities = v_opacities; p.v_sh = v_sh_coeffs;
   const bool vec4 = sh_degree >= 0 && (K * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(sh_coeffs) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(v_sh_coeffs) % 16 == 0);
+  if (vec4 && K == 16) {
+    // the reference's layout (K = 16): coalesced shared-memory staged rows
+    constexpr int kSmem = 2 * kPB2Warps * 32 * kRowStride * (int)sizeof(float);
+    static const cudaError_t attr_rc =
+        cudaFuncSetAttribute(projection_bwd_sh16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (attr_rc != cudaSuccess) return fail((int)attr_rc, "projection_bwd: shared memory opt-in failed: %s", cudaGetErrorString(attr_rc));
+    projection_bwd_sh16_kernel<<<(unsigned)ceil_div(N, kPB2Threads), kPB2Threads, kSmem, (cudaStream_t)stream>>>(p);
+    return check_launch("projection_bwd_sh16_kernel");
+  }
   unsigned grid = (unsigned)ceil_div(N, kProjBwdThreads);
   if (vec4) projection_bwd_kernel<true><<<grid, kProjBwdThreads, 0, (cudaStream_t)stream>>>(p);
   else      projection_bwd_kernel<false><<<grid, kProjBwdThreads, 0, (cudaStream_t)stream>>>(p);

@@ -26,6 +26,30 @@ from . import stages
 __all__ = ["rasterization"]
 
 
+class _LazyMeta(dict):
+    """``meta`` dict whose ``isect_ids`` entry (64-bit sorted keys, pure meta data: nothing downstream of the
+    reference reads it) is rebuilt on first access instead of costing a pass over every intersection per call."""
+
+    def _resolve(self, key):
+        v = dict.__getitem__(self, key)
+        if callable(v) and not isinstance(v, torch.Tensor):
+            v = v()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def __getitem__(self, key):
+        return self._resolve(key)
+
+    def get(self, key, default=None):
+        return self._resolve(key) if key in self else default
+
+    def items(self):
+        return [(k, self._resolve(k)) for k in self.keys()]
+
+    def values(self):
+        return [self._resolve(k) for k in self.keys()]
+
+
 class _Rasterization(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg):
@@ -36,8 +60,10 @@ class _Rasterization(torch.autograd.Function):
                                      radius_clip=cfg["radius_clip"])
         tw, th = stages.tile_grid(width, height)
         tiles_per_gauss = proj["tiles_per_gauss"]
-        isect_ids, flatten_ids, isect_offsets = stages.isect_sorted(
-            proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th)
+        isect_ids_thunk, flatten_ids, isect_offsets = stages.isect_sorted(
+            proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th,
+            materialize_ids=False)
+        cfg["isect_ids_thunk"] = isect_ids_thunk  # handed to the wrapper (not a tensor: cannot be an output)
         render_colors, render_alphas, last_ids = stages.rasterize_fwd(
             proj["splats"], isect_offsets, flatten_ids, backgrounds, width, height)
 
@@ -46,7 +72,7 @@ class _Rasterization(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(means, quats, scales, colors, viewmats, Ks, backgrounds, proj["radii"], proj["colors"],
                               proj["splats"], isect_offsets, flatten_ids, render_alphas, last_ids)
-        nondiff = (proj["radii"], proj["depths"], proj["conics"], proj["colors"], tiles_per_gauss, isect_ids,
+        nondiff = (proj["radii"], proj["depths"], proj["conics"], proj["colors"], tiles_per_gauss,
                    flatten_ids, isect_offsets, last_ids)
         ctx.mark_non_differentiable(*nondiff)
         return (render_colors, render_alphas, means2d) + nondiff
@@ -173,13 +199,14 @@ def rasterization(
     cfg = dict(width=width, height=height, sh_degree=sh_degree, eps2d=float(eps2d), near_plane=float(near_plane),
                far_plane=float(far_plane), radius_clip=float(radius_clip), absgrad=bool(absgrad))
     outs = _Rasterization.apply(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg)
-    (render_colors, render_alphas, means2d, radii, depths, conics, colors_rgb, tiles_per_gauss, isect_ids,
+    (render_colors, render_alphas, means2d, radii, depths, conics, colors_rgb, tiles_per_gauss,
      flatten_ids, isect_offsets, _last_ids) = outs
+    isect_ids = cfg.pop("isect_ids_thunk")
     if absgrad and render_colors.grad_fn is not None:
         # the backward node tags .absgrad on exactly this tensor object (weak: no reference cycle)
         render_colors.grad_fn.means2d_ref = weakref.ref(means2d)
     tw, th = stages.tile_grid(width, height)
-    meta = {
+    meta = _LazyMeta({
         "camera_ids": None,
         "gaussian_ids": None,
         "radii": radii,
@@ -198,5 +225,5 @@ def rasterization(
         "height": height,
         "tile_size": tile_size,
         "n_cameras": C,
-    }
+    })
     return render_colors, render_alphas, meta

@@ -200,12 +200,13 @@ def radix_sort_pairs_u32(keys: Tensor, vals: Tensor, end_bit: int) -> Tuple[Tens
 
 
 def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
-                 tile_width: int, tile_height: int) -> Tuple[Tensor, Tensor, Tensor]:
+                 tile_width: int, tile_height: int, materialize_ids: bool = True):
     """g3+g4+g5 fast path -> (isect_ids[n] i64 sorted, flatten_ids[n] i32, isect_offsets[C,th,tw] i32).
 
     Bit-identical to ``isect_tiles(sort=True)`` + ``isect_offset_encode`` (a stable sort on cam|tile|depth
     equals a stable depth sort of the visible Gaussians followed by a stable sort on the tile index), but the
-    n_isects-sized passes move 8-byte pairs through 2-3 radix passes instead of 12-byte pairs through 6."""
+    n_isects-sized passes move 8-byte pairs through 2-3 radix passes instead of 12-byte pairs through 6.
+    With ``materialize_ids=False`` the first element is a zero-argument callable that builds isect_ids on demand."""
     lib = _lib.load()
     means2d, depths = _f32c(means2d, "means2d"), _f32c(depths, "depths")
     radii, tiles_per_gauss = radii.contiguous(), tiles_per_gauss.contiguous()
@@ -225,10 +226,10 @@ def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss
     _lib.check(rc, "egs_isect_visible_keys")
     n_vis, n_isects = (int(v) for v in totals.tolist())  # the one host sync of the forward pass
     offsets = torch.empty(C, tile_height, tile_width, dtype=torch.int32, device=dev)
-    isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
     if n_isects == 0:
         offsets.zero_()
-        return isect_ids, torch.empty(0, dtype=torch.int32, device=dev), offsets
+        empty_ids = torch.empty(0, dtype=torch.int64, device=dev)
+        return (empty_ids if materialize_ids else (lambda: empty_ids)), torch.empty(0, dtype=torch.int32, device=dev), offsets
     if n_isects >= 2 ** 31 - 1:
         raise RuntimeError(f"{n_isects} tile intersections do not fit int32 offsets; render fewer cameras per call")
     # level 1: visible Gaussians in (camera, depth, index) order
@@ -248,11 +249,20 @@ def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss
     # level 2: stable sort on the dense (camera, tile) index
     end_bit = max(1, int(C * n_tiles - 1).bit_length())
     tile_keys, flat_vals = radix_sort_pairs_u32(tile_keys, flat_vals, end_bit)
-    with torch.cuda.device(dev):
-        rc = lib.egs_isect_finalize(n_isects, _ptr(tile_keys), _ptr(flat_vals), _ptr(depths), C, n_tiles, nbits,
-                                    _ptr(isect_ids), _ptr(offsets), _stream(dev))
-    _lib.check(rc, "egs_isect_finalize")
-    return isect_ids, flat_vals, offsets
+
+    def finalize(want_ids: bool, want_offsets: bool):
+        ids = torch.empty(n_isects, dtype=torch.int64, device=dev) if want_ids else None
+        with torch.cuda.device(dev):
+            rc_ = lib.egs_isect_finalize(n_isects, _ptr(tile_keys), _ptr(flat_vals), _ptr(depths), C, n_tiles, nbits,
+                                         _ptr(ids), _ptr(offsets) if want_offsets else None, _stream(dev))
+        _lib.check(rc_, "egs_isect_finalize")
+        return ids
+
+    if materialize_ids:
+        return finalize(True, True), flat_vals, offsets
+    finalize(False, True)
+    # the 64-bit keys are only meta data for the caller: rebuild them (bit-identically) on first access
+    return (lambda: finalize(True, False)), flat_vals, offsets
 
 
 def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height: int) -> Tensor:

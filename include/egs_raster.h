@@ -119,7 +119,8 @@ int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, 
  *   egs_exclusive_scan_gather : out[i] = sum_{j<i} src[gather[j]]  (tile counts in depth order)
  *   egs_isect_emit_sorted  : warp-cooperative emission of tile_keys = cam*n_tiles + tile (u32), flat_vals
  *   (sort tile_keys/flat_vals with egs_radix_sort_pairs_u32_u32 on bits [0, ceil(log2(C*n_tiles))))
- *   egs_isect_finalize     : rebuilds the 64-bit isect_ids and derives the tile offsets */
+ *   egs_isect_finalize     : derives the tile offsets and/or rebuilds the 64-bit isect_ids (either output
+ *                            pointer may be NULL: the Python side materialises isect_ids lazily, on first access) */
 int64_t egs_isect_scan_workspace_bytes(int64_t n);
 int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths, uint64_t* keys1,
                            uint32_t* vals1, int64_t* totals, void* workspace, int64_t workspace_bytes,
