@@ -96,6 +96,107 @@ __global__ void __launch_bounds__(kProjThreads) projection_fwd_kernel(const Proj
   p.colors[idx * 3 + 0] = rgb[0]; p.colors[idx * 3 + 1] = rgb[1]; p.colors[idx * 3 + 2] = rgb[2];
 }
 
+// Forward, K = 16 SH coefficients (the reference's layout): only the coefficient rows of VISIBLE Gaussians
+// are read, each as one contiguous 192-byte run by 12 lanes (a row-masked cooperative copy into a
+// shared-memory tile), instead of twelve 16-byte loads per thread at a 192-byte lane stride.
+constexpr int kPF2Threads = 128;
+constexpr int kFwdRowStride = 52;  // floats; conflict-free float4 row reads for a quarter warp
+
+__global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const ProjFwdParams p) {
+  __shared__ Camera cam;
+  __shared__ __align__(16) float tile[kPF2Threads / 32][32 * kFwdRowStride];
+  const int c = blockIdx.y;
+  if (threadIdx.x == 0) load_camera(p.viewmats + (size_t)c * 16, p.Ks + (size_t)c * 9, cam);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_base = blockIdx.x * kPF2Threads + warp * 32;
+  const int n = n_base + lane;
+  const bool in_range = n < p.N;
+  const size_t idx = (size_t)c * p.N + (in_range ? n : 0);
+
+  float mean[3] = {0.f, 0.f, 0.f};
+  ProjOut o;
+  o.m2x = 0.f; o.m2y = 0.f; o.depth = 0.f; o.ca = 0.f; o.cb = 0.f; o.cc = 0.f; o.radius = 0; o.lambda_max = 0.f;
+  bool vis = false;
+  if (in_range) {
+    float quat[4], scale[3];
+    mean[0] = __ldg(p.means + 3 * (size_t)n + 0);
+    mean[1] = __ldg(p.means + 3 * (size_t)n + 1);
+    mean[2] = __ldg(p.means + 3 * (size_t)n + 2);
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(p.quats) + n);
+    quat[0] = q4.x; quat[1] = q4.y; quat[2] = q4.z; quat[3] = q4.w;
+    scale[0] = __ldg(p.scales + 3 * (size_t)n + 0);
+    scale[1] = __ldg(p.scales + 3 * (size_t)n + 1);
+    scale[2] = __ldg(p.scales + 3 * (size_t)n + 2);
+    ProjState st;
+    vis = project_fwd(mean, quat, scale, cam, p.width, p.height, p.eps2d, p.near_plane, p.far_plane, p.radius_clip, st, o);
+  }
+  const uint32_t vis_mask = __ballot_sync(0xffffffffu, vis);
+  const int nb = (p.sh_degree + 1) * (p.sh_degree + 1);
+  const int need4 = (nb * 3 + 3) / 4;  // float4s of a row that hold active bands
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.sh) + (size_t)n_base * 12;
+    float* t = tile[warp];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const int f = i * 32 + lane;
+      const int row = f / 12, c4 = f - row * 12;
+      if (((vis_mask >> row) & 1u) && c4 < need4)
+        *reinterpret_cast<float4*>(t + row * kFwdRowStride + c4 * 4) = __ldg(src + f);
+    }
+  }
+  __syncwarp();
+  if (!in_range) return;
+  int32_t ntiles = 0;
+  float rgb[3] = {0.f, 0.f, 0.f};
+  if (vis) {
+    int32_t x0, y0, x1, y1;
+    tile_rect(o.m2x, o.m2y, o.radius, p.tile_size, p.tile_w, p.tile_h, x0, y0, x1, y1);
+    ntiles = (x1 - x0) * (y1 - y0);
+    const float* row = tile[warp] + lane * kFwdRowStride;
+    const float dx = mean[0] - cam.campos[0], dy = mean[1] - cam.campos[1], dz = mean[2] - cam.campos[2];
+    const float inorm = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    float Y[16];
+    sh_basis(p.sh_degree, dx * inorm, dy * inorm, dz * inorm, Y);
+    float r = 0.f, g = 0.f, b = 0.f;
+    // same accumulation order as sh_color_fwd: band by band
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j * 4 < nb) {
+        float cf[12];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(row + j * 12 + q * 4);
+          cf[q * 4 + 0] = t4.x; cf[q * 4 + 1] = t4.y; cf[q * 4 + 2] = t4.z; cf[q * 4 + 3] = t4.w;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = j * 4 + kk;
+          if (k < nb) {
+            r += Y[k] * cf[3 * kk + 0];
+            g += Y[k] * cf[3 * kk + 1];
+            b += Y[k] * cf[3 * kk + 2];
+          }
+        }
+      }
+    }
+    rgb[0] = fmaxf(r + 0.5f, 0.f);
+    rgb[1] = fmaxf(g + 0.5f, 0.f);
+    rgb[2] = fmaxf(b + 0.5f, 0.f);
+    const float opac = __ldg(p.opacities + n);
+    float4* s = p.splats + idx * 3;
+    s[0] = make_float4(o.m2x, o.m2y, o.ca, o.cb);
+    s[1] = make_float4(o.cc, opac, rgb[0], rgb[1]);
+    s[2] = make_float4(rgb[2], o.depth, 0.f, sigma_cutoff(opac));
+  }
+  p.radii[idx] = o.radius;
+  p.tiles_per_gauss[idx] = ntiles;
+  reinterpret_cast<float2*>(p.means2d)[idx] = make_float2(o.m2x, o.m2y);
+  p.depths[idx] = o.depth;
+  p.conics[idx * 3 + 0] = o.ca; p.conics[idx * 3 + 1] = o.cb; p.conics[idx * 3 + 2] = o.cc;
+  p.colors[idx * 3 + 0] = rgb[0]; p.colors[idx * 3 + 1] = rgb[1]; p.colors[idx * 3 + 2] = rgb[2];
+}
+
 struct ProjBwdParams {
   int C, N, K, sh_degree, colors_per_camera;
   const float *means, *quats, *scales, *sh, *viewmats, *Ks;
@@ -105,6 +206,7 @@ struct ProjBwdParams {
   const float4* v_splats;
   const float* v_means2d_extra;
   float *v_means, *v_quats, *v_scales, *v_opacities, *v_sh;
+  float2* absgrad;  // nullable [C,N]: sum over pixels of |d L / d means2d|, copied out of the gradient records
 };
 
 constexpr int kProjBwdThreads = 128;
@@ -147,6 +249,11 @@ __global__ void __launch_bounds__(kProjBwdThreads) projection_bwd_kernel(const P
     const size_t idx = (size_t)c * p.N + n;
     const bool vis = p.radii[idx] > 0;
     float v_rgb[3] = {0.f, 0.f, 0.f};
+    if (p.absgrad != nullptr) {
+      float2 ag = make_float2(0.f, 0.f);
+      if (vis) { const float4 g2a = p.v_splats[idx * 3 + 2]; ag = make_float2(g2a.y, g2a.z); }
+      p.absgrad[idx] = ag;
+    }
     if (vis) {
       Camera cam_local;
       const Camera* cam = &cams[c < kMaxCamerasSmem ? c : 0];
@@ -258,6 +365,14 @@ __global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const 
   // phase 2: thread-private work on its own Gaussian / its own two rows
   float v_mean[3] = {0.f, 0.f, 0.f}, v_quat[4] = {0.f, 0.f, 0.f, 0.f}, v_scale[3] = {0.f, 0.f, 0.f};
   float v_opac = 0.f;
+  if (in_range && p.absgrad != nullptr) {
+    for (int c = 0; c < p.C; ++c) {
+      const size_t idx = (size_t)c * p.N + n;
+      float2 ag = make_float2(0.f, 0.f);
+      if (p.radii[idx] > 0) { const float4 g2a = p.v_splats[idx * 3 + 2]; ag = make_float2(g2a.y, g2a.z); }
+      p.absgrad[idx] = ag;
+    }
+  }
   if (seen) {
     float mean[3], quat[4], scale[3];
     mean[0] = __ldg(p.means + 3 * (size_t)n + 0);
@@ -387,6 +502,11 @@ extern "C" int egs_projection_fwd(int32_t C, int32_t N, const float* means, cons
   p.tiles_per_gauss = tiles_per_gauss; p.splats = reinterpret_cast<float4*>(splats);
   dim3 grid((unsigned)ceil_div(N, kProjThreads), (unsigned)C);
   const bool vec4 = sh_degree >= 0 && (K * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(sh_coeffs) % 16 == 0);
+  if (vec4 && K == 16) {
+    dim3 grid2((unsigned)ceil_div(N, kPF2Threads), (unsigned)C);
+    projection_fwd_sh16_kernel<<<grid2, kPF2Threads, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("projection_fwd_sh16_kernel");
+  }
   if (vec4) projection_fwd_kernel<true><<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(p);
   else      projection_fwd_kernel<false><<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(p);
   return check_launch("projection_fwd_kernel");
@@ -397,7 +517,7 @@ extern "C" int egs_projection_bwd(int32_t C, int32_t N, const float* means, cons
                                   const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
                                   const int32_t* radii, const float* colors, const float* v_splats,
                                   const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
-                                  float* v_opacities, float* v_sh_coeffs, egs_stream_t stream) {
+                                  float* v_opacities, float* v_sh_coeffs, float* absgrad, egs_stream_t stream) {
   EGS_REQUIRE(C >= 0 && N >= 0, "projection_bwd: negative sizes C=%d N=%d", C, N);
   EGS_REQUIRE(sh_degree <= 3, "projection_bwd: sh_degree %d > 3 is not supported", sh_degree);
   if (N == 0) return 0;
@@ -408,6 +528,7 @@ extern "C" int egs_projection_bwd(int32_t C, int32_t N, const float* means, cons
   p.radii = radii; p.colors = colors; p.v_splats = reinterpret_cast<const float4*>(v_splats);
   p.v_means2d_extra = v_means2d_extra;
   p.v_means = v_means; p.v_quats = v_quats; p.v_scales = v_scales; p.v_opacities = v_opacities; p.v_sh = v_sh_coeffs;
+  p.absgrad = reinterpret_cast<float2*>(absgrad);
   const bool vec4 = sh_degree >= 0 && (K * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(sh_coeffs) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(v_sh_coeffs) % 16 == 0);
   if (vec4 && K == 16) {

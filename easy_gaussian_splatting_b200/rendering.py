@@ -90,15 +90,14 @@ class _Rasterization(torch.autograd.Function):
             v_alphas = torch.zeros(C, height, width, 1, dtype=torch.float32, device=means.device)
         v_splats = stages.rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height,
                                         render_alphas, last_ids, v_colors, v_alphas)
-        if cfg["absgrad"]:
-            ref = getattr(ctx, "means2d_ref", None)
-            target = ref() if ref is not None else None
-            if target is not None:
-                # same contract as gsplat: attribute tagging on the tensor object handed out in meta
-                target.absgrad = v_splats[..., 9:11].contiguous()
-        v_means, v_quats, v_scales, v_opac, v_cols = stages.projection_bwd(
-            means, quats, scales, colors, viewmats, Ks, width, height, cfg["sh_degree"], cfg["eps2d"], radii,
-            colors_rgb, v_splats, v_means2d)
+        ref = getattr(ctx, "means2d_ref", None) if cfg["absgrad"] else None
+        target = ref() if ref is not None else None
+        out = stages.projection_bwd(means, quats, scales, colors, viewmats, Ks, width, height, cfg["sh_degree"],
+                                    cfg["eps2d"], radii, colors_rgb, v_splats, v_means2d, want_absgrad=target is not None)
+        v_means, v_quats, v_scales, v_opac, v_cols = out[:5]
+        if target is not None:
+            # same contract as gsplat: attribute tagging on the tensor object handed out in meta
+            target.absgrad = out[5]
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[7]:
             v_bg = ((1.0 - render_alphas) * v_colors).sum(dim=(1, 2))

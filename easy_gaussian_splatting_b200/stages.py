@@ -88,8 +88,10 @@ def projection_fwd(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tens
 
 def projection_bwd(means: Tensor, quats: Tensor, scales: Tensor, colors: Tensor, viewmats: Tensor, Ks: Tensor,
                    width: int, height: int, sh_degree: Optional[int], eps2d: float, radii: Tensor,
-                   colors_rgb: Tensor, v_splats: Tensor, v_means2d_extra: Optional[Tensor] = None):
-    """g8+g9. -> v_means[N,3], v_quats[N,4], v_scales[N,3], v_opacities[N], v_colors (shape of colors)."""
+                   colors_rgb: Tensor, v_splats: Tensor, v_means2d_extra: Optional[Tensor] = None,
+                   want_absgrad: bool = False):
+    """g8+g9. -> v_means[N,3], v_quats[N,4], v_scales[N,3], v_opacities[N], v_colors (shape of colors)
+    (+ absgrad[C,N,2] when want_absgrad)."""
     lib = _lib.load()
     dev = means.device
     N, C = means.shape[0], viewmats.shape[0]
@@ -104,12 +106,16 @@ def projection_bwd(means: Tensor, quats: Tensor, scales: Tensor, colors: Tensor,
     v_colors = torch.empty_like(colors)
     if v_means2d_extra is not None:
         v_means2d_extra = _f32c(v_means2d_extra, "v_means2d")
+    absgrad = torch.empty(C, N, 2, dtype=torch.float32, device=dev) if want_absgrad else None
     with torch.cuda.device(dev):
         rc = lib.egs_projection_bwd(C, N, _ptr(means), _ptr(quats), _ptr(scales), _ptr(colors), K, deg, per_cam,
                                     _ptr(viewmats), _ptr(Ks), int(width), int(height), float(eps2d), _ptr(radii),
                                     _ptr(colors_rgb), _ptr(v_splats), _ptr(v_means2d_extra), _ptr(v_means),
-                                    _ptr(v_quats), _ptr(v_scales), _ptr(v_opac), _ptr(v_colors), _stream(dev))
+                                    _ptr(v_quats), _ptr(v_scales), _ptr(v_opac), _ptr(v_colors), _ptr(absgrad),
+                                    _stream(dev))
     _lib.check(rc, "egs_projection_bwd")
+    if want_absgrad:
+        return v_means, v_quats, v_scales, v_opac, v_colors, absgrad
     return v_means, v_quats, v_scales, v_opac, v_colors
 
 

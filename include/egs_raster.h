@@ -73,13 +73,15 @@ int egs_projection_fwd(int32_t C, int32_t N, const float* means, const float* qu
  *   v_splats[C,N,12]: packed gradient records produced by egs_rasterize_bwd
  *   v_means2d_extra[C,N,2] (nullable): user gradient that arrived on meta["means2d"] itself
  * outputs (dense, written for every Gaussian): v_means[N,3], v_quats[N,4], v_scales[N,3],
- *   v_opacities[N], v_sh_coeffs (same shape as sh_coeffs; inactive bands and culled entries are 0). */
+ *   v_opacities[N], v_sh_coeffs (same shape as sh_coeffs; inactive bands and culled entries are 0);
+ *   absgrad[C,N,2] (nullable): the |v_x|,|v_y| slots of the gradient records as a dense tensor — what the
+ *   reference reads as meta["means2d"].absgrad (model/gaussian.py:191). */
 int egs_projection_bwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
                        const float* sh_coeffs, int32_t K, int32_t sh_degree, int32_t colors_per_camera,
                        const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
                        const int32_t* radii, const float* colors, const float* v_splats,
                        const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
-                       float* v_opacities, float* v_sh_coeffs, egs_stream_t stream);
+                       float* v_opacities, float* v_sh_coeffs, float* absgrad, egs_stream_t stream);
 
 /* ---- g3: exclusive scan of tiles_per_gauss, then key emission -------------------------------------
  * Replaces `torch.cumsum` + the second launch of gsplat `isect_tiles`.
