@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-timing", action="store_true")
     ap.add_argument("--ref-crop", type=int, default=8, help="reference arm: crop = 1/ref_crop of W and of H")
+    ap.add_argument("--forward-only", action="store_true", help="no_grad forward renders only (cfg5-style latency runs; not the headline metric)")
     return ap.parse_args()
 
 
@@ -221,6 +222,11 @@ def ours(args):
     d2h_bytes = 4
 
     def one_view(viewmat, K, Wc, Wa, want_loss):
+        if args.forward_only:
+            with torch.no_grad():
+                rc, ra, meta = rasterization(params[0], params[1], params[2], params[3], params[4], viewmat, K, W, H,
+                                             sh_degree=3, packed=False, absgrad=False, backgrounds=bg)
+            return rc.sum() if want_loss else None
         rc, ra, meta = rasterization(params[0], params[1], params[2], params[3], params[4], viewmat, K, W, H,
                                      sh_degree=3, packed=False, absgrad=True, backgrounds=bg)
         loss = (rc * Wc).sum() + (ra * Wa).sum()
@@ -329,6 +335,9 @@ def ours(args):
     }
     if args.n_gaussians:
         line["invalid"] = "N overridden (debug run)"
+    if args.forward_only:
+        line["invalid"] = "forward-only latency run, not the fwd+bwd metric"
+        line["config"]["mode"] = "no_grad forward only"
 
     if rank == 0 and not args.no_stage_timing:
         line.update(stage_rooflines(lib, stages, params, dev_views[0], bg, dev_Wc, dev_Wa, W, H, dev))
@@ -356,7 +365,9 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     N = means.shape[0]
     tw, th = stages.tile_grid(W, H)
 
-    def tm(fn, reps=reps):
+    def tm(fn, reps=reps, inner=4):
+        """median over `reps` of (CUDA-event time of `inner` back-to-back calls) / inner — back to back so the
+        host-side launch work of call i+1 overlaps the device work of call i, as it does inside a real step"""
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -364,10 +375,11 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            for _ in range(inner):
+                fn()
             e1.record()
             e1.synchronize()
-            ts.append(e0.elapsed_time(e1))
+            ts.append(e0.elapsed_time(e1) / inner)
         return statistics.median(ts)
 
     # FP32 peak probe (dependent FMA chains, 8 per thread)
@@ -450,6 +462,13 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     roof = dict(stages_out[dominant])
     roof["kernel"] = dominant
     roof["traffic"] = None
+    tj = ROOT / "profiles" / "traffic.json"
+    if tj.exists():  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        tk = json.loads(tj.read_text())
+        for name, e in tk["kernels"].items():
+            if name.startswith(dominant.replace("rasterize_bwd", "rasterize_bwd_kernel").replace("rasterize_fwd", "rasterize_fwd_kernel")):
+                roof["traffic"] = e["dram_bytes_per_launch"]
+                roof["traffic_source"] = tk["source"]
     roof["peak_source"] = pk["source"] if roof["bound"] == "hbm" else \
         f"measured live: dependent-FMA probe kernel, {fp32_peak:.1f} TFLOP/s (theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)"
     return {"roofline": roof, "stages": stages_out, "stages_standalone": standalone,

@@ -223,42 +223,56 @@ __global__ void __launch_bounds__(kBlendThreads) rasterize_fwd_kernel(
       const int batch_size = min(kBatch, wv.range_end - batch_start);
       const int ns = cull_and_compact(st, b & 1, batch_size, lane, rx_lo, rx_hi, ry_lo, ry_hi);
       const float4* s = st.rec[b & 1];
-      int slot = st.list[0];
-      for (int t = 0; t < ns; ++t) {
-        if (__all_sync(0xffffffffu, all_done)) break;  // warp-uniform exit + reconvergence point
-        const int cur = slot;
-        slot = st.list[min(t + 1, kBatch - 1)];  // next survivor, fetched one iteration ahead
-        const float4 g0 = s[cur * 3 + 0];  // x, y, conic_a, conic_b
-        const float4 g1 = s[cur * 3 + 1];  // conic_c, opacity, r, g
-        const float cbl = s[cur * 3 + 2].x;
-        // q(dx,dy) = -log2(e) * sigma, separable parts shared by the rows / columns of the pixel block
-        const float la = (0.5f * kNegLog2e) * g0.z, lc = (0.5f * kNegLog2e) * g1.x, lb = kNegLog2e * g0.w;
-        const float dx0 = g0.x - px0, dx1 = g0.x - px1, dy0 = g0.y - py0, dy1 = g0.y - py1;
-        const float qx0 = la * dx0 * dx0, qx1 = la * dx1 * dx1, bx0 = lb * dx0, bx1 = lb * dx1;
-        const float qy0 = lc * dy0 * dy0, qy1 = lc * dy1 * dy1;
-        const float q[4] = {fmaf(bx0, dy0, qx0 + qy0), fmaf(bx1, dy0, qx1 + qy0), fmaf(bx0, dy1, qx0 + qy1),
-                            fmaf(bx1, dy1, qx1 + qy1)};
+      // Two survivors per trip: their alphas do not depend on the running transmittance, so both are evaluated
+      // up front (independent LDS / FMA / MUFU chains = twice the ILP for a warp that walks a long list alone),
+      // then blended in order.  The vote at the top is the warp-uniform exit and the reconvergence point.
+      for (int t = 0; t < ns; t += 2) {
+        if (__all_sync(0xffffffffu, all_done)) break;
+        const bool has_b = t + 1 < ns;  // warp-uniform
+        const int cur_a = st.list[t], cur_b = st.list[has_b ? t + 1 : t];
+        float4 g0[2], g1[2];
+        float cbl[2], alpha[2][4], q[2][4];
+        g0[0] = s[cur_a * 3 + 0]; g1[0] = s[cur_a * 3 + 1]; cbl[0] = s[cur_a * 3 + 2].x;
+        g0[1] = s[cur_b * 3 + 0]; g1[1] = s[cur_b * 3 + 1]; cbl[1] = s[cur_b * 3 + 2].x;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          // q(dx,dy) = -log2(e) * sigma, separable parts shared by the rows / columns of the pixel block
+          const float la = (0.5f * kNegLog2e) * g0[e].z, lc = (0.5f * kNegLog2e) * g1[e].x, lb = kNegLog2e * g0[e].w;
+          const float dx0 = g0[e].x - px0, dx1 = g0[e].x - px1, dy0 = g0[e].y - py0, dy1 = g0[e].y - py1;
+          const float qx0 = la * dx0 * dx0, qx1 = la * dx1 * dx1, bx0 = lb * dx0, bx1 = lb * dx1;
+          const float qy0 = lc * dy0 * dy0, qy1 = lc * dy1 * dy1;
+          q[e][0] = fmaf(bx0, dy0, qx0 + qy0); q[e][1] = fmaf(bx1, dy0, qx1 + qy0);
+          q[e][2] = fmaf(bx0, dy1, qx0 + qy1); q[e][3] = fmaf(bx1, dy1, qx1 + qy1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) alpha[e][j] = fminf(kAlphaMax, g1[e].y * fast_ex2(q[e][j]));
+        }
         float tmax = -1.0f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float alpha = fminf(kAlphaMax, g1.y * fast_ex2(q[j]));
-          if (T[j] > 0.f && q[j] <= 0.f && alpha >= kAlphaMin) {  // sigma >= 0  <=>  q <= 0
-            const float next_T = T[j] * (1.0f - alpha);
-            if (next_T <= kTMin) {
-              T[j] = -T[j];  // finished: this Gaussian is not blended
-              if (COUNT) term[j] = batch_start + cur;
-            } else {
-              const float w = alpha * T[j];
-              cr[j] = fmaf(g1.z, w, cr[j]);
-              cg[j] = fmaf(g1.w, w, cg[j]);
-              cb[j] = fmaf(cbl, w, cb[j]);
-              last[j] = batch_start + cur;
-              T[j] = next_T;
-              if (COUNT) ++n_acc;
+        for (int e = 0; e < 2; ++e) {
+          if (e == 0 || has_b) {
+            const int cur = e == 0 ? cur_a : cur_b;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (T[j] > 0.f && q[e][j] <= 0.f && alpha[e][j] >= kAlphaMin) {  // sigma >= 0  <=>  q <= 0
+                const float next_T = T[j] * (1.0f - alpha[e][j]);
+                if (next_T <= kTMin) {
+                  T[j] = -T[j];  // finished: this Gaussian is not blended
+                  if (COUNT) term[j] = batch_start + cur;
+                } else {
+                  const float w = alpha[e][j] * T[j];
+                  cr[j] = fmaf(g1[e].z, w, cr[j]);
+                  cg[j] = fmaf(g1[e].w, w, cg[j]);
+                  cb[j] = fmaf(cbl[e], w, cb[j]);
+                  last[j] = batch_start + cur;
+                  T[j] = next_T;
+                  if (COUNT) ++n_acc;
+                }
+              }
             }
           }
-          tmax = fmaxf(tmax, T[j]);
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmax = fmaxf(tmax, T[j]);
         all_done = !(tmax > 0.f);
       }
       if (__all_sync(0xffffffffu, all_done)) break;  // this warp needs nothing further down the list

@@ -3,7 +3,7 @@
 Usage: ncu_blocks.py report.ncu-rep kernel-regex"""
 import csv, io, subprocess, sys
 rep, rx = sys.argv[1], sys.argv[2]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{rx}", "--launch-count", "1"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{rx}", "--launch-skip", sys.argv[3] if len(sys.argv) > 3 else "0", "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = [r for r in csv.reader(io.StringIO(raw))]
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]; data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
