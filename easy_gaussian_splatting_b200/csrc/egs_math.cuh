@@ -185,7 +185,7 @@ EGS_HD bool project_fwd(const float mean[3], const float quat[4], const float sc
 EGS_HD float sigma_cutoff(float opacity) {
   const float t = 255.0f * opacity;
   if (!(t > 1.0f)) return -1.0f;
-  return logf(t) * 1.0001f + 1e-4f;
+  return logf(t) * 1.001f + 2e-3f;  // margin >> fp32 cancellation error of sigma for strongly anisotropic conics
 }
 
 // Tile rectangle of a visible Gaussian: min inclusive, max exclusive.

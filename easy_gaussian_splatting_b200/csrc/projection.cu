@@ -534,7 +534,7 @@ extern "C" int egs_projection_bwd(int32_t C, int32_t N, const float* means, cons
   if (vec4 && K == 16) {
     // the reference's layout (K = 16): coalesced shared-memory staged rows
     constexpr int kSmem = 2 * kPB2Warps * 32 * kRowStride * (int)sizeof(float);
-    static const cudaError_t attr_rc =
+    const cudaError_t attr_rc =  // per-device attribute: set on every call (cheap), not once per process
         cudaFuncSetAttribute(projection_bwd_sh16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (attr_rc != cudaSuccess) return fail((int)attr_rc, "projection_bwd: shared memory opt-in failed: %s", cudaGetErrorString(attr_rc));
     projection_bwd_sh16_kernel<<<(unsigned)ceil_div(N, kPB2Threads), kPB2Threads, kSmem, (cudaStream_t)stream>>>(p);

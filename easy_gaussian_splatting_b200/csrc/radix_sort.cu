@@ -379,7 +379,7 @@ template <typename KeyT, int ITEMS>
 static int run_passes(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int passes,
                       const SortWorkspace& w, cudaStream_t stream) {
   constexpr int kSmem = (int)sizeof(SortSmem<KeyT, ITEMS>);
-  static const cudaError_t attr_rc =
+  const cudaError_t attr_rc =  // per-device attribute: set on every call (cheap), not once per process
       cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (attr_rc != cudaSuccess)
     return fail((int)attr_rc, "radix_sort: cannot opt in to %d bytes of shared memory: %s", kSmem, cudaGetErrorString(attr_rc));
