@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-timing", action="store_true")
     ap.add_argument("--ref-crop", type=int, default=8, help="reference arm: crop = 1/ref_crop of W and of H")
+    ap.add_argument("--train-step", action="store_true",
+                    help="cfg4-style full training step: --total-views views per step split across the ranks (strong "
+                         "scaling), gradient + densify-stat all-reduce, fused Adam")
+    ap.add_argument("--total-views", type=int, default=64)
     ap.add_argument("--forward-only", action="store_true", help="no_grad forward renders only (cfg5-style latency runs; not the headline metric)")
     return ap.parse_args()
 
@@ -199,6 +203,10 @@ def ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     V = args.views_per_rank
+    if args.train_step:
+        if args.total_views % world:
+            raise SystemExit("--total-views must be divisible by the number of GPUs")
+        V = args.total_views // world
     cfg = CONFIGS[args.workload]
     W, H = cfg["width"], cfg["height"]
 
@@ -210,6 +218,11 @@ def ours(args):
     params = [getattr(sc_cpu, k).to(dev).requires_grad_(True) for k in names]
     bucket = FlatGradBucket(params)
     stats = DensifyStats(N, dev)
+    optimizer = None
+    if args.train_step:
+        from easy_gaussian_splatting_b200.optim import FusedAdam
+        lrs = dict(means=1e-3, quats=1e-3, scales=1e-2, opacities=5e-2, colors=2.5e-3)  # configs/*.yaml learning rates
+        optimizer = FusedAdam([{"params": [p_], "lr": lrs[k], "name": k} for k, p_ in zip(names, params)], eps=1e-15)
     bg = sc_cpu.background[None].to(dev)
     Wc_cpu, Wa_cpu = loss_weights(sc_cpu.seed, 1, H, W)
     # pinned host copies of the per-step inputs (camera + loss weights = the "target image" of a training step)
@@ -242,6 +255,8 @@ def ours(args):
         if world > 1:
             bucket.all_reduce()
             stats.all_reduce_delta(before)
+        if optimizer is not None:
+            optimizer.step()
 
     # e2e: per-view inputs travel host -> device inside the timed region, double buffered on a copy stream so
     # the copy of view i+1 overlaps the rendering of view i; the step's loss is read back once per step.
@@ -279,6 +294,8 @@ def ours(args):
         if world > 1:
             bucket.all_reduce()
             stats.all_reduce_delta(before)
+        if optimizer is not None:
+            optimizer.step()
         return total.item()  # device -> host read of the step's result (train.py:107-108 reads the loss)
 
     def barrier():
@@ -335,6 +352,10 @@ def ours(args):
     }
     if args.n_gaussians:
         line["invalid"] = "N overridden (debug run)"
+    if args.train_step:
+        line["scaling"] = "strong"
+        line["train_step"] = {"it_per_s": 1e3 / ms_step, "views_per_step": world * V, "optimizer": "fused Adam (csrc/adam.cu)",
+                              "what": "fwd+bwd of every view, gradient + densify-stat all-reduce, Adam step"}
     if args.forward_only:
         line["invalid"] = "forward-only latency run, not the fwd+bwd metric"
         line["config"]["mode"] = "no_grad forward only"

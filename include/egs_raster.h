@@ -179,6 +179,14 @@ int egs_densify_stats_update(int32_t C, int32_t N, const int32_t* radii, const f
                              float* max_radii, float* grad_norm_accum, float* collecting_counts,
                              egs_stream_t stream);
 
+/* ---- §8f-3: fused Adam over up to 8 parameter groups ---------------------------------------------------------
+ * Replaces torch.optim.Adam for the reference's six groups (/root/reference/model/gaussian.py:389-412,
+ * train.py:156-157): default Adam (no weight decay, no amsgrad), one launch, 28 B/element.
+ * params/grads/exp_avg/exp_avg_sq: HOST arrays of n_groups DEVICE pointers; numels, lrs: HOST arrays; step >= 1. */
+int egs_fused_adam(int32_t n_groups, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* numels, const float* lrs, float beta1, float beta2,
+                   float eps, int64_t step, egs_stream_t stream);
+
 /* ---- measurement utility (bench.py only) -----------------------------------------------------------------
  * Dependent-FMA throughput probe: the FP32-SIMT roofline denominator for the blending kernels
  * (BASELINE.md §3).  blocks x 256 threads x iters x 32 FMAs; *host_flops (HOST double) = flops issued. */
