@@ -6,7 +6,7 @@
 //   1 histogram: reads the keys once (8 B/pair) and builds all P digit histograms
 //   1 scan     : exclusive scan of each 256-bin histogram -> global digit bases
 //   P passes   : each reads 12 B/pair and writes 12 B/pair; a tile of 4096 pairs is ranked in
-//                shared memory (warp-level ballot multisplit, stable), its per-digit counts are
+//                shared memory (warp-level shared-memory atomicOr multisplit, stable), its per-digit counts are
 //                chained to the preceding tiles with decoupled look-back, and the tile is written
 //                out digit-run by digit-run so stores are coalesced.
 // HBM traffic: 8 + 24*P bytes per pair = 152 B at P = 6.  Integer work only.
@@ -140,6 +140,7 @@ struct SortSmem {
   KeyT keys[kSortTile];                     // 32 KB (u64) / 16 KB (u32)  tile-sorted keys
   uint32_t vals[kSortTile];                 // 16 KB  tile-sorted values
   uint32_t warp_hist[kSortWarps][kRadix];   // 16 KB  per-warp digit counts, then per-warp exclusive offsets
+  uint32_t match[kSortWarps][kRadix];       // 16 KB  per-warp, per-digit lane masks (zero between items)
   uint32_t digit_start[kRadix];             // first slot of each digit inside the tile
   uint32_t dst_base[kRadix];                // global base - digit_start (mod 2^32)
   uint32_t warp_tot[kRadix / 32];
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // dynamic tile id: a tile only waits on tiles that have already started (no look-back deadlock)
   if (tid == 0) sm.tile = atomicAdd(tile_counter, 1u);
-  for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
+  for (int i = tid; i < 2 * kSortWarps * kRadix; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;  // warp_hist + match
   __syncthreads();
   const uint32_t tile = sm.tile;
   const int64_t tile_base = (int64_t)tile * kSortTile;
@@ -186,20 +187,21 @@ __global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 
   for (int i = 0; i < kSortItems; ++i) {
     const bool valid = (warp_off + i * 32) < tile_count;
     const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
-    // lanes holding the same digit: 8 ballots (one per digit bit) instead of match.any, whose cost grows with
-    // the number of distinct values in the warp (ncu r1e: short-scoreboard stalls of 10-14 warps per issue on
-    // high-entropy digits)
-    uint32_t m = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-    for (int b = 0; b < kRadixBits; ++b) {
-      const uint32_t bit = (d >> b) & 1u;
-      const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-      m &= bit ? bal : ~bal;
-    }
+    // lanes holding the same digit: each lane ORs its bit into a per-warp, per-digit mask word in shared
+    // memory (ATOMS.OR), then reads the word back.  ~12 instructions per item; 8 ballots cost ~48 (ALU bound,
+    // ncu r1g) and match.any stalls 10-14 warps per issue on high-entropy digits (ncu r1e).  The group leader
+    // clears the word again, so the masks never need a bulk reset.
+    uint32_t* mm = sm.match[warp];
+    if (valid) atomicOr(&mm[d], 1u << lane);
+    __syncwarp();
+    const uint32_t m = valid ? mm[d] : 0u;
     const uint32_t before = __popc(m & lanemask_lt);
     const uint32_t prev = wh[d];
     __syncwarp();
-    if (valid && before == 0) wh[d] = prev + (uint32_t)__popc(m);
+    if (valid && before == 0) {
+      wh[d] = prev + (uint32_t)__popc(m);
+      mm[d] = 0u;
+    }
     __syncwarp();
     const uint32_t rank = prev + before;
     if (i & 1) packed[i / 2] |= rank << 16;
