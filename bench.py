@@ -52,6 +52,8 @@ def parse_args():
                     help="cfg4-style full training step: --total-views views per step split across the ranks (strong "
                          "scaling), gradient + densify-stat all-reduce, fused Adam")
     ap.add_argument("--total-views", type=int, default=64)
+    ap.add_argument("--no-view-pipelining", action="store_true",
+                    help="render the views of a step strictly one after the other on one stream")
     ap.add_argument("--forward-only", action="store_true", help="no_grad forward renders only (cfg5-style latency runs; not the headline metric)")
     return ap.parse_args()
 
@@ -234,24 +236,34 @@ def ours(args):
     h2d_bytes = V * (host_views[0][0].numel() * 4 + host_views[0][1].numel() * 4 + host_Wc.numel() * 4 + host_Wa.numel() * 4)
     d2h_bytes = 4
 
-    def one_view(viewmat, K, Wc, Wa, want_loss):
+    # View pipelining (easy_gaussian_splatting_b200/training.py): consecutive views alternate between two CUDA
+    # streams so that the forward pass of view i+1 overlaps the backward pass of view i.
+    from easy_gaussian_splatting_b200.training import ViewPipeline
+    pipelined = not args.no_view_pipelining and not args.forward_only
+    pipe = ViewPipeline(dev, enabled=pipelined)
+    view_streams = pipe.streams
+
+    def one_view(viewmat, K, Wc, Wa, want_loss, slot=0):
+        if not args.forward_only:
+            loss = pipe.render_backward(slot, params, viewmat, K, W, H, lambda rc, ra: (rc * Wc).sum() + (ra * Wa).sum(),
+                                        sh_degree=3, backgrounds=bg, absgrad=True,
+                                        after_backward=lambda meta: stats.update_local(meta["radii"], meta["means2d"].absgrad, W, H))
+            return loss if want_loss else None
         if args.forward_only:
             with torch.no_grad():
                 rc, ra, meta = rasterization(params[0], params[1], params[2], params[3], params[4], viewmat, K, W, H,
                                              sh_degree=3, packed=False, absgrad=False, backgrounds=bg)
             return rc.sum() if want_loss else None
-        rc, ra, meta = rasterization(params[0], params[1], params[2], params[3], params[4], viewmat, K, W, H,
-                                     sh_degree=3, packed=False, absgrad=True, backgrounds=bg)
-        loss = (rc * Wc).sum() + (ra * Wa).sum()
-        loss.backward()
-        stats.update_local(meta["radii"], meta["means2d"].absgrad, W, H)
-        return loss if want_loss else None
+
+    fork_streams, join_streams = pipe.fork, pipe.join
 
     def step_resident():
         bucket.zero_()
         before = stats.clone() if world > 1 else None
-        for (vm, K) in dev_views:
-            one_view(vm, K, dev_Wc, dev_Wa, False)
+        fork_streams()
+        for i, (vm, K) in enumerate(dev_views):
+            one_view(vm, K, dev_Wc, dev_Wa, False, slot=i)
+        join_streams()
         if world > 1:
             bucket.all_reduce()
             stats.all_reduce_delta(before)
@@ -290,15 +302,20 @@ def ours(args):
                 b["free"].record(main)
             stage_view(k0)
             e2e_state["staged"] = k0
+        fork_streams()
+        losses = []
         for k in range(k0, k0 + V):
             b = stage[k % 2]
             # the copy of the NEXT view (the first view of the next step included) overlaps this view's rendering
             stage_view(k + 1)
             e2e_state["staged"] = k + 1
-            main.wait_event(b["ready"])
-            loss = one_view(b["vm"], b["K"], b["Wc"], b["Wa"], True)
-            total += loss.detach()
-            b["free"].record(main)
+            run_on = view_streams[k % 2] if pipelined else main
+            run_on.wait_event(b["ready"])
+            losses.append(one_view(b["vm"], b["K"], b["Wc"], b["Wa"], True, slot=k))
+            b["free"].record(run_on)
+        join_streams()
+        for l_ in losses:
+            total += l_.detach()
         e2e_state["next"] = k0 + V
         if world > 1:
             bucket.all_reduce()
@@ -348,6 +365,7 @@ def ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "views_per_rank_per_step": V, "views_per_step": world * V,
+                   "view_pipelining": pipelined,
                    "l2": "inputs larger than L2 (236 MB parameters + 96 MB splat/gradient records per view vs 126 MB L2)",
                    "exchange": "none (1 GPU)" if world == 1 else "NCCL all-reduce of the flat 236 B/Gaussian gradient bucket + 12 B/Gaussian densify stats each step"},
         "clocks": clocks,
