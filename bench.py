@@ -54,6 +54,10 @@ def parse_args():
     ap.add_argument("--total-views", type=int, default=64)
     ap.add_argument("--no-view-pipelining", action="store_true",
                     help="render the views of a step strictly one after the other on one stream")
+    ap.add_argument("--activations", default="pre", choices=["pre", "torch", "folded"],
+                    help="pre: activated tensors are the inputs (the metric's definition); torch: raw parameters, "
+                         "exp/sigmoid/cat per view in torch like GaussianModel's properties; folded: raw parameters "
+                         "through rasterization_from_parameters (activations folded into the kernels)")
     ap.add_argument("--forward-only", action="store_true", help="no_grad forward renders only (cfg5-style latency runs; not the headline metric)")
     return ap.parse_args()
 
@@ -217,13 +221,20 @@ def ours(args):
     N = sc_cpu.means.shape[0]
     my_views = list(range(rank * V, rank * V + V))
     names = ("means", "quats", "scales", "opacities", "colors")
-    params = [getattr(sc_cpu, k).to(dev).requires_grad_(True) for k in names]
+    if args.activations == "pre":
+        params = [getattr(sc_cpu, k).to(dev).requires_grad_(True) for k in names]
+    else:  # the reference's six raw parameter tensors (model/gaussian.py:32-54)
+        names = ("means", "quats", "log_scales", "logit_opacities", "sh_0", "sh_rest")
+        raw = [sc_cpu.means, sc_cpu.quats, torch.log(sc_cpu.scales), torch.logit(sc_cpu.opacities),
+               sc_cpu.colors[:, :1].contiguous(), sc_cpu.colors[:, 1:].contiguous()]
+        params = [t.to(dev).requires_grad_(True) for t in raw]
     bucket = FlatGradBucket(params)
     stats = DensifyStats(N, dev)
     optimizer = None
     if args.train_step:
         from easy_gaussian_splatting_b200.optim import FusedAdam
-        lrs = dict(means=1e-3, quats=1e-3, scales=1e-2, opacities=5e-2, colors=2.5e-3)  # configs/*.yaml learning rates
+        lrs = dict(means=1e-3, quats=1e-3, scales=1e-2, opacities=5e-2, colors=2.5e-3, log_scales=1e-2,
+                   logit_opacities=5e-2, sh_0=2.5e-3, sh_rest=1.25e-4)  # configs/*.yaml learning rates
         optimizer = FusedAdam([{"params": [p_], "lr": lrs[k], "name": k} for k, p_ in zip(names, params)], eps=1e-15)
     bg = sc_cpu.background[None].to(dev)
     Wc_cpu, Wa_cpu = loss_weights(sc_cpu.seed, 1, H, W)
@@ -243,10 +254,23 @@ def ours(args):
     pipe = ViewPipeline(dev, enabled=pipelined)
     view_streams = pipe.streams
 
+    render = None
+    if args.activations == "torch":
+        def render(viewmat, K):  # what GaussianModel.forward does through its properties (gaussian.py:97-107,353-367)
+            m, q, ls, lo, s0, sr = params
+            return rasterization(m, q, torch.exp(ls), torch.sigmoid(lo), torch.cat([s0, sr], dim=1), viewmat, K, W, H,
+                                 sh_degree=3, packed=False, absgrad=True, backgrounds=bg)
+    elif args.activations == "folded":
+        from easy_gaussian_splatting_b200 import rasterization_from_parameters
+
+        def render(viewmat, K):
+            m, q, ls, lo, s0, sr = params
+            return rasterization_from_parameters(m, q, ls, lo, s0, sr, viewmat, K, W, H, 3, backgrounds=bg, absgrad=True)
+
     def one_view(viewmat, K, Wc, Wa, want_loss, slot=0):
         if not args.forward_only:
             loss = pipe.render_backward(slot, params, viewmat, K, W, H, lambda rc, ra: (rc * Wc).sum() + (ra * Wa).sum(),
-                                        sh_degree=3, backgrounds=bg, absgrad=True,
+                                        sh_degree=3, backgrounds=bg, absgrad=True, render=render,
                                         after_backward=lambda meta: stats.update_local(meta["radii"], meta["means2d"].absgrad, W, H))
             return loss if want_loss else None
         if args.forward_only:
@@ -365,7 +389,7 @@ def ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "views_per_rank_per_step": V, "views_per_step": world * V,
-                   "view_pipelining": pipelined,
+                   "view_pipelining": pipelined, "activations": args.activations,
                    "l2": "inputs larger than L2 (236 MB parameters + 96 MB splat/gradient records per view vs 126 MB L2)",
                    "exchange": "none (1 GPU)" if world == 1 else "NCCL all-reduce of the flat 236 B/Gaussian gradient bucket + 12 B/Gaussian densify stats each step"},
         "clocks": clocks,
@@ -387,7 +411,7 @@ def ours(args):
         line["invalid"] = "forward-only latency run, not the fwd+bwd metric"
         line["config"]["mode"] = "no_grad forward only"
 
-    if rank == 0 and not args.no_stage_timing:
+    if rank == 0 and not args.no_stage_timing and args.activations == "pre":
         line.update(stage_rooflines(lib, stages, params, dev_views[0], bg, dev_Wc, dev_Wa, W, H, dev))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

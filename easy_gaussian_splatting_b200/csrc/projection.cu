@@ -20,7 +20,15 @@ struct ProjFwdParams {
   float *means2d, *depths, *conics, *colors;
   int32_t* tiles_per_gauss;
   float4* splats;
+  // raw-parameter mode (§8f-2): `scales` holds log-scales, `opacities` logits, `sh` the [N,1,3] DC band and
+  // `sh_rest` the [N,15,3] remainder — exp / sigmoid / cat are folded into this kernel
+  int raw;
+  const float* sh_rest;
 };
+
+// exactly torch's CUDA elementwise formulas, so the folded path reproduces exp()/sigmoid() of the caller
+__device__ __forceinline__ float act_exp(float x) { return expf(x); }
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // Load the first `nfloats` floats of a per-Gaussian coefficient block into registers.
 // VEC4: the block start is 16-byte aligned (K*3 % 4 == 0) -> 128-bit loads.
@@ -96,6 +104,88 @@ __global__ void __launch_bounds__(kProjThreads) projection_fwd_kernel(const Proj
   p.colors[idx * 3 + 0] = rgb[0]; p.colors[idx * 3 + 1] = rgb[1]; p.colors[idx * 3 + 2] = rgb[2];
 }
 
+
+// ---- raw-parameter mode (§8f-2): the "cat" of sh_0 [N,1,3] and sh_rest [N,15,3] done in flight --------------------
+// A warp's 32 rows are one contiguous, 16-byte aligned block in each source (32*45 and 32*3 floats), so the blocks
+// travel with 128-bit global accesses; only the shared-memory side is scalar (row r, column c of the row tile
+// <- element r*45 + (c-3) of the block).  Loads are unpredicated with a selected address (per-load predicates
+// serialise them); blocks of the last, partial warp fall back to scalar accesses.
+template <int RS>
+__device__ __forceinline__ void load_rows_raw(float* __restrict__ tile, const float* __restrict__ sh0,
+                                              const float* __restrict__ shrest, int n_base, int N, uint32_t row_mask,
+                                              int lane) {
+  const int rows = min(32, N - n_base);
+  const float* b0 = sh0 + (size_t)n_base * 3;
+  const float* b1 = shrest + (size_t)n_base * 45;
+  if (rows == 32) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {  // 360 float4 of the sh_rest block
+      const int q = i * 32 + lane;
+      if (q < 360) {
+        const int e = q * 4, r0 = e / 45, r3 = (e + 3) / 45;
+        const bool need = ((row_mask >> r0) | (row_mask >> r3)) & 1u;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(need ? b1 + e : b1));
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int ee = e + k, r = ee / 45, c = ee - r * 45;
+          tile[r * RS + 3 + c] = vv[k];
+        }
+      }
+    }
+    if (lane < 24) {  // 24 float4 of the sh_0 block
+      const int e = lane * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(b0 + e));
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ee = e + k, r = ee / 3, c = ee - r * 3;
+        tile[r * RS + c] = vv[k];
+      }
+    }
+  } else {
+    for (int e = lane; e < rows * 45; e += 32) { const int r = e / 45, c = e - r * 45; tile[r * RS + 3 + c] = __ldg(b1 + e); }
+    for (int e = lane; e < rows * 3; e += 32) { const int r = e / 3, c = e - r * 3; tile[r * RS + c] = __ldg(b0 + e); }
+  }
+}
+
+template <int RS>
+__device__ __forceinline__ void store_rows_raw(const float* __restrict__ tile, float* __restrict__ v_sh0,
+                                               float* __restrict__ v_shrest, int n_base, int N, int lane) {
+  const int rows = min(32, N - n_base);
+  float* b0 = v_sh0 + (size_t)n_base * 3;
+  float* b1 = v_shrest + (size_t)n_base * 45;
+  if (rows == 32) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const int q = i * 32 + lane;
+      if (q < 360) {
+        const int e = q * 4;
+        float vv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int ee = e + k, r = ee / 45, c = ee - r * 45;
+          vv[k] = tile[r * RS + 3 + c];
+        }
+        *reinterpret_cast<float4*>(b1 + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      }
+    }
+    if (lane < 24) {
+      const int e = lane * 4;
+      float vv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ee = e + k, r = ee / 3, c = ee - r * 3;
+        vv[k] = tile[r * RS + c];
+      }
+      *reinterpret_cast<float4*>(b0 + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+  } else {
+    for (int e = lane; e < rows * 45; e += 32) { const int r = e / 45, c = e - r * 45; b1[e] = tile[r * RS + 3 + c]; }
+    for (int e = lane; e < rows * 3; e += 32) { const int r = e / 3, c = e - r * 3; b0[e] = tile[r * RS + c]; }
+  }
+}
+
 // Forward, K = 16 SH coefficients (the reference's layout): only the coefficient rows of VISIBLE Gaussians
 // are read, each as one contiguous 192-byte run by 12 lanes (a row-masked cooperative copy into a
 // shared-memory tile), instead of twelve 16-byte loads per thread at a 192-byte lane stride.
@@ -128,13 +218,14 @@ __global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const 
     scale[0] = __ldg(p.scales + 3 * (size_t)n + 0);
     scale[1] = __ldg(p.scales + 3 * (size_t)n + 1);
     scale[2] = __ldg(p.scales + 3 * (size_t)n + 2);
+    if (p.raw) { scale[0] = act_exp(scale[0]); scale[1] = act_exp(scale[1]); scale[2] = act_exp(scale[2]); }
     ProjState st;
     vis = project_fwd(mean, quat, scale, cam, p.width, p.height, p.eps2d, p.near_plane, p.far_plane, p.radius_clip, st, o);
   }
   const uint32_t vis_mask = __ballot_sync(0xffffffffu, vis);
   const int nb = (p.sh_degree + 1) * (p.sh_degree + 1);
   const int need4 = (nb * 3 + 3) / 4;  // float4s of a row that hold active bands
-  {
+  if (!p.raw) {
     const float4* src = reinterpret_cast<const float4*>(p.sh) + (size_t)n_base * 12;
     float* t = tile[warp];
 #pragma unroll
@@ -144,6 +235,8 @@ __global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const 
       if (((vis_mask >> row) & 1u) && c4 < need4)
         *reinterpret_cast<float4*>(t + row * kFwdRowStride + c4 * 4) = __ldg(src + f);
     }
+  } else {
+    load_rows_raw<kFwdRowStride>(tile[warp], p.sh, p.sh_rest, n_base, p.N, vis_mask, lane);
   }
   __syncwarp();
   if (!in_range) return;
@@ -183,7 +276,8 @@ __global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const 
     rgb[0] = fmaxf(r + 0.5f, 0.f);
     rgb[1] = fmaxf(g + 0.5f, 0.f);
     rgb[2] = fmaxf(b + 0.5f, 0.f);
-    const float opac = __ldg(p.opacities + n);
+    float opac = __ldg(p.opacities + n);
+    if (p.raw) opac = act_sigmoid(opac);
     float4* s = p.splats + idx * 3;
     s[0] = make_float4(o.m2x, o.m2y, o.ca, o.cb);
     s[1] = make_float4(o.cc, opac, rgb[0], rgb[1]);
@@ -206,6 +300,10 @@ struct ProjBwdParams {
   const float4* v_splats;
   const float* v_means2d_extra;
   float *v_means, *v_quats, *v_scales, *v_opacities, *v_sh;
+  int raw;                    // see ProjFwdParams: inputs are raw parameters, outputs are their gradients
+  const float* sh_rest;
+  const float* opacities;     // logits (raw mode only: needed for the sigmoid VJP)
+  float* v_sh_rest;
   float2* absgrad;  // nullable [C,N]: sum over pixels of |d L / d means2d|, copied out of the gradient records
 };
 
@@ -348,7 +446,7 @@ __global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const 
   const uint32_t seen_mask = __ballot_sync(0xffffffffu, seen);
 
   // phase 1: coalesced load of the coefficient rows that are needed; zero the gradient rows
-  {
+  if (!p.raw) {
     const float4* src = reinterpret_cast<const float4*>(p.sh) + (size_t)n_base * (kRowFloats / 4);
 #pragma unroll
     for (int i = 0; i < kRowFloats / 4; ++i) {
@@ -357,6 +455,14 @@ __global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const 
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.sh_degree >= 1 && ((seen_mask >> row) & 1u)) v = __ldg(src + f);
       *reinterpret_cast<float4*>(co_tile + row * kRowStride + c4 * 4) = v;
+      *reinterpret_cast<float4*>(vc_tile + row * kRowStride + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    if (p.sh_degree >= 1) load_rows_raw<kRowStride>(co_tile, p.sh, p.sh_rest, n_base, p.N, seen_mask, lane);
+#pragma unroll
+    for (int i = 0; i < kRowFloats / 4; ++i) {
+      const int f = i * 32 + lane;
+      const int row = f / 12, c4 = f - row * 12;
       *reinterpret_cast<float4*>(vc_tile + row * kRowStride + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -383,6 +489,7 @@ __global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const 
     scale[0] = __ldg(p.scales + 3 * (size_t)n + 0);
     scale[1] = __ldg(p.scales + 3 * (size_t)n + 1);
     scale[2] = __ldg(p.scales + 3 * (size_t)n + 2);
+    if (p.raw) { scale[0] = act_exp(scale[0]); scale[1] = act_exp(scale[1]); scale[2] = act_exp(scale[2]); }
     const float* co = co_tile + lane * kRowStride;
     float* vc = vc_tile + lane * kRowStride;
     for (int c = 0; c < p.C; ++c) {
@@ -455,8 +562,16 @@ __global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const 
   }
   __syncwarp();
 
+  // VJPs of the folded activations: d exp = exp, d sigmoid = o (1 - o)
+  if (p.raw && seen) {
+    v_scale[0] *= act_exp(__ldg(p.scales + 3 * (size_t)n + 0));
+    v_scale[1] *= act_exp(__ldg(p.scales + 3 * (size_t)n + 1));
+    v_scale[2] *= act_exp(__ldg(p.scales + 3 * (size_t)n + 2));
+    const float o_ = act_sigmoid(__ldg(p.opacities + n));
+    v_opac *= o_ * (1.0f - o_);
+  }
   // phase 3: coalesced store of the gradient rows; small per-Gaussian outputs directly
-  {
+  if (!p.raw) {
     float4* dst = reinterpret_cast<float4*>(p.v_sh) + (size_t)n_base * (kRowFloats / 4);
 #pragma unroll
     for (int i = 0; i < kRowFloats / 4; ++i) {
@@ -464,6 +579,8 @@ __global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const 
       const int row = f / 12, c4 = f - row * 12;
       if (n_base + row < p.N) dst[f] = *reinterpret_cast<const float4*>(vc_tile + row * kRowStride + c4 * 4);
     }
+  } else {
+    store_rows_raw<kRowStride>(vc_tile, p.v_sh, p.v_sh_rest, n_base, p.N, lane);
   }
   if (in_range) {
     p.v_means[3 * (size_t)n + 0] = v_mean[0]; p.v_means[3 * (size_t)n + 1] = v_mean[1]; p.v_means[3 * (size_t)n + 2] = v_mean[2];
@@ -477,13 +594,14 @@ __global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const 
 
 using namespace egs;
 
-extern "C" int egs_projection_fwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
-                                  const float* opacities, const float* sh_coeffs, int32_t K, int32_t sh_degree,
-                                  int32_t colors_per_camera, const float* viewmats, const float* Ks, int32_t width,
-                                  int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
-                                  int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii,
-                                  float* means2d, float* depths, float* conics, float* colors,
-                                  int32_t* tiles_per_gauss, float* splats, egs_stream_t stream) {
+static int projection_fwd_impl(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                               const float* opacities, const float* sh_coeffs, const float* sh_rest, int32_t K,
+                               int32_t sh_degree, int32_t colors_per_camera, const float* viewmats, const float* Ks,
+                               int32_t width, int32_t height, float eps2d, float near_plane, float far_plane,
+                               float radius_clip, int32_t tile_size, int32_t tile_width, int32_t tile_height,
+                               int32_t* radii, float* means2d, float* depths, float* conics, float* colors,
+                               int32_t* tiles_per_gauss, float* splats, egs_stream_t stream) {
+  const int raw = sh_rest != nullptr;
   EGS_REQUIRE(C >= 0 && N >= 0, "projection_fwd: negative sizes C=%d N=%d", C, N);
   EGS_REQUIRE(C <= 65535, "projection_fwd: C=%d exceeds 65535 cameras per call", C);
   EGS_REQUIRE(width >= 1 && height >= 1, "projection_fwd: width/height must be >= 1 (got %d x %d)", width, height);
@@ -500,9 +618,13 @@ extern "C" int egs_projection_fwd(int32_t C, int32_t N, const float* means, cons
   p.tile_w = tile_width; p.tile_h = tile_height;
   p.radii = radii; p.means2d = means2d; p.depths = depths; p.conics = conics; p.colors = colors;
   p.tiles_per_gauss = tiles_per_gauss; p.splats = reinterpret_cast<float4*>(splats);
+  p.raw = raw; p.sh_rest = sh_rest;
   dim3 grid((unsigned)ceil_div(N, kProjThreads), (unsigned)C);
   const bool vec4 = sh_degree >= 0 && (K * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(sh_coeffs) % 16 == 0);
-  if (vec4 && K == 16) {
+  if (raw) {
+    EGS_REQUIRE(K == 16 && sh_degree >= 0, "projection_fwd_raw: needs sh_0 [N,1,3] + sh_rest [N,15,3] and sh_degree >= 0");
+  }
+  if (raw || (vec4 && K == 16)) {
     dim3 grid2((unsigned)ceil_div(N, kPF2Threads), (unsigned)C);
     projection_fwd_sh16_kernel<<<grid2, kPF2Threads, 0, (cudaStream_t)stream>>>(p);
     return check_launch("projection_fwd_sh16_kernel");
@@ -512,12 +634,42 @@ extern "C" int egs_projection_fwd(int32_t C, int32_t N, const float* means, cons
   return check_launch("projection_fwd_kernel");
 }
 
-extern "C" int egs_projection_bwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
-                                  const float* sh_coeffs, int32_t K, int32_t sh_degree, int32_t colors_per_camera,
-                                  const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
-                                  const int32_t* radii, const float* colors, const float* v_splats,
-                                  const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
-                                  float* v_opacities, float* v_sh_coeffs, float* absgrad, egs_stream_t stream) {
+extern "C" int egs_projection_fwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                                  const float* opacities, const float* sh_coeffs, int32_t K, int32_t sh_degree,
+                                  int32_t colors_per_camera, const float* viewmats, const float* Ks, int32_t width,
+                                  int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
+                                  int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii,
+                                  float* means2d, float* depths, float* conics, float* colors,
+                                  int32_t* tiles_per_gauss, float* splats, egs_stream_t stream) {
+  return projection_fwd_impl(C, N, means, quats, scales, opacities, sh_coeffs, nullptr, K, sh_degree, colors_per_camera,
+                             viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
+                             tile_width, tile_height, radii, means2d, depths, conics, colors, tiles_per_gauss, splats,
+                             stream);
+}
+
+extern "C" int egs_projection_fwd_raw(int32_t C, int32_t N, const float* means, const float* quats,
+                                      const float* log_scales, const float* logit_opacities, const float* sh_0,
+                                      const float* sh_rest, int32_t sh_degree, const float* viewmats, const float* Ks,
+                                      int32_t width, int32_t height, float eps2d, float near_plane, float far_plane,
+                                      float radius_clip, int32_t tile_size, int32_t tile_width, int32_t tile_height,
+                                      int32_t* radii, float* means2d, float* depths, float* conics, float* colors,
+                                      int32_t* tiles_per_gauss, float* splats, egs_stream_t stream) {
+  EGS_REQUIRE(sh_rest != nullptr && sh_0 != nullptr, "projection_fwd_raw: sh_0 and sh_rest are required");
+  EGS_REQUIRE(reinterpret_cast<uintptr_t>(sh_0) % 16 == 0 && reinterpret_cast<uintptr_t>(sh_rest) % 16 == 0,
+              "projection_fwd_raw: sh_0 and sh_rest must be 16-byte aligned");
+  return projection_fwd_impl(C, N, means, quats, log_scales, logit_opacities, sh_0, sh_rest, 16, sh_degree, 0, viewmats,
+                             Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size, tile_width,
+                             tile_height, radii, means2d, depths, conics, colors, tiles_per_gauss, splats, stream);
+}
+
+static int projection_bwd_impl(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                               const float* opacities_raw, const float* sh_coeffs, const float* sh_rest, int32_t K,
+                               int32_t sh_degree, int32_t colors_per_camera, const float* viewmats, const float* Ks,
+                               int32_t width, int32_t height, float eps2d, const int32_t* radii, const float* colors,
+                               const float* v_splats, const float* v_means2d_extra, float* v_means, float* v_quats,
+                               float* v_scales, float* v_opacities, float* v_sh_coeffs, float* v_sh_rest, float* absgrad,
+                               egs_stream_t stream) {
+  const int raw = sh_rest != nullptr;
   EGS_REQUIRE(C >= 0 && N >= 0, "projection_bwd: negative sizes C=%d N=%d", C, N);
   EGS_REQUIRE(sh_degree <= 3, "projection_bwd: sh_degree %d > 3 is not supported", sh_degree);
   if (N == 0) return 0;
@@ -529,9 +681,14 @@ extern "C" int egs_projection_bwd(int32_t C, int32_t N, const float* means, cons
   p.v_means2d_extra = v_means2d_extra;
   p.v_means = v_means; p.v_quats = v_quats; p.v_scales = v_scales; p.v_opacities = v_opacities; p.v_sh = v_sh_coeffs;
   p.absgrad = reinterpret_cast<float2*>(absgrad);
+  p.raw = raw; p.sh_rest = sh_rest; p.opacities = opacities_raw; p.v_sh_rest = v_sh_rest;
   const bool vec4 = sh_degree >= 0 && (K * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(sh_coeffs) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(v_sh_coeffs) % 16 == 0);
-  if (vec4 && K == 16) {
+  if (raw) {
+    EGS_REQUIRE(K == 16 && sh_degree >= 0 && v_sh_rest != nullptr && opacities_raw != nullptr,
+                "projection_bwd_raw: needs sh_0 / sh_rest (K = 16), logits and sh_degree >= 0");
+  }
+  if (raw || (vec4 && K == 16)) {
     // the reference's layout (K = 16): coalesced shared-memory staged rows
     constexpr int kSmem = 2 * kPB2Warps * 32 * kRowStride * (int)sizeof(float);
     const cudaError_t attr_rc =  // per-device attribute: set on every call (cheap), not once per process
@@ -544,4 +701,31 @@ extern "C" int egs_projection_bwd(int32_t C, int32_t N, const float* means, cons
   if (vec4) projection_bwd_kernel<true><<<grid, kProjBwdThreads, 0, (cudaStream_t)stream>>>(p);
   else      projection_bwd_kernel<false><<<grid, kProjBwdThreads, 0, (cudaStream_t)stream>>>(p);
   return check_launch("projection_bwd_kernel");
+}
+
+extern "C" int egs_projection_bwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                                  const float* sh_coeffs, int32_t K, int32_t sh_degree, int32_t colors_per_camera,
+                                  const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
+                                  const int32_t* radii, const float* colors, const float* v_splats,
+                                  const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
+                                  float* v_opacities, float* v_sh_coeffs, float* absgrad, egs_stream_t stream) {
+  return projection_bwd_impl(C, N, means, quats, scales, nullptr, sh_coeffs, nullptr, K, sh_degree, colors_per_camera,
+                             viewmats, Ks, width, height, eps2d, radii, colors, v_splats, v_means2d_extra, v_means,
+                             v_quats, v_scales, v_opacities, v_sh_coeffs, nullptr, absgrad, stream);
+}
+
+extern "C" int egs_projection_bwd_raw(int32_t C, int32_t N, const float* means, const float* quats,
+                                      const float* log_scales, const float* logit_opacities, const float* sh_0,
+                                      const float* sh_rest, int32_t sh_degree, const float* viewmats, const float* Ks,
+                                      int32_t width, int32_t height, float eps2d, const int32_t* radii,
+                                      const float* colors, const float* v_splats, const float* v_means2d_extra,
+                                      float* v_means, float* v_quats, float* v_log_scales, float* v_logit_opacities,
+                                      float* v_sh_0, float* v_sh_rest, float* absgrad, egs_stream_t stream) {
+  EGS_REQUIRE(sh_rest != nullptr && sh_0 != nullptr, "projection_bwd_raw: sh_0 and sh_rest are required");
+  EGS_REQUIRE(reinterpret_cast<uintptr_t>(sh_0) % 16 == 0 && reinterpret_cast<uintptr_t>(sh_rest) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(v_sh_0) % 16 == 0 && reinterpret_cast<uintptr_t>(v_sh_rest) % 16 == 0,
+              "projection_bwd_raw: sh_0 / sh_rest and their gradients must be 16-byte aligned");
+  return projection_bwd_impl(C, N, means, quats, log_scales, logit_opacities, sh_0, sh_rest, 16, sh_degree, 0, viewmats,
+                             Ks, width, height, eps2d, radii, colors, v_splats, v_means2d_extra, v_means, v_quats,
+                             v_log_scales, v_logit_opacities, v_sh_0, v_sh_rest, absgrad, stream);
 }

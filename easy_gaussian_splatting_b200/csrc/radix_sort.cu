@@ -10,8 +10,6 @@
 //                chained to the preceding tiles with decoupled look-back, and the tile is written
 //                out digit-run by digit-run so stores are coalesced.
 // HBM traffic: 8 + 24*P bytes per pair = 152 B at P = 6.  Integer work only.
-#include <stdlib.h>
-
 #include "egs_common.cuh"
 
 namespace egs {
@@ -21,7 +19,7 @@ constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
 constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
-// pairs per thread is a template parameter ITEMS (8 or 16): tile = 512 * ITEMS pairs
+// pairs per thread is the template parameter ITEMS (8 in production: tile = 4096 pairs; 16 was measured slower)
 
 constexpr int kLookWindow = 8;
 constexpr uint32_t kFlagAggregate = 1u << 30;
@@ -368,12 +366,6 @@ static int radix_sort_pairs_impl(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT
   if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
   radix_histogram_kernel<KeyT><<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, passes, w.hist);
   radix_scan_hist_kernel<<<passes, kRadix, 0, stream>>>(w.hist);
-  static const int items = [] {  // tuning knob: pairs per thread (tile = 512 * items)
-    const char* e = getenv("EGS_SORT_ITEMS");
-    const int v = e ? atoi(e) : 8;
-    return (v == 16) ? 16 : 8;
-  }();
-  if (items == 16) return run_passes<KeyT, 16>(n, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
   return run_passes<KeyT, 8>(n, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
 }
 

@@ -23,7 +23,7 @@ from torch import Tensor
 
 from . import stages
 
-__all__ = ["rasterization"]
+__all__ = ["rasterization", "rasterization_from_parameters"]
 
 
 class _LazyMeta(dict):
@@ -102,6 +102,61 @@ class _Rasterization(torch.autograd.Function):
         if backgrounds is not None and ctx.needs_input_grad[7]:
             v_bg = ((1.0 - render_alphas) * v_colors).sum(dim=(1, 2))
         return v_means, v_quats, v_scales, v_opac, v_cols, None, None, v_bg, None
+
+
+class _RasterizationRaw(torch.autograd.Function):
+    """Same pipeline fed with the reference's raw parameters: exp / sigmoid / cat and their VJPs
+    live inside the projection kernels, nothing else changes."""
+
+    @staticmethod
+    def forward(ctx, means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds, cfg):
+        width, height, sh_degree = cfg["width"], cfg["height"], cfg["sh_degree"]
+        C = viewmats.shape[0]
+        proj = stages.projection_fwd_raw(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, width,
+                                         height, sh_degree, eps2d=cfg["eps2d"], near_plane=cfg["near_plane"],
+                                         far_plane=cfg["far_plane"], radius_clip=cfg["radius_clip"])
+        tw, th = stages.tile_grid(width, height)
+        tiles_per_gauss = proj["tiles_per_gauss"]
+        isect_ids_thunk, flatten_ids, isect_offsets = stages.isect_sorted(
+            proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th,
+            materialize_ids=False)
+        cfg["isect_ids_thunk"] = isect_ids_thunk
+        render_colors, render_alphas, last_ids = stages.rasterize_fwd(
+            proj["splats"], isect_offsets, flatten_ids, backgrounds, width, height)
+        ctx.cfg = cfg
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds,
+                              proj["radii"], proj["colors"], proj["splats"], isect_offsets, flatten_ids, render_alphas,
+                              last_ids)
+        nondiff = (proj["radii"], proj["depths"], proj["conics"], proj["colors"], tiles_per_gauss,
+                   flatten_ids, isect_offsets, last_ids)
+        ctx.mark_non_differentiable(*nondiff)
+        return (render_colors, render_alphas, proj["means2d"]) + nondiff
+
+    @staticmethod
+    def backward(ctx, v_colors, v_alphas, v_means2d, *_unused):
+        (means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds, radii, colors_rgb, splats,
+         isect_offsets, flatten_ids, render_alphas, last_ids) = ctx.saved_tensors
+        cfg = ctx.cfg
+        width, height = cfg["width"], cfg["height"]
+        C = viewmats.shape[0]
+        if v_colors is None:
+            v_colors = torch.zeros(C, height, width, 3, dtype=torch.float32, device=means.device)
+        if v_alphas is None:
+            v_alphas = torch.zeros(C, height, width, 1, dtype=torch.float32, device=means.device)
+        v_splats = stages.rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height,
+                                        render_alphas, last_ids, v_colors, v_alphas)
+        ref = getattr(ctx, "means2d_ref", None) if cfg["absgrad"] else None
+        target = ref() if ref is not None else None
+        out = stages.projection_bwd_raw(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, width,
+                                        height, cfg["sh_degree"], cfg["eps2d"], radii, colors_rgb, v_splats, v_means2d,
+                                        want_absgrad=target is not None)
+        if target is not None:
+            target.absgrad = out[6]
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[8]:
+            v_bg = ((1.0 - render_alphas) * v_colors).sum(dim=(1, 2))
+        return (*out[:6], None, None, v_bg, None)
 
 
 def _check_inputs(means, quats, scales, opacities, colors, viewmats, Ks, sh_degree, backgrounds):
@@ -198,6 +253,10 @@ def rasterization(
     cfg = dict(width=width, height=height, sh_degree=sh_degree, eps2d=float(eps2d), near_plane=float(near_plane),
                far_plane=float(far_plane), radius_clip=float(radius_clip), absgrad=bool(absgrad))
     outs = _Rasterization.apply(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg)
+    return _finish(outs, cfg, opacities[None].expand(C, -1), width, height, tile_size, C, absgrad)
+
+
+def _finish(outs, cfg, opacities_cn, width, height, tile_size, C, absgrad):
     (render_colors, render_alphas, means2d, radii, depths, conics, colors_rgb, tiles_per_gauss,
      flatten_ids, isect_offsets, _last_ids) = outs
     isect_ids = cfg.pop("isect_ids_thunk")
@@ -212,7 +271,7 @@ def rasterization(
         "means2d": means2d,
         "depths": depths,
         "conics": conics,
-        "opacities": opacities[None].expand(C, -1),
+        "opacities": opacities_cn,
         "colors": colors_rgb,
         "tile_width": tw,
         "tile_height": th,
@@ -226,3 +285,50 @@ def rasterization(
         "n_cameras": C,
     })
     return render_colors, render_alphas, meta
+
+
+def rasterization_from_parameters(
+    means: Tensor,  # [N, 3]
+    quats: Tensor,  # [N, 4]
+    log_scales: Tensor,  # [N, 3]   (GaussianModel.log_scales)
+    logit_opacities: Tensor,  # [N]  (GaussianModel.logit_opacities)
+    sh_0: Tensor,  # [N, 1, 3]
+    sh_rest: Tensor,  # [N, 15, 3]
+    viewmats: Tensor,
+    Ks: Tensor,
+    width: int,
+    height: int,
+    sh_degree: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    backgrounds: Optional[Tensor] = None,
+    absgrad: bool = False,
+) -> Tuple[Tensor, Tensor, Dict]:
+    """Opt-in entry point: identical to
+    ``rasterization(means, quats, exp(log_scales), sigmoid(logit_opacities), cat([sh_0, sh_rest], 1), ...,
+    packed=False)`` — what ``GaussianModel.forward`` computes through its ``scales`` / ``opacities`` / ``shs``
+    properties (/root/reference/model/gaussian.py:97-107, 353-367) — but the three activations and their backward
+    passes run inside the projection kernels: no ``cat`` (384 B/Gaussian each way), no separate exp / sigmoid
+    kernels, and gradients arrive directly on the six parameter tensors."""
+    width, height = int(width), int(height)
+    if width < 1 or height < 1:
+        raise ValueError(f"width and height must be >= 1, got {width} x {height}")
+    N, C = means.shape[0], viewmats.shape[0]
+    if log_scales.shape != (N, 3) or logit_opacities.shape != (N,):
+        raise ValueError("log_scales must be [N,3] and logit_opacities [N]")
+    if sh_0.shape != (N, 1, 3) or sh_rest.shape != (N, 15, 3):
+        raise ValueError("sh_0 must be [N,1,3] and sh_rest [N,15,3] (K = 16, the reference's sh_degree 3 layout)")
+    # shape / device / dtype checks shared with rasterization(); sh_0.expand is a zero-copy [N,16,3] stand-in
+    _check_inputs(means, quats, log_scales, logit_opacities, sh_0.expand(N, 16, 3), viewmats, Ks, sh_degree, backgrounds)
+    for name, t in (("sh_0", sh_0), ("sh_rest", sh_rest)):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"{name} must be a float32 CUDA tensor: this rasterizer has no CPU path")
+    if viewmats.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("gradients w.r.t. viewmats are not implemented")
+    cfg = dict(width=width, height=height, sh_degree=int(sh_degree), eps2d=float(eps2d), near_plane=float(near_plane),
+               far_plane=float(far_plane), radius_clip=float(radius_clip), absgrad=bool(absgrad))
+    outs = _RasterizationRaw.apply(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds, cfg)
+    opac = torch.sigmoid(logit_opacities.detach())[None].expand(C, -1)
+    return _finish(outs, cfg, opac, width, height, 16, C, absgrad)

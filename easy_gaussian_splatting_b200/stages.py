@@ -119,6 +119,64 @@ def projection_bwd(means: Tensor, quats: Tensor, scales: Tensor, colors: Tensor,
     return v_means, v_quats, v_scales, v_opac, v_colors
 
 
+def projection_fwd_raw(means: Tensor, quats: Tensor, log_scales: Tensor, logit_opacities: Tensor, sh_0: Tensor,
+                       sh_rest: Tensor, viewmats: Tensor, Ks: Tensor, width: int, height: int, sh_degree: int,
+                       eps2d: float = 0.3, near_plane: float = 0.01, far_plane: float = 1e10,
+                       radius_clip: float = 0.0, tile_size: int = TILE_SIZE) -> Dict[str, Tensor]:
+    """§8f-2: projection_fwd on the reference's raw parameters (exp / sigmoid / cat folded into the kernel)."""
+    lib = _lib.load()
+    ts = [_f32c(t, n) for t, n in ((means, "means"), (quats, "quats"), (log_scales, "log_scales"),
+                                   (logit_opacities, "logit_opacities"), (sh_0, "sh_0"), (sh_rest, "sh_rest"),
+                                   (viewmats, "viewmats"), (Ks, "Ks"))]
+    means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks = ts
+    dev = means.device
+    N, C = means.shape[0], viewmats.shape[0]
+    if sh_0.shape != (N, 1, 3) or sh_rest.shape != (N, 15, 3):
+        raise ValueError(f"sh_0 must be [N,1,3] and sh_rest [N,15,3], got {tuple(sh_0.shape)} and {tuple(sh_rest.shape)}")
+    tw, th = tile_grid(width, height, tile_size)
+    out = {
+        "radii": torch.empty(C, N, dtype=torch.int32, device=dev),
+        "means2d": torch.empty(C, N, 2, dtype=torch.float32, device=dev),
+        "depths": torch.empty(C, N, dtype=torch.float32, device=dev),
+        "conics": torch.empty(C, N, 3, dtype=torch.float32, device=dev),
+        "colors": torch.empty(C, N, 3, dtype=torch.float32, device=dev),
+        "tiles_per_gauss": torch.empty(C, N, dtype=torch.int32, device=dev),
+        "splats": torch.empty(C, N, SPLAT_FLOATS, dtype=torch.float32, device=dev),
+    }
+    with torch.cuda.device(dev):
+        rc = lib.egs_projection_fwd_raw(C, N, _ptr(means), _ptr(quats), _ptr(log_scales), _ptr(logit_opacities),
+                                        _ptr(sh_0), _ptr(sh_rest), int(sh_degree), _ptr(viewmats), _ptr(Ks),
+                                        int(width), int(height), float(eps2d), float(near_plane), float(far_plane),
+                                        float(radius_clip), int(tile_size), tw, th, _ptr(out["radii"]),
+                                        _ptr(out["means2d"]), _ptr(out["depths"]), _ptr(out["conics"]),
+                                        _ptr(out["colors"]), _ptr(out["tiles_per_gauss"]), _ptr(out["splats"]),
+                                        _stream(dev))
+    _lib.check(rc, "egs_projection_fwd_raw")
+    return out
+
+
+def projection_bwd_raw(means: Tensor, quats: Tensor, log_scales: Tensor, logit_opacities: Tensor, sh_0: Tensor,
+                       sh_rest: Tensor, viewmats: Tensor, Ks: Tensor, width: int, height: int, sh_degree: int,
+                       eps2d: float, radii: Tensor, colors_rgb: Tensor, v_splats: Tensor,
+                       v_means2d_extra: Optional[Tensor] = None, want_absgrad: bool = False):
+    """-> v_means, v_quats, v_log_scales, v_logit_opacities, v_sh_0, v_sh_rest (, absgrad)."""
+    lib = _lib.load()
+    dev = means.device
+    N, C = means.shape[0], viewmats.shape[0]
+    outs = [torch.empty_like(t) for t in (means, quats, log_scales, logit_opacities, sh_0, sh_rest)]
+    if v_means2d_extra is not None:
+        v_means2d_extra = _f32c(v_means2d_extra, "v_means2d")
+    absgrad = torch.empty(C, N, 2, dtype=torch.float32, device=dev) if want_absgrad else None
+    with torch.cuda.device(dev):
+        rc = lib.egs_projection_bwd_raw(C, N, _ptr(means), _ptr(quats), _ptr(log_scales), _ptr(logit_opacities),
+                                        _ptr(sh_0), _ptr(sh_rest), int(sh_degree), _ptr(viewmats), _ptr(Ks),
+                                        int(width), int(height), float(eps2d), _ptr(radii), _ptr(colors_rgb),
+                                        _ptr(v_splats), _ptr(v_means2d_extra), *[_ptr(o) for o in outs],
+                                        _ptr(absgrad), _stream(dev))
+    _lib.check(rc, "egs_projection_bwd_raw")
+    return (*outs, absgrad) if want_absgrad else tuple(outs)
+
+
 def exclusive_scan(counts: Tensor) -> Tuple[Tensor, Tensor]:
     """int32[n] -> (exclusive prefix int64[n], total int64[1]) — device side, no sync."""
     lib = _lib.load()

@@ -43,14 +43,20 @@ class ViewPipeline:
     def render_backward(self, slot: int, params: Sequence[Tensor], viewmat: Tensor, K: Tensor, width: int, height: int,
                         loss_fn: Callable[[Tensor, Tensor], Tensor], sh_degree: Optional[int] = 3,
                         backgrounds: Optional[Tensor] = None, absgrad: bool = True,
-                        after_backward: Optional[Callable[[dict], None]] = None) -> Tensor:
+                        after_backward: Optional[Callable[[dict], None]] = None,
+                        render: Optional[Callable] = None) -> Tensor:
         """Forward + ``loss_fn(render_colors, render_alphas).backward()`` of one view in pipeline slot ``slot``.
-        ``after_backward(meta)`` runs on the view's stream after the backward pass (e.g. the densify-stat update)."""
-        means, quats, scales, opacities, colors = params
+        ``after_backward(meta)`` runs on the view's stream after the backward pass (e.g. the densify-stat update).
+        ``render(viewmat, K)`` may replace the default call (``rasterization`` on the five activated tensors in
+        ``params``), e.g. with ``rasterization_from_parameters`` on raw parameters."""
 
         def run():
-            rc, ra, meta = rasterization(means, quats, scales, opacities, colors, viewmat, K, width, height,
-                                         sh_degree=sh_degree, packed=False, absgrad=absgrad, backgrounds=backgrounds)
+            if render is not None:
+                rc, ra, meta = render(viewmat, K)
+            else:
+                means, quats, scales, opacities, colors = params
+                rc, ra, meta = rasterization(means, quats, scales, opacities, colors, viewmat, K, width, height,
+                                             sh_degree=sh_degree, packed=False, absgrad=absgrad, backgrounds=backgrounds)
             loss = loss_fn(rc, ra)
             if self.enabled:
                 me = self.streams[slot % 2]

@@ -83,6 +83,26 @@ int egs_projection_bwd(int32_t C, int32_t N, const float* means, const float* qu
                        const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
                        float* v_opacities, float* v_sh_coeffs, float* absgrad, egs_stream_t stream);
 
+/* ---- §8f-2: the same two kernels fed with the reference's RAW parameters ---------------------------------------
+ * GaussianModel recomputes scales = exp(log_scales), opacities = sigmoid(logit_opacities) and
+ * shs = cat(sh_0, sh_rest) on every access (/root/reference/model/gaussian.py:97-107); the cat alone moves
+ * 384 B/Gaussian forward and again backward.  These entry points take log_scales[N,3], logit_opacities[N],
+ * sh_0[N,1,3], sh_rest[N,15,3] and fold exp / sigmoid / cat and their VJPs into the kernels (torch's exact CUDA
+ * formulas: expf(x), 1/(1+expf(-x))).  Outputs as above; gradients are w.r.t. the raw parameters. */
+int egs_projection_fwd_raw(int32_t C, int32_t N, const float* means, const float* quats, const float* log_scales,
+                           const float* logit_opacities, const float* sh_0, const float* sh_rest, int32_t sh_degree,
+                           const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
+                           float near_plane, float far_plane, float radius_clip, int32_t tile_size,
+                           int32_t tile_width, int32_t tile_height, int32_t* radii, float* means2d, float* depths,
+                           float* conics, float* colors, int32_t* tiles_per_gauss, float* splats, egs_stream_t stream);
+int egs_projection_bwd_raw(int32_t C, int32_t N, const float* means, const float* quats, const float* log_scales,
+                           const float* logit_opacities, const float* sh_0, const float* sh_rest, int32_t sh_degree,
+                           const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
+                           const int32_t* radii, const float* colors, const float* v_splats,
+                           const float* v_means2d_extra, float* v_means, float* v_quats, float* v_log_scales,
+                           float* v_logit_opacities, float* v_sh_0, float* v_sh_rest, float* absgrad,
+                           egs_stream_t stream);
+
 /* ---- g3: exclusive scan of tiles_per_gauss, then key emission -------------------------------------
  * Replaces `torch.cumsum` + the second launch of gsplat `isect_tiles`.
  * egs_exclusive_scan: out[i] = sum_{j<i} in[j] (int64), *total = sum of all (device int64). */

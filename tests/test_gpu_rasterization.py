@@ -215,3 +215,39 @@ def test_view_pipeline_matches_sequential_accumulation():
     assert rel_err(g1.cpu(), g0.cpu()) <= 1e-5
     assert torch.equal(s0[1], s1[1]) and torch.equal(s0[2], s1[2])  # counts and max radii are exact
     assert rel_err(s1[0].cpu(), s0[0].cpu()) <= 1e-5
+
+
+@pytest.mark.parametrize("sh_degree", [0, 2, 3])
+def test_folded_activations_match_unfolded(sh_degree):
+    """§8f-2: rasterization_from_parameters(raw params) == rasterization(exp, sigmoid, cat of them), forward and
+    gradients w.r.t. the raw parameters (autograd through torch's exp / sigmoid / cat on the unfolded side)."""
+    from easy_gaussian_splatting_b200 import rasterization, rasterization_from_parameters
+    sc = make_scene("outdoor", 30_000, 320, 200, 200.0, 11, n_views=2).to("cuda")
+    W, H = sc.width, sc.height
+    raw = dict(means=sc.means, quats=sc.quats, log_scales=torch.log(sc.scales), logit_opacities=torch.logit(sc.opacities),
+               sh_0=sc.colors[:, :1].contiguous(), sh_rest=sc.colors[:, 1:].contiguous())
+    g = torch.Generator().manual_seed(2)
+    Wc, Wa = torch.rand(2, H, W, 3, generator=g).cuda(), torch.rand(2, H, W, 1, generator=g).cuda()
+    bg = sc.background[None].expand(2, 3).contiguous()
+
+    a = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
+    rc_a, ra_a, meta_a = rasterization(a["means"], a["quats"], torch.exp(a["log_scales"]), torch.sigmoid(a["logit_opacities"]),
+                                       torch.cat([a["sh_0"], a["sh_rest"]], 1), sc.viewmats, sc.Ks, W, H,
+                                       sh_degree=sh_degree, packed=False, absgrad=True, backgrounds=bg)
+    ((rc_a * Wc).sum() + (ra_a * Wa).sum()).backward()
+
+    b = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
+    rc_b, ra_b, meta_b = rasterization_from_parameters(b["means"], b["quats"], b["log_scales"], b["logit_opacities"],
+                                                       b["sh_0"], b["sh_rest"], sc.viewmats, sc.Ks, W, H, sh_degree,
+                                                       backgrounds=bg, absgrad=True)
+    ((rc_b * Wc).sum() + (ra_b * Wa).sum()).backward()
+
+    assert torch.equal(meta_a["radii"], meta_b["radii"]) and torch.equal(meta_a["flatten_ids"], meta_b["flatten_ids"])
+    assert torch.equal(meta_a["means2d"], meta_b["means2d"])
+    assert float((rc_a - rc_b).abs().max()) <= 1e-6 and float((ra_a - ra_b).abs().max()) <= 1e-6
+    for k in raw:
+        assert rel_err(b[k].grad.cpu(), a[k].grad.cpu()) <= 1e-5, k
+    assert rel_err(meta_b["means2d"].absgrad.cpu(), meta_a["means2d"].absgrad.cpu()) <= 1e-5
+    nb = (sh_degree + 1) ** 2
+    if nb < 16:
+        assert float(b["sh_rest"].grad[:, nb - 1:].abs().sum()) == 0.0  # inactive bands get exactly zero
