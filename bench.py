@@ -58,6 +58,8 @@ def parse_args():
                     help="pre: activated tensors are the inputs (the metric's definition); torch: raw parameters, "
                          "exp/sigmoid/cat per view in torch like GaussianModel's properties; folded: raw parameters "
                          "through rasterization_from_parameters (activations folded into the kernels)")
+    ap.add_argument("--views-per-call", type=int, default=4,
+                    help="views batched into one rasterization() call (viewmats [C,4,4]); 1 = one call per view as in the reference's loop")
     ap.add_argument("--forward-only", action="store_true", help="no_grad forward renders only (cfg5-style latency runs; not the headline metric)")
     return ap.parse_args()
 
@@ -236,21 +238,29 @@ def ours(args):
         lrs = dict(means=1e-3, quats=1e-3, scales=1e-2, opacities=5e-2, colors=2.5e-3, log_scales=1e-2,
                    logit_opacities=5e-2, sh_0=2.5e-3, sh_rest=1.25e-4)  # configs/*.yaml learning rates
         optimizer = FusedAdam([{"params": [p_], "lr": lrs[k], "name": k} for k, p_ in zip(names, params)], eps=1e-15)
-    bg = sc_cpu.background[None].to(dev)
-    Wc_cpu, Wa_cpu = loss_weights(sc_cpu.seed, 1, H, W)
-    # pinned host copies of the per-step inputs (camera + loss weights = the "target image" of a training step)
+    # The step's V views are rendered by V / C calls of C views each (viewmats [C,4,4], the call's own batching):
+    # every kernel of a call then works on C views' worth of tiles, which fills the 148 SMs where one view's
+    # longest tiles would leave most of them idle.  C = 1 is the reference's one-view-per-call loop.
+    C = 1 if args.forward_only else max(1, min(args.views_per_call, V))  # forward-only runs report per-frame latency
+    if V % C:
+        raise SystemExit("--views-per-call must divide the number of views per rank")
+    n_calls = V // C
+    bg = sc_cpu.background[None].expand(C, 3).contiguous().to(dev)
+    Wc_cpu, Wa_cpu = loss_weights(sc_cpu.seed, C, H, W)  # one "target image" worth of loss weights per view
+    # pinned host copies of the per-step inputs (cameras + loss weights = the target images of a training step)
     pin = lambda t: t.contiguous().pin_memory()
-    host_views = [(pin(sc_cpu.viewmats[v:v + 1]), pin(sc_cpu.Ks[v:v + 1])) for v in my_views]
+    host_views = [(pin(sc_cpu.viewmats[my_views[g * C]:my_views[g * C] + C]), pin(sc_cpu.Ks[my_views[g * C]:my_views[g * C] + C]))
+                  for g in range(n_calls)]
     host_Wc, host_Wa = pin(Wc_cpu), pin(Wa_cpu)
     dev_views = [(a.to(dev), b.to(dev)) for a, b in host_views]
     dev_Wc, dev_Wa = host_Wc.to(dev), host_Wa.to(dev)
-    h2d_bytes = V * (host_views[0][0].numel() * 4 + host_views[0][1].numel() * 4 + host_Wc.numel() * 4 + host_Wa.numel() * 4)
+    h2d_bytes = n_calls * (host_views[0][0].numel() * 4 + host_views[0][1].numel() * 4 + host_Wc.numel() * 4 + host_Wa.numel() * 4)
     d2h_bytes = 4
 
-    # View pipelining (easy_gaussian_splatting_b200/training.py): consecutive views alternate between two CUDA
-    # streams so that the forward pass of view i+1 overlaps the backward pass of view i.
+    # View pipelining (easy_gaussian_splatting_b200/training.py): consecutive calls alternate between two CUDA
+    # streams so that the forward pass of call i+1 overlaps the backward pass of call i.
     from easy_gaussian_splatting_b200.training import ViewPipeline
-    pipelined = not args.no_view_pipelining and not args.forward_only
+    pipelined = not args.no_view_pipelining and not args.forward_only and n_calls > 1
     pipe = ViewPipeline(dev, enabled=pipelined)
     view_streams = pipe.streams
 
@@ -302,9 +312,9 @@ def ours(args):
                   ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
 
     def stage_view(k):
-        """k-th view since the start (view k % V of its step) -> staging buffer k % 2, on the copy stream"""
+        """k-th call since the start (call k % n_calls of its step) -> staging buffer k % 2, on the copy stream"""
         b = stage[k % 2]
-        i = k % V
+        i = k % n_calls
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(b["free"])  # the view that used this buffer two views ago has finished
             b["vm"].copy_(host_views[i][0], non_blocking=True)
@@ -328,7 +338,7 @@ def ours(args):
             e2e_state["staged"] = k0
         fork_streams()
         losses = []
-        for k in range(k0, k0 + V):
+        for k in range(k0, k0 + n_calls):
             b = stage[k % 2]
             # the copy of the NEXT view (the first view of the next step included) overlaps this view's rendering
             stage_view(k + 1)
@@ -340,7 +350,7 @@ def ours(args):
         join_streams()
         for l_ in losses:
             total += l_.detach()
-        e2e_state["next"] = k0 + V
+        e2e_state["next"] = k0 + n_calls
         if world > 1:
             bucket.all_reduce()
             stats.all_reduce_delta(before)
@@ -388,18 +398,19 @@ def ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "views_per_rank_per_step": V, "views_per_step": world * V,
+        "config": {"workload": workload_name(args), "views_per_rank_per_step": V, "views_per_step": world * V, "views_per_call": C,
                    "view_pipelining": pipelined, "activations": args.activations,
                    "l2": "inputs larger than L2 (236 MB parameters + 96 MB splat/gradient records per view vs 126 MB L2)",
                    "exchange": "none (1 GPU)" if world == 1 else "NCCL all-reduce of the flat 236 B/Gaussian gradient bucket + 12 B/Gaussian densify stats each step"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e_total / args.steps,
-                "what": "rasterization() fwd+bwd per view with the view's camera and loss weights (target-image sized) copied "
+                "what": "rasterization() fwd+bwd per call with its views' cameras and loss weights (one target-image-sized buffer per view) copied "
                         "from pinned host memory inside the timed region (double buffered on a copy stream) and the step's loss "
                         "read back with .item(); Gaussian parameters stay resident (they are the model, "
                         "/root/reference/train.py:97-108)"},
-        "gpu_launches": 23 * V * args.steps + (1 if args.train_step else 0) * args.steps,  # 23 of our kernels per view (profiles/r1g_launches.csv)
+        # 23 of our kernels per rasterization() call + backward (profiles/r1g_launches.csv), whatever its view count
+        "gpu_launches": 23 * n_calls * args.steps + (1 if args.train_step else 0) * args.steps,
     }
     if args.n_gaussians:
         line["invalid"] = "N overridden (debug run)"
@@ -433,8 +444,9 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     import ctypes
     pk = peaks()
     means, quats, scales, opac, colors = [p.detach() for p in params]
-    vm, K = view
-    N = means.shape[0]
+    vm, K = view  # the C views of one call
+    Cn = vm.shape[0]
+    N = means.shape[0] * Cn  # (camera, Gaussian) pairs one launch works on
     tw, th = stages.tile_grid(W, H)
 
     def tm(fn, reps=reps, inner=4):
@@ -469,9 +481,9 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     tpg, ids_u, flat_u = stages.isect_tiles(proj["means2d"], proj["radii"], proj["depths"], 16, tw, th, sort=False,
                                             tiles_per_gauss=proj["tiles_per_gauss"])
     n_isects = ids_u.numel()
-    nbits = stages.tile_n_bits(tw, th)
+    nbits = stages.tile_n_bits(tw, th) + stages.camera_n_bits(Cn)
     ids, flat = stages.radix_sort_pairs(ids_u.clone(), flat_u.clone(), 32 + nbits)
-    offs = stages.isect_offset_encode(ids, 1, tw, th)
+    offs = stages.isect_offset_encode(ids, Cn, tw, th)
     rc, ra, last, pairs = stages.rasterize_fwd(proj["splats"], offs, flat, bg, W, H, count_pairs=True)
     p_eval, p_acc = int(pairs[0]), int(pairs[1])
     v_splats = stages.rasterize_bwd(proj["splats"], offs, flat, bg, W, H, ra, last, Wc, Wa)
@@ -499,12 +511,12 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
         stages.radix_sort_pairs(ka, va, 32 + nbits)
     copy_ms = tm(lambda: (ka.copy_(ids_u), va.copy_(flat_u)))
     u["radix_sort_u64"] = tm(sort_once) - copy_ms
-    u["offset_encode"] = tm(lambda: stages.isect_offset_encode(ids, 1, tw, th))
+    u["offset_encode"] = tm(lambda: stages.isect_offset_encode(ids, Cn, tw, th))
     passes = math.ceil((32 + nbits) / 8)
     sort_bytes = (8 + 24 * passes) * n_isects
     work = {  # algorithmic bytes (HBM-bound stages) or flops (blend) per launch, BASELINE.md section 4 (frozen)
         "projection_sh_fwd": ("hbm", 68 * N + 204 * n_vis),
-        "binning_fast_path": ("hbm", 44 * N + 12 * n_isects + sort_bytes + 8 * n_isects + 4 * tw * th),
+        "binning_fast_path": ("hbm", 44 * N + 12 * n_isects + sort_bytes + 8 * n_isects + 4 * Cn * tw * th),
         "rasterize_fwd": ("fp32", 16 * p_eval + 10 * p_acc),
         "rasterize_bwd": ("fp32", 16 * p_eval + 54 * p_acc),
         "projection_sh_bwd": ("hbm", 108 * N + 12 * N + 408 * n_vis + 192 * (N - n_vis)),
@@ -513,7 +525,7 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
         "scan": ("hbm", 12 * N),
         "emit_u64": ("hbm", 32 * N + 12 * n_isects),
         "radix_sort_u64": ("hbm", sort_bytes),
-        "offset_encode": ("hbm", 8 * n_isects + 4 * tw * th),
+        "offset_encode": ("hbm", 8 * n_isects + 4 * Cn * tw * th),
     }
 
     def line(ms, bound, w):
@@ -544,7 +556,7 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     roof["peak_source"] = pk["source"] if roof["bound"] == "hbm" else \
         f"measured live: dependent-FMA probe kernel, {fp32_peak:.1f} TFLOP/s (theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)"
     return {"roofline": roof, "stages": stages_out, "stages_standalone": standalone,
-            "scene_stats": {"N": N, "N_vis": n_vis, "n_isects": n_isects, "isects_per_visible": n_isects / max(n_vis, 1),
+            "scene_stats": {"views_per_launch": Cn, "N": N // Cn, "N_vis": n_vis, "n_isects": n_isects, "isects_per_visible": n_isects / max(n_vis, 1),
                             "P_eval": p_eval, "P_acc": p_acc, "fp32_peak_tflops_measured": fp32_peak,
                             "sum_stage_ms": sum(t.values())}}
 

@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_fwd_kernel(
   for (int i = 0; i < PX; ++i) pxf[i] = opaque((float)(wv.x0 + i) + 0.5f);
 #pragma unroll
   for (int i = 0; i < PY; ++i) pyf[i] = opaque((float)(wv.y0 + i) + 0.5f);
+  const float2 npx2 = make_float2(-pxf[0], -pxf[PX - 1]), npy2 = make_float2(-pyf[0], -pyf[PY - 1]);
   const float rx_lo = opaque(wv.rx_lo), rx_hi = opaque(wv.rx_hi), ry_lo = opaque(wv.ry_lo), ry_hi = opaque(wv.ry_hi);
   // T[j] > 0: transmittance of a live pixel; T[j] < 0: pixel finished, |T[j]| is its final transmittance
   // (the "done" flag lives in the sign bit, so liveness is one more FSETP in the accept test).
@@ -272,15 +273,34 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_fwd_kernel(
         for (int e = 0; e < 2; ++e) {
           // q(dx,dy) = -log2(e) * sigma, separable parts shared by the rows / columns of the pixel block
           const float la = (0.5f * kNegLog2e) * g0[e].z, lc = (0.5f * kNegLog2e) * g1[e].x, lb = kNegLog2e * g0[e].w;
-          float qx[PX], bx[PX], dy[PY], qy[PY];
+          if constexpr (PX == 2 && PY == 2) {
+            // packed fp32 (FADD2 / FMUL2 / FFMA2, sm_100): the two pixels of a row share one instruction.  The
+            // kernel is issue bound, not FMA-pipe bound (profiles/r1g), so halving the issue slots of the
+            // arithmetic is what counts.
+            const float2 dx = __fadd2_rn(make_float2(g0[e].x, g0[e].x), npx2);
+            const float2 dyv = __fadd2_rn(make_float2(g0[e].y, g0[e].y), npy2);
+            const float2 qx = __fmul2_rn(__fmul2_rn(dx, make_float2(la, la)), dx);
+            const float2 bx = __fmul2_rn(dx, make_float2(lb, lb));
+            const float2 qy = __fmul2_rn(__fmul2_rn(dyv, make_float2(lc, lc)), dyv);
+            const float2 o2 = make_float2(g1[e].y, g1[e].y);
+            const float2 q0 = __ffma2_rn(bx, make_float2(dyv.x, dyv.x), __fadd2_rn(qx, make_float2(qy.x, qy.x)));
+            const float2 q1 = __ffma2_rn(bx, make_float2(dyv.y, dyv.y), __fadd2_rn(qx, make_float2(qy.y, qy.y)));
+            const float2 a0 = __fmul2_rn(o2, make_float2(fast_ex2(q0.x), fast_ex2(q0.y)));
+            const float2 a1 = __fmul2_rn(o2, make_float2(fast_ex2(q1.x), fast_ex2(q1.y)));
+            q[e][0] = q0.x; q[e][1] = q0.y; q[e][2] = q1.x; q[e][3] = q1.y;
+            alpha[e][0] = fminf(kAlphaMax, a0.x); alpha[e][1] = fminf(kAlphaMax, a0.y);
+            alpha[e][2] = fminf(kAlphaMax, a1.x); alpha[e][3] = fminf(kAlphaMax, a1.y);
+          } else {
+            float qx[PX], bx[PX], dy[PY], qy[PY];
 #pragma unroll
-          for (int i = 0; i < PX; ++i) { const float dx = g0[e].x - pxf[i]; qx[i] = la * dx * dx; bx[i] = lb * dx; }
+            for (int i = 0; i < PX; ++i) { const float dx = g0[e].x - pxf[i]; qx[i] = la * dx * dx; bx[i] = lb * dx; }
 #pragma unroll
-          for (int i = 0; i < PY; ++i) { dy[i] = g0[e].y - pyf[i]; qy[i] = lc * dy[i] * dy[i]; }
+            for (int i = 0; i < PY; ++i) { dy[i] = g0[e].y - pyf[i]; qy[i] = lc * dy[i] * dy[i]; }
 #pragma unroll
-          for (int j = 0; j < NP; ++j) {
-            q[e][j] = fmaf(bx[j % PX], dy[j / PX], qx[j % PX] + qy[j / PX]);
-            alpha[e][j] = fminf(kAlphaMax, g1[e].y * fast_ex2(q[e][j]));
+            for (int j = 0; j < NP; ++j) {
+              q[e][j] = fmaf(bx[j % PX], dy[j / PX], qx[j % PX] + qy[j / PX]);
+              alpha[e][j] = fminf(kAlphaMax, g1[e].y * fast_ex2(q[e][j]));
+            }
           }
         }
         float tmax = -1.0f;
@@ -288,21 +308,52 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_fwd_kernel(
         for (int e = 0; e < 2; ++e) {
           if (e == 0 || has_b) {
             const int cur = e == 0 ? cur_a : cur_b;
+            if constexpr (PX == 2 && PY == 2) {
+              // branch-free, two pixels (one row of the lane's block) per packed instruction: a rejected or
+              // finished pixel blends with weight 0 (exact: c + g * 0 = c) and keeps its T
 #pragma unroll
-            for (int j = 0; j < NP; ++j) {
-              if (T[j] > 0.f && q[e][j] <= 0.f && alpha[e][j] >= kAlphaMin) {  // sigma >= 0  <=>  q <= 0
-                const float next_T = T[j] * (1.0f - alpha[e][j]);
-                if (next_T <= kTMin) {
-                  T[j] = -T[j];  // finished: this Gaussian is not blended
-                  if (COUNT) term[j] = batch_start + cur;
-                } else {
-                  const float w = alpha[e][j] * T[j];
-                  cr[j] = fmaf(g1[e].z, w, cr[j]);
-                  cg[j] = fmaf(g1[e].w, w, cg[j]);
-                  cb[j] = fmaf(cbl[e], w, cb[j]);
-                  last[j] = batch_start + cur;
-                  T[j] = next_T;
-                  if (COUNT) ++n_acc;
+              for (int r = 0; r < 2; ++r) {
+                const int j0 = 2 * r, j1 = 2 * r + 1;
+                const float2 a2 = make_float2(alpha[e][j0], alpha[e][j1]);
+                const float2 T2 = make_float2(T[j0], T[j1]);
+                const float2 nT = __fmul2_rn(T2, __ffma2_rn(a2, make_float2(-1.f, -1.f), make_float2(1.f, 1.f)));
+                float2 w = __fmul2_rn(a2, T2);
+                const bool acc0 = T[j0] > 0.f && q[e][j0] <= 0.f && alpha[e][j0] >= kAlphaMin;
+                const bool acc1 = T[j1] > 0.f && q[e][j1] <= 0.f && alpha[e][j1] >= kAlphaMin;
+                const bool bl0 = acc0 && nT.x > kTMin, bl1 = acc1 && nT.y > kTMin;
+                w.x = bl0 ? w.x : 0.f;
+                w.y = bl1 ? w.y : 0.f;
+                if (acc0) T[j0] = bl0 ? nT.x : -T[j0];  // not blended: finished, sign flags it
+                if (acc1) T[j1] = bl1 ? nT.y : -T[j1];
+                if (bl0) last[j0] = batch_start + cur;
+                if (bl1) last[j1] = batch_start + cur;
+                if (COUNT) {
+                  if (acc0 && !bl0) term[j0] = batch_start + cur;
+                  if (acc1 && !bl1) term[j1] = batch_start + cur;
+                  n_acc += (bl0 ? 1u : 0u) + (bl1 ? 1u : 0u);
+                }
+                const float2 c_r = __ffma2_rn(make_float2(g1[e].z, g1[e].z), w, make_float2(cr[j0], cr[j1]));
+                const float2 c_g = __ffma2_rn(make_float2(g1[e].w, g1[e].w), w, make_float2(cg[j0], cg[j1]));
+                const float2 c_b = __ffma2_rn(make_float2(cbl[e], cbl[e]), w, make_float2(cb[j0], cb[j1]));
+                cr[j0] = c_r.x; cr[j1] = c_r.y; cg[j0] = c_g.x; cg[j1] = c_g.y; cb[j0] = c_b.x; cb[j1] = c_b.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < NP; ++j) {
+                if (T[j] > 0.f && q[e][j] <= 0.f && alpha[e][j] >= kAlphaMin) {  // sigma >= 0  <=>  q <= 0
+                  const float next_T = T[j] * (1.0f - alpha[e][j]);
+                  if (next_T <= kTMin) {
+                    T[j] = -T[j];  // finished: this Gaussian is not blended
+                    if (COUNT) term[j] = batch_start + cur;
+                  } else {
+                    const float w = alpha[e][j] * T[j];
+                    cr[j] = fmaf(g1[e].z, w, cr[j]);
+                    cg[j] = fmaf(g1[e].w, w, cg[j]);
+                    cb[j] = fmaf(cbl[e], w, cb[j]);
+                    last[j] = batch_start + cur;
+                    T[j] = next_T;
+                    if (COUNT) ++n_acc;
+                  }
                 }
               }
             }
