@@ -54,6 +54,8 @@ constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.999f;
 constexpr float kTMin = 1e-4f;
 constexpr float kNegLog2e = -1.4426950408889634f;
+constexpr int kGradValues = 11;  // floats of the packed gradient record that the backward blend produces
+constexpr int kRedStride = 36;   // words per row of the backward kernel's warp-sum scratch (32 lanes + 4: conflict-free LDS.128)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -446,8 +448,10 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_bwd_kernel(
   constexpr int NP = G::NP;
   constexpr int RPL = G::RPL, kBatch = G::kBatch;
   __shared__ __align__(16) WarpStage<kBatch> stage[G::kWarps];
+  __shared__ __align__(16) float red_all[G::kWarps][kGradValues * kRedStride];
   const int lane = threadIdx.x & 31;
   WarpStage<kBatch>& st = stage[threadIdx.x >> 5];
+  float* red = red_all[threadIdx.x >> 5];
   const WarpView wv = warp_setup<G>(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total);
   {
     const int len = wv.range_end - wv.range_start;
@@ -459,11 +463,13 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_bwd_kernel(
   for (int i = 0; i < PX; ++i) pxf[i] = opaque((float)(wv.x0 + i) + 0.5f);
 #pragma unroll
   for (int i = 0; i < PY; ++i) pyf[i] = opaque((float)(wv.y0 + i) + 0.5f);
+  const float2 npx2 = make_float2(-pxf[0], -pxf[PX - 1]), npy2 = make_float2(-pyf[0], -pyf[PY - 1]);
   const float rx_lo = opaque(wv.rx_lo), rx_hi = opaque(wv.rx_hi), ry_lo = opaque(wv.ry_lo), ry_hi = opaque(wv.ry_hi);
 
-  // per-pixel replay state.  bdot = sum over the Gaussians behind of fac * (rgb . v_colour), which is all
-  // the backward pass needs of the colour accumulated behind; tfv = T_final * (v_alpha_out - bg . v_colour).
-  float T[NP], bdot[NP], vcr[NP], vcg[NP], vcb[NP], tfv[NP];
+  // per-pixel replay state.  nbt_ = tfv - bdot with bdot = sum over the Gaussians behind of fac * (rgb . v_colour),
+  // which is all the backward pass needs of the colour accumulated behind, and
+  // tfv = T_final * (v_alpha_out - bg . v_colour).
+  float T[NP], nbt_[NP], vcr[NP], vcg[NP], vcb[NP];
   int bin_final[NP];
   int my_last = -1;
   float bgr = 0.f, bgg = 0.f, bgb = 0.f;
@@ -473,7 +479,7 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_bwd_kernel(
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const int x = wv.x0 + (j % PX), y = wv.y0 + (j / PX);
-    T[j] = 1.f; bdot[j] = 0.f; vcr[j] = 0.f; vcg[j] = 0.f; vcb[j] = 0.f; tfv[j] = 0.f;
+    T[j] = 1.f; nbt_[j] = 0.f; vcr[j] = 0.f; vcg[j] = 0.f; vcb[j] = 0.f;
     bin_final[j] = -1;  // pixels outside the image never match any index
     if (x < width && y < height) {
       const size_t pix = ((size_t)wv.cam * height + y) * width + x;
@@ -483,7 +489,7 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_bwd_kernel(
       vcr[j] = v_render_colors[pix * 3 + 0];
       vcg[j] = v_render_colors[pix * 3 + 1];
       vcb[j] = v_render_colors[pix * 3 + 2];
-      tfv[j] = T_final * (v_render_alphas[pix] - (bgr * vcr[j] + bgg * vcg[j] + bgb * vcb[j]));
+      nbt_[j] = T_final * (v_render_alphas[pix] - (bgr * vcr[j] + bgg * vcg[j] + bgb * vcb[j]));
     }
     my_last = max(my_last, bin_final[j]);
   }
@@ -542,63 +548,152 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_bwd_kernel(
       const float4 g0 = s[cur * 3 + 0];  // x, y, conic_a, conic_b
       const float4 g1 = s[cur * 3 + 1];  // conic_c, opacity, r, g
       const float la = (0.5f * kNegLog2e) * g0.z, lc = (0.5f * kNegLog2e) * g1.x, lb = kNegLog2e * g0.w;
-      float dx[PX], qx[PX], bx[PX], dy[PY], qy[PY];
-#pragma unroll
-      for (int i = 0; i < PX; ++i) { dx[i] = g0.x - pxf[i]; qx[i] = la * dx[i] * dx[i]; bx[i] = lb * dx[i]; }
-#pragma unroll
-      for (int i = 0; i < PY; ++i) { dy[i] = g0.y - pyf[i]; qy[i] = lc * dy[i] * dy[i]; }
-      float ov[NP];  // opacity * exp(-sigma), before the 0.999 clamp
-      bool valid[NP];
-      bool any_valid = false;
-#pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        const float q = fmaf(bx[j % PX], dy[j / PX], qx[j % PX] + qy[j / PX]);  // -log2(e) * sigma
-        ov[j] = g1.y * fast_ex2(q);
-        valid[j] = idx <= bin_final[j] && q <= 0.f && ov[j] >= kAlphaMin;  // min(.999, ov) >= 1/255 <=> ov >= 1/255
-        any_valid = any_valid || valid[j];
-      }
-      if (!__any_sync(0xffffffffu, any_valid)) continue;  // warp-uniform
       const float cbl = s[cur * 3 + 2].x;
       const float inv_o = fast_rcp(g1.y);
       // v[2], v[3], v[4] accumulate sx*dx, sx*dy, sy*dy (the 0.5 of the conic gradient is applied once, after
       // the per-lane sum); v[5] accumulates ov * v_alpha (the 1/opacity is applied after the per-lane sum).
-      float v[16];
+      float v[kGradValues];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = 0.f;
+      for (int k = 0; k < kGradValues; ++k) v[k] = 0.f;
+      if constexpr (PX == 2 && PY == 2) {
+        // Packed fp32 (FADD2 / FMUL2 / FFMA2): the two pixels of a row of the lane's block share one instruction,
+        // and the replay is branch free — a pixel that does not take part gets alpha = 0 and ov = 0, which makes
+        // every one of its contributions an exact zero and leaves its running state untouched.
+        const float2 dx2 = __fadd2_rn(make_float2(g0.x, g0.x), npx2);
+        const float2 dy2 = __fadd2_rn(make_float2(g0.y, g0.y), npy2);
+        const float2 qx = __fmul2_rn(__fmul2_rn(dx2, make_float2(la, la)), dx2);
+        const float2 bx = __fmul2_rn(dx2, make_float2(lb, lb));
+        const float2 qy = __fmul2_rn(__fmul2_rn(dy2, make_float2(lc, lc)), dy2);
+        const float2 o2 = make_float2(g1.y, g1.y);
+        float2 ov2[2];
+        bool valid[NP];
+        bool any_valid = false;
 #pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        if (valid[j]) {
-          const float ddx = dx[j % PX], ddy = dy[j / PX];
-          const float alpha = fminf(kAlphaMax, ov[j]);
-          const float ra = fast_rcp(1.0f - alpha);
-          T[j] *= ra;  // transmittance in front of this Gaussian
-          const float fac = alpha * T[j];
-          v[6] = fmaf(fac, vcr[j], v[6]);
-          v[7] = fmaf(fac, vcg[j], v[7]);
-          v[8] = fmaf(fac, vcb[j], v[8]);
-          const float cdot = fmaf(cbl, vcb[j], fmaf(g1.w, vcg[j], g1.z * vcr[j]));
-          const float v_alpha = fmaf(T[j], cdot, -ra * (bdot[j] - tfv[j]));
-          bdot[j] = fmaf(cdot, fac, bdot[j]);
-          if (ov[j] <= kAlphaMax) {  // the clamp was inactive: alpha depends on sigma and opacity
-            const float w = ov[j] * v_alpha;  // = opacity * d(alpha)/d(opacity) * v_alpha = -v_sigma
-            const float sx = -w * ddx, sy = -w * ddy;
-            v[2] = fmaf(sx, ddx, v[2]);
-            v[3] = fmaf(sx, ddy, v[3]);
-            v[4] = fmaf(sy, ddy, v[4]);
-            const float gx = fmaf(g0.w, sy, g0.z * sx);
-            const float gy = fmaf(g1.x, sy, g0.w * sx);
-            v[0] += gx;
-            v[1] += gy;
-            v[9] += fabsf(gx);
-            v[10] += fabsf(gy);
-            v[5] += w;
+        for (int r = 0; r < 2; ++r) {
+          const float dyr = r == 0 ? dy2.x : dy2.y, qyr = r == 0 ? qy.x : qy.y;
+          const float2 q = __ffma2_rn(bx, make_float2(dyr, dyr), __fadd2_rn(qx, make_float2(qyr, qyr)));
+          ov2[r] = __fmul2_rn(o2, make_float2(fast_ex2(q.x), fast_ex2(q.y)));
+          valid[2 * r] = idx <= bin_final[2 * r] && q.x <= 0.f && ov2[r].x >= kAlphaMin;
+          valid[2 * r + 1] = idx <= bin_final[2 * r + 1] && q.y <= 0.f && ov2[r].y >= kAlphaMin;
+          any_valid = any_valid || valid[2 * r] || valid[2 * r + 1];
+        }
+        if (!__any_sync(0xffffffffu, any_valid)) continue;  // warp-uniform
+        float2 s_gx = make_float2(0.f, 0.f), s_gy = s_gx, s_xx = s_gx, s_xy = s_gx, s_yy = s_gx, s_w = s_gx, s_r = s_gx,
+               s_g = s_gx, s_b = s_gx, s_ax = s_gx, s_ay = s_gx;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int j0 = 2 * r, j1 = 2 * r + 1;
+          const float dyr = r == 0 ? dy2.x : dy2.y;
+          const float2 dyb = make_float2(dyr, dyr);
+          float2 ae, oe;  // alpha and ov of the pixels that take part, 0 for the others
+          ae.x = valid[j0] ? fminf(kAlphaMax, ov2[r].x) : 0.f;
+          ae.y = valid[j1] ? fminf(kAlphaMax, ov2[r].y) : 0.f;
+          oe.x = (valid[j0] && ov2[r].x <= kAlphaMax) ? ov2[r].x : 0.f;  // clamp inactive: alpha depends on sigma, opacity
+          oe.y = (valid[j1] && ov2[r].y <= kAlphaMax) ? ov2[r].y : 0.f;
+          const float2 om = __ffma2_rn(ae, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+          const float2 ra = make_float2(fast_rcp(om.x), fast_rcp(om.y));
+          const float2 Tn = __fmul2_rn(make_float2(T[j0], T[j1]), ra);  // transmittance in front of this Gaussian
+          const float2 Tf = make_float2(valid[j0] ? Tn.x : T[j0], valid[j1] ? Tn.y : T[j1]);
+          T[j0] = Tf.x; T[j1] = Tf.y;
+          const float2 fac = __fmul2_rn(ae, Tf);
+          const float2 vr2 = make_float2(vcr[j0], vcr[j1]), vg2 = make_float2(vcg[j0], vcg[j1]), vb2 = make_float2(vcb[j0], vcb[j1]);
+          s_r = __ffma2_rn(fac, vr2, s_r);
+          s_g = __ffma2_rn(fac, vg2, s_g);
+          s_b = __ffma2_rn(fac, vb2, s_b);
+          const float2 cdot = __ffma2_rn(make_float2(cbl, cbl), vb2,
+                                         __ffma2_rn(make_float2(g1.w, g1.w), vg2, __fmul2_rn(make_float2(g1.z, g1.z), vr2)));
+          // nbt = tfv - bdot (kept negated so that v_alpha is one FMUL2 + one FFMA2)
+          const float2 nbt = make_float2(nbt_[j0], nbt_[j1]);
+          const float2 v_alpha = __ffma2_rn(Tf, cdot, __fmul2_rn(ra, nbt));
+          const float2 nfac = make_float2(-fac.x, -fac.y);
+          const float2 nbt_new = __ffma2_rn(cdot, nfac, nbt);
+          nbt_[j0] = nbt_new.x; nbt_[j1] = nbt_new.y;
+          const float2 w = __fmul2_rn(oe, v_alpha);  // = opacity * d(alpha)/d(opacity) * v_alpha = -v_sigma
+          const float2 nw = make_float2(-w.x, -w.y);
+          const float2 sx = __fmul2_rn(nw, dx2), sy = __fmul2_rn(nw, dyb);
+          s_xx = __ffma2_rn(sx, dx2, s_xx);
+          s_xy = __ffma2_rn(sx, dyb, s_xy);
+          s_yy = __ffma2_rn(sy, dyb, s_yy);
+          const float2 gx = __ffma2_rn(make_float2(g0.w, g0.w), sy, __fmul2_rn(make_float2(g0.z, g0.z), sx));
+          const float2 gy = __ffma2_rn(make_float2(g1.x, g1.x), sy, __fmul2_rn(make_float2(g0.w, g0.w), sx));
+          s_gx = __fadd2_rn(s_gx, gx);
+          s_gy = __fadd2_rn(s_gy, gy);
+          s_ax = __fadd2_rn(s_ax, make_float2(fabsf(gx.x), fabsf(gx.y)));
+          s_ay = __fadd2_rn(s_ay, make_float2(fabsf(gy.x), fabsf(gy.y)));
+          s_w = __fadd2_rn(s_w, w);
+        }
+        v[0] = s_gx.x + s_gx.y; v[1] = s_gy.x + s_gy.y; v[2] = s_xx.x + s_xx.y; v[3] = s_xy.x + s_xy.y;
+        v[4] = s_yy.x + s_yy.y; v[5] = s_w.x + s_w.y; v[6] = s_r.x + s_r.y; v[7] = s_g.x + s_g.y;
+        v[8] = s_b.x + s_b.y; v[9] = s_ax.x + s_ax.y; v[10] = s_ay.x + s_ay.y;
+      } else {
+        float dx[PX], qx[PX], bx[PX], dy[PY], qy[PY];
+#pragma unroll
+        for (int i = 0; i < PX; ++i) { dx[i] = g0.x - pxf[i]; qx[i] = la * dx[i] * dx[i]; bx[i] = lb * dx[i]; }
+#pragma unroll
+        for (int i = 0; i < PY; ++i) { dy[i] = g0.y - pyf[i]; qy[i] = lc * dy[i] * dy[i]; }
+        float ov[NP];  // opacity * exp(-sigma), before the 0.999 clamp
+        bool valid[NP];
+        bool any_valid = false;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const float q = fmaf(bx[j % PX], dy[j / PX], qx[j % PX] + qy[j / PX]);  // -log2(e) * sigma
+          ov[j] = g1.y * fast_ex2(q);
+          valid[j] = idx <= bin_final[j] && q <= 0.f && ov[j] >= kAlphaMin;  // min(.999, ov) >= 1/255 <=> ov >= 1/255
+          any_valid = any_valid || valid[j];
+        }
+        if (!__any_sync(0xffffffffu, any_valid)) continue;  // warp-uniform
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          if (valid[j]) {
+            const float ddx = dx[j % PX], ddy = dy[j / PX];
+            const float alpha = fminf(kAlphaMax, ov[j]);
+            const float ra = fast_rcp(1.0f - alpha);
+            T[j] *= ra;  // transmittance in front of this Gaussian
+            const float fac = alpha * T[j];
+            v[6] = fmaf(fac, vcr[j], v[6]);
+            v[7] = fmaf(fac, vcg[j], v[7]);
+            v[8] = fmaf(fac, vcb[j], v[8]);
+            const float cdot = fmaf(cbl, vcb[j], fmaf(g1.w, vcg[j], g1.z * vcr[j]));
+            const float v_alpha = fmaf(T[j], cdot, ra * nbt_[j]);
+            nbt_[j] = fmaf(cdot, -fac, nbt_[j]);
+            if (ov[j] <= kAlphaMax) {  // the clamp was inactive: alpha depends on sigma and opacity
+              const float w = ov[j] * v_alpha;  // = opacity * d(alpha)/d(opacity) * v_alpha = -v_sigma
+              const float sx = -w * ddx, sy = -w * ddy;
+              v[2] = fmaf(sx, ddx, v[2]);
+              v[3] = fmaf(sx, ddy, v[3]);
+              v[4] = fmaf(sy, ddy, v[4]);
+              const float gx = fmaf(g0.w, sy, g0.z * sx);
+              const float gy = fmaf(g1.x, sy, g0.w * sx);
+              v[0] += gx;
+              v[1] += gy;
+              v[9] += fabsf(gx);
+              v[10] += fabsf(gy);
+              v[5] += w;
+            }
           }
         }
       }
       v[2] *= 0.5f; v[4] *= 0.5f; v[5] *= inv_o;
-      const float total = warp_reduce_scatter16(v, lane);
+      // Warp sum of the 11 values through shared memory: every lane stores its 11 partials (row k = value k,
+      // row stride 36 words: conflict free), then lane 2k+p adds half p of row k (4 LDS.128, a packed add tree),
+      // one shuffle joins the halves and lane 2k issues the RED.  ~40 issue slots against ~90 for the 16-slot
+      // shuffle reduce-scatter (32 selects + 16 SHFL + 16 FADD) — the kernel is issue bound.
+      __syncwarp();  // the previous survivor's row reads are complete
+#pragma unroll
+      for (int k = 0; k < kGradValues; ++k) red[k * kRedStride + lane] = v[k];
+      __syncwarp();
       const int out_slot = lane >> 1;
-      if ((lane & 1) == 0 && out_slot < 11) atomicAdd(v_splats + (size_t)sid[cur] * EGS_SPLAT_FLOATS + out_slot, total);
+      const float4* row = reinterpret_cast<const float4*>(red + min(out_slot, kGradValues - 1) * kRedStride + (lane & 1) * 16);
+      const float4 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3];
+      float2 s0 = __fadd2_rn(make_float2(r0.x, r0.y), make_float2(r0.z, r0.w));
+      float2 s1 = __fadd2_rn(make_float2(r1.x, r1.y), make_float2(r1.z, r1.w));
+      float2 s2 = __fadd2_rn(make_float2(r2.x, r2.y), make_float2(r2.z, r2.w));
+      float2 s3 = __fadd2_rn(make_float2(r3.x, r3.y), make_float2(r3.z, r3.w));
+      s0 = __fadd2_rn(__fadd2_rn(s0, s1), __fadd2_rn(s2, s3));
+      float total = s0.x + s0.y;
+      total += __shfl_xor_sync(0xffffffffu, total, 1);
+      if ((lane & 1) == 0 && out_slot < kGradValues)
+        atomicAdd(v_splats + (size_t)sid[cur] * EGS_SPLAT_FLOATS + out_slot, total);
     }
     __syncwarp();  // buffer b&1, its ids and the list are free again
   }
