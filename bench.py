@@ -409,8 +409,8 @@ def ours(args):
                         "from pinned host memory inside the timed region (double buffered on a copy stream) and the step's loss "
                         "read back with .item(); Gaussian parameters stay resident (they are the model, "
                         "/root/reference/train.py:97-108)"},
-        # 23 of our kernels per rasterization() call + backward (profiles/r1g_launches.csv), whatever its view count
-        "gpu_launches": 23 * n_calls * args.steps + (1 if args.train_step else 0) * args.steps,
+        "gpu_launches": (launches_per_call(stages, C, W, H, backward=not args.forward_only) * n_calls
+                         + (1 if args.train_step else 0)) * args.steps,
     }
     if args.n_gaussians:
         line["invalid"] = "N overridden (debug run)"
@@ -436,6 +436,17 @@ def ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def launches_per_call(stages, C, W, H, backward=True):
+    """Our kernels launched by one rasterization() call of C views and its backward pass (checked against the ncu
+    launch lists profiles/r1h_launches.csv, C = 1: 23, and profiles/r1i_launches.csv, C = 4: 24):
+    projection fwd, 3 visible-scan kernels, 2 x (histogram + histogram scan), the onesweep passes of both sorts,
+    3 tile-count scan kernels, emit, finalize, blend fwd | blend bwd, projection bwd, densify-stat update."""
+    tw, th = stages.tile_grid(W, H)
+    p64 = math.ceil((32 + stages.camera_n_bits(C)) / 8)
+    p32 = math.ceil(max(1, int(C * tw * th - 1).bit_length()) / 8)
+    return 14 + p64 + p32 + (3 if backward else 0)
 
 
 def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):

@@ -23,10 +23,14 @@
 // under independent thread scheduling: measured with ncu on the first version of the forward kernel,
 // 1.9 active threads per instruction and a 20x slowdown (profiles/r1a_*).
 //
+// Packed fp32.  Both kernels are issue bound (ncu: 80 % issue-active, FMA pipe 40 % before this change), so in
+// the 2x2 layout the two pixels of a row share FADD2 / FMUL2 / FFMA2 instructions (sm_100) and the per-pixel
+// updates are branch free: a pixel that does not take part blends with weight 0.
+//
 // Backward: per-pixel back-to-front replay from the warp's own last blended index; the 11 per-Gaussian
-// partial gradients are summed over the lane's 4 pixels in registers, combined across the warp with a
-// 16-slot shuffle reduce-scatter (16 SHFL instead of the 55 of a per-value butterfly), and 11 lanes issue
-// one coalesced RED.ADD.F32 into the packed 48-byte gradient record of the Gaussian.
+// partial gradients are summed over the lane's 4 pixels in registers, then over the warp through a 1.6 KB
+// shared-memory scratch (11 conflict-free row stores, 4 LDS.128 + a packed add tree per lane, one shuffle), and
+// 11 lanes issue one coalesced RED.ADD.F32 into the packed 48-byte gradient record of the Gaussian.
 #include <stdlib.h>
 
 #include "egs_common.cuh"
@@ -406,36 +410,6 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_fwd_kernel(
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-
-// 16-slot reduce-scatter across the warp: on return every lane holds the warp total of slot
-// (lane >> 1).  16 shuffles.
-__device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane) {
-  float a8[8], a4[4], a2[2];
-  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float send = b4 ? v[j] : v[j + 8];
-    const float keep = b4 ? v[j + 8] : v[j];
-    a8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float send = b3 ? a8[j] : a8[j + 4];
-    const float keep = b3 ? a8[j + 4] : a8[j];
-    a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const float send = b2 ? a4[j] : a4[j + 2];
-    const float keep = b2 ? a4[j + 2] : a4[j];
-    a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  const float send = b1 ? a2[0] : a2[1];
-  const float keep = b1 ? a2[1] : a2[0];
-  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  r += __shfl_xor_sync(0xffffffffu, r, 1);
-  return r;
-}
 
 template <int PX, int PY>
 __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_bwd_kernel(
