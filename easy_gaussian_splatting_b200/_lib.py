@@ -24,6 +24,10 @@ _SIGNATURES = {
                                      I32, I32, I32, P, P, P, P, P, P, P, P]),
     "egs_projection_bwd": (c_int32, [I32, I32, P, P, P, P, I32, I32, I32, P, P, I32, I32, F32, P, P, P, P,
                                      P, P, P, P, P, P, P]),
+    "egs_projection_fwd_antialiased": (c_int32, [I32, I32, P, P, P, P, P, I32, I32, I32, P, P, I32, I32, F32, F32, F32,
+                                                 F32, I32, I32, I32, P, P, P, P, P, P, P, P, P]),
+    "egs_projection_bwd_antialiased": (c_int32, [I32, I32, P, P, P, P, P, I32, I32, I32, P, P, I32, I32, F32, P, P, P,
+                                                 P, P, P, P, P, P, P, P]),
     "egs_projection_fwd_raw": (c_int32, [I32, I32, P, P, P, P, P, P, I32, P, P, I32, I32, F32, F32, F32, F32,
                                          I32, I32, I32, P, P, P, P, P, P, P, P]),
     "egs_projection_bwd_raw": (c_int32, [I32, I32, P, P, P, P, P, P, I32, P, P, I32, I32, F32, P, P, P, P,

@@ -83,12 +83,14 @@ struct ProjState {
   float rz, rz2, tx, ty;
   float J00, J02, J11, J12;
   float a, b, d, det;         // blurred 2D covariance and its determinant
+  float det_orig;             // determinant before the eps2d blur (antialiased mode: compensation factor)
   bool clamp_x, clamp_y;      // fov clamp active
 };
 
 struct ProjOut {
   float m2x, m2y, depth, ca, cb, cc;
   float lambda_max;           // largest eigenvalue of the blurred 2D covariance (clamped like the radius)
+  float comp;                 // sqrt(max(0, det_orig / det_blur)): opacity compensation of rasterize_mode="antialiased"
   int32_t radius;             // 0 = culled
 };
 
@@ -96,7 +98,7 @@ struct ProjOut {
 EGS_HD bool project_fwd(const float mean[3], const float quat[4], const float scale[3], const Camera& cam,
                         float width, float height, float eps2d, float near_plane, float far_plane,
                         float radius_clip, ProjState& st, ProjOut& o) {
-  o.m2x = 0.f; o.m2y = 0.f; o.depth = 0.f; o.ca = 0.f; o.cb = 0.f; o.cc = 0.f; o.radius = 0; o.lambda_max = 0.f;
+  o.m2x = 0.f; o.m2y = 0.f; o.depth = 0.f; o.ca = 0.f; o.cb = 0.f; o.cc = 0.f; o.radius = 0; o.lambda_max = 0.f; o.comp = 0.f;
   quat_to_rotmat(quat, st.R, st.qn, st.inv_norm);
   const float* R = st.R;
   float* M = st.M;
@@ -157,10 +159,11 @@ EGS_HD bool project_fwd(const float mean[3], const float quat[4], const float sc
   float d = B11 * J11 + B12 * J12;
   float m2x = (fx * x) * rz + cam.cx;
   float m2y = (fy * y) * rz + cam.cy;
+  const float det_orig = a * d - b * b;
   a = a + eps2d;
   d = d + eps2d;
   float det = a * d - b * b;
-  st.a = a; st.b = b; st.d = d; st.det = det;
+  st.a = a; st.b = b; st.d = d; st.det = det; st.det_orig = det_orig;
   if (!(det > 0.f)) return false;
   float mid = 0.5f * (a + d);
   float v1 = mid + sqrtf(fmaxf(mid * mid - det, 0.01f));
@@ -174,6 +177,7 @@ EGS_HD bool project_fwd(const float mean[3], const float quat[4], const float sc
   o.cc = a * inv_det;
   o.m2x = m2x; o.m2y = m2y; o.depth = z;
   o.lambda_max = v1;
+  o.comp = sqrtf(fmaxf(0.f, det_orig / det));
   o.radius = (int32_t)fminf(radius, 2147483520.0f);
   return true;
 }
@@ -204,7 +208,7 @@ EGS_HD void tile_rect(float m2x, float m2y, int32_t radius, float tile_size, int
 // v_mean[3], v_quat[4], v_scale[3].
 EGS_HD void project_bwd(const ProjState& st, const float scale[3], const Camera& cam, float v_m2x, float v_m2y,
                         float v_depth, float v_ca, float v_cb, float v_cc, const ProjOut& o, float v_mean[3],
-                        float v_quat[4], float v_scale[3]) {
+                        float v_quat[4], float v_scale[3], float v_comp = 0.f, float eps2d = 0.f) {
   // conic = inverse(cov2d'):  V = -Q * G * Q with G = [[v_ca, v_cb/2],[v_cb/2, v_cc]]
   float q00 = o.ca, q01 = o.cb, q11 = o.cc;
   float g00 = v_ca, g01 = 0.5f * v_cb, g11 = v_cc;
@@ -213,6 +217,16 @@ EGS_HD void project_bwd(const ProjState& st, const float scale[3], const Camera&
   float V00 = -(h00 * q00 + h01 * q01);
   float V01 = -(h00 * q01 + h01 * q11);
   float V11 = -(h10 * q01 + h11 * q11);
+  if (v_comp != 0.f) {
+    // antialiased mode: comp^2 = det_orig / det_blur, so d comp^2 / d cov2d = ((1 - comp^2) conic - eps2d det(conic) I)
+    // (gsplat 1.0.0 add_blur_vjp, including its 1e-6 guard on the division by comp)
+    const float vs = v_comp * 0.5f / (o.comp + 1e-6f);
+    const float om = 1.0f - o.comp * o.comp;
+    const float detc = q00 * q11 - q01 * q01;
+    V00 += vs * (om * q00 - eps2d * detc);
+    V01 += vs * (om * q01);
+    V11 += vs * (om * q11 - eps2d * detc);
+  }
   // cov2d = J Sc J^T ;  v_Sc = J^T V J ; v_J = 2 V J Sc
   float J00 = st.J00, J02 = st.J02, J11 = st.J11, J12 = st.J12;
   const float* k = st.k;

@@ -24,6 +24,10 @@ struct ProjFwdParams {
   // `sh_rest` the [N,15,3] remainder — exp / sigmoid / cat are folded into this kernel
   int raw;
   const float* sh_rest;
+  // rasterize_mode="antialiased": opacity is multiplied by the compensation factor sqrt(det_orig / det_blur),
+  // which is also written to compensations[C,N]
+  int antialiased;
+  float* compensations;
 };
 
 // exactly torch's CUDA elementwise formulas, so the folded path reproduces exp()/sigmoid() of the caller
@@ -90,7 +94,8 @@ __global__ void __launch_bounds__(kProjThreads) projection_fwd_kernel(const Proj
       const float* cp = p.sh + (p.colors_per_camera ? idx : (size_t)n) * 3;
       rgb[0] = __ldg(cp + 0); rgb[1] = __ldg(cp + 1); rgb[2] = __ldg(cp + 2);
     }
-    const float opac = __ldg(p.opacities + n);
+    float opac = __ldg(p.opacities + n);
+    if (p.antialiased) opac = opac * o.comp;
     float4* s = p.splats + idx * 3;
     s[0] = make_float4(o.m2x, o.m2y, o.ca, o.cb);
     s[1] = make_float4(o.cc, opac, rgb[0], rgb[1]);
@@ -102,6 +107,7 @@ __global__ void __launch_bounds__(kProjThreads) projection_fwd_kernel(const Proj
   p.depths[idx] = o.depth;
   p.conics[idx * 3 + 0] = o.ca; p.conics[idx * 3 + 1] = o.cb; p.conics[idx * 3 + 2] = o.cc;
   p.colors[idx * 3 + 0] = rgb[0]; p.colors[idx * 3 + 1] = rgb[1]; p.colors[idx * 3 + 2] = rgb[2];
+  if (p.antialiased) p.compensations[idx] = o.comp;
 }
 
 
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const 
 
   float mean[3] = {0.f, 0.f, 0.f};
   ProjOut o;
-  o.m2x = 0.f; o.m2y = 0.f; o.depth = 0.f; o.ca = 0.f; o.cb = 0.f; o.cc = 0.f; o.radius = 0; o.lambda_max = 0.f;
+  o.m2x = 0.f; o.m2y = 0.f; o.depth = 0.f; o.ca = 0.f; o.cb = 0.f; o.cc = 0.f; o.radius = 0; o.lambda_max = 0.f; o.comp = 0.f;
   bool vis = false;
   if (in_range) {
     float quat[4], scale[3];
@@ -278,6 +284,7 @@ __global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const 
     rgb[2] = fmaxf(b + 0.5f, 0.f);
     float opac = __ldg(p.opacities + n);
     if (p.raw) opac = act_sigmoid(opac);
+    if (p.antialiased) opac = opac * o.comp;
     float4* s = p.splats + idx * 3;
     s[0] = make_float4(o.m2x, o.m2y, o.ca, o.cb);
     s[1] = make_float4(o.cc, opac, rgb[0], rgb[1]);
@@ -289,6 +296,7 @@ __global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const 
   p.depths[idx] = o.depth;
   p.conics[idx * 3 + 0] = o.ca; p.conics[idx * 3 + 1] = o.cb; p.conics[idx * 3 + 2] = o.cc;
   p.colors[idx * 3 + 0] = rgb[0]; p.colors[idx * 3 + 1] = rgb[1]; p.colors[idx * 3 + 2] = rgb[2];
+  if (p.antialiased) p.compensations[idx] = o.comp;
 }
 
 struct ProjBwdParams {
@@ -302,7 +310,8 @@ struct ProjBwdParams {
   float *v_means, *v_quats, *v_scales, *v_opacities, *v_sh;
   int raw;                    // see ProjFwdParams: inputs are raw parameters, outputs are their gradients
   const float* sh_rest;
-  const float* opacities;     // logits (raw mode only: needed for the sigmoid VJP)
+  const float* opacities;     // logits (raw mode: needed for the sigmoid VJP) / opacities (antialiased mode)
+  int antialiased;            // v_splats' opacity slot is d L / d (opacity * compensation)
   float* v_sh_rest;
   float2* absgrad;  // nullable [C,N]: sum over pixels of |d L / d means2d|, copied out of the gradient records
 };
@@ -369,8 +378,10 @@ __global__ void __launch_bounds__(kProjBwdThreads) projection_bwd_kernel(const P
       project_fwd(mean, quat, scale, *cam, p.width, p.height, p.eps2d, 0.f, INFINITY, -1.f, st, o);
       // (culling thresholds are irrelevant here: visibility was decided by the forward pass; the
       //  off-screen test cannot fire differently because it only depends on the same values.)
-      if (o.radius > 0) project_bwd(st, scale, *cam, v_m2x, v_m2y, 0.f, g0.z, g0.w, g1.x, o, v_mean, v_quat, v_scale);
-      v_opac += g1.y;
+      float v_comp = 0.f, w_opac = 1.f;
+      if (p.antialiased) { v_comp = g1.y * __ldg(p.opacities + n); w_opac = o.comp; }
+      if (o.radius > 0) project_bwd(st, scale, *cam, v_m2x, v_m2y, 0.f, g0.z, g0.w, g1.x, o, v_mean, v_quat, v_scale, v_comp, p.eps2d);
+      v_opac += g1.y * w_opac;
       v_rgb[0] = g1.z; v_rgb[1] = g1.w; v_rgb[2] = g2.x;
       if (has_sh) {
         if (!co_loaded) { load_coeffs<VEC4>(p.sh + (size_t)n * p.K * 3, nb * 3, co); co_loaded = true; }
@@ -510,9 +521,15 @@ __global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const 
         ProjState st;
         ProjOut o;
         project_fwd(mean, quat, scale, *cam, p.width, p.height, p.eps2d, 0.f, INFINITY, -1.f, st, o);
-        if (o.radius > 0) project_bwd(st, scale, *cam, v_m2x, v_m2y, 0.f, g0.z, g0.w, g1.x, o, v_mean, v_quat, v_scale);
+        float v_comp = 0.f, w_opac = 1.f;
+        if (p.antialiased) {
+          float op = __ldg(p.opacities + n);
+          if (p.raw) op = act_sigmoid(op);
+          v_comp = g1.y * op; w_opac = o.comp;
+        }
+        if (o.radius > 0) project_bwd(st, scale, *cam, v_m2x, v_m2y, 0.f, g0.z, g0.w, g1.x, o, v_mean, v_quat, v_scale, v_comp, p.eps2d);
+        v_opac += g1.y * w_opac;
       }
-      v_opac += g1.y;
       // SH: rgb = max(sum + 0.5, 0) -> gradient passes where the stored colour is > 0
       const float* col = p.colors + idx * 3;
       const float vr = (col[0] > 0.f) ? g1.z : 0.f, vg = (col[1] > 0.f) ? g1.w : 0.f, vb = (col[2] > 0.f) ? g2.x : 0.f;
@@ -600,7 +617,8 @@ static int projection_fwd_impl(int32_t C, int32_t N, const float* means, const f
                                int32_t width, int32_t height, float eps2d, float near_plane, float far_plane,
                                float radius_clip, int32_t tile_size, int32_t tile_width, int32_t tile_height,
                                int32_t* radii, float* means2d, float* depths, float* conics, float* colors,
-                               int32_t* tiles_per_gauss, float* splats, egs_stream_t stream) {
+                               int32_t* tiles_per_gauss, float* splats, egs_stream_t stream,
+                               float* compensations = nullptr) {
   const int raw = sh_rest != nullptr;
   EGS_REQUIRE(C >= 0 && N >= 0, "projection_fwd: negative sizes C=%d N=%d", C, N);
   EGS_REQUIRE(C <= 65535, "projection_fwd: C=%d exceeds 65535 cameras per call", C);
@@ -619,6 +637,7 @@ static int projection_fwd_impl(int32_t C, int32_t N, const float* means, const f
   p.radii = radii; p.means2d = means2d; p.depths = depths; p.conics = conics; p.colors = colors;
   p.tiles_per_gauss = tiles_per_gauss; p.splats = reinterpret_cast<float4*>(splats);
   p.raw = raw; p.sh_rest = sh_rest;
+  p.antialiased = compensations != nullptr; p.compensations = compensations;
   dim3 grid((unsigned)ceil_div(N, kProjThreads), (unsigned)C);
   const bool vec4 = sh_degree >= 0 && (K * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(sh_coeffs) % 16 == 0);
   if (raw) {
@@ -647,6 +666,19 @@ extern "C" int egs_projection_fwd(int32_t C, int32_t N, const float* means, cons
                              stream);
 }
 
+extern "C" int egs_projection_fwd_antialiased(
+    int32_t C, int32_t N, const float* means, const float* quats, const float* scales, const float* opacities,
+    const float* sh_coeffs, int32_t K, int32_t sh_degree, int32_t colors_per_camera, const float* viewmats,
+    const float* Ks, int32_t width, int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
+    int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii, float* means2d, float* depths,
+    float* conics, float* colors, int32_t* tiles_per_gauss, float* splats, float* compensations, egs_stream_t stream) {
+  EGS_REQUIRE(compensations != nullptr, "projection_fwd_antialiased: compensations output is required");
+  return projection_fwd_impl(C, N, means, quats, scales, opacities, sh_coeffs, nullptr, K, sh_degree, colors_per_camera,
+                             viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
+                             tile_width, tile_height, radii, means2d, depths, conics, colors, tiles_per_gauss, splats,
+                             stream, compensations);
+}
+
 extern "C" int egs_projection_fwd_raw(int32_t C, int32_t N, const float* means, const float* quats,
                                       const float* log_scales, const float* logit_opacities, const float* sh_0,
                                       const float* sh_rest, int32_t sh_degree, const float* viewmats, const float* Ks,
@@ -668,7 +700,7 @@ static int projection_bwd_impl(int32_t C, int32_t N, const float* means, const f
                                int32_t width, int32_t height, float eps2d, const int32_t* radii, const float* colors,
                                const float* v_splats, const float* v_means2d_extra, float* v_means, float* v_quats,
                                float* v_scales, float* v_opacities, float* v_sh_coeffs, float* v_sh_rest, float* absgrad,
-                               egs_stream_t stream) {
+                               egs_stream_t stream, int antialiased = 0) {
   const int raw = sh_rest != nullptr;
   EGS_REQUIRE(C >= 0 && N >= 0, "projection_bwd: negative sizes C=%d N=%d", C, N);
   EGS_REQUIRE(sh_degree <= 3, "projection_bwd: sh_degree %d > 3 is not supported", sh_degree);
@@ -682,6 +714,8 @@ static int projection_bwd_impl(int32_t C, int32_t N, const float* means, const f
   p.v_means = v_means; p.v_quats = v_quats; p.v_scales = v_scales; p.v_opacities = v_opacities; p.v_sh = v_sh_coeffs;
   p.absgrad = reinterpret_cast<float2*>(absgrad);
   p.raw = raw; p.sh_rest = sh_rest; p.opacities = opacities_raw; p.v_sh_rest = v_sh_rest;
+  p.antialiased = antialiased;
+  EGS_REQUIRE(!antialiased || opacities_raw != nullptr, "projection_bwd: antialiased mode needs the opacities");
   const bool vec4 = sh_degree >= 0 && (K * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(sh_coeffs) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(v_sh_coeffs) % 16 == 0);
   if (raw) {
@@ -712,6 +746,17 @@ extern "C" int egs_projection_bwd(int32_t C, int32_t N, const float* means, cons
   return projection_bwd_impl(C, N, means, quats, scales, nullptr, sh_coeffs, nullptr, K, sh_degree, colors_per_camera,
                              viewmats, Ks, width, height, eps2d, radii, colors, v_splats, v_means2d_extra, v_means,
                              v_quats, v_scales, v_opacities, v_sh_coeffs, nullptr, absgrad, stream);
+}
+
+extern "C" int egs_projection_bwd_antialiased(
+    int32_t C, int32_t N, const float* means, const float* quats, const float* scales, const float* opacities,
+    const float* sh_coeffs, int32_t K, int32_t sh_degree, int32_t colors_per_camera, const float* viewmats,
+    const float* Ks, int32_t width, int32_t height, float eps2d, const int32_t* radii, const float* colors,
+    const float* v_splats, const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
+    float* v_opacities, float* v_sh_coeffs, float* absgrad, egs_stream_t stream) {
+  return projection_bwd_impl(C, N, means, quats, scales, opacities, sh_coeffs, nullptr, K, sh_degree, colors_per_camera,
+                             viewmats, Ks, width, height, eps2d, radii, colors, v_splats, v_means2d_extra, v_means,
+                             v_quats, v_scales, v_opacities, v_sh_coeffs, nullptr, absgrad, stream, 1);
 }
 
 extern "C" int egs_projection_bwd_raw(int32_t C, int32_t N, const float* means, const float* quats,

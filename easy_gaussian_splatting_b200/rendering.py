@@ -50,6 +50,11 @@ class _LazyMeta(dict):
         return [self._resolve(k) for k in self.keys()]
 
 
+def _tag_absgrad(target: Tensor, absgrad: Tensor, packed_index: Optional[Tensor]) -> None:
+    """``meta["means2d"].absgrad`` in the layout of ``meta["means2d"]``: dense [C,N,2], or [nnz,2] when packed."""
+    target.absgrad = absgrad if packed_index is None else absgrad.reshape(-1, 2)[packed_index]
+
+
 class _Rasterization(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg):
@@ -57,7 +62,8 @@ class _Rasterization(torch.autograd.Function):
         C, N = viewmats.shape[0], means.shape[0]
         proj = stages.projection_fwd(means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree,
                                      eps2d=cfg["eps2d"], near_plane=cfg["near_plane"], far_plane=cfg["far_plane"],
-                                     radius_clip=cfg["radius_clip"])
+                                     radius_clip=cfg["radius_clip"], antialiased=cfg["antialiased"])
+        cfg["compensations"] = proj.get("compensations")  # non-differentiable side output, like the thunk below
         tw, th = stages.tile_grid(width, height)
         tiles_per_gauss = proj["tiles_per_gauss"]
         isect_ids_thunk, flatten_ids, isect_offsets = stages.isect_sorted(
@@ -71,7 +77,8 @@ class _Rasterization(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(means, quats, scales, colors, viewmats, Ks, backgrounds, proj["radii"], proj["colors"],
-                              proj["splats"], isect_offsets, flatten_ids, render_alphas, last_ids)
+                              proj["splats"], isect_offsets, flatten_ids, render_alphas, last_ids,
+                              opacities if cfg["antialiased"] else None)
         nondiff = (proj["radii"], proj["depths"], proj["conics"], proj["colors"], tiles_per_gauss,
                    flatten_ids, isect_offsets, last_ids)
         ctx.mark_non_differentiable(*nondiff)
@@ -80,7 +87,7 @@ class _Rasterization(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_colors, v_alphas, v_means2d, *_unused):
         (means, quats, scales, colors, viewmats, Ks, backgrounds, radii, colors_rgb, splats, isect_offsets,
-         flatten_ids, render_alphas, last_ids) = ctx.saved_tensors
+         flatten_ids, render_alphas, last_ids, aa_opacities) = ctx.saved_tensors
         cfg = ctx.cfg
         width, height = cfg["width"], cfg["height"]
         C = viewmats.shape[0]
@@ -93,11 +100,12 @@ class _Rasterization(torch.autograd.Function):
         ref = getattr(ctx, "means2d_ref", None) if cfg["absgrad"] else None
         target = ref() if ref is not None else None
         out = stages.projection_bwd(means, quats, scales, colors, viewmats, Ks, width, height, cfg["sh_degree"],
-                                    cfg["eps2d"], radii, colors_rgb, v_splats, v_means2d, want_absgrad=target is not None)
+                                    cfg["eps2d"], radii, colors_rgb, v_splats, v_means2d, want_absgrad=target is not None,
+                                    antialiased_opacities=aa_opacities)
         v_means, v_quats, v_scales, v_opac, v_cols = out[:5]
         if target is not None:
             # same contract as gsplat: attribute tagging on the tensor object handed out in meta
-            target.absgrad = out[5]
+            _tag_absgrad(target, out[5], getattr(ctx, "packed_index", None))
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[7]:
             v_bg = ((1.0 - render_alphas) * v_colors).sum(dim=(1, 2))
@@ -152,7 +160,7 @@ class _RasterizationRaw(torch.autograd.Function):
                                         height, cfg["sh_degree"], cfg["eps2d"], radii, colors_rgb, v_splats, v_means2d,
                                         want_absgrad=target is not None)
         if target is not None:
-            target.absgrad = out[6]
+            _tag_absgrad(target, out[6], None)
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[8]:
             v_bg = ((1.0 - render_alphas) * v_colors).sum(dim=(1, 2))
@@ -234,13 +242,10 @@ def rasterization(
     reference never requests raise ``NotImplementedError`` instead of silently approximating."""
     if render_mode != "RGB":
         raise NotImplementedError(f"render_mode={render_mode!r}: only 'RGB' is implemented (the reference's mode)")
-    if rasterize_mode != "classic":
-        raise NotImplementedError(f"rasterize_mode={rasterize_mode!r}: only 'classic' is implemented")
+    if rasterize_mode not in ("classic", "antialiased"):
+        raise ValueError(f"rasterize_mode must be 'classic' or 'antialiased', got {rasterize_mode!r}")
     if sparse_grad:
         raise NotImplementedError("sparse_grad=True is not implemented")
-    if packed:
-        raise NotImplementedError("packed=True is not implemented; the reference calls with packed=False "
-                                  "(model/gaussian.py:366) and results do not depend on it")
     if tile_size != stages.TILE_SIZE:
         raise NotImplementedError(f"tile_size={tile_size}: the blending kernels are specialised for 16")
     width, height = int(width), int(height)
@@ -251,22 +256,48 @@ def rasterization(
         raise NotImplementedError("gradients w.r.t. viewmats are not implemented (the reference never asks for them)")
     C = viewmats.shape[0]
     cfg = dict(width=width, height=height, sh_degree=sh_degree, eps2d=float(eps2d), near_plane=float(near_plane),
-               far_plane=float(far_plane), radius_clip=float(radius_clip), absgrad=bool(absgrad))
+               far_plane=float(far_plane), radius_clip=float(radius_clip), absgrad=bool(absgrad),
+               antialiased=rasterize_mode == "antialiased")
     outs = _Rasterization.apply(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg)
-    return _finish(outs, cfg, opacities[None].expand(C, -1), width, height, tile_size, C, absgrad)
+    opacities_cn = opacities.detach()[None].expand(C, -1)
+    comp = cfg.pop("compensations", None)
+    if comp is not None:
+        opacities_cn = opacities_cn * comp  # gsplat: meta["opacities"] = opacities * compensations
+    return _finish(outs, cfg, opacities_cn, width, height, tile_size, C, absgrad, packed=bool(packed))
 
 
-def _finish(outs, cfg, opacities_cn, width, height, tile_size, C, absgrad):
+def _finish(outs, cfg, opacities_cn, width, height, tile_size, C, absgrad, packed=False):
     (render_colors, render_alphas, means2d, radii, depths, conics, colors_rgb, tiles_per_gauss,
      flatten_ids, isect_offsets, _last_ids) = outs
     isect_ids = cfg.pop("isect_ids_thunk")
-    if absgrad and render_colors.grad_fn is not None:
+    cfg.pop("compensations", None)
+    camera_ids = gaussian_ids = None
+    node = render_colors.grad_fn
+    if packed:
+        # gsplat's packed layout: per-(camera, Gaussian) tensors hold only the nnz visible
+        # entries, in flat (camera, Gaussian) order, with camera_ids / gaussian_ids naming them, and flatten_ids
+        # index that packed list.  The kernels above still work on the dense [C,N] intermediates — this reproduces
+        # the packed INTERFACE, not upstream's memory saving; rendered images and gradients are the same either way.
+        N = radii.shape[1]
+        visible = radii.reshape(-1) > 0
+        packed_index = visible.nonzero(as_tuple=True)[0]  # one host sync (sizes the packed tensors), as upstream
+        camera_ids = torch.div(packed_index, N, rounding_mode="floor")
+        gaussian_ids = packed_index - camera_ids * N
+        rank = torch.cumsum(visible, 0, dtype=torch.int32) - 1  # flat (c,n) index -> row of the packed list
+        flatten_ids = rank[flatten_ids.long()]
+        means2d = means2d.reshape(-1, 2)[packed_index]  # differentiable gather: gradients on it reach the dense one
+        radii, depths, tiles_per_gauss = (t.reshape(-1)[packed_index] for t in (radii, depths, tiles_per_gauss))
+        conics, colors_rgb = (t.reshape(-1, 3)[packed_index] for t in (conics, colors_rgb))
+        opacities_cn = opacities_cn.reshape(-1)[packed_index]
+        if node is not None:
+            node.packed_index = packed_index
+    if absgrad and node is not None:
         # the backward node tags .absgrad on exactly this tensor object (weak: no reference cycle)
-        render_colors.grad_fn.means2d_ref = weakref.ref(means2d)
+        node.means2d_ref = weakref.ref(means2d)
     tw, th = stages.tile_grid(width, height)
     meta = _LazyMeta({
-        "camera_ids": None,
-        "gaussian_ids": None,
+        "camera_ids": camera_ids,
+        "gaussian_ids": gaussian_ids,
         "radii": radii,
         "means2d": means2d,
         "depths": depths,

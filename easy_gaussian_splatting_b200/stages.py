@@ -53,8 +53,11 @@ def camera_n_bits(C: int) -> int:
 def projection_fwd(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, colors: Tensor,
                    viewmats: Tensor, Ks: Tensor, width: int, height: int, sh_degree: Optional[int],
                    eps2d: float = 0.3, near_plane: float = 0.01, far_plane: float = 1e10,
-                   radius_clip: float = 0.0, tile_size: int = TILE_SIZE) -> Dict[str, Tensor]:
-    """g1+g2+count(g3).  colors: [N,K,3] SH coefficients when sh_degree is not None, else [N,3]/[C,N,3]."""
+                   radius_clip: float = 0.0, tile_size: int = TILE_SIZE,
+                   antialiased: bool = False) -> Dict[str, Tensor]:
+    """g1+g2+count(g3).  colors: [N,K,3] SH coefficients when sh_degree is not None, else [N,3]/[C,N,3].
+    antialiased: gsplat's rasterize_mode="antialiased" — adds out["compensations"] [C,N]; the splat records then
+    carry opacity * compensation."""
     lib = _lib.load()
     means, quats, scales = _f32c(means, "means"), _f32c(quats, "quats"), _f32c(scales, "scales")
     opacities, colors = _f32c(opacities, "opacities"), _f32c(colors, "colors")
@@ -75,13 +78,16 @@ def projection_fwd(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tens
         "tiles_per_gauss": torch.empty(C, N, dtype=torch.int32, device=dev),
         "splats": torch.empty(C, N, SPLAT_FLOATS, dtype=torch.float32, device=dev),
     }
+    args = (C, N, _ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(colors), K, deg, per_cam,
+            _ptr(viewmats), _ptr(Ks), int(width), int(height), float(eps2d), float(near_plane), float(far_plane),
+            float(radius_clip), int(tile_size), tw, th, _ptr(out["radii"]), _ptr(out["means2d"]), _ptr(out["depths"]),
+            _ptr(out["conics"]), _ptr(out["colors"]), _ptr(out["tiles_per_gauss"]), _ptr(out["splats"]))
     with torch.cuda.device(dev):
-        rc = lib.egs_projection_fwd(C, N, _ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(colors),
-                                    K, deg, per_cam, _ptr(viewmats), _ptr(Ks), int(width), int(height),
-                                    float(eps2d), float(near_plane), float(far_plane), float(radius_clip),
-                                    int(tile_size), tw, th, _ptr(out["radii"]), _ptr(out["means2d"]),
-                                    _ptr(out["depths"]), _ptr(out["conics"]), _ptr(out["colors"]),
-                                    _ptr(out["tiles_per_gauss"]), _ptr(out["splats"]), _stream(dev))
+        if antialiased:
+            out["compensations"] = torch.empty(C, N, dtype=torch.float32, device=dev)
+            rc = lib.egs_projection_fwd_antialiased(*args, _ptr(out["compensations"]), _stream(dev))
+        else:
+            rc = lib.egs_projection_fwd(*args, _stream(dev))
     _lib.check(rc, "egs_projection_fwd")
     return out
 
@@ -89,9 +95,9 @@ def projection_fwd(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tens
 def projection_bwd(means: Tensor, quats: Tensor, scales: Tensor, colors: Tensor, viewmats: Tensor, Ks: Tensor,
                    width: int, height: int, sh_degree: Optional[int], eps2d: float, radii: Tensor,
                    colors_rgb: Tensor, v_splats: Tensor, v_means2d_extra: Optional[Tensor] = None,
-                   want_absgrad: bool = False):
+                   want_absgrad: bool = False, antialiased_opacities: Optional[Tensor] = None):
     """g8+g9. -> v_means[N,3], v_quats[N,4], v_scales[N,3], v_opacities[N], v_colors (shape of colors)
-    (+ absgrad[C,N,2] when want_absgrad)."""
+    (+ absgrad[C,N,2] when want_absgrad).  antialiased_opacities: the opacities[N] of an antialiased forward."""
     lib = _lib.load()
     dev = means.device
     N, C = means.shape[0], viewmats.shape[0]
@@ -107,12 +113,15 @@ def projection_bwd(means: Tensor, quats: Tensor, scales: Tensor, colors: Tensor,
     if v_means2d_extra is not None:
         v_means2d_extra = _f32c(v_means2d_extra, "v_means2d")
     absgrad = torch.empty(C, N, 2, dtype=torch.float32, device=dev) if want_absgrad else None
+    tail = (_ptr(colors), K, deg, per_cam, _ptr(viewmats), _ptr(Ks), int(width), int(height), float(eps2d),
+            _ptr(radii), _ptr(colors_rgb), _ptr(v_splats), _ptr(v_means2d_extra), _ptr(v_means), _ptr(v_quats),
+            _ptr(v_scales), _ptr(v_opac), _ptr(v_colors), _ptr(absgrad), _stream(dev))
     with torch.cuda.device(dev):
-        rc = lib.egs_projection_bwd(C, N, _ptr(means), _ptr(quats), _ptr(scales), _ptr(colors), K, deg, per_cam,
-                                    _ptr(viewmats), _ptr(Ks), int(width), int(height), float(eps2d), _ptr(radii),
-                                    _ptr(colors_rgb), _ptr(v_splats), _ptr(v_means2d_extra), _ptr(v_means),
-                                    _ptr(v_quats), _ptr(v_scales), _ptr(v_opac), _ptr(v_colors), _ptr(absgrad),
-                                    _stream(dev))
+        if antialiased_opacities is not None:
+            aa_op = _f32c(antialiased_opacities, "opacities")
+            rc = lib.egs_projection_bwd_antialiased(C, N, _ptr(means), _ptr(quats), _ptr(scales), _ptr(aa_op), *tail)
+        else:
+            rc = lib.egs_projection_bwd(C, N, _ptr(means), _ptr(quats), _ptr(scales), *tail)
     _lib.check(rc, "egs_projection_bwd")
     if want_absgrad:
         return v_means, v_quats, v_scales, v_opac, v_colors, absgrad

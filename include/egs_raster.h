@@ -83,6 +83,29 @@ int egs_projection_bwd(int32_t C, int32_t N, const float* means, const float* qu
                        const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
                        float* v_opacities, float* v_sh_coeffs, float* absgrad, egs_stream_t stream);
 
+/* ---- §8f-4: rasterize_mode="antialiased" of the same two kernels ---------------------------------------------
+ * gsplat 1.0.0 `fully_fused_projection(calc_compensations=True)` + the Python glue `opacities * compensations`
+ * (the reference passes the default rasterize_mode="classic", model/gaussian.py:353-367; this is the other value the
+ * call accepts).  compensation = sqrt(max(0, det(cov2d) / det(cov2d + eps2d I))) is written to compensations[C,N]
+ * (0 for culled entries) and the splat records carry opacity * compensation.  The backward takes the activated
+ * opacities[N] as well: v_opacities = sum_c v_record_opacity * compensation, and the compensation's gradient
+ * v_record_opacity * opacity flows into the 2D covariance (gsplat's add_blur_vjp, 1e-6 guard included). */
+int egs_projection_fwd_antialiased(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                                   const float* opacities, const float* sh_coeffs, int32_t K, int32_t sh_degree,
+                                   int32_t colors_per_camera, const float* viewmats, const float* Ks, int32_t width,
+                                   int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
+                                   int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii,
+                                   float* means2d, float* depths, float* conics, float* colors,
+                                   int32_t* tiles_per_gauss, float* splats, float* compensations,
+                                   egs_stream_t stream);
+int egs_projection_bwd_antialiased(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                                   const float* opacities, const float* sh_coeffs, int32_t K, int32_t sh_degree,
+                                   int32_t colors_per_camera, const float* viewmats, const float* Ks, int32_t width,
+                                   int32_t height, float eps2d, const int32_t* radii, const float* colors,
+                                   const float* v_splats, const float* v_means2d_extra, float* v_means,
+                                   float* v_quats, float* v_scales, float* v_opacities, float* v_sh_coeffs,
+                                   float* absgrad, egs_stream_t stream);
+
 /* ---- §8f-2: the same two kernels fed with the reference's RAW parameters ---------------------------------------
  * GaussianModel recomputes scales = exp(log_scales), opacities = sigmoid(logit_opacities) and
  * shs = cat(sh_0, sh_rest) on every access (/root/reference/model/gaussian.py:97-107); the cat alone moves

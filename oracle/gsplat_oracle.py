@@ -144,11 +144,28 @@ def _project_elementwise(px, py, pz, cov6, V, fx, fy, cx, cy, width, height, eps
     d = B11 * J11 + B12 * J12
     m2x = (fx * x) * rz + cx
     m2y = (fy * y) * rz + cy
-    # add_blur
+    # add_blur (det_orig feeds the antialiased-mode compensation factor)
+    det_orig = a * d - b * b
     a = a + eps2d
     d = d + eps2d
     det = a * d - b * b
-    return x, y, z, a, b, d, det, m2x, m2y
+    return x, y, z, a, b, d, det, m2x, m2y, det_orig
+
+
+class _CompensationSqrt(torch.autograd.Function):
+    """compensation = sqrt(max(0, r)), r = det_orig / det_blur, with gsplat 1.0.0's add_blur_vjp guard:
+    d comp / d r = 0.5 / (comp + 1e-6)  (rasterize_mode="antialiased")."""
+
+    @staticmethod
+    def forward(ctx, r):
+        comp = _sqrt_rn(torch.clamp_min(r, 0.0))
+        ctx.save_for_backward(comp)
+        return comp
+
+    @staticmethod
+    def backward(ctx, v):
+        (comp,) = ctx.saved_tensors
+        return v * 0.5 / (comp + 1e-6)
 
 
 def _view_entries(viewmats: Tensor, Ks: Tensor, shape_suffix=(1,)):
@@ -177,8 +194,10 @@ def fully_fused_projection(
     near_plane: float = 0.01,
     far_plane: float = 1e10,
     radius_clip: float = 0.0,
-) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """Returns radii[C,N] int32, means2d[C,N,2], depths[C,N], conics[C,N,3].
+    calc_compensations: bool = False,
+):
+    """Returns radii[C,N] int32, means2d[C,N,2], depths[C,N], conics[C,N,3]
+    (+ compensations[C,N] = sqrt(max(0, det(cov2d) / det(cov2d + eps2d I))) when calc_compensations).
 
     Culled entries (radii == 0) have all float outputs exactly 0 (upstream leaves
     them uninitialised).  Differentiable w.r.t. means, quats,
@@ -197,7 +216,7 @@ def fully_fused_projection(
         return _project_elementwise(px, py, pz, cov6, Vd, fx_, fy_, cx_, cy_, wdt, hdt, eps2d)
 
     with torch.no_grad():
-        x, y, z, a, b, d, det, m2x, m2y = body(means.detach(), quats.detach(), scales.detach(),
+        x, y, z, a, b, d, det, m2x, m2y, det_orig = body(means.detach(), quats.detach(), scales.detach(),
                                               {k: v.detach() for k, v in V.items()},
                                               fx.detach(), fy.detach(), cx.detach(), cy.detach())
         valid = (z >= near_plane) & (z <= far_plane)  # cull if z < near or z > far
@@ -227,18 +246,24 @@ def fully_fused_projection(
         means2d = torch.stack([torch.where(valid, m2x, zero), torch.where(valid, m2y, zero)], -1)
         depths = torch.where(valid, z, zero).expand(C, N).contiguous()
         conics = torch.stack([torch.where(valid, ca, zero), torch.where(valid, cb, zero), torch.where(valid, cc, zero)], -1)
+        if calc_compensations:
+            comp = torch.where(valid, _sqrt_rn(torch.clamp_min(det_orig / det, 0.0)), zero).expand(C, N).contiguous()
+            return radii, means2d.contiguous(), depths, conics.contiguous(), comp
         return radii, means2d.contiguous(), depths, conics.contiguous()
 
     # differentiable recomputation on the valid subset only (keeps NaNs of culled
     # entries out of the backward pass)
     ci, ni = valid.nonzero(as_tuple=True)
     Vs = {k: v[ci, 0] for k, v in V.items()}
-    x, y, z, a, b, d, det, m2x, m2y = body(means[ni], quats[ni], scales[ni], Vs, fx[ci, 0], fy[ci, 0], cx[ci, 0], cy[ci, 0])
+    x, y, z, a, b, d, det, m2x, m2y, det_orig = body(means[ni], quats[ni], scales[ni], Vs, fx[ci, 0], fy[ci, 0], cx[ci, 0], cy[ci, 0])
     inv_det = 1.0 / det
     ca, cb, cc = d * inv_det, -(b * inv_det), a * inv_det
     means2d = means2d.index_put((ci, ni), torch.stack([m2x, m2y], -1))
     depths = depths.index_put((ci, ni), z)
     conics = conics.index_put((ci, ni), torch.stack([ca, cb, cc], -1))
+    if calc_compensations:
+        comp = torch.zeros(C, N, dtype=dt).index_put((ci, ni), _CompensationSqrt.apply(det_orig / det))
+        return radii, means2d, depths, conics, comp
     return radii, means2d, depths, conics
 
 
@@ -530,12 +555,15 @@ def rasterization(
 ) -> Tuple[Tensor, Tensor, Dict]:
     """Oracle for the whole path.  ``packed`` only changes upstream's memory layout, not
     results, so the oracle computes the dense (packed=False) form for either value."""
-    if render_mode != "RGB" or rasterize_mode != "classic" or sparse_grad:
-        raise NotImplementedError("oracle covers render_mode='RGB', rasterize_mode='classic', sparse_grad=False")
+    if render_mode != "RGB" or rasterize_mode not in ("classic", "antialiased") or sparse_grad:
+        raise NotImplementedError("oracle covers render_mode='RGB', rasterize_mode='classic'/'antialiased', sparse_grad=False")
     N, C = means.shape[0], viewmats.shape[0]
-    radii, means2d, depths, conics = fully_fused_projection(
-        means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip)
+    proj = fully_fused_projection(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                                  radius_clip, calc_compensations=rasterize_mode == "antialiased")
+    radii, means2d, depths, conics = proj[:4]
     opac = opacities[None, :].expand(C, N)
+    if rasterize_mode == "antialiased":
+        opac = opac * proj[4]  # gsplat 1.0.0 rendering.py: opacities = opacities * compensations
     if sh_degree is None:
         cols = colors[None].expand(C, N, colors.shape[-1]) if colors.dim() == 2 else colors
     else:

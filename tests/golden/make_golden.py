@@ -22,12 +22,15 @@ CASES = {
     "blob_c1": dict(kind="blob", N=96, width=48, height=32, fx=40.0, seed=101, n_views=1, sh_degree=3),
     "blob_c2_ragged": dict(kind="blob", N=64, width=37, height=21, fx=30.0, seed=102, n_views=2, sh_degree=2),
     "object_white": dict(kind="object", N=120, width=40, height=40, fx=60.0, seed=103, n_views=1, sh_degree=1, white_background=True),
+    # rasterize_mode="antialiased" (adds in_antialiased = 1 and the compensated opacities)
+    "blob_antialiased": dict(kind="blob", N=80, width=40, height=24, fx=34.0, seed=104, n_views=1, sh_degree=3, antialiased=True),
 }
 
 
 def run(case):
     kw = dict(case)
     deg = kw.pop("sh_degree")
+    mode = "antialiased" if kw.pop("antialiased", False) else "classic"
     sc = make_scene(**kw)
     names = ("means", "quats", "scales", "opacities", "colors")
     leaves = {k: getattr(sc, k).clone().requires_grad_(True) for k in names}
@@ -36,7 +39,7 @@ def run(case):
     counters = {}
     rc, ra, meta = O.rasterization(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"], leaves["colors"],
                                    sc.viewmats, sc.Ks, sc.width, sc.height, sh_degree=deg, packed=False, absgrad=True,
-                                   backgrounds=bg, counters=counters)
+                                   backgrounds=bg, counters=counters, rasterize_mode=mode)
     Wc, Wa = loss_weights(sc.seed, C, sc.height, sc.width)
     ((rc * Wc).sum() + (ra * Wa).sum()).backward()
     out = {f"in_{k}": getattr(sc, k).numpy() for k in names}
@@ -51,11 +54,16 @@ def run(case):
                absgrad=meta["means2d"].absgrad.numpy(), borderline=counters["borderline"].numpy(),
                P_eval=np.int64(counters["P_eval"]), P_acc=np.int64(counters["P_acc"]))
     out.update({f"grad_{k}": leaves[k].grad.numpy() for k in names})
+    if mode == "antialiased":
+        out.update(in_antialiased=np.int32(1), opacities=meta["opacities"].detach().numpy())
     return out
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate; default = all
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         out = run(case)
         path = Path(__file__).parent / f"{name}.npz"
         np.savez_compressed(path, **out)

@@ -32,17 +32,18 @@ def projection_fwd(sc, sh_degree, eps2d=0.3, near=0.01, far=1e10, clip=0.0, tile
     f = lambda t: np.ascontiguousarray(t.detach().numpy(), dtype=np.float32)
     out = dict(radii=np.zeros((C, N), np.int32), means2d=np.zeros((C, N, 2), np.float32),
                depths=np.zeros((C, N), np.float32), conics=np.zeros((C, N, 3), np.float32),
-               colors=np.zeros((C, N, 3), np.float32), tiles_per_gauss=np.zeros((C, N), np.int32))
+               colors=np.zeros((C, N, 3), np.float32), tiles_per_gauss=np.zeros((C, N), np.int32),
+               compensations=np.zeros((C, N), np.float32))
     arrs = [f(sc.means), f(sc.quats), f(sc.scales), f(sc.colors), f(sc.viewmats), f(sc.Ks)]
     lib.hh_projection_fwd(C, N, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), K, sh_degree, _p(arrs[4]),
                           _p(arrs[5]), sc.width, sc.height, ctypes.c_float(eps2d), ctypes.c_float(near),
                           ctypes.c_float(far), ctypes.c_float(clip), tile, tw, th, _p(out["radii"]),
                           _p(out["means2d"]), _p(out["depths"]), _p(out["conics"]), _p(out["colors"]),
-                          _p(out["tiles_per_gauss"]))
+                          _p(out["tiles_per_gauss"]), _p(out["compensations"]))
     return out
 
 
-def projection_bwd(sc, sh_degree, radii, colors, v_means2d, v_conics, v_colors, eps2d=0.3):
+def projection_bwd(sc, sh_degree, radii, colors, v_means2d, v_conics, v_colors, eps2d=0.3, v_comps=None):
     lib = load()
     C, N = sc.viewmats.shape[0], sc.means.shape[0]
     K = sc.colors.shape[1]
@@ -50,10 +51,11 @@ def projection_bwd(sc, sh_degree, radii, colors, v_means2d, v_conics, v_colors, 
     arrs = [f(sc.means), f(sc.quats), f(sc.scales), f(sc.colors), f(sc.viewmats), f(sc.Ks), f(colors), f(v_means2d),
             f(v_conics), f(v_colors)]
     radii = np.ascontiguousarray(radii, dtype=np.int32)
+    vc = None if v_comps is None else f(v_comps)
     out = dict(v_means=np.zeros((N, 3), np.float32), v_quats=np.zeros((N, 4), np.float32),
                v_scales=np.zeros((N, 3), np.float32), v_sh=np.zeros((N, K, 3), np.float32))
     lib.hh_projection_bwd(C, N, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), K, sh_degree, _p(arrs[4]),
                           _p(arrs[5]), sc.width, sc.height, ctypes.c_float(eps2d), _p(radii), _p(arrs[6]),
                           _p(arrs[7]), _p(arrs[8]), _p(arrs[9]), _p(out["v_means"]), _p(out["v_quats"]),
-                          _p(out["v_scales"]), _p(out["v_sh"]))
+                          _p(out["v_scales"]), _p(out["v_sh"]), None if v_comps is None else _p(vc))
     return out

@@ -15,7 +15,7 @@ extern "C" void hh_projection_fwd(int C, int N, const float* means, const float*
                                   const float* sh, int K, int deg, const float* viewmats, const float* Ks, int W,
                                   int H, float eps2d, float near_plane, float far_plane, float radius_clip,
                                   int tile_size, int tw, int th, int32_t* radii, float* means2d, float* depths,
-                                  float* conics, float* colors, int32_t* tiles) {
+                                  float* conics, float* colors, int32_t* tiles, float* comps /* nullable */) {
   for (int c = 0; c < C; ++c) {
     Camera cam;
     load_camera(viewmats + c * 16, Ks + c * 9, cam);
@@ -42,6 +42,7 @@ extern "C" void hh_projection_fwd(int C, int N, const float* means, const float*
       means2d[idx * 2] = o.m2x; means2d[idx * 2 + 1] = o.m2y; depths[idx] = o.depth;
       conics[idx * 3] = o.ca; conics[idx * 3 + 1] = o.cb; conics[idx * 3 + 2] = o.cc;
       colors[idx * 3] = rgb[0]; colors[idx * 3 + 1] = rgb[1]; colors[idx * 3 + 2] = rgb[2];
+      if (comps) comps[idx] = o.comp;
     }
   }
 }
@@ -50,7 +51,8 @@ extern "C" void hh_projection_bwd(int C, int N, const float* means, const float*
                                   const float* sh, int K, int deg, const float* viewmats, const float* Ks, int W,
                                   int H, float eps2d, const int32_t* radii, const float* colors,
                                   const float* v_means2d, const float* v_conics, const float* v_colors,
-                                  float* v_means, float* v_quats, float* v_scales, float* v_sh) {
+                                  float* v_means, float* v_quats, float* v_scales, float* v_sh,
+                                  const float* v_comps /* nullable: antialiased-mode compensation gradients */) {
   memset(v_means, 0, sizeof(float) * 3 * N);
   memset(v_quats, 0, sizeof(float) * 4 * N);
   memset(v_scales, 0, sizeof(float) * 3 * N);
@@ -66,7 +68,8 @@ extern "C" void hh_projection_bwd(int C, int N, const float* means, const float*
       project_fwd(means + 3 * n, quats + 4 * n, scales + 3 * n, cam, (float)W, (float)H, eps2d, 0.f, INFINITY, -1.f, st, o);
       if (o.radius > 0)
         project_bwd(st, scales + 3 * n, cam, v_means2d[idx * 2], v_means2d[idx * 2 + 1], 0.f, v_conics[idx * 3],
-                    v_conics[idx * 3 + 1], v_conics[idx * 3 + 2], o, v_means + 3 * n, v_quats + 4 * n, v_scales + 3 * n);
+                    v_conics[idx * 3 + 1], v_conics[idx * 3 + 2], o, v_means + 3 * n, v_quats + 4 * n, v_scales + 3 * n,
+                    v_comps ? v_comps[idx] : 0.f, eps2d);
       if (deg >= 0) {
         float co[48], vco[48];
         int nb = (deg + 1) * (deg + 1);

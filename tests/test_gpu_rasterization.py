@@ -118,13 +118,66 @@ def test_direct_colors_and_unsupported_modes():
     d = sc.to("cuda")
     rc, ra, _ = rasterization(d.means, d.quats, d.scales, d.opacities, cols.cuda(), d.viewmats, d.Ks, 80, 60, sh_degree=None, packed=False)
     assert (rc.cpu() - rc_o).abs().max() <= 1e-4 + 1e-2 * 0  # tiny scene: no borderline pixels expected
-    for kw in (dict(render_mode="RGB+D"), dict(rasterize_mode="antialiased"), dict(sparse_grad=True), dict(packed=True), dict(tile_size=8)):
+    for kw in (dict(render_mode="RGB+D"), dict(sparse_grad=True), dict(tile_size=8)):
         base = dict(sh_degree=3, packed=False)
         base.update(kw)
         with pytest.raises(NotImplementedError):
             rasterization(d.means, d.quats, d.scales, d.opacities, d.colors, d.viewmats, d.Ks, 80, 60, **base)
     with pytest.raises(RuntimeError):
         rasterization(sc.means, sc.quats, sc.scales, sc.opacities, sc.colors, sc.viewmats, sc.Ks, 80, 60, sh_degree=3, packed=False)
+
+
+@pytest.mark.parametrize("cfg", [CASES[0], CASES[1], CASES[3]])
+def test_antialiased_mode_parity(cfg):
+    """rasterize_mode="antialiased" (opacity * sqrt(det_orig / det_blur)) against the oracle."""
+    sc = make_scene(**cfg)
+    ref = oracle_run(sc, rasterize_mode="antialiased")
+    out = cuda_run(sc, rasterize_mode="antialiased")
+    m, mo = out["meta"], ref["meta"]
+    for k in ("radii", "flatten_ids", "isect_offsets"):
+        assert torch.equal(m[k].cpu(), mo[k])
+    assert torch.equal(m["opacities"].cpu(), mo["opacities"].detach())  # opacity * compensation, bit-exact
+    vis = mo["radii"] > 0
+    assert float(mo["opacities"][vis].max()) < float(sc.opacities.max()) + 1e-6
+    border = ref["counters"]["borderline"]
+    rep_c = image_report(out["colors"], ref["colors"], border)
+    rep_a = image_report(out["alphas"], ref["alphas"], border)
+    assert rep_c["max_clean"] <= 1e-4 and rep_a["max_clean"] <= 1e-4
+    errs = {k: rel_err(out["grads"][k], ref["grads"][k]) for k in PARAMS}
+    errs["absgrad"] = rel_err(out["absgrad"], ref["absgrad"])
+    print("grad rel errs", errs)
+    assert all(e <= 1e-3 for e in errs.values()), errs
+    # and it is a different image from the classic mode (the factor is < 1 for every visible Gaussian)
+    classic = cuda_run(sc, backward=False)
+    assert (classic["alphas"] - out["alphas"]).abs().max() > 1e-3
+
+
+@pytest.mark.parametrize("cfg", [CASES[1], CASES[3]])
+@pytest.mark.parametrize("mode", ["classic", "antialiased"])
+def test_packed_mode_matches_dense(cfg, mode):
+    """packed=True returns gsplat's packed layout (nnz visible (camera, Gaussian) entries in flat
+    order, camera_ids / gaussian_ids, flatten_ids into the packed list); images and gradients equal the dense call."""
+    sc = make_scene(**cfg)
+    dense = cuda_run(sc, rasterize_mode=mode)
+    pk = cuda_run(sc, rasterize_mode=mode, packed=True)
+    assert torch.equal(pk["colors"], dense["colors"]) and torch.equal(pk["alphas"], dense["alphas"])
+    md, mp = dense["meta"], pk["meta"]
+    C, N = md["radii"].shape
+    vis = md["radii"] > 0
+    cam, gid = vis.nonzero(as_tuple=True)
+    nnz = cam.numel()
+    assert torch.equal(mp["camera_ids"], cam) and torch.equal(mp["gaussian_ids"], gid)
+    assert mp["radii"].shape == (nnz,) and mp["means2d"].shape == (nnz, 2) and mp["conics"].shape == (nnz, 3)
+    for k in ("radii", "depths", "tiles_per_gauss", "opacities"):
+        assert torch.equal(mp[k], md[k][vis]), k
+    for k in ("means2d", "conics", "colors"):
+        assert torch.equal(mp[k].detach(), md[k].detach()[vis]), k
+    assert torch.equal(mp["isect_ids"], md["isect_ids"]) and torch.equal(mp["isect_offsets"], md["isect_offsets"])
+    flat = cam * N + gid
+    assert torch.equal(flat[mp["flatten_ids"].long()].int(), md["flatten_ids"])
+    assert pk["absgrad"].shape == (nnz, 2) and torch.equal(pk["absgrad"], dense["absgrad"][vis.cpu()])
+    for k in PARAMS:  # same kernels, same inputs: only the atomic order differs
+        assert rel_err(pk["grads"][k], dense["grads"][k]) <= 1e-5, k
 
 
 GOLDEN = sorted(__import__("pathlib").Path(__file__).parent.glob("golden/*.npz"))
@@ -140,8 +193,11 @@ def test_cuda_matches_committed_golden_vectors(path):
     p = {k: t(f"in_{k}").clone().requires_grad_(True) for k in PARAMS}
     W, H, deg = int(g["in_width"]), int(g["in_height"]), int(g["in_sh_degree"])
     rc, ra, meta = rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], t("in_viewmats"),
-                                 t("in_Ks"), W, H, sh_degree=deg, packed=False, absgrad=True, backgrounds=t("in_background"))
+                                 t("in_Ks"), W, H, sh_degree=deg, packed=False, absgrad=True, backgrounds=t("in_background"),
+                                 rasterize_mode="antialiased" if "in_antialiased" in g else "classic")
     ((rc * t("in_Wc")).sum() + (ra * t("in_Wa")).sum()).backward()
+    if "in_antialiased" in g:
+        assert torch.equal(meta["opacities"].cpu(), torch.from_numpy(g["opacities"]))
     for k in ("radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"):
         assert torch.equal(meta[k].cpu(), torch.from_numpy(g[k])), k
     assert torch.equal(meta["means2d"].detach().cpu(), torch.from_numpy(g["means2d"]))

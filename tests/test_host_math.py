@@ -26,6 +26,9 @@ def test_projection_forward_bit_exact(cfg):
     assert np.array_equal(h["means2d"], m2.numpy())
     assert np.array_equal(h["depths"], dep.numpy())
     assert np.array_equal(h["conics"], con.numpy())
+    comp = O.fully_fused_projection(sc.means, sc.quats, sc.scales, sc.viewmats, sc.Ks, sc.width, sc.height,
+                                    calc_compensations=True)[4]
+    assert np.array_equal(h["compensations"], comp.numpy())  # antialiased-mode factor, bit-exact too
     tw, th = -(-sc.width // 16), -(-sc.height // 16)
     tpg, _, _ = O.isect_tiles(m2, radii, dep, 16, tw, th, sort=False)
     assert np.array_equal(h["tiles_per_gauss"], tpg.numpy())
@@ -66,3 +69,30 @@ def test_projection_sh_backward_vs_fp64_autograd(cfg, deg):
         assert rel <= 2e-5, (name, rel)
     nb = (deg + 1) ** 2
     assert float(np.abs(out["v_sh"][:, nb:]).sum()) == 0.0  # inactive bands get exactly zero
+
+
+@pytest.mark.parametrize("cfg", [CASES[0], CASES[3]])
+def test_compensation_backward_vs_fp64_autograd(cfg):
+    """rasterize_mode="antialiased": the gradient of the compensation factor through the 2D covariance
+    (gsplat 1.0.0 add_blur_vjp) against fp64 autograd of sqrt(det_orig / det_blur)."""
+    cfg = dict(cfg)
+    cfg["N"] = min(cfg["N"], 4000)
+    sc = make_scene(**cfg)
+    V, N = sc.viewmats.shape[0], sc.means.shape[0]
+    h = hh.projection_fwd(sc, 0)
+    m = sc.means.double().requires_grad_(True)
+    q = sc.quats.double().requires_grad_(True)
+    s = sc.scales.double().requires_grad_(True)
+    comp = O.fully_fused_projection(m, q, s, sc.viewmats.double(), sc.Ks.double(), sc.width, sc.height,
+                                    calc_compensations=True)[4]
+    vis = torch.from_numpy(h["radii"] > 0)
+    assert 0.0 < float(comp[vis].min()) and float(comp[vis].max()) < 1.0
+    g = torch.Generator().manual_seed(5)
+    v_comp = torch.randn(V, N, generator=g, dtype=torch.float64)
+    (comp * v_comp * vis.double()).sum().backward()
+    z2, z3 = torch.zeros(V, N, 2), torch.zeros(V, N, 3)
+    out = hh.projection_bwd(sc, -1, h["radii"], h["colors"], z2, z3, z3, v_comps=v_comp.float())
+    for name, ref in (("v_means", m.grad), ("v_quats", q.grad), ("v_scales", s.grad)):
+        a = torch.from_numpy(out[name]).double()
+        rel = ((a - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+        assert rel <= 5e-5, (name, rel)

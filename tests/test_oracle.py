@@ -23,8 +23,11 @@ def test_oracle_matches_golden(path):
     W, H, deg = int(g["in_width"]), int(g["in_height"]), int(g["in_sh_degree"])
     rc, ra, meta = O.rasterization(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"], leaves["colors"],
                                    t("in_viewmats"), t("in_Ks"), W, H, sh_degree=deg, packed=False, absgrad=True,
-                                   backgrounds=t("in_background"))
+                                   backgrounds=t("in_background"),
+                                   rasterize_mode="antialiased" if "in_antialiased" in g else "classic")
     ((rc * t("in_Wc")).sum() + (ra * t("in_Wa")).sum()).backward()
+    if "in_antialiased" in g:
+        assert torch.equal(meta["opacities"].detach(), t("opacities"))
     for k in ("radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets", "last_ids"):
         assert torch.equal(meta[k], t(k)), k
     assert torch.equal(meta["means2d"].detach(), t("means2d"))

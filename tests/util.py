@@ -7,7 +7,8 @@ from oracle import gsplat_oracle as O
 PARAMS = ("means", "quats", "scales", "opacities", "colors")
 
 
-def oracle_run(sc, sh_degree=3, absgrad=True, backward=True, with_bg=True, dtype=torch.float32, weights=None):
+def oracle_run(sc, sh_degree=3, absgrad=True, backward=True, with_bg=True, dtype=torch.float32, weights=None,
+               rasterize_mode="classic"):
     """Runs the CPU oracle fwd (+bwd of the benchmark functional).  Returns a dict."""
     leaves = {k: getattr(sc, k).detach().clone().to(dtype).requires_grad_(backward) for k in PARAMS}
     C = sc.viewmats.shape[0]
@@ -16,7 +17,7 @@ def oracle_run(sc, sh_degree=3, absgrad=True, backward=True, with_bg=True, dtype
     rc, ra, meta = O.rasterization(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"],
                                    leaves["colors"], sc.viewmats.to(dtype), sc.Ks.to(dtype), sc.width, sc.height,
                                    sh_degree=sh_degree, packed=False, absgrad=absgrad, backgrounds=bg,
-                                   counters=counters)
+                                   counters=counters, rasterize_mode=rasterize_mode)
     out = dict(colors=rc.detach(), alphas=ra.detach(), meta=meta, counters=counters)
     if backward:
         Wc, Wa = weights if weights is not None else loss_weights(sc.seed, C, sc.height, sc.width)
@@ -27,7 +28,8 @@ def oracle_run(sc, sh_degree=3, absgrad=True, backward=True, with_bg=True, dtype
     return out
 
 
-def cuda_run(sc, sh_degree=3, absgrad=True, backward=True, with_bg=True, weights=None, device="cuda"):
+def cuda_run(sc, sh_degree=3, absgrad=True, backward=True, with_bg=True, weights=None, device="cuda",
+             rasterize_mode="classic", packed=False):
     from easy_gaussian_splatting_b200 import rasterization
 
     leaves = {k: getattr(sc, k).detach().clone().to(device).requires_grad_(backward) for k in PARAMS}
@@ -35,7 +37,8 @@ def cuda_run(sc, sh_degree=3, absgrad=True, backward=True, with_bg=True, weights
     bg = sc.background[None].expand(C, 3).contiguous().to(device) if with_bg else None
     rc, ra, meta = rasterization(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"],
                                  leaves["colors"], sc.viewmats.to(device), sc.Ks.to(device), sc.width, sc.height,
-                                 sh_degree=sh_degree, packed=False, absgrad=absgrad, backgrounds=bg)
+                                 sh_degree=sh_degree, packed=packed, absgrad=absgrad, backgrounds=bg,
+                                 rasterize_mode=rasterize_mode)
     out = dict(colors=rc.detach().cpu(), alphas=ra.detach().cpu(), meta=meta)
     if backward:
         Wc, Wa = weights if weights is not None else loss_weights(sc.seed, C, sc.height, sc.width)
