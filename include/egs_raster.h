@@ -235,6 +235,19 @@ int egs_fused_adam(int32_t n_groups, float* const* params, const float* const* g
  * (BASELINE.md §3).  blocks x 256 threads x iters x 32 FMAs; *host_flops (HOST double) = flops issued. */
 int egs_probe_fp32_fma(int32_t blocks, int32_t iters, float* out, double* host_flops, egs_stream_t stream);
 
+/* ---- §8f-4: fused L1 + SSIM photometric loss (LossComputer, /root/reference/model/gaussian.py:415-453) ----------
+ * x = mask * gt + (1 - mask) * render; l1 = mean |x - gt|; ssim_loss = 1 - SSIM(gt, x) with torchmetrics'
+ * StructuralSimilarityIndexMeasure(data_range=1.0) defaults (11-tap Gaussian window, sigma 1.5, k1 .01, k2 .03,
+ * reflect pad + crop == valid window over the unpadded image); total = (1 - lambda) l1 + lambda ssim_loss.
+ *   render, gt [C,H,W,3] (the layout rasterization() returns), mask [C,H,W] (nullable = all zeros), H, W >= 11
+ *   egs_l1_ssim_fwd: sums[C,2] (double, zeroed by the caller) += {sum |x - gt|, sum of the SSIM map};
+ *                    maps (nullable: no gradient wanted) = 3 planes [C,H-10,W-10,3] of SSIM partial derivatives
+ *   egs_l1_ssim_bwd: v_render[C,H,W,3] = v_total[c] * d total_c / d render  (v_total: DEVICE array [C]) */
+int egs_l1_ssim_fwd(int32_t C, int32_t H, int32_t W, const float* render, const float* gt, const float* mask,
+                    float* maps, double* sums, egs_stream_t stream);
+int egs_l1_ssim_bwd(int32_t C, int32_t H, int32_t W, const float* render, const float* gt, const float* mask,
+                    const float* maps, float lambda_ssim, const float* v_total, float* v_render, egs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
