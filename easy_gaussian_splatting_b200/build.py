@@ -57,6 +57,11 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    override = os.environ.get("EGS_RASTER_LIB")  # development only: an A/B variant from scripts/build_variant.py
+    if override:
+        if not Path(override).exists():
+            raise RuntimeError(f"EGS_RASTER_LIB={override} does not exist")
+        return Path(override)
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()

@@ -38,6 +38,18 @@
 namespace egs {
 
 constexpr int kTileSize = 16;
+// Resident CTAs per SM the compiler must leave room for (register cap = 65536 / (threads * this)); tuning knobs,
+// overridable at build time for A/B runs (scripts/build_variant.py).
+#ifdef EGS_FWD_MIN_CTAS
+#define EGS_FWD_BOUNDS(T, PX) __launch_bounds__(T, (PX) == 2 ? EGS_FWD_MIN_CTAS : 1)
+#else
+#define EGS_FWD_BOUNDS(T, PX) __launch_bounds__(T)
+#endif
+#ifdef EGS_BWD_MIN_CTAS
+#define EGS_BWD_BOUNDS(T, PX) __launch_bounds__(T, (PX) == 2 ? EGS_BWD_MIN_CTAS : 1)
+#else
+#define EGS_BWD_BOUNDS(T, PX) __launch_bounds__(T)
+#endif
 // A lane owns PX x PY pixels, a warp 8 x 4 lanes = (8 PX) x (4 PY) pixels.  <2,2>: 2 warps of 16x8 pixels per
 // tile — the throughput configuration.  <1,1>: 8 warps of 8x4 pixels per tile — more warps, smaller culling
 // rectangles and a shorter per-entry chain; used only for tiles whose list is so long that the serial walk of
@@ -81,6 +93,13 @@ __device__ __forceinline__ float fast_rcp(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// predicated RED.ADD.F32 on a known-global address (no branch, no reconvergence barrier around it)
+__device__ __forceinline__ void red_add_f32_if(int flag, float* gptr, float v) {
+  asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p red.global.add.f32 [%1], %2; }" ::"r"(flag), "l"(gptr), "f"(v) : "memory");
 }
 // Stops ptxas from re-deriving a loop-invariant value inside the loop (it otherwise rematerialises
 // the pixel-centre coordinates with I2FP + FADD in every iteration to save two registers).
@@ -187,7 +206,7 @@ __device__ __forceinline__ int cull_and_compact(WarpStage<32 * RPL>& st, int buf
 // The CTA handles its tile only when len_lo <= (tile list length) < len_hi: the <2,2> launch takes the
 // ordinary tiles, the <1,1> launch the very long ones (see Geo).
 template <int PX, int PY, bool COUNT>
-__global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_fwd_kernel(
+__global__ void EGS_FWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_fwd_kernel(
     int64_t n_isects, const float4* __restrict__ splats, const int32_t* __restrict__ tile_offsets,
     const int32_t* __restrict__ flatten_ids, const float* __restrict__ backgrounds, int width, int height, int tile_w,
     int tile_h, int n_tiles_total, int len_lo, int len_hi, float* __restrict__ render_colors,
@@ -412,7 +431,7 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_fwd_kernel(
 // ------------------------------------------------------------------------------------------------
 
 template <int PX, int PY>
-__global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_bwd_kernel(
+__global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel(
     int64_t n_isects, const float4* __restrict__ splats, const int32_t* __restrict__ tile_offsets,
     const int32_t* __restrict__ flatten_ids, const float* __restrict__ backgrounds, int width, int height, int tile_w,
     int tile_h, int n_tiles_total, int len_lo, int len_hi, const float* __restrict__ render_alphas,
@@ -495,6 +514,18 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_bwd_kernel(
     }
     cp_async_commit();
   };
+
+  // Addresses of the warp-sum scratch and of the gradient slot this lane reduces, pinned in registers: ptxas
+  // otherwise re-derives them from %tid / the CTA's shared window for every survivor (~12 of the loop's ~200
+  // instructions).
+  const int out_slot = lane >> 1;
+  int red_flag = ((lane & 1) == 0 && out_slot < kGradValues) ? 1 : 0;
+  asm volatile("" : "+r"(red_flag));
+  uint32_t red_st = (uint32_t)__cvta_generic_to_shared(red + lane);
+  asm volatile("" : "+r"(red_st));
+  const float4* row = reinterpret_cast<const float4*>(red + min(out_slot, kGradValues - 1) * kRedStride + (lane & 1) * 16);
+  float* out_base = v_splats + min(out_slot, kGradValues - 1);
+  asm volatile("" : "+l"(out_base));
 
   int ids[RPL];
   load_ids(0, ids);
@@ -654,10 +685,8 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_bwd_kernel(
       // shuffle reduce-scatter (32 selects + 16 SHFL + 16 FADD) — the kernel is issue bound.
       __syncwarp();  // the previous survivor's row reads are complete
 #pragma unroll
-      for (int k = 0; k < kGradValues; ++k) red[k * kRedStride + lane] = v[k];
+      for (int k = 0; k < kGradValues; ++k) sts_f32(red_st + k * kRedStride * 4, v[k]);
       __syncwarp();
-      const int out_slot = lane >> 1;
-      const float4* row = reinterpret_cast<const float4*>(red + min(out_slot, kGradValues - 1) * kRedStride + (lane & 1) * 16);
       const float4 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3];
       float2 s0 = __fadd2_rn(make_float2(r0.x, r0.y), make_float2(r0.z, r0.w));
       float2 s1 = __fadd2_rn(make_float2(r1.x, r1.y), make_float2(r1.z, r1.w));
@@ -666,8 +695,7 @@ __global__ void __launch_bounds__(Geo<PX, PY>::kThreads) rasterize_bwd_kernel(
       s0 = __fadd2_rn(__fadd2_rn(s0, s1), __fadd2_rn(s2, s3));
       float total = s0.x + s0.y;
       total += __shfl_xor_sync(0xffffffffu, total, 1);
-      if ((lane & 1) == 0 && out_slot < kGradValues)
-        atomicAdd(v_splats + (size_t)sid[cur] * EGS_SPLAT_FLOATS + out_slot, total);
+      red_add_f32_if(red_flag, out_base + (size_t)sid[cur] * EGS_SPLAT_FLOATS, total);
     }
     __syncwarp();  // buffer b&1, its ids and the list are free again
   }

@@ -217,7 +217,7 @@ EGS_HD void project_bwd(const ProjState& st, const float scale[3], const Camera&
   float V00 = -(h00 * q00 + h01 * q01);
   float V01 = -(h00 * q01 + h01 * q11);
   float V11 = -(h10 * q01 + h11 * q11);
-  if (v_comp != 0.f) {
+  if (v_comp != 0.f) {  // (a literal 0 in the classic instantiations: the block is compiled out)
     // antialiased mode: comp^2 = det_orig / det_blur, so d comp^2 / d cov2d = ((1 - comp^2) conic - eps2d det(conic) I)
     // (gsplat 1.0.0 add_blur_vjp, including its 1e-6 guard on the division by comp)
     const float vs = v_comp * 0.5f / (o.comp + 1e-6f);

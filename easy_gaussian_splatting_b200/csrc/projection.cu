@@ -436,6 +436,7 @@ constexpr int kRowStride = 52;
 constexpr int kPB2Threads = 128;
 constexpr int kPB2Warps = kPB2Threads / 32;
 
+template <bool AA>  // AA: rasterize_mode="antialiased" (a separate instantiation keeps the classic kernel at 128 registers)
 __global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const ProjBwdParams p) {
   extern __shared__ __align__(16) float smem_pb[];
   __shared__ Camera cams[kMaxCamerasSmem];
@@ -521,14 +522,16 @@ __global__ void __launch_bounds__(kPB2Threads) projection_bwd_sh16_kernel(const 
         ProjState st;
         ProjOut o;
         project_fwd(mean, quat, scale, *cam, p.width, p.height, p.eps2d, 0.f, INFINITY, -1.f, st, o);
-        float v_comp = 0.f, w_opac = 1.f;
-        if (p.antialiased) {
+        if constexpr (AA) {
           float op = __ldg(p.opacities + n);
           if (p.raw) op = act_sigmoid(op);
-          v_comp = g1.y * op; w_opac = o.comp;
+          if (o.radius > 0)
+            project_bwd(st, scale, *cam, v_m2x, v_m2y, 0.f, g0.z, g0.w, g1.x, o, v_mean, v_quat, v_scale, g1.y * op, p.eps2d);
+          v_opac += g1.y * o.comp;
+        } else {
+          if (o.radius > 0) project_bwd(st, scale, *cam, v_m2x, v_m2y, 0.f, g0.z, g0.w, g1.x, o, v_mean, v_quat, v_scale);
+          v_opac += g1.y;
         }
-        if (o.radius > 0) project_bwd(st, scale, *cam, v_m2x, v_m2y, 0.f, g0.z, g0.w, g1.x, o, v_mean, v_quat, v_scale, v_comp, p.eps2d);
-        v_opac += g1.y * w_opac;
       }
       // SH: rgb = max(sum + 0.5, 0) -> gradient passes where the stored colour is > 0
       const float* col = p.colors + idx * 3;
@@ -725,10 +728,11 @@ static int projection_bwd_impl(int32_t C, int32_t N, const float* means, const f
   if (raw || (vec4 && K == 16)) {
     // the reference's layout (K = 16): coalesced shared-memory staged rows
     constexpr int kSmem = 2 * kPB2Warps * 32 * kRowStride * (int)sizeof(float);
+    auto kern = antialiased ? projection_bwd_sh16_kernel<true> : projection_bwd_sh16_kernel<false>;
     const cudaError_t attr_rc =  // per-device attribute: set on every call (cheap), not once per process
-        cudaFuncSetAttribute(projection_bwd_sh16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (attr_rc != cudaSuccess) return fail((int)attr_rc, "projection_bwd: shared memory opt-in failed: %s", cudaGetErrorString(attr_rc));
-    projection_bwd_sh16_kernel<<<(unsigned)ceil_div(N, kPB2Threads), kPB2Threads, kSmem, (cudaStream_t)stream>>>(p);
+    kern<<<(unsigned)ceil_div(N, kPB2Threads), kPB2Threads, kSmem, (cudaStream_t)stream>>>(p);
     return check_launch("projection_bwd_sh16_kernel");
   }
   unsigned grid = (unsigned)ceil_div(N, kProjBwdThreads);

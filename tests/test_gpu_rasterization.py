@@ -175,7 +175,7 @@ def test_packed_mode_matches_dense(cfg, mode):
     assert torch.equal(mp["isect_ids"], md["isect_ids"]) and torch.equal(mp["isect_offsets"], md["isect_offsets"])
     flat = cam * N + gid
     assert torch.equal(flat[mp["flatten_ids"].long()].int(), md["flatten_ids"])
-    assert pk["absgrad"].shape == (nnz, 2) and torch.equal(pk["absgrad"], dense["absgrad"][vis.cpu()])
+    assert pk["absgrad"].shape == (nnz, 2) and rel_err(pk["absgrad"], dense["absgrad"][vis.cpu()]) <= 1e-5
     for k in PARAMS:  # same kernels, same inputs: only the atomic order differs
         assert rel_err(pk["grads"][k], dense["grads"][k]) <= 1e-5, k
 
