@@ -591,14 +591,17 @@ __global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel
           const float dyr = r == 0 ? dy2.x : dy2.y;
           const float2 dyb = make_float2(dyr, dyr);
           float2 ae, oe;  // alpha and ov of the pixels that take part, 0 for the others
-          ae.x = valid[j0] ? fminf(kAlphaMax, ov2[r].x) : 0.f;
-          ae.y = valid[j1] ? fminf(kAlphaMax, ov2[r].y) : 0.f;
-          oe.x = (valid[j0] && ov2[r].x <= kAlphaMax) ? ov2[r].x : 0.f;  // clamp inactive: alpha depends on sigma, opacity
-          oe.y = (valid[j1] && ov2[r].y <= kAlphaMax) ? ov2[r].y : 0.f;
+          // ov of the pixels that take part, 0 for the others; everything downstream is then an exact no-op for
+          // a pixel that does not take part: alpha = 0, 1 - alpha = 1, MUFU.RCP(1) = 1 exactly
+          // (scripts/probes/rcp_one.cu), so T * 1 = T needs no select
+          const float ovx = valid[j0] ? ov2[r].x : 0.f, ovy = valid[j1] ? ov2[r].y : 0.f;
+          ae.x = fminf(kAlphaMax, ovx);
+          ae.y = fminf(kAlphaMax, ovy);
+          oe.x = ovx <= kAlphaMax ? ovx : 0.f;  // clamp inactive: alpha depends on sigma, opacity
+          oe.y = ovy <= kAlphaMax ? ovy : 0.f;
           const float2 om = __ffma2_rn(ae, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
           const float2 ra = make_float2(fast_rcp(om.x), fast_rcp(om.y));
-          const float2 Tn = __fmul2_rn(make_float2(T[j0], T[j1]), ra);  // transmittance in front of this Gaussian
-          const float2 Tf = make_float2(valid[j0] ? Tn.x : T[j0], valid[j1] ? Tn.y : T[j1]);
+          const float2 Tf = __fmul2_rn(make_float2(T[j0], T[j1]), ra);  // transmittance in front of this Gaussian
           T[j0] = Tf.x; T[j1] = Tf.y;
           const float2 fac = __fmul2_rn(ae, Tf);
           const float2 vr2 = make_float2(vcr[j0], vcr[j1]), vg2 = make_float2(vcg[j0], vcg[j1]), vb2 = make_float2(vcb[j0], vcb[j1]);
