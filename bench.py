@@ -523,6 +523,15 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     copy_ms = tm(lambda: (ka.copy_(ids_u), va.copy_(flat_u)))
     u["radix_sort_u64"] = tm(sort_once) - copy_ms
     u["offset_encode"] = tm(lambda: stages.isect_offset_encode(ids, Cn, tw, th))
+    # §8f-4: fused L1 + SSIM loss (LossComputer drop-in) on one call's rendered views against random targets
+    from easy_gaussian_splatting_b200.loss import fused_l1_ssim_loss
+    if H >= 11 and W >= 11:
+        img = rc.detach().clamp(0, 1).requires_grad_(True)
+        gt_img = torch.rand_like(img)
+        msk = (torch.rand(Cn, H, W, device=dev) < 0.1).float()
+        u["l1_ssim_loss_fwd"] = tm(lambda: fused_l1_ssim_loss(img, gt_img, msk, 0.2))
+        tot = fused_l1_ssim_loss(img, gt_img, msk, 0.2)[0].sum()
+        u["l1_ssim_loss_bwd"] = tm(lambda: torch.autograd.grad(tot, img, retain_graph=True))
     passes = math.ceil((32 + nbits) / 8)
     sort_bytes = (8 + 24 * passes) * n_isects
     work = {  # algorithmic bytes (HBM-bound stages) or flops (blend) per launch, BASELINE.md section 4 (frozen)
@@ -537,6 +546,9 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
         "emit_u64": ("hbm", 32 * N + 12 * n_isects),
         "radix_sort_u64": ("hbm", sort_bytes),
         "offset_encode": ("hbm", 8 * n_isects + 4 * Cn * tw * th),
+        # render 12 + target 12 + mask 4 read, 3 derivative maps (36) written | maps 36 + images 28 read, gradient 12 written
+        "l1_ssim_loss_fwd": ("hbm", 64 * Cn * H * W),
+        "l1_ssim_loss_bwd": ("hbm", 76 * Cn * H * W),
     }
 
     def line(ms, bound, w):
@@ -552,7 +564,7 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     stages_out = {k: line(t[k], *work[k]) for k in work}
     stages_out["binning_fast_path"]["note"] = ("algorithmic bytes are the frozen figure of the classic route (emit 64-bit keys, "
                                                "6-pass LSD sort, offset encode = 172 B/isect); the two-level route moves ~3x less")
-    standalone = {k: line(u[k], *work_u[k]) for k in work_u}
+    standalone = {k: line(u[k], *work_u[k]) for k in work_u if k in u}
     dominant = max(t, key=lambda k: t[k])
     roof = dict(stages_out[dominant])
     roof["kernel"] = dominant
