@@ -32,7 +32,7 @@ class _L1SSIM(torch.autograd.Function):
         dev = render.device
         need_grad = render.requires_grad
         sums = torch.zeros(C, 2, dtype=torch.float64, device=dev)
-        maps = torch.empty(3, C, H - _WIN + 1, W - _WIN + 1, 3, dtype=torch.float32, device=dev) if need_grad else None
+        maps = torch.empty(3, C, 3, H - _WIN + 1, W - _WIN + 1, dtype=torch.float32, device=dev) if need_grad else None
         with torch.cuda.device(dev):
             rc = lib.egs_l1_ssim_fwd(C, H, W, _ptr(render), _ptr(gt), _ptr(mask), _ptr(maps), _ptr(sums), _stream(dev))
         _lib.check(rc, "egs_l1_ssim_fwd")

@@ -241,7 +241,8 @@ int egs_probe_fp32_fma(int32_t blocks, int32_t iters, float* out, double* host_f
  * reflect pad + crop == valid window over the unpadded image); total = (1 - lambda) l1 + lambda ssim_loss.
  *   render, gt [C,H,W,3] (the layout rasterization() returns), mask [C,H,W] (nullable = all zeros), H, W >= 11
  *   egs_l1_ssim_fwd: sums[C,2] (double, zeroed by the caller) += {sum |x - gt|, sum of the SSIM map};
- *                    maps (nullable: no gradient wanted) = 3 planes [C,H-10,W-10,3] of SSIM partial derivatives
+ *                    maps (nullable: no gradient wanted) = 3 planes [C,3,H-10,W-10] (channel planar, internal to
+ *                    this pair of calls) of SSIM partial derivatives
  *   egs_l1_ssim_bwd: v_render[C,H,W,3] = v_total[c] * d total_c / d render  (v_total: DEVICE array [C]) */
 int egs_l1_ssim_fwd(int32_t C, int32_t H, int32_t W, const float* render, const float* gt, const float* mask,
                     float* maps, double* sums, egs_stream_t stream);
