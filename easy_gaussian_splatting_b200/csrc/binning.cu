@@ -353,6 +353,35 @@ __global__ void __launch_bounds__(kOffThreads) isect_finalize_kernel(int64_t n_i
   }
 }
 
+// Offsets only (the product path: the 64-bit keys are rebuilt lazily, on the rare read of meta["isect_ids"]).
+// HBM-bound shape: one 128-bit load of 4 sorted keys per thread plus the key in front of them, 32-bit arithmetic;
+// tile t's offset is written by the thread that sees the first key >= t (runs of empty tiles are filled by it too).
+constexpr int kOff4Threads = 256;
+__global__ void __launch_bounds__(kOff4Threads) isect_offsets4_kernel(int32_t n_isects, const uint32_t* __restrict__ tile_keys,
+                                                                       int32_t n_slots, int32_t* __restrict__ offsets) {
+  const int32_t i0 = (blockIdx.x * kOff4Threads + threadIdx.x) * 4;
+  if (i0 >= n_isects) return;
+  uint32_t k[4];
+  if (i0 + 4 <= n_isects) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(tile_keys + i0));
+    k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[j] = tile_keys[min(i0 + j, n_isects - 1)];
+  }
+  uint32_t prev = i0 > 0 ? __ldg(tile_keys + i0 - 1) : 0xffffffffu;  // 0xffffffff + 1 = 0: tile 0 starts the fill
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int32_t i = i0 + j;
+    if (i < n_isects && k[j] != prev) {
+      for (uint32_t t = prev + 1u; t <= k[j] && t < (uint32_t)n_slots; ++t) offsets[t] = i;
+    }
+    prev = k[j];
+    if (i == n_isects - 1)
+      for (uint32_t t = k[j] + 1u; t < (uint32_t)n_slots; ++t) offsets[t] = n_isects;
+  }
+}
+
 }  // namespace egs
 
 using namespace egs;
@@ -482,6 +511,11 @@ extern "C" int egs_isect_finalize(int64_t n_isects, const uint32_t* tile_keys_so
   if (n_isects == 0) {
     if (offsets != nullptr) EGS_CUDA(cudaMemsetAsync(offsets, 0, n_slots * sizeof(int32_t), stream));
     return 0;
+  }
+  if (isect_ids == nullptr && offsets != nullptr && reinterpret_cast<uintptr_t>(tile_keys_sorted) % 16 == 0) {
+    isect_offsets4_kernel<<<(unsigned)ceil_div(n_isects, 4 * kOff4Threads), kOff4Threads, 0, stream>>>(
+        (int32_t)n_isects, tile_keys_sorted, (int32_t)n_slots, offsets);
+    return check_launch("isect_offsets4_kernel");
   }
   isect_finalize_kernel<<<(unsigned)ceil_div(n_isects, kOffThreads), kOffThreads, 0, stream>>>(
       n_isects, tile_keys_sorted, flat_sorted, depths, n_tiles, tile_n_bits, n_slots, isect_ids, offsets);
