@@ -122,15 +122,26 @@ struct WarpView {
   float rx_lo, rx_hi, ry_lo, ry_hi;  // pixel-centre rectangle of the warp (16 x 8 pixels)
 };
 
+// tile_id < 0: the tile is the block's position in the (tile_w, tile_h, C) grid; otherwise the given flat tile index
+// (cam * tile_h + ty) * tile_w + tx (the segment launch of the backward pass maps blocks to list segments).
 template <class G>
 __device__ __forceinline__ WarpView warp_setup(int tile_w, int tile_h, int64_t n_isects,
-                                               const int32_t* __restrict__ tile_offsets, int n_tiles_total) {
+                                               const int32_t* __restrict__ tile_offsets, int n_tiles_total,
+                                               int tile_id = -1) {
   WarpView v;
+  int bx = blockIdx.x, by = blockIdx.y;
   v.cam = blockIdx.z;
-  const int tile_id = (v.cam * tile_h + blockIdx.y) * tile_w + blockIdx.x;
+  if (tile_id < 0) {
+    tile_id = (v.cam * tile_h + by) * tile_w + bx;
+  } else {
+    v.cam = tile_id / (tile_w * tile_h);
+    const int rem = tile_id - v.cam * (tile_w * tile_h);
+    by = rem / tile_w;
+    bx = rem - by * tile_w;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wx = warp % G::kWarpsX, wy = warp / G::kWarpsX;
-  const int wx0 = blockIdx.x * kTileSize + wx * G::kWarpW, wy0 = blockIdx.y * kTileSize + wy * G::kWarpH;
+  const int wx0 = bx * kTileSize + wx * G::kWarpW, wy0 = by * kTileSize + wy * G::kWarpH;
   v.x0 = wx0 + (lane & 7) * (G::kWarpW / 8);
   v.y0 = wy0 + (lane >> 3) * (G::kWarpH / 4);
   v.range_start = tile_offsets[tile_id];
@@ -210,7 +221,8 @@ __global__ void EGS_FWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_fwd_kernel
     int64_t n_isects, const float4* __restrict__ splats, const int32_t* __restrict__ tile_offsets,
     const int32_t* __restrict__ flatten_ids, const float* __restrict__ backgrounds, int width, int height, int tile_w,
     int tile_h, int n_tiles_total, int len_lo, int len_hi, float* __restrict__ render_colors,
-    float* __restrict__ render_alphas, int32_t* __restrict__ last_ids, unsigned long long* __restrict__ pair_counters) {
+    float* __restrict__ render_alphas, int32_t* __restrict__ last_ids, unsigned long long* __restrict__ pair_counters,
+    float4* __restrict__ ckpt, int ckpt_k) {
   using G = Geo<PX, PY>;
   constexpr int NP = G::NP;
   constexpr int RPL = G::RPL, kBatch = G::kBatch;
@@ -389,6 +401,18 @@ __global__ void EGS_FWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_fwd_kernel
         all_done = !(tmax > 0.f);
       }
       if (__all_sync(0xffffffffu, all_done)) break;  // this warp needs nothing further down the list
+      if constexpr (PX == 2 && PY == 2) {
+        // Per-pixel state after every ckpt_k entries of a long list: lets the backward pass start its back-to-front
+        // replay at any of these boundaries, one warp per segment (see rasterize_bwd_kernel).  Slot numbering
+        // floor(start / K) + k is collision free across tiles because their list ranges are disjoint and ordered.
+        const int done_local = (b + 1) * kBatch;
+        if (ckpt != nullptr && done_local % ckpt_k == 0 && done_local < wv.range_end - wv.range_start) {
+          const size_t slot = (size_t)(wv.range_start / ckpt_k + done_local / ckpt_k);
+          float4* dst = ckpt + ((slot * G::kWarps + (threadIdx.x >> 5)) * NP) * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < NP; ++j) dst[j * 32] = make_float4(T[j], cr[j], cg[j], cb[j]);
+        }
+      }
       __syncwarp();  // every lane is done with buffer b&1 and the list before they are overwritten
     }
     cp_async_wait<0>();
@@ -436,7 +460,13 @@ __global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel
     const int32_t* __restrict__ flatten_ids, const float* __restrict__ backgrounds, int width, int height, int tile_w,
     int tile_h, int n_tiles_total, int len_lo, int len_hi, const float* __restrict__ render_alphas,
     const int32_t* __restrict__ last_ids, const float* __restrict__ v_render_colors,
-    const float* __restrict__ v_render_alphas, float* __restrict__ v_splats) {
+    const float* __restrict__ v_render_alphas, float* __restrict__ v_splats,
+    // Segmented replay of long lists (ckpt != nullptr): the forward pass left the per-pixel state after every ckpt_k
+    // entries of a list, so a list of L entries is replayed by ceil(L / ckpt_k) independent warps per tile half.
+    // seg_launch = 0: blocks are tiles and replay the LAST segment their warp needs (from the warp's last blended
+    // entry down to the segment boundary below it, initial state = the final image, as without segments);
+    // seg_launch = 1: blocks are checkpoint slots and replay the full segment that ends at their checkpoint.
+    const float* __restrict__ render_colors, const float4* __restrict__ ckpt, int ckpt_k, int seg_launch) {
   using G = Geo<PX, PY>;
   constexpr int NP = G::NP;
   constexpr int RPL = G::RPL, kBatch = G::kBatch;
@@ -445,10 +475,24 @@ __global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel
   const int lane = threadIdx.x & 31;
   WarpStage<kBatch>& st = stage[threadIdx.x >> 5];
   float* red = red_all[threadIdx.x >> 5];
-  const WarpView wv = warp_setup<G>(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total);
+  int seg_tile = -1, seg_k = 0;
+  if (seg_launch) {
+    // slot j = blockIdx.x + 1 belongs to the last tile whose list starts before entry j * K (empty tiles share
+    // their successor's start, so the last one is the tile that really holds that entry)
+    const int64_t bound = ((int64_t)blockIdx.x + 1) * ckpt_k;
+    int lo_t = 0, hi_t = n_tiles_total - 1;
+    while (lo_t < hi_t) {
+      const int mid = (lo_t + hi_t + 1) >> 1;
+      if ((int64_t)tile_offsets[mid] < bound) lo_t = mid; else hi_t = mid - 1;
+    }
+    seg_tile = lo_t;
+    seg_k = (int)(blockIdx.x + 1) - tile_offsets[seg_tile] / ckpt_k;
+  }
+  const WarpView wv = warp_setup<G>(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total, seg_tile);
   {
     const int len = wv.range_end - wv.range_start;
     if (len <= 0 || len < len_lo || len >= len_hi) return;  // block-uniform: empty, or owned by the other launch
+    if (seg_launch && (seg_k < 1 || (int64_t)seg_k * ckpt_k >= len)) return;  // block-uniform: slot not in use
   }
 
   float pxf[PX], pyf[PY];
@@ -488,15 +532,48 @@ __global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel
   }
   // nothing behind the last blended Gaussian of any pixel of the warp can receive gradient
   const int warp_last = __reduce_max_sync(0xffffffffu, my_last);
-  const int end_idx = min(wv.range_end - 1, warp_last);
+  int end_idx = min(wv.range_end - 1, warp_last);
   if (end_idx < wv.range_start) return;  // warp-uniform
-  const int nb = (end_idx - wv.range_start + 1 + kBatch - 1) / kBatch;
+  int lo_idx = wv.range_start;  // the replay walks end_idx, end_idx - 1, ..., lo_idx
+  if constexpr (PX == 2 && PY == 2) {
+    if (ckpt != nullptr && wv.range_end - wv.range_start > ckpt_k) {
+      const int last_seg = (end_idx - wv.range_start) / ckpt_k;  // segment that holds the warp's last blended entry
+      if (!seg_launch) {
+        lo_idx = wv.range_start + last_seg * ckpt_k;
+      } else {
+        if (seg_k > last_seg) return;  // warp-uniform: nothing of this warp reaches into or beyond this segment
+        end_idx = wv.range_start + seg_k * ckpt_k - 1;
+        lo_idx = end_idx + 1 - ckpt_k;
+        // state after entry end_idx: transmittance and colour accumulated in front of the boundary (the forward
+        // checkpoint); what lies behind it is the final colour minus that
+        const size_t slot = (size_t)(wv.range_start / ckpt_k + seg_k);
+        const float4* src = ckpt + ((slot * G::kWarps + (threadIdx.x >> 5)) * NP) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const int x = wv.x0 + (j % PX), y = wv.y0 + (j / PX);
+          if (x < width && y < height) {
+            const size_t pix = ((size_t)wv.cam * height + y) * width + x;
+            const float4 ck = src[j * 32];
+            const float T_final = T[j];
+            const float br = render_colors[pix * 3 + 0] - T_final * bgr - ck.y;
+            const float bgn = render_colors[pix * 3 + 1] - T_final * bgg - ck.z;
+            const float bb = render_colors[pix * 3 + 2] - T_final * bgb - ck.w;
+            nbt_[j] -= br * vcr[j] + bgn * vcg[j] + bb * vcb[j];
+            T[j] = fabsf(ck.x);
+          }
+        }
+      }
+    } else if (seg_launch) {
+      return;
+    }
+  }
+  const int nb = (end_idx - lo_idx + 1 + kBatch - 1) / kBatch;
 
   auto load_ids = [&](int b, int (&ids)[RPL]) {
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
       const int idx = end_idx - b * kBatch - (r * 32 + lane);
-      ids[r] = (b < nb && idx >= wv.range_start) ? __ldg(flatten_ids + idx) : -1;
+      ids[r] = (b < nb && idx >= lo_idx) ? __ldg(flatten_ids + idx) : -1;
     }
   };
   auto issue = [&](int buf, const int (&ids)[RPL]) {
@@ -541,7 +618,7 @@ __global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel
     }
     __syncwarp();
     const int batch_end = end_idx - b * kBatch;  // sorted index held in slot 0 (the one furthest back)
-    const int batch_size = min(kBatch, batch_end + 1 - wv.range_start);
+    const int batch_size = min(kBatch, batch_end + 1 - lo_idx);
     const int ns = cull_and_compact<RPL>(st, b & 1, batch_size, lane, rx_lo, rx_hi, ry_lo, ry_hi);
     const float4* s = st.rec[b & 1];
     const int* sid = st.id[b & 1];
@@ -737,20 +814,22 @@ template <bool COUNT>
 static int launch_fwd(int32_t C, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
                       const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
                       int32_t tile_width, int32_t tile_height, float* render_colors, float* render_alphas,
-                      int32_t* last_ids, uint64_t* pair_counters, egs_stream_t stream) {
+                      int32_t* last_ids, uint64_t* pair_counters, egs_stream_t stream, float* checkpoints = nullptr,
+                      int32_t segment = 0) {
   dim3 grid(tile_width, tile_height, C);
   const int n_tiles = C * tile_width * tile_height;
   const int thr = long_tile_threshold(n_isects, n_tiles);
+  float4* ck = (segment > 0 && thr == 0x7fffffff) ? reinterpret_cast<float4*>(checkpoints) : nullptr;
   const float4* sp = reinterpret_cast<const float4*>(splats);
   unsigned long long* pc = reinterpret_cast<unsigned long long*>(pair_counters);
   cudaStream_t st = (cudaStream_t)stream;
   rasterize_fwd_kernel<2, 2, COUNT><<<grid, Geo<2, 2>::kThreads, 0, st>>>(
       n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
-      render_colors, render_alphas, last_ids, pc);
+      render_colors, render_alphas, last_ids, pc, ck, segment);
   if (n_isects >= thr)  // otherwise no tile can be that long
     rasterize_fwd_kernel<1, 1, COUNT><<<grid, Geo<1, 1>::kThreads, 0, st>>>(
         n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, thr,
-        0x7fffffff, render_colors, render_alphas, last_ids, pc);
+        0x7fffffff, render_colors, render_alphas, last_ids, pc, nullptr, 0);
   return check_launch("rasterize_fwd_kernel");
 }
 
@@ -780,6 +859,59 @@ extern "C" int egs_rasterize_fwd_count(int32_t C, int32_t N, int64_t n_isects, c
                           tile_height, render_colors, render_alphas, last_ids, pair_counters, stream);
 }
 
+static int segment_ok(const char* who, int32_t segment) {
+  EGS_REQUIRE(segment == 0 || (segment >= 64 && segment % 64 == 0), "%s: segment=%d must be 0 or a multiple of 64", who, segment);
+  return 0;
+}
+
+extern "C" int64_t egs_rasterize_checkpoint_bytes(int64_t n_isects, int32_t segment) {
+  if (n_isects < 0 || segment <= 0) return 0;
+  // slots 0 .. n_isects / segment, each: 2 warps x 4 pixels x 32 lanes x float4
+  return (n_isects / segment + 2) * (int64_t)(Geo<2, 2>::kWarps * Geo<2, 2>::NP * 32 * sizeof(float4));
+}
+
+extern "C" int egs_rasterize_fwd_checkpointed(int32_t C, int32_t N, int64_t n_isects, const float* splats,
+                                              const int32_t* tile_offsets, const int32_t* flatten_ids,
+                                              const float* backgrounds, int32_t width, int32_t height,
+                                              int32_t tile_width, int32_t tile_height, float* render_colors,
+                                              float* render_alphas, int32_t* last_ids, float* checkpoints,
+                                              int32_t segment, egs_stream_t stream) {
+  (void)N;
+  if (int rc = check_raster_args("rasterize_fwd_checkpointed", C, n_isects, width, height, tile_width, tile_height)) return rc;
+  if (int rc = segment_ok("rasterize_fwd_checkpointed", segment)) return rc;
+  EGS_REQUIRE(segment == 0 || checkpoints != nullptr, "rasterize_fwd_checkpointed: checkpoints buffer is required");
+  if (C == 0) return 0;
+  return launch_fwd<false>(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width,
+                           tile_height, render_colors, render_alphas, last_ids, nullptr, stream, checkpoints, segment);
+}
+
+static int launch_bwd(int32_t C, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
+                      const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
+                      int32_t tile_width, int32_t tile_height, const float* render_alphas, const int32_t* last_ids,
+                      const float* v_render_colors, const float* v_render_alphas, float* v_splats,
+                      const float* render_colors, const float* checkpoints, int32_t segment, egs_stream_t stream) {
+  dim3 grid(tile_width, tile_height, C);
+  const int n_tiles = C * tile_width * tile_height;
+  const int thr = long_tile_threshold(n_isects, n_tiles);
+  const float4* sp = reinterpret_cast<const float4*>(splats);
+  const float4* ck = (segment > 0 && thr == 0x7fffffff) ? reinterpret_cast<const float4*>(checkpoints) : nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the segment launch goes first: its warps all have full segments to replay, the tile launch then fills in
+  const int64_t n_slots = ck != nullptr ? n_isects / segment : 0;
+  if (n_slots > 0)
+    rasterize_bwd_kernel<2, 2><<<(unsigned)n_slots, Geo<2, 2>::kThreads, 0, st>>>(
+        n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
+        render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, 1);
+  rasterize_bwd_kernel<2, 2><<<grid, Geo<2, 2>::kThreads, 0, st>>>(
+      n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
+      render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, 0);
+  if (n_isects >= thr)
+    rasterize_bwd_kernel<1, 1><<<grid, Geo<1, 1>::kThreads, 0, st>>>(
+        n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, thr,
+        0x7fffffff, render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, nullptr, nullptr, 0, 0);
+  return check_launch("rasterize_bwd_kernel");
+}
+
 extern "C" int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const float* splats,
                                  const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
                                  int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
@@ -788,17 +920,24 @@ extern "C" int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const f
   (void)N;
   if (int rc = check_raster_args("rasterize_bwd", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (C == 0 || n_isects == 0) return 0;
-  dim3 grid(tile_width, tile_height, C);
-  const int n_tiles = C * tile_width * tile_height;
-  const int thr = long_tile_threshold(n_isects, n_tiles);
-  const float4* sp = reinterpret_cast<const float4*>(splats);
-  cudaStream_t st = (cudaStream_t)stream;
-  rasterize_bwd_kernel<2, 2><<<grid, Geo<2, 2>::kThreads, 0, st>>>(
-      n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
-      render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats);
-  if (n_isects >= thr)
-    rasterize_bwd_kernel<1, 1><<<grid, Geo<1, 1>::kThreads, 0, st>>>(
-        n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, thr,
-        0x7fffffff, render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats);
-  return check_launch("rasterize_bwd_kernel");
+  return launch_bwd(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height,
+                    render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int egs_rasterize_bwd_segmented(int32_t C, int32_t N, int64_t n_isects, const float* splats,
+                                           const int32_t* tile_offsets, const int32_t* flatten_ids,
+                                           const float* backgrounds, int32_t width, int32_t height, int32_t tile_width,
+                                           int32_t tile_height, const float* render_colors, const float* render_alphas,
+                                           const int32_t* last_ids, const float* v_render_colors,
+                                           const float* v_render_alphas, const float* checkpoints, int32_t segment,
+                                           float* v_splats, egs_stream_t stream) {
+  (void)N;
+  if (int rc = check_raster_args("rasterize_bwd_segmented", C, n_isects, width, height, tile_width, tile_height)) return rc;
+  if (int rc = segment_ok("rasterize_bwd_segmented", segment)) return rc;
+  EGS_REQUIRE(segment == 0 || (checkpoints != nullptr && render_colors != nullptr),
+              "rasterize_bwd_segmented: checkpoints and render_colors are required");
+  if (C == 0 || n_isects == 0) return 0;
+  return launch_bwd(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height,
+                    render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, checkpoints,
+                    segment, stream);
 }

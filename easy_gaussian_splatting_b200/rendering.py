@@ -55,6 +55,24 @@ def _tag_absgrad(target: Tensor, absgrad: Tensor, packed_index: Optional[Tensor]
     target.absgrad = absgrad if packed_index is None else absgrad.reshape(-1, 2)[packed_index]
 
 
+def _blend_forward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width, height):
+    """Blend forward; when a backward pass will follow and long-list segmentation is on, the checkpointed variant."""
+    seg = stages.backward_segment() if any(ctx.needs_input_grad) else 0
+    ctx.segment = seg
+    if seg > 0:
+        return stages.rasterize_fwd_checkpointed(splats, isect_offsets, flatten_ids, backgrounds, width, height, seg)
+    return (*stages.rasterize_fwd(splats, isect_offsets, flatten_ids, backgrounds, width, height), None)
+
+
+def _blend_backward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_colors, render_alphas,
+                    last_ids, v_colors, v_alphas, ckpt):
+    if ckpt is not None:
+        return stages.rasterize_bwd_segmented(splats, isect_offsets, flatten_ids, backgrounds, width, height,
+                                              render_colors, render_alphas, last_ids, v_colors, v_alphas, ckpt, ctx.segment)
+    return stages.rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, render_alphas, last_ids,
+                                v_colors, v_alphas)
+
+
 class _Rasterization(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg):
@@ -70,15 +88,15 @@ class _Rasterization(torch.autograd.Function):
             proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th,
             materialize_ids=False)
         cfg["isect_ids_thunk"] = isect_ids_thunk  # handed to the wrapper (not a tensor: cannot be an output)
-        render_colors, render_alphas, last_ids = stages.rasterize_fwd(
-            proj["splats"], isect_offsets, flatten_ids, backgrounds, width, height)
+        render_colors, render_alphas, last_ids, ckpt = _blend_forward(ctx, proj["splats"], isect_offsets, flatten_ids,
+                                                                     backgrounds, width, height)
 
         means2d = proj["means2d"]
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(means, quats, scales, colors, viewmats, Ks, backgrounds, proj["radii"], proj["colors"],
                               proj["splats"], isect_offsets, flatten_ids, render_alphas, last_ids,
-                              opacities if cfg["antialiased"] else None)
+                              opacities if cfg["antialiased"] else None, ckpt, render_colors if ckpt is not None else None)
         nondiff = (proj["radii"], proj["depths"], proj["conics"], proj["colors"], tiles_per_gauss,
                    flatten_ids, isect_offsets, last_ids)
         ctx.mark_non_differentiable(*nondiff)
@@ -87,7 +105,7 @@ class _Rasterization(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_colors, v_alphas, v_means2d, *_unused):
         (means, quats, scales, colors, viewmats, Ks, backgrounds, radii, colors_rgb, splats, isect_offsets,
-         flatten_ids, render_alphas, last_ids, aa_opacities) = ctx.saved_tensors
+         flatten_ids, render_alphas, last_ids, aa_opacities, ckpt, render_colors) = ctx.saved_tensors
         cfg = ctx.cfg
         width, height = cfg["width"], cfg["height"]
         C = viewmats.shape[0]
@@ -95,8 +113,8 @@ class _Rasterization(torch.autograd.Function):
             v_colors = torch.zeros(C, height, width, 3, dtype=torch.float32, device=means.device)
         if v_alphas is None:
             v_alphas = torch.zeros(C, height, width, 1, dtype=torch.float32, device=means.device)
-        v_splats = stages.rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height,
-                                        render_alphas, last_ids, v_colors, v_alphas)
+        v_splats = _blend_backward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_colors,
+                                   render_alphas, last_ids, v_colors, v_alphas, ckpt)
         ref = getattr(ctx, "means2d_ref", None) if cfg["absgrad"] else None
         target = ref() if ref is not None else None
         out = stages.projection_bwd(means, quats, scales, colors, viewmats, Ks, width, height, cfg["sh_degree"],
@@ -129,13 +147,13 @@ class _RasterizationRaw(torch.autograd.Function):
             proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th,
             materialize_ids=False)
         cfg["isect_ids_thunk"] = isect_ids_thunk
-        render_colors, render_alphas, last_ids = stages.rasterize_fwd(
-            proj["splats"], isect_offsets, flatten_ids, backgrounds, width, height)
+        render_colors, render_alphas, last_ids, ckpt = _blend_forward(ctx, proj["splats"], isect_offsets, flatten_ids,
+                                                                     backgrounds, width, height)
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds,
                               proj["radii"], proj["colors"], proj["splats"], isect_offsets, flatten_ids, render_alphas,
-                              last_ids)
+                              last_ids, ckpt, render_colors if ckpt is not None else None)
         nondiff = (proj["radii"], proj["depths"], proj["conics"], proj["colors"], tiles_per_gauss,
                    flatten_ids, isect_offsets, last_ids)
         ctx.mark_non_differentiable(*nondiff)
@@ -144,7 +162,7 @@ class _RasterizationRaw(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_colors, v_alphas, v_means2d, *_unused):
         (means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds, radii, colors_rgb, splats,
-         isect_offsets, flatten_ids, render_alphas, last_ids) = ctx.saved_tensors
+         isect_offsets, flatten_ids, render_alphas, last_ids, ckpt, render_colors) = ctx.saved_tensors
         cfg = ctx.cfg
         width, height = cfg["width"], cfg["height"]
         C = viewmats.shape[0]
@@ -152,8 +170,8 @@ class _RasterizationRaw(torch.autograd.Function):
             v_colors = torch.zeros(C, height, width, 3, dtype=torch.float32, device=means.device)
         if v_alphas is None:
             v_alphas = torch.zeros(C, height, width, 1, dtype=torch.float32, device=means.device)
-        v_splats = stages.rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height,
-                                        render_alphas, last_ids, v_colors, v_alphas)
+        v_splats = _blend_backward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_colors,
+                                   render_alphas, last_ids, v_colors, v_alphas, ckpt)
         ref = getattr(ctx, "means2d_ref", None) if cfg["absgrad"] else None
         target = ref() if ref is not None else None
         out = stages.projection_bwd_raw(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, width,

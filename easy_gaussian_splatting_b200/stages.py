@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -380,6 +381,60 @@ def rasterize_fwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, ba
             rc = lib.egs_rasterize_fwd(*args, _stream(dev))
     _lib.check(rc, "egs_rasterize_fwd")
     return (colors, alphas, last, counters) if count_pairs else (colors, alphas, last)
+
+
+def backward_segment() -> int:
+    """List entries per backward-replay segment; 0 (the default) = off.  With EGS_BWD_SEGMENT=<multiple of 64> tile
+    lists longer than that are replayed by one warp per segment instead of one warp per tile half.  Measured
+    (BASELINE.md section 5): object-centric scenes whose few hundred busy tiles hold 5-6 k entries gain 7-14 % at 256-512;
+    scenes with ordinary lists (the 1 M-Gaussian benchmark, ~900 entries per tile) lose 2-5 % to the checkpoint stores
+    and the extra launch, hence opt-in."""
+    v = int(os.environ.get("EGS_BWD_SEGMENT", "0"))
+    if v < 0 or v % 64 != 0:
+        raise ValueError(f"EGS_BWD_SEGMENT={v}: must be 0 or a multiple of 64")
+    return v
+
+
+def rasterize_fwd_checkpointed(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor,
+                               backgrounds: Optional[Tensor], width: int, height: int, segment: int):
+    """g6 for a forward that will be differentiated: as rasterize_fwd, plus the per-pixel state after every
+    `segment` entries of a tile's list -> render_colors, render_alphas, last_ids, checkpoints."""
+    lib = _lib.load()
+    dev = splats.device
+    C, N = splats.shape[:2]
+    th, tw = isect_offsets.shape[1:]
+    n_isects = flatten_ids.numel()
+    colors = torch.empty(C, height, width, 3, dtype=torch.float32, device=dev)
+    alphas = torch.empty(C, height, width, 1, dtype=torch.float32, device=dev)
+    last = torch.empty(C, height, width, dtype=torch.int32, device=dev)
+    ckpt = torch.empty(max(lib.egs_rasterize_checkpoint_bytes(n_isects, segment) // 4, 4), dtype=torch.float32, device=dev)
+    bg = None if backgrounds is None else _f32c(backgrounds, "backgrounds")
+    with torch.cuda.device(dev):
+        rc = lib.egs_rasterize_fwd_checkpointed(C, N, n_isects, _ptr(splats), _ptr(isect_offsets), _ptr(flatten_ids),
+                                                _ptr(bg), int(width), int(height), tw, th, _ptr(colors), _ptr(alphas),
+                                                _ptr(last), _ptr(ckpt), int(segment), _stream(dev))
+    _lib.check(rc, "egs_rasterize_fwd_checkpointed")
+    return colors, alphas, last, ckpt
+
+
+def rasterize_bwd_segmented(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],
+                            width: int, height: int, render_colors: Tensor, render_alphas: Tensor, last_ids: Tensor,
+                            v_render_colors: Tensor, v_render_alphas: Tensor, checkpoints: Tensor, segment: int) -> Tensor:
+    """g7 with one warp per list segment (see include/egs_raster.h) -> v_splats[C,N,12]."""
+    lib = _lib.load()
+    dev = splats.device
+    C, N = splats.shape[:2]
+    th, tw = isect_offsets.shape[1:]
+    v_splats = torch.zeros(C, N, SPLAT_FLOATS, dtype=torch.float32, device=dev)
+    bg = None if backgrounds is None else _f32c(backgrounds, "backgrounds")
+    v_c, v_a = _f32c(v_render_colors, "v_render_colors"), _f32c(v_render_alphas, "v_render_alphas")
+    with torch.cuda.device(dev):
+        rc = lib.egs_rasterize_bwd_segmented(C, N, flatten_ids.numel(), _ptr(splats), _ptr(isect_offsets),
+                                             _ptr(flatten_ids), _ptr(bg), int(width), int(height), tw, th,
+                                             _ptr(render_colors), _ptr(render_alphas), _ptr(last_ids), _ptr(v_c), _ptr(v_a),
+                                             _ptr(checkpoints), int(segment), _ptr(v_splats), _stream(dev))
+    _lib.check(rc, "egs_rasterize_bwd_segmented")
+    return v_splats
 
 
 def rasterize_bwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],

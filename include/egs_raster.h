@@ -213,6 +213,27 @@ int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const float* splat
                       const int32_t* last_ids, const float* v_render_colors, const float* v_render_alphas,
                       float* v_splats, egs_stream_t stream);
 
+/* ---- g7 on long lists: segmented replay ---------------------------------------------------------------------------
+ * A tile whose list has thousands of entries (object-centric scenes: a few hundred tiles hold the whole object) makes
+ * the backward pass a serial walk of one warp per tile half.  The checkpointed forward stores the per-pixel state
+ * {T, r, g, b} after every `segment` entries of a list (segment: a multiple of 64; checkpoints: caller-allocated,
+ * egs_rasterize_checkpoint_bytes(n_isects, segment) bytes, need not be cleared); the segmented backward then replays
+ * every segment with its own warp (an extra launch over the checkpoint slots), starting from the checkpoint and
+ * from "final colour minus colour in front" for what lies behind.  Results equal egs_rasterize_fwd / _bwd up to fp32
+ * summation order; segment = 0 is exactly those two calls. */
+int64_t egs_rasterize_checkpoint_bytes(int64_t n_isects, int32_t segment);
+int egs_rasterize_fwd_checkpointed(int32_t C, int32_t N, int64_t n_isects, const float* splats,
+                                   const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
+                                   int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
+                                   float* render_colors, float* render_alphas, int32_t* last_ids, float* checkpoints,
+                                   int32_t segment, egs_stream_t stream);
+int egs_rasterize_bwd_segmented(int32_t C, int32_t N, int64_t n_isects, const float* splats,
+                                const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
+                                int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
+                                const float* render_colors, const float* render_alphas, const int32_t* last_ids,
+                                const float* v_render_colors, const float* v_render_alphas, const float* checkpoints,
+                                int32_t segment, float* v_splats, egs_stream_t stream);
+
 /* ---- §8f-1: fused, sync-free densification statistics (C-aware) ----------------------------------------
  * Replaces GaussianModel.update_statistics, /root/reference/model/gaussian.py:188-197, applied once
  * per camera: visible = radii > 0; max_radii = max(max_radii, radii / max_hw);

@@ -180,6 +180,30 @@ def test_packed_mode_matches_dense(cfg, mode):
         assert rel_err(pk["grads"][k], dense["grads"][k]) <= 1e-5, k
 
 
+@pytest.mark.parametrize("cfg", [CASES[1], CASES[2], CASES[3]])
+@pytest.mark.parametrize("segment", [64, 192, 1024])
+def test_segmented_backward_matches_unsegmented(cfg, segment, monkeypatch):
+    """Long tile lists are replayed by one warp per `segment` entries, starting from forward checkpoints
+    (include/egs_raster.h, egs_rasterize_bwd_segmented).  Same images bit for bit, same gradients up to fp32
+    summation order, for segment lengths from one batch (every list is segmented) to the default."""
+    sc = make_scene(**cfg)
+    monkeypatch.setenv("EGS_BWD_SEGMENT", "0")
+    base = cuda_run(sc)
+    monkeypatch.setenv("EGS_BWD_SEGMENT", str(segment))
+    seg = cuda_run(sc)
+    assert torch.equal(seg["colors"], base["colors"]) and torch.equal(seg["alphas"], base["alphas"])
+    n_long = int(((base["meta"]["isect_offsets"].flatten()[1:] - base["meta"]["isect_offsets"].flatten()[:-1]) > segment).sum())
+    print("tiles longer than", segment, ":", n_long)
+    if segment == 64:
+        assert n_long > 0  # the test must exercise the segment launch
+    for k in PARAMS:
+        assert rel_err(seg["grads"][k], base["grads"][k]) <= 2e-5, k
+    assert rel_err(seg["absgrad"], base["absgrad"]) <= 2e-5
+    ref = oracle_run(sc)
+    for k in PARAMS:
+        assert rel_err(seg["grads"][k], ref["grads"][k]) <= 1e-3, k
+
+
 GOLDEN = sorted(__import__("pathlib").Path(__file__).parent.glob("golden/*.npz"))
 
 
