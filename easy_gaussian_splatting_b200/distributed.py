@@ -50,6 +50,26 @@ class FlatGradBucket:
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                 p.grad = v
 
+    def begin_direct(self) -> None:
+        """For a step with ONE backward pass (all of the step's views in one ``rasterization()`` call): the fused
+        projection backward writes every gradient element exactly once, so it is pointed straight at the bucket —
+        no zero fill before and no accumulate pass after the backward (2 x 236 B/Gaussian of traffic less).  Call
+        ``end_direct()`` after ``backward()``."""
+        from . import stages
+        for p, v in zip(self.params, self.views):
+            p.grad = None
+            stages.register_grad_target(p, v)
+
+    def end_direct(self) -> None:
+        from . import stages
+        stages.clear_grad_targets()
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():  # the gradient took another route (e.g. torch ops in front)
+                v.copy_(p.grad)
+            p.grad = v
+
     def all_reduce(self, group=None, async_op: bool = False):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)

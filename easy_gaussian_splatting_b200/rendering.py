@@ -96,7 +96,7 @@ class _Rasterization(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(means, quats, scales, colors, viewmats, Ks, backgrounds, proj["radii"], proj["colors"],
                               proj["splats"], isect_offsets, flatten_ids, render_alphas, last_ids,
-                              opacities if cfg["antialiased"] else None, ckpt, render_colors if ckpt is not None else None)
+                              opacities, ckpt, render_colors if ckpt is not None else None)
         nondiff = (proj["radii"], proj["depths"], proj["conics"], proj["colors"], tiles_per_gauss,
                    flatten_ids, isect_offsets, last_ids)
         ctx.mark_non_differentiable(*nondiff)
@@ -105,7 +105,7 @@ class _Rasterization(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_colors, v_alphas, v_means2d, *_unused):
         (means, quats, scales, colors, viewmats, Ks, backgrounds, radii, colors_rgb, splats, isect_offsets,
-         flatten_ids, render_alphas, last_ids, aa_opacities, ckpt, render_colors) = ctx.saved_tensors
+         flatten_ids, render_alphas, last_ids, opacities, ckpt, render_colors) = ctx.saved_tensors
         cfg = ctx.cfg
         width, height = cfg["width"], cfg["height"]
         C = viewmats.shape[0]
@@ -119,7 +119,7 @@ class _Rasterization(torch.autograd.Function):
         target = ref() if ref is not None else None
         out = stages.projection_bwd(means, quats, scales, colors, viewmats, Ks, width, height, cfg["sh_degree"],
                                     cfg["eps2d"], radii, colors_rgb, v_splats, v_means2d, want_absgrad=target is not None,
-                                    antialiased_opacities=aa_opacities)
+                                    antialiased_opacities=opacities if cfg["antialiased"] else None, opacities=opacities)
         v_means, v_quats, v_scales, v_opac, v_cols = out[:5]
         if target is not None:
             # same contract as gsplat: attribute tagging on the tensor object handed out in meta

@@ -23,6 +23,29 @@ SPLAT_FLOATS = 12
 TILE_SIZE = 16
 
 
+# Caller-owned gradient storage (see distributed.FlatGradBucket.begin_direct): parameter data_ptr -> buffer.  The
+# projection backward writes EVERY element of every parameter gradient exactly once, so it can write straight into a
+# registered buffer — no zero fill, no accumulate pass, and ``param.grad`` becomes a view of the caller's bucket.
+_GRAD_TARGETS: Dict[int, Tensor] = {}
+
+
+def register_grad_target(param: Tensor, buffer: Tensor) -> None:
+    if buffer.numel() != param.numel() or buffer.dtype != param.dtype or buffer.device != param.device or not buffer.is_contiguous():
+        raise ValueError("gradient target must be a contiguous buffer of the parameter's size, dtype and device")
+    _GRAD_TARGETS[param.data_ptr()] = buffer
+
+
+def clear_grad_targets() -> None:
+    _GRAD_TARGETS.clear()
+
+
+def _grad_buffer(inp: Tensor) -> Tensor:
+    tgt = _GRAD_TARGETS.get(inp.data_ptr()) if _GRAD_TARGETS else None
+    if tgt is not None and tgt.numel() == inp.numel() and inp.is_contiguous():
+        return tgt.view(inp.shape)  # a fresh tensor object over the caller's storage: autograd adopts it as .grad
+    return torch.empty_like(inp)
+
+
 def _ptr(t: Optional[Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -96,9 +119,11 @@ def projection_fwd(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tens
 def projection_bwd(means: Tensor, quats: Tensor, scales: Tensor, colors: Tensor, viewmats: Tensor, Ks: Tensor,
                    width: int, height: int, sh_degree: Optional[int], eps2d: float, radii: Tensor,
                    colors_rgb: Tensor, v_splats: Tensor, v_means2d_extra: Optional[Tensor] = None,
-                   want_absgrad: bool = False, antialiased_opacities: Optional[Tensor] = None):
+                   want_absgrad: bool = False, antialiased_opacities: Optional[Tensor] = None,
+                   opacities: Optional[Tensor] = None):
     """g8+g9. -> v_means[N,3], v_quats[N,4], v_scales[N,3], v_opacities[N], v_colors (shape of colors)
-    (+ absgrad[C,N,2] when want_absgrad).  antialiased_opacities: the opacities[N] of an antialiased forward."""
+    (+ absgrad[C,N,2] when want_absgrad).  antialiased_opacities: the opacities[N] of an antialiased forward;
+    opacities: only consulted for a registered gradient buffer (register_grad_target)."""
     lib = _lib.load()
     dev = means.device
     N, C = means.shape[0], viewmats.shape[0]
@@ -106,11 +131,12 @@ def projection_bwd(means: Tensor, quats: Tensor, scales: Tensor, colors: Tensor,
         K, deg, per_cam = 1, -1, int(colors.dim() == 3)
     else:
         K, deg, per_cam = colors.shape[-2], int(sh_degree), 0
-    v_means = torch.empty_like(means)
-    v_quats = torch.empty_like(quats)
-    v_scales = torch.empty_like(scales)
-    v_opac = torch.empty(N, dtype=torch.float32, device=dev)
-    v_colors = torch.empty_like(colors)
+    v_means = _grad_buffer(means)
+    v_quats = _grad_buffer(quats)
+    v_scales = _grad_buffer(scales)
+    op_ref = antialiased_opacities if antialiased_opacities is not None else opacities
+    v_opac = _grad_buffer(op_ref) if op_ref is not None else torch.empty(N, dtype=torch.float32, device=dev)
+    v_colors = _grad_buffer(colors)
     if v_means2d_extra is not None:
         v_means2d_extra = _f32c(v_means2d_extra, "v_means2d")
     absgrad = torch.empty(C, N, 2, dtype=torch.float32, device=dev) if want_absgrad else None
@@ -173,7 +199,7 @@ def projection_bwd_raw(means: Tensor, quats: Tensor, log_scales: Tensor, logit_o
     lib = _lib.load()
     dev = means.device
     N, C = means.shape[0], viewmats.shape[0]
-    outs = [torch.empty_like(t) for t in (means, quats, log_scales, logit_opacities, sh_0, sh_rest)]
+    outs = [_grad_buffer(t) for t in (means, quats, log_scales, logit_opacities, sh_0, sh_rest)]
     if v_means2d_extra is not None:
         v_means2d_extra = _f32c(v_means2d_extra, "v_means2d")
     absgrad = torch.empty(C, N, 2, dtype=torch.float32, device=dev) if want_absgrad else None

@@ -331,3 +331,38 @@ def test_folded_activations_match_unfolded(sh_degree):
     nb = (sh_degree + 1) ** 2
     if nb < 16:
         assert float(b["sh_rest"].grad[:, nb - 1:].abs().sum()) == 0.0  # inactive bands get exactly zero
+
+
+def test_direct_gradient_bucket():
+    """FlatGradBucket.begin_direct(): the fused backward writes the gradients straight into the caller's flat bucket
+    (param.grad becomes a view of it, no zero fill / accumulate pass) — same numbers as the ordinary route."""
+    from easy_gaussian_splatting_b200 import rasterization
+    from easy_gaussian_splatting_b200.distributed import FlatGradBucket
+    from easy_gaussian_splatting_b200.synthetic import loss_weights
+    sc = make_scene(**CASES[1]).to("cuda")
+    C = sc.viewmats.shape[0]
+    Wc, Wa = (t.cuda() for t in loss_weights(sc.seed, C, sc.height, sc.width))
+
+    def run(params):
+        rc, ra, _ = rasterization(*params, sc.viewmats, sc.Ks, sc.width, sc.height, sh_degree=3, packed=False,
+                                  absgrad=True, backgrounds=sc.background[None].expand(C, 3).contiguous())
+        ((rc * Wc).sum() + (ra * Wa).sum()).backward()
+
+    ref = [getattr(sc, k).clone().requires_grad_(True) for k in PARAMS]
+    run(ref)
+    params = [getattr(sc, k).clone().requires_grad_(True) for k in PARAMS]
+    bucket = FlatGradBucket(params)
+    bucket.flat.fill_(float("nan"))  # direct mode must overwrite every element without a zero fill
+    bucket.begin_direct()
+    run(params)
+    direct_ptrs = [p.grad.data_ptr() for p in params]
+    bucket.end_direct()
+    assert direct_ptrs == [v.data_ptr() for v in bucket.views], "autograd did not adopt the bucket views"
+    assert torch.isfinite(bucket.flat).all()
+    for p, r, k in zip(params, ref, PARAMS):
+        assert p.grad.data_ptr() == bucket.views[PARAMS.index(k)].data_ptr()
+        assert rel_err(p.grad.cpu(), r.grad.cpu()) <= 1e-5, k
+    # a second, ordinary backward accumulates on top (the registry is cleared)
+    run(params)
+    for p, r, k in zip(params, ref, PARAMS):
+        assert rel_err(p.grad.cpu(), 2 * r.grad.cpu()) <= 1e-5, k
