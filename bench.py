@@ -52,6 +52,8 @@ def parse_args():
                     help="cfg4-style full training step: --total-views views per step split across the ranks (strong "
                          "scaling), gradient + densify-stat all-reduce, fused Adam")
     ap.add_argument("--total-views", type=int, default=64)
+    ap.add_argument("--no-train-step", action="store_true",
+                    help="skip the extra cfg4 training-step measurement that the default run appends as line['train_step']")
     ap.add_argument("--no-view-pipelining", action="store_true",
                     help="render the views of a step strictly one after the other on one stream")
     ap.add_argument("--activations", default="pre", choices=["pre", "torch", "folded"],
@@ -207,7 +209,7 @@ def ours(args):
         raise RuntimeError("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     V = args.views_per_rank
@@ -235,8 +237,12 @@ def ours(args):
     optimizer = None
     if args.train_step:
         from easy_gaussian_splatting_b200.optim import FusedAdam
-        lrs = dict(means=1e-3, quats=1e-3, scales=1e-2, opacities=5e-2, colors=2.5e-3, log_scales=1e-2,
-                   logit_opacities=5e-2, sh_0=2.5e-3, sh_rest=1.25e-4)  # configs/*.yaml learning rates
+        # configs/*.yaml learning rates x 1e-4: Adam moves every parameter by ~lr per step whatever the gradient, and
+        # the synthetic objective (a random linear functional) has no minimum — at the real rates the splats grow
+        # step after step, n_isects with them, and the "step time" measures how long the run has been diverging
+        # (seen as 113..323 ms for the same command).  Adam's work does not depend on the learning rate.
+        lrs = {k: v * 1e-4 for k, v in dict(means=1e-3, quats=1e-3, scales=1e-2, opacities=5e-2, colors=2.5e-3,
+                                            log_scales=1e-2, logit_opacities=5e-2, sh_0=2.5e-3, sh_rest=1.25e-4).items()}
         optimizer = FusedAdam([{"params": [p_], "lr": lrs[k], "name": k} for k, p_ in zip(names, params)], eps=1e-15)
     # The step's V views are rendered by V / C calls of C views each (viewmats [C,4,4], the call's own batching):
     # every kernel of a call then works on C views' worth of tiles, which fills the 148 SMs where one view's
@@ -400,7 +406,15 @@ def ours(args):
         return ms, clocks
 
     W_ = max(args.warmup, 3)
+    for _ in range(W_):  # warm-up before the allocator snapshot (timed() warms up again: >= 3 untimed steps either way)
+        step_resident()
+    ms0 = torch.cuda.memory_stats(dev)
     ms_total, clocks = timed(step_resident, args.steps, W_, sample_clocks=True)
+    ms1 = torch.cuda.memory_stats(dev)
+    alloc_stats = {"cudaMalloc_calls_in_timed_region": ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0),
+                   "cudaFree_calls_in_timed_region": ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0),
+                   "alloc_retries": ms1.get("num_alloc_retries", 0),
+                   "reserved_gb": ms1.get("reserved_bytes.all.peak", 0) / 1e9}
     ms_step = ms_total / args.steps
     pixels_per_step = world * V * W * H
     value = pixels_per_step / (ms_step * 1e-3) / 1e6
@@ -416,7 +430,7 @@ def ours(args):
                    "l2": "inputs larger than L2 (236 MB parameters + 96 MB splat/gradient records per view vs 126 MB L2)",
                    "gradients": "written straight into the flat bucket by the fused backward (one backward per step)" if direct else "accumulated into the flat bucket by autograd",
                    "exchange": "none (1 GPU)" if world == 1 else "NCCL all-reduce of the flat 236 B/Gaussian gradient bucket + 12 B/Gaussian densify stats each step"},
-        "clocks": clocks,
+        "clocks": clocks, "allocator": alloc_stats,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e_total / args.steps,
                 "what": "rasterization() fwd+bwd per call with its views' cameras and loss weights (one target-image-sized buffer per view) copied "
@@ -438,18 +452,18 @@ def ours(args):
 
     if rank == 0 and not args.no_stage_timing and args.activations == "pre":
         line.update(stage_rooflines(lib, stages, params, dev_views[0], bg, dev_Wc, dev_Wa, W, H, dev))
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        sc, sample = cpu_sample_scene(args.workload, args.ref_crop, args.n_gaussians)
-        med, mpix, _ = run_cpu_oracle(sc, 3, 1)
-        line["cpu_baseline"] = {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                                "ms_per_sample": med * 1e3}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    return line
+
+
+def add_cpu_baseline(args, line):
+    """rank 0, N = 1: the oracle on a bounded crop of the same workload, all host cores (run last: it leaves the
+    host's thread pool busy, which slows the launch-bound parts of whatever is timed after it)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sc, sample = cpu_sample_scene(args.workload, args.ref_crop, args.n_gaussians)
+    med, mpix, _ = run_cpu_oracle(sc, 3, 1)
+    line["cpu_baseline"] = {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                            "ms_per_sample": med * 1e3}
 
 
 def launches_per_call(stages, C, W, H, backward=True):
@@ -602,8 +616,29 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         reference_arm(args)
-    else:
-        ours(args)
+        return
+    import copy
+    import torch.distributed as dist
+    line = ours(args)
+    if args.workload == "metric" and not (args.train_step or args.forward_only or args.no_train_step or args.n_gaussians):
+        # second half of BASELINE.json's metric ("train it/s at 1/2/4/8 GPU"): BASELINE config 4, the view-sharded
+        # training step — 3 M Gaussians, 1920x1080, 64 views per step split across the ranks (strong scaling),
+        # fwd+bwd of every view, NCCL all-reduce of gradients and densify statistics, fused Adam
+        a2 = copy.copy(args)
+        a2.train_step, a2.workload, a2.total_views, a2.views_per_call = True, "cfg4", 64, 8
+        a2.steps, a2.warmup, a2.no_stage_timing, a2.no_cpu_baseline, a2.activations = 5, 5, True, True, "pre"
+        l2 = ours(a2)
+        line["train_step"] = dict(l2["train_step"], ms_per_step=l2["ms_per_step"], mpix_per_s=l2["value"], scaling="strong",
+                                  steps=a2.steps, workload=l2["config"]["workload"], views_per_call=l2["config"]["views_per_call"],
+                                  exchange=l2["config"]["exchange"], allocator=l2["allocator"])
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if int(os.environ.get("RANK", "0")) == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            add_cpu_baseline(args, line)
+        print(json.dumps(line), flush=True)
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
