@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs on the GPU box: the headline bench (with cpu baseline), the reference arm, and the other BASELINE configs.
 mkdir -p gpurun_out
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_metric.log 2>&1; echo "metric rc=$?"
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_metric.log 2>&1; echo "metric rc=$?"
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.log 2>&1; echo "reference rc=$?"
 timeout 600 python bench.py --workload cfg2 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_cfg2.log 2>&1; echo "cfg2 rc=$?"
 timeout 600 python bench.py --workload cfg3 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_cfg3.log 2>&1; echo "cfg3 rc=$?"
@@ -18,8 +18,8 @@ except Exception as e:
     print("$f parse failed", e); print(open("gpurun_out/bench_$f.log").read()[-1500:])
 PY
 done
-timeout 600 python bench.py --views-per-call 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_metric_c1.log 2>&1; echo "metric C=1 rc=$?"
-timeout 600 python bench.py --activations folded --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_metric_folded.log 2>&1; echo "folded rc=$?"
-timeout 600 python bench.py --activations torch --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_metric_torch.log 2>&1; echo "torch rc=$?"
-timeout 600 python bench.py --workload cfg4 --train-step --total-views 64 --views-per-call 8 --steps 3 --warmup 3 --no-cpu-baseline --no-stage-timing > gpurun_out/bench_cfg4_train.log 2>&1; echo "train rc=$?"
+timeout 600 python bench.py --views-per-call 1 --steps 20 --warmup 5 --no-cpu-baseline --no-train-step > gpurun_out/bench_metric_c1.log 2>&1; echo "metric C=1 rc=$?"
+timeout 600 python bench.py --activations folded --steps 20 --warmup 5 --no-cpu-baseline --no-train-step > gpurun_out/bench_metric_folded.log 2>&1; echo "folded rc=$?"
+timeout 600 python bench.py --activations torch --steps 20 --warmup 5 --no-cpu-baseline --no-train-step > gpurun_out/bench_metric_torch.log 2>&1; echo "torch rc=$?"
+timeout 600 python bench.py --workload cfg4 --train-step --total-views 64 --views-per-call 8 --steps 5 --warmup 3 --no-cpu-baseline --no-stage-timing > gpurun_out/bench_cfg4_train.log 2>&1; echo "train rc=$?"
 python scripts/show_bench.py gpurun_out/bench_metric_c1.log gpurun_out/bench_metric_folded.log gpurun_out/bench_metric_torch.log gpurun_out/bench_cfg4_train.log
