@@ -429,7 +429,7 @@ def ours(args):
                    "view_pipelining": pipelined, "activations": args.activations,
                    "l2": "inputs larger than L2 (236 MB parameters + 96 MB splat/gradient records per view vs 126 MB L2)",
                    "gradients": "written straight into the flat bucket by the fused backward (one backward per step)" if direct else "accumulated into the flat bucket by autograd",
-                   "exchange": "none (1 GPU)" if world == 1 else "NCCL all-reduce of the flat 236 B/Gaussian gradient bucket + 12 B/Gaussian densify stats each step"},
+                   "exchange": "none (1 GPU)" if world == 1 else f"{bucket.exchange} of the flat 236 B/Gaussian gradient bucket + NCCL all-reduce of 12 B/Gaussian densify stats each step"},
         "clocks": clocks, "allocator": alloc_stats,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e_total / args.steps,

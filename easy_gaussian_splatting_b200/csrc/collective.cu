@@ -1,0 +1,114 @@
+// Gradient exchange of the view-sharded training step as a hand-written two-shot all-reduce over
+// NVLink peer memory: every rank's flat gradient bucket lives in symmetric memory (the same virtual layout on every
+// GPU, each mapped into every peer), rank r sums slice r of all buckets with peer LOADS and writes the result back
+// into every bucket with peer STORES.  Each GPU moves (R-1)/R of the bucket in and out once — the NVSwitch gives
+// every pair full bandwidth, so this is the traffic floor of an all-reduce — and the sum is taken in rank order by
+// exactly one GPU per element, so all replicas receive bit-identical gradients.  The two inter-rank barriers around
+// the kernel are the caller's (torch symmetric-memory signal pads, stream ordered).
+#include "egs_common.cuh"
+
+namespace egs {
+
+constexpr int kArThreads = 256;
+constexpr int kArMaxWorld = 16;
+
+template <int WORLD>
+__global__ void __launch_bounds__(kArThreads) allreduce_two_shot_kernel(float* const* __restrict__ bufs, int rank,
+                                                                        int64_t n4) {
+  float4* b[WORLD];
+#pragma unroll
+  for (int p = 0; p < WORLD; ++p) b[p] = reinterpret_cast<float4*>(bufs[p]);
+  const int64_t per = (n4 + WORLD - 1) / WORLD;
+  const int64_t lo = (int64_t)rank * per, hi = min(n4, lo + per);
+  const int64_t stride = (int64_t)gridDim.x * kArThreads;
+  for (int64_t i = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < hi; i += 2 * stride) {
+    const int64_t i1 = i + stride;
+    const bool two = i1 < hi;
+    float4 v0[WORLD], v1[WORLD];
+#pragma unroll
+    for (int p = 0; p < WORLD; ++p) {  // every peer load of the trip in flight before the first add
+      v0[p] = b[p][i];
+      v1[p] = two ? b[p][i1] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 a0 = v0[0], a1 = v1[0];
+#pragma unroll
+    for (int p = 1; p < WORLD; ++p) {  // fixed rank order: deterministic, identical on every replica
+      a0.x += v0[p].x; a0.y += v0[p].y; a0.z += v0[p].z; a0.w += v0[p].w;
+      a1.x += v1[p].x; a1.y += v1[p].y; a1.z += v1[p].z; a1.w += v1[p].w;
+    }
+#pragma unroll
+    for (int p = 0; p < WORLD; ++p) {
+      b[p][i] = a0;
+      if (two) b[p][i1] = a1;
+    }
+  }
+}
+
+// Same exchange through the NVSwitch's multicast / in-switch reduction (NVLS): one multimem.ld_reduce pulls the SUM
+// of an element over all replicas (the switch reads every GPU's copy and adds in flight), one multimem.st pushes it
+// back to all of them.  Per GPU only 1/R of the bucket crosses its own link in each direction.
+__global__ void __launch_bounds__(kArThreads) allreduce_multimem_kernel(float* __restrict__ mc, int world, int rank,
+                                                                        int64_t n4) {
+  const int64_t per = (n4 + world - 1) / world;
+  const int64_t lo = (int64_t)rank * per, hi = min(n4, lo + per);
+  const int64_t stride = (int64_t)gridDim.x * kArThreads;
+  float4* m4 = reinterpret_cast<float4*>(mc);
+  for (int64_t i = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < hi; i += 2 * stride) {
+    const int64_t i1 = i + stride;
+    const bool two = i1 < hi;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(m4 + i) : "memory");
+    if (two)
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(m4 + i1) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(m4 + i), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+    if (two)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(m4 + i1), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+  }
+}
+
+}  // namespace egs
+
+using namespace egs;
+
+extern "C" int egs_allreduce_sum_f32_multimem(int32_t world, int32_t rank, void* multicast_ptr, int64_t n_floats,
+                                              egs_stream_t stream) {
+  EGS_REQUIRE(world >= 1 && rank >= 0 && rank < world, "allreduce_multimem: bad world=%d rank=%d", world, rank);
+  EGS_REQUIRE(n_floats >= 0 && n_floats % 4 == 0, "allreduce_multimem: n_floats=%lld must be a multiple of 4", (long long)n_floats);
+  EGS_REQUIRE(multicast_ptr != nullptr, "allreduce_multimem: multicast pointer is required");
+  if (n_floats == 0 || world == 1) return 0;
+  const int64_t n4 = n_floats / 4;
+  int64_t blocks = ceil_div(ceil_div(n4, world), 2 * kArThreads);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  allreduce_multimem_kernel<<<(unsigned)blocks, kArThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<float*>(multicast_ptr), world, rank, n4);
+  return check_launch("allreduce_multimem_kernel");
+}
+
+extern "C" int egs_allreduce_sum_f32_peer(int32_t world, int32_t rank, const void* peer_buffers_dev, int64_t n_floats,
+                                          egs_stream_t stream) {
+  EGS_REQUIRE(world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world, "allreduce_peer: bad world=%d rank=%d", world, rank);
+  EGS_REQUIRE(n_floats >= 0 && n_floats % 4 == 0, "allreduce_peer: n_floats=%lld must be a multiple of 4", (long long)n_floats);
+  EGS_REQUIRE(peer_buffers_dev != nullptr, "allreduce_peer: peer buffer table is required");
+  if (n_floats == 0 || world == 1) return 0;
+  float* const* bufs = reinterpret_cast<float* const*>(peer_buffers_dev);
+  const int64_t n4 = n_floats / 4;
+  const int64_t per = (n4 + world - 1) / world;
+  int64_t blocks = ceil_div(per, 2 * kArThreads);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const unsigned grid = (unsigned)blocks;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (world) {
+    case 2: allreduce_two_shot_kernel<2><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
+    case 3: allreduce_two_shot_kernel<3><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
+    case 4: allreduce_two_shot_kernel<4><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
+    case 5: allreduce_two_shot_kernel<5><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
+    case 6: allreduce_two_shot_kernel<6><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
+    case 7: allreduce_two_shot_kernel<7><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
+    case 8: allreduce_two_shot_kernel<8><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
+    default: return fail(EGS_ERR_UNSUPPORTED, "allreduce_peer: world=%d is not instantiated (2..8)", world);
+  }
+  return check_launch("allreduce_two_shot_kernel");
+}

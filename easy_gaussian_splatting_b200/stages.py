@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes
 import math
 import os
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -26,13 +27,13 @@ TILE_SIZE = 16
 # Caller-owned gradient storage (see distributed.FlatGradBucket.begin_direct): parameter data_ptr -> buffer.  The
 # projection backward writes EVERY element of every parameter gradient exactly once, so it can write straight into a
 # registered buffer — no zero fill, no accumulate pass, and ``param.grad`` becomes a view of the caller's bucket.
-_GRAD_TARGETS: Dict[int, Tensor] = {}
+_GRAD_TARGETS: Dict[int, Tuple["weakref.ref", Tensor]] = {}
 
 
 def register_grad_target(param: Tensor, buffer: Tensor) -> None:
     if buffer.numel() != param.numel() or buffer.dtype != param.dtype or buffer.device != param.device or not buffer.is_contiguous():
         raise ValueError("gradient target must be a contiguous buffer of the parameter's size, dtype and device")
-    _GRAD_TARGETS[param.data_ptr()] = buffer
+    _GRAD_TARGETS[param.data_ptr()] = (weakref.ref(param), buffer)
 
 
 def clear_grad_targets() -> None:
@@ -40,9 +41,12 @@ def clear_grad_targets() -> None:
 
 
 def _grad_buffer(inp: Tensor) -> Tensor:
-    tgt = _GRAD_TARGETS.get(inp.data_ptr()) if _GRAD_TARGETS else None
-    if tgt is not None and tgt.numel() == inp.numel() and inp.is_contiguous():
-        return tgt.view(inp.shape)  # a fresh tensor object over the caller's storage: autograd adopts it as .grad
+    entry = _GRAD_TARGETS.get(inp.data_ptr()) if _GRAD_TARGETS else None
+    if entry is not None:
+        owner, tgt = entry
+        live = owner()  # a registration whose parameter is gone must not capture a new tensor at the same address
+        if live is not None and live.data_ptr() == inp.data_ptr() and live.shape == inp.shape and inp.is_contiguous():
+            return tgt.view(inp.shape)  # a fresh tensor object over the caller's storage: autograd adopts it as .grad
     return torch.empty_like(inp)
 
 

@@ -251,6 +251,19 @@ int egs_fused_adam(int32_t n_groups, float* const* params, const float* const* g
                    float* const* exp_avg_sq, const int64_t* numels, const float* lrs, float beta1, float beta2,
                    float eps, int64_t step, egs_stream_t stream);
 
+/* ---- §8e: gradient exchange as a two-shot all-reduce over NVLink peer memory -------------------------------------
+ * Every rank's flat fp32 gradient bucket (n_floats, a multiple of 4) is mapped into every peer (symmetric memory);
+ * peer_buffers_dev: DEVICE array of `world` device pointers, entry p = rank p's bucket as mapped on this GPU.
+ * Rank r sums slice r over all buckets in rank order (peer loads) and writes it into every bucket (peer stores):
+ * in-place SUM all-reduce, bit-identical on all replicas.  The caller brackets the call with inter-rank barriers
+ * (all buckets complete before, all slices written after); world = 1 is a no-op. */
+int egs_allreduce_sum_f32_peer(int32_t world, int32_t rank, const void* peer_buffers_dev, int64_t n_floats,
+                               egs_stream_t stream);
+/* The same exchange through the NVSwitch (NVLS): multicast_ptr is the multicast mapping of the symmetric bucket;
+ * rank r pulls the in-switch SUM of slice r (multimem.ld_reduce) and broadcasts it back (multimem.st). */
+int egs_allreduce_sum_f32_multimem(int32_t world, int32_t rank, void* multicast_ptr, int64_t n_floats,
+                                   egs_stream_t stream);
+
 /* ---- measurement utility (bench.py only) -----------------------------------------------------------------
  * Dependent-FMA throughput probe: the FP32-SIMT roofline denominator for the blending kernels
  * (BASELINE.md §3).  blocks x 256 threads x iters x 32 FMAs; *host_flops (HOST double) = flops issued. */
