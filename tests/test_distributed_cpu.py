@@ -108,3 +108,41 @@ def test_flat_bucket_survives_optimizer_zero_grad():
     opt.zero_grad(set_to_none=True)
     bucket.zero_()
     assert all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, bucket.views))
+
+
+def test_direct_gradient_routes_on_cpu():
+    """FlatGradBucket.direct(): gradients that reach a parameter by another route than the fused backward (here plain
+    autograd on CPU tensors) are copied into the bucket and .grad is re-pointed at the bucket view; the registry of
+    gradient targets never captures a tensor whose registration is stale."""
+    import torch
+    from easy_gaussian_splatting_b200 import stages
+    from easy_gaussian_splatting_b200.distributed import FlatGradBucket
+    params = [torch.randn(5, 3, requires_grad=True), torch.randn(7, requires_grad=True)]
+    bucket = FlatGradBucket(params)
+    assert bucket.exchange == "NCCL all-reduce" and bucket.flat.numel() % 4 == 0
+    with bucket.direct():
+        assert all(p.grad is None for p in params)
+        ((params[0] * 2.0).sum() + (params[1] * 3.0).sum()).backward()
+    assert not stages._GRAD_TARGETS  # registration removed
+    for p, v, k in zip(params, bucket.views, (2.0, 3.0)):
+        assert p.grad.data_ptr() == v.data_ptr() and torch.equal(p.grad, torch.full_like(p, k))
+    # a parameter without gradient in a direct step ends with a zero bucket slice
+    with bucket.direct():
+        (params[0] * 1.0).sum().backward()
+    assert torch.equal(bucket.views[1], torch.zeros(7)) and torch.equal(bucket.views[0], torch.ones(5, 3))
+    # _grad_buffer: registered target is used while the owner lives, ignored once it is gone
+    owner = torch.zeros(4, 3)
+    target = torch.zeros(12)
+    stages.register_grad_target(owner, target)
+    out = stages._grad_buffer(owner)
+    assert out.data_ptr() == target.data_ptr() and out.shape == owner.shape
+    key = owner.data_ptr()
+    del owner, out
+    import gc
+    gc.collect()
+    impostor = torch.zeros(4, 3)
+    stages._GRAD_TARGETS[impostor.data_ptr()] = stages._GRAD_TARGETS.pop(key)  # same address, dead owner
+    assert stages._grad_buffer(impostor).data_ptr() != target.data_ptr()
+    stages.clear_grad_targets()
+    with pytest.raises(ValueError):
+        stages.register_grad_target(torch.zeros(3), torch.zeros(4))
