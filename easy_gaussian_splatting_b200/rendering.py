@@ -55,22 +55,26 @@ def _tag_absgrad(target: Tensor, absgrad: Tensor, packed_index: Optional[Tensor]
     target.absgrad = absgrad if packed_index is None else absgrad.reshape(-1, 2)[packed_index]
 
 
-def _blend_forward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width, height):
-    """Blend forward; when a backward pass will follow and long-list segmentation is on, the checkpointed variant."""
-    seg = stages.backward_segment() if any(ctx.needs_input_grad) else 0
+def _blend_forward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width, height, grad_enabled=True):
+    """Blend forward; when a backward pass will follow and long-list segmentation is on, the checkpointed variant.
+    (grad_enabled is the CALLER's grad mode: inside Function.forward it is always off, and needs_input_grad stays
+    true under no_grad.)"""
+    seg = stages.backward_segment() if (grad_enabled and any(ctx.needs_input_grad)) else 0
     ctx.segment = seg
-    if seg > 0:
-        return stages.rasterize_fwd_checkpointed(splats, isect_offsets, flatten_ids, backgrounds, width, height, seg)
-    return (*stages.rasterize_fwd(splats, isect_offsets, flatten_ids, backgrounds, width, height), None)
+    with stages.nvtx_range("egs.rasterize_fwd"):
+        if seg > 0:
+            return stages.rasterize_fwd_checkpointed(splats, isect_offsets, flatten_ids, backgrounds, width, height, seg)
+        return (*stages.rasterize_fwd(splats, isect_offsets, flatten_ids, backgrounds, width, height), None)
 
 
 def _blend_backward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_colors, render_alphas,
                     last_ids, v_colors, v_alphas, ckpt):
-    if ckpt is not None:
-        return stages.rasterize_bwd_segmented(splats, isect_offsets, flatten_ids, backgrounds, width, height,
-                                              render_colors, render_alphas, last_ids, v_colors, v_alphas, ckpt, ctx.segment)
-    return stages.rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, render_alphas, last_ids,
-                                v_colors, v_alphas)
+    with stages.nvtx_range("egs.rasterize_bwd"):
+        if ckpt is not None:
+            return stages.rasterize_bwd_segmented(splats, isect_offsets, flatten_ids, backgrounds, width, height,
+                                                  render_colors, render_alphas, last_ids, v_colors, v_alphas, ckpt, ctx.segment)
+        return stages.rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, render_alphas, last_ids,
+                                    v_colors, v_alphas)
 
 
 class _Rasterization(torch.autograd.Function):
@@ -78,18 +82,20 @@ class _Rasterization(torch.autograd.Function):
     def forward(ctx, means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg):
         width, height, sh_degree = cfg["width"], cfg["height"], cfg["sh_degree"]
         C, N = viewmats.shape[0], means.shape[0]
-        proj = stages.projection_fwd(means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree,
-                                     eps2d=cfg["eps2d"], near_plane=cfg["near_plane"], far_plane=cfg["far_plane"],
-                                     radius_clip=cfg["radius_clip"], antialiased=cfg["antialiased"])
+        with stages.nvtx_range("egs.projection_fwd"):
+            proj = stages.projection_fwd(means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree,
+                                         eps2d=cfg["eps2d"], near_plane=cfg["near_plane"], far_plane=cfg["far_plane"],
+                                         radius_clip=cfg["radius_clip"], antialiased=cfg["antialiased"])
         cfg["compensations"] = proj.get("compensations")  # non-differentiable side output, like the thunk below
         tw, th = stages.tile_grid(width, height)
         tiles_per_gauss = proj["tiles_per_gauss"]
-        isect_ids_thunk, flatten_ids, isect_offsets = stages.isect_sorted(
-            proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th,
-            materialize_ids=False)
+        with stages.nvtx_range("egs.binning"):
+            isect_ids_thunk, flatten_ids, isect_offsets = stages.isect_sorted(
+                proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th,
+                materialize_ids=False)
         cfg["isect_ids_thunk"] = isect_ids_thunk  # handed to the wrapper (not a tensor: cannot be an output)
         render_colors, render_alphas, last_ids, ckpt = _blend_forward(ctx, proj["splats"], isect_offsets, flatten_ids,
-                                                                     backgrounds, width, height)
+                                                                     backgrounds, width, height, cfg.get("grad_enabled", True))
 
         means2d = proj["means2d"]
         ctx.cfg = cfg
@@ -117,9 +123,10 @@ class _Rasterization(torch.autograd.Function):
                                    render_alphas, last_ids, v_colors, v_alphas, ckpt)
         ref = getattr(ctx, "means2d_ref", None) if cfg["absgrad"] else None
         target = ref() if ref is not None else None
-        out = stages.projection_bwd(means, quats, scales, colors, viewmats, Ks, width, height, cfg["sh_degree"],
-                                    cfg["eps2d"], radii, colors_rgb, v_splats, v_means2d, want_absgrad=target is not None,
-                                    antialiased_opacities=opacities if cfg["antialiased"] else None, opacities=opacities)
+        with stages.nvtx_range("egs.projection_bwd"):
+            out = stages.projection_bwd(means, quats, scales, colors, viewmats, Ks, width, height, cfg["sh_degree"],
+                                        cfg["eps2d"], radii, colors_rgb, v_splats, v_means2d, want_absgrad=target is not None,
+                                        antialiased_opacities=opacities if cfg["antialiased"] else None, opacities=opacities)
         v_means, v_quats, v_scales, v_opac, v_cols = out[:5]
         if target is not None:
             # same contract as gsplat: attribute tagging on the tensor object handed out in meta
@@ -138,17 +145,19 @@ class _RasterizationRaw(torch.autograd.Function):
     def forward(ctx, means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds, cfg):
         width, height, sh_degree = cfg["width"], cfg["height"], cfg["sh_degree"]
         C = viewmats.shape[0]
-        proj = stages.projection_fwd_raw(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, width,
-                                         height, sh_degree, eps2d=cfg["eps2d"], near_plane=cfg["near_plane"],
-                                         far_plane=cfg["far_plane"], radius_clip=cfg["radius_clip"])
+        with stages.nvtx_range("egs.projection_fwd_raw"):
+            proj = stages.projection_fwd_raw(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, width,
+                                             height, sh_degree, eps2d=cfg["eps2d"], near_plane=cfg["near_plane"],
+                                             far_plane=cfg["far_plane"], radius_clip=cfg["radius_clip"])
         tw, th = stages.tile_grid(width, height)
         tiles_per_gauss = proj["tiles_per_gauss"]
-        isect_ids_thunk, flatten_ids, isect_offsets = stages.isect_sorted(
-            proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th,
-            materialize_ids=False)
+        with stages.nvtx_range("egs.binning"):
+            isect_ids_thunk, flatten_ids, isect_offsets = stages.isect_sorted(
+                proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th,
+                materialize_ids=False)
         cfg["isect_ids_thunk"] = isect_ids_thunk
         render_colors, render_alphas, last_ids, ckpt = _blend_forward(ctx, proj["splats"], isect_offsets, flatten_ids,
-                                                                     backgrounds, width, height)
+                                                                     backgrounds, width, height, cfg.get("grad_enabled", True))
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds,
@@ -275,7 +284,7 @@ def rasterization(
     C = viewmats.shape[0]
     cfg = dict(width=width, height=height, sh_degree=sh_degree, eps2d=float(eps2d), near_plane=float(near_plane),
                far_plane=float(far_plane), radius_clip=float(radius_clip), absgrad=bool(absgrad),
-               antialiased=rasterize_mode == "antialiased")
+               antialiased=rasterize_mode == "antialiased", grad_enabled=torch.is_grad_enabled())
     outs = _Rasterization.apply(means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg)
     opacities_cn = opacities.detach()[None].expand(C, -1)
     comp = cfg.pop("compensations", None)
@@ -377,7 +386,8 @@ def rasterization_from_parameters(
     if viewmats.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError("gradients w.r.t. viewmats are not implemented")
     cfg = dict(width=width, height=height, sh_degree=int(sh_degree), eps2d=float(eps2d), near_plane=float(near_plane),
-               far_plane=float(far_plane), radius_clip=float(radius_clip), absgrad=bool(absgrad))
+               far_plane=float(far_plane), radius_clip=float(radius_clip), absgrad=bool(absgrad),
+               grad_enabled=torch.is_grad_enabled())
     outs = _RasterizationRaw.apply(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds, cfg)
     opac = torch.sigmoid(logit_opacities.detach())[None].expand(C, -1)
     return _finish(outs, cfg, opac, width, height, 16, C, absgrad)

@@ -9,6 +9,7 @@ around each call).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
 import os
@@ -22,6 +23,26 @@ from . import _lib
 
 SPLAT_FLOATS = 12
 TILE_SIZE = 16
+
+
+# Tracing (the reference has none): EGS_NVTX=1 wraps every stage of a call in an NVTX range, so an
+# Nsight timeline shows projection / binning / blend fwd / blend bwd / projection bwd by name.  Off by default and
+# free when off (a shared null context).
+_NVTX = os.environ.get("EGS_NVTX", "0") == "1"
+_NULL_CONTEXT = contextlib.nullcontext()
+
+
+@contextlib.contextmanager
+def _nvtx_on(name: str):
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
+
+
+def nvtx_range(name: str):
+    return _nvtx_on(name) if _NVTX else _NULL_CONTEXT
 
 
 # Caller-owned gradient storage (see distributed.FlatGradBucket.begin_direct): parameter data_ptr -> buffer.  The

@@ -1,0 +1,209 @@
+"""CPU tests of the HOST logic of the boundary call (rendering.py): autograd wiring, meta contract, `.absgrad` tagging,
+packed layout, antialiased plumbing, backward-segment plumbing, zero-copy gradient buckets and NVTX ranges — with the
+per-stage operators (stages.*, i.e. the CUDA kernels) replaced by shape-faithful CPU stand-ins.  What the kernels
+compute is covered by the -m gpu parity tests; this file pins everything around them without a GPU."""
+import weakref
+
+import pytest
+import torch
+
+from easy_gaussian_splatting_b200 import rendering, stages
+from easy_gaussian_splatting_b200.distributed import FlatGradBucket
+
+
+class FakeStages:
+    """Deterministic stand-ins with the real operators' signatures, shapes and dtypes."""
+
+    def __init__(self):
+        self.calls = []
+
+    def projection_fwd(self, means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree, eps2d=0.3,
+                       near_plane=0.01, far_plane=1e10, radius_clip=0.0, tile_size=16, antialiased=False):
+        self.calls.append("projection_fwd")
+        C, N = viewmats.shape[0], means.shape[0]
+        vis = (torch.arange(C * N).reshape(C, N) % 3) != 0  # two thirds visible
+        out = {
+            "radii": torch.where(vis, torch.full((C, N), 4), torch.zeros(C, N, dtype=torch.long)).int(),
+            "means2d": (means.detach()[None, :, :2] + torch.arange(C)[:, None, None]) * vis[..., None],
+            "depths": (means.detach()[None, :, 2].abs() + 1.0).expand(C, N) * vis,
+            "conics": torch.ones(C, N, 3) * vis[..., None],
+            "colors": torch.full((C, N, 3), 0.5) * vis[..., None],
+            "tiles_per_gauss": vis.int() * 2,
+            "splats": torch.zeros(C, N, stages.SPLAT_FLOATS),
+        }
+        if antialiased:
+            out["compensations"] = torch.full((C, N), 0.5) * vis
+        return out
+
+    def isect_sorted(self, means2d, radii, depths, tiles_per_gauss, tile_size, tw, th, materialize_ids=False):
+        self.calls.append("isect_sorted")
+        C, N = radii.shape
+        flat = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0].int()
+        flatten_ids = flat.repeat_interleave(2)
+        offsets = torch.zeros(C, th, tw, dtype=torch.int32)
+        thunk = lambda: torch.arange(flatten_ids.numel(), dtype=torch.int64)
+        return thunk, flatten_ids, offsets
+
+    def _images(self, C, width, height):
+        return (torch.full((C, height, width, 3), 0.25), torch.full((C, height, width, 1), 0.5),
+                torch.zeros(C, height, width, dtype=torch.int32))
+
+    def rasterize_fwd(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, count_pairs=False):
+        self.calls.append("rasterize_fwd")
+        return self._images(splats.shape[0], width, height)
+
+    def rasterize_fwd_checkpointed(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, segment):
+        self.calls.append(f"rasterize_fwd_checkpointed({segment})")
+        return (*self._images(splats.shape[0], width, height), torch.zeros(16))
+
+    def rasterize_bwd(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_alphas, last_ids,
+                      v_render_colors, v_render_alphas):
+        self.calls.append("rasterize_bwd")
+        return torch.ones_like(splats)
+
+    def rasterize_bwd_segmented(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_colors,
+                                render_alphas, last_ids, v_render_colors, v_render_alphas, checkpoints, segment):
+        self.calls.append(f"rasterize_bwd_segmented({segment})")
+        assert checkpoints.numel() == 16 and render_colors.shape[-1] == 3
+        return torch.ones_like(splats)
+
+    def projection_bwd(self, means, quats, scales, colors, viewmats, Ks, width, height, sh_degree, eps2d, radii, colors_rgb,
+                       v_splats, v_means2d_extra=None, want_absgrad=False, antialiased_opacities=None, opacities=None):
+        self.calls.append("projection_bwd" + ("+aa" if antialiased_opacities is not None else ""))
+        C, N = radii.shape
+        outs = [stages._grad_buffer(t) for t in (means, quats, scales, opacities, colors)]
+        for i, o in enumerate(outs):
+            o.fill_(float(i + 1))
+        if want_absgrad:
+            return (*outs, torch.arange(C * N * 2, dtype=torch.float32).reshape(C, N, 2))
+        return tuple(outs)
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    f = FakeStages()
+    for name in ("projection_fwd", "isect_sorted", "rasterize_fwd", "rasterize_fwd_checkpointed", "rasterize_bwd",
+                 "rasterize_bwd_segmented", "projection_bwd"):
+        monkeypatch.setattr(stages, name, getattr(f, name))
+    monkeypatch.setattr(rendering, "_check_inputs", lambda *a, **k: None)  # the real one refuses CPU tensors
+    monkeypatch.delenv("EGS_BWD_SEGMENT", raising=False)
+    return f
+
+
+def _inputs(N=12, C=2):
+    g = torch.Generator().manual_seed(0)
+    p = [torch.randn(N, 3, generator=g), torch.randn(N, 4, generator=g), torch.rand(N, 3, generator=g),
+         torch.rand(N, generator=g), torch.randn(N, 16, 3, generator=g)]
+    p = [t.requires_grad_(True) for t in p]
+    return p, torch.eye(4)[None].repeat(C, 1, 1), torch.eye(3)[None].repeat(C, 1, 1)
+
+
+def test_meta_contract_absgrad_tagging_and_call_order(fake):
+    p, vm, K = _inputs()
+    rc, ra, meta = rendering.rasterization(*p, vm, K, 40, 24, sh_degree=3, packed=False, absgrad=True,
+                                           backgrounds=torch.zeros(2, 3))
+    assert rc.shape == (2, 24, 40, 3) and ra.shape == (2, 24, 40, 1)
+    assert meta["radii"].shape == (2, 12) and meta["radii"].dtype == torch.int32 and meta["means2d"].shape == (2, 12, 2)
+    assert meta["camera_ids"] is None and meta["gaussian_ids"] is None and meta["n_cameras"] == 2
+    assert (meta["tile_width"], meta["tile_height"], meta["tile_size"]) == (3, 2, 16)
+    assert meta["isect_ids"].dtype == torch.int64  # lazy entry resolves on first access
+    xys = meta["means2d"]
+    assert not hasattr(xys, "absgrad")
+    (rc.sum() + ra.sum()).backward()
+    assert hasattr(xys, "absgrad") and xys.absgrad.shape == (2, 12, 2)  # tagged on the very object handed out
+    assert [t.grad.flatten()[0].item() for t in p] == [1.0, 2.0, 3.0, 4.0, 5.0]
+    assert fake.calls == ["projection_fwd", "isect_sorted", "rasterize_fwd", "rasterize_bwd", "projection_bwd"]
+    # the backward node holds the tagged tensor only weakly
+    ref = weakref.ref(xys)
+    del xys, meta
+    import gc
+    gc.collect()
+    assert ref() is None or rc.grad_fn is not None
+
+
+def test_no_grad_and_absgrad_off(fake):
+    p, vm, K = _inputs()
+    with torch.no_grad():
+        rc, _, meta = rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False, absgrad=True)
+    assert rc.grad_fn is None and not hasattr(meta["means2d"], "absgrad")
+    rc, ra, meta = rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False, absgrad=False)
+    rc.sum().backward()
+    assert not hasattr(meta["means2d"], "absgrad") and p[0].grad is not None
+
+
+def test_packed_layout(fake):
+    p, vm, K = _inputs()
+    rc, ra, meta = rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=True, absgrad=True)
+    dense_vis = (torch.arange(24).reshape(2, 12) % 3) != 0
+    cam, gid = dense_vis.nonzero(as_tuple=True)
+    nnz = cam.numel()
+    assert torch.equal(meta["camera_ids"], cam) and torch.equal(meta["gaussian_ids"], gid)
+    for k, tail in (("radii", ()), ("depths", ()), ("tiles_per_gauss", ()), ("opacities", ()), ("means2d", (2,)),
+                    ("conics", (3,)), ("colors", (3,))):
+        assert meta[k].shape == (nnz, *tail), k
+    assert int(meta["flatten_ids"].max()) == nnz - 1 and int(meta["flatten_ids"].min()) == 0
+    xys = meta["means2d"]
+    rc.sum().backward()
+    flat = cam * 12 + gid
+    expect = torch.arange(48, dtype=torch.float32).reshape(24, 2)[flat]
+    assert torch.equal(xys.absgrad, expect)  # the dense absgrad gathered into the packed order
+
+
+def test_antialiased_plumbing(fake):
+    p, vm, K = _inputs()
+    rc, ra, meta = rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False, absgrad=True,
+                                           rasterize_mode="antialiased")
+    vis = (torch.arange(24).reshape(2, 12) % 3) != 0
+    assert torch.allclose(meta["opacities"], p[3].detach()[None].expand(2, -1) * 0.5 * vis)  # opacity * compensation
+    rc.sum().backward()
+    assert fake.calls[-1] == "projection_bwd+aa"
+    with pytest.raises(ValueError):
+        rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False, rasterize_mode="bogus")
+    for kw in (dict(render_mode="RGB+D"), dict(sparse_grad=True), dict(tile_size=8)):
+        with pytest.raises(NotImplementedError):
+            rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False, **kw)
+
+
+def test_backward_segment_plumbing(fake, monkeypatch):
+    p, vm, K = _inputs()
+    monkeypatch.setenv("EGS_BWD_SEGMENT", "128")
+    rc, _, _ = rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False, absgrad=True)
+    rc.sum().backward()
+    assert "rasterize_fwd_checkpointed(128)" in fake.calls and "rasterize_bwd_segmented(128)" in fake.calls
+    fake.calls.clear()
+    with torch.no_grad():  # nothing to differentiate: plain forward, no checkpoints
+        rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False)
+    assert fake.calls == ["projection_fwd", "isect_sorted", "rasterize_fwd"]
+    monkeypatch.setenv("EGS_BWD_SEGMENT", "100")
+    with pytest.raises(ValueError):
+        rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False)
+
+
+def test_direct_bucket_adopts_backward_outputs(fake):
+    p, vm, K = _inputs()
+    bucket = FlatGradBucket(p)
+    bucket.flat.fill_(float("nan"))
+    with bucket.direct():
+        rc, _, _ = rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False, absgrad=True)
+        rc.sum().backward()
+        adopted = [t.grad.data_ptr() for t in p]
+    assert adopted == [v.data_ptr() for v in bucket.views]  # autograd kept the bucket views, no clone
+    assert torch.isfinite(bucket.flat[:sum(t.numel() for t in p)]).all()
+    assert [v.flatten()[0].item() for v in bucket.views] == [1.0, 2.0, 3.0, 4.0, 5.0]
+
+
+def test_nvtx_ranges_balanced(fake, monkeypatch):
+    events = []
+    monkeypatch.setattr(stages, "_NVTX", True)
+    monkeypatch.setattr(torch.cuda.nvtx, "range_push", lambda name: events.append(("push", name)))
+    monkeypatch.setattr(torch.cuda.nvtx, "range_pop", lambda: events.append(("pop", None)))
+    p, vm, K = _inputs()
+    rc, _, _ = rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False, absgrad=True)
+    rc.sum().backward()
+    names = [n for kind, n in events if kind == "push"]
+    assert names == ["egs.projection_fwd", "egs.binning", "egs.rasterize_fwd", "egs.rasterize_bwd", "egs.projection_bwd"]
+    depth = 0
+    for kind, _ in events:
+        depth += 1 if kind == "push" else -1
+        assert depth in (0, 1)
+    assert depth == 0
