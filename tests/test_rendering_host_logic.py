@@ -79,11 +79,30 @@ class FakeStages:
         return tuple(outs)
 
 
+def _raw_fwd(self, means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, width, height, sh_degree,
+             eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0, tile_size=16):
+    self.calls.append("projection_fwd_raw")
+    return FakeStages.projection_fwd(self, means, quats, log_scales, logit_opacities, sh_0, viewmats, Ks, width, height,
+                                     sh_degree)
+
+
+def _raw_bwd(self, means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, width, height, sh_degree, eps2d,
+             radii, colors_rgb, v_splats, v_means2d_extra=None, want_absgrad=False):
+    self.calls.append("projection_bwd_raw")
+    C, N = radii.shape
+    outs = [stages._grad_buffer(t).fill_(float(i + 1)) for i, t in enumerate((means, quats, log_scales, logit_opacities, sh_0, sh_rest))]
+    return (*outs, torch.zeros(C, N, 2)) if want_absgrad else tuple(outs)
+
+
+FakeStages.projection_fwd_raw = _raw_fwd
+FakeStages.projection_bwd_raw = _raw_bwd
+
+
 @pytest.fixture()
 def fake(monkeypatch):
     f = FakeStages()
     for name in ("projection_fwd", "isect_sorted", "rasterize_fwd", "rasterize_fwd_checkpointed", "rasterize_bwd",
-                 "rasterize_bwd_segmented", "projection_bwd"):
+                 "rasterize_bwd_segmented", "projection_bwd", "projection_fwd_raw", "projection_bwd_raw"):
         monkeypatch.setattr(stages, name, getattr(f, name))
     monkeypatch.setattr(rendering, "_check_inputs", lambda *a, **k: None)  # the real one refuses CPU tensors
     monkeypatch.delenv("EGS_BWD_SEGMENT", raising=False)
@@ -207,3 +226,28 @@ def test_nvtx_ranges_balanced(fake, monkeypatch):
         depth += 1 if kind == "push" else -1
         assert depth in (0, 1)
     assert depth == 0
+
+
+def test_raw_parameter_entry_point(fake):
+    N, C = 10, 1
+    g = torch.Generator().manual_seed(1)
+    raw = [torch.randn(N, 3, generator=g), torch.randn(N, 4, generator=g), torch.randn(N, 3, generator=g),
+           torch.randn(N, generator=g), torch.randn(N, 1, 3, generator=g), torch.randn(N, 15, 3, generator=g)]
+    raw = [t.requires_grad_(True) for t in raw]
+    # the public wrapper refuses CPU tensors before anything else (checked at the end); drive its body directly
+    cfg = dict(width=32, height=16, sh_degree=3, eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0, absgrad=True,
+               grad_enabled=True)
+    outs = rendering._RasterizationRaw.apply(*raw, torch.eye(4)[None], torch.eye(3)[None], torch.ones(1, 3), cfg)
+    opac = torch.sigmoid(raw[3].detach())[None].expand(C, -1)
+    rc, ra, meta = rendering._finish(outs, cfg, opac, 32, 16, 16, C, True)
+    assert rc.shape == (1, 16, 32, 3) and meta["opacities"].shape == (1, N)
+    xys = meta["means2d"]
+    (rc.sum() + ra.sum()).backward()
+    assert hasattr(xys, "absgrad")
+    assert [t.grad.flatten()[0].item() for t in raw] == [1.0, 2.0, 3.0, 4.0, 5.0, 6.0]
+    assert fake.calls == ["projection_fwd_raw", "projection_fwd", "isect_sorted", "rasterize_fwd", "rasterize_bwd", "projection_bwd_raw"]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rendering.rasterization_from_parameters(*raw, torch.eye(4)[None], torch.eye(3)[None], 32, 16, 3)
+    with pytest.raises(ValueError):
+        rendering.rasterization_from_parameters(raw[0], raw[1], raw[2], raw[3], raw[4], raw[5][:, :3], torch.eye(4)[None],
+                                                torch.eye(3)[None], 32, 16, 3)
