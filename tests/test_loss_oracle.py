@@ -78,3 +78,17 @@ def test_gradient_vs_finite_differences(use_mask):
         assert abs(fd - g[i, j, c].item()) <= 1e-6 * max(1.0, abs(fd)) + 2e-9, (i, j, c, fd, g[i, j, c].item())
     if use_mask:
         assert float(g[mask.bool()].abs().sum()) == 0.0  # masked pixels take the ground truth: no gradient
+
+
+def test_fused_loss_wrapper_validates_before_any_launch():
+    """The product wrapper (easy_gaussian_splatting_b200/loss.py) rejects bad shapes and CPU tensors loudly."""
+    from easy_gaussian_splatting_b200.loss import fused_l1_ssim_loss
+    r, g = torch.rand(16, 16, 3), torch.rand(16, 16, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fused_l1_ssim_loss(r, g)
+    with pytest.raises(ValueError, match="at least 11x11"):
+        fused_l1_ssim_loss(r[:10], g[:10])
+    with pytest.raises(ValueError, match=r"\[H,W,3\]"):
+        fused_l1_ssim_loss(r[..., :2], g[..., :2])
+    with pytest.raises(ValueError, match="mask must be"):
+        fused_l1_ssim_loss(r, g, torch.zeros(16, 15))
