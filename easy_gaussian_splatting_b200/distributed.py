@@ -43,14 +43,18 @@ class FlatGradBucket:
 
     def __init__(self, params: Sequence[Tensor], symmetric: Optional[bool] = None):
         self.params = list(params)
-        total = sum(p.numel() for p in self.params)
+        # every parameter's slice starts on a 16-byte boundary (4 floats): the fused backward stores float4s into
+        # it, and N is arbitrary after the first densify / prune
+        total = sum(-(-p.numel() // 4) * 4 for p in self.params)
         ref = self.params[0]
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         padded = -(-total // (4 * max(world, 1))) * (4 * max(world, 1))  # whole float4s per rank slice
         self._symm = None
         self._mode = "nccl"
         if symmetric is None:
-            symmetric = ref.is_cuda and world > 1 and os.environ.get("EGS_PEER_ALLREDUCE", "1") != "0"
+            symmetric = os.environ.get("EGS_PEER_ALLREDUCE", "1") != "0"
+        # peer memory only makes sense (and its rendezvous only works) with an initialised group of > 1 CUDA ranks
+        symmetric = bool(symmetric) and ref.is_cuda and world > 1
         self.flat = self._symmetric_buffer(padded, ref, world) if symmetric else None
         if self.flat is None:
             self.flat = torch.zeros(padded, dtype=ref.dtype, device=ref.device)
@@ -60,7 +64,7 @@ class FlatGradBucket:
             v = self.flat[off:off + p.numel()].view_as(p)
             p.grad = v
             self.views.append(v)
-            off += p.numel()
+            off += -(-p.numel() // 4) * 4
 
     def _symmetric_buffer(self, n: int, ref: Tensor, world: int) -> Optional[Tensor]:
         buf, ok = None, 0
@@ -152,16 +156,34 @@ class FlatGradBucket:
             self.end_direct()
 
     def all_reduce(self, group=None, async_op: bool = False):
-        if self._symm is not None and group is None:
+        """SUM all-reduce of the whole bucket.  Returns ``None`` (``async_op=False``) or a work handle with ``wait()``
+        and ``is_completed()``.  The peer-memory kernels are stream ordered like every other kernel of the step, so
+        in that mode the handle is already complete; a non-default ``group`` cannot use the WORLD rendezvous of the
+        symmetric buffer and is refused rather than silently rerouted."""
+        if self._symm is not None:
+            if group is not None and group is not dist.group.WORLD:
+                raise ValueError("the symmetric-memory bucket was rendezvoused on the WORLD group; build the bucket with "
+                                 "symmetric=False to all-reduce over another group")
             self._peer_all_reduce(self.flat)
-            return None
+            return _CompletedWork() if async_op else None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
-        return None
+        return _CompletedWork() if async_op else None
 
     @property
     def nbytes(self) -> int:
         return self.flat.numel() * self.flat.element_size()
+
+
+class _CompletedWork:
+    """Stand-in for a torch.distributed work handle when the exchange was stream ordered (or there was nothing to
+    exchange): ``wait()`` returns immediately."""
+
+    def wait(self, timeout=None) -> bool:
+        return True
+
+    def is_completed(self) -> bool:
+        return True
 
 
 class DensifyStats:

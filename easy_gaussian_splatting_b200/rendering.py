@@ -28,7 +28,10 @@ __all__ = ["rasterization", "rasterization_from_parameters"]
 
 class _LazyMeta(dict):
     """``meta`` dict whose ``isect_ids`` entry (64-bit sorted keys, pure meta data: nothing downstream of the
-    reference reads it) is rebuilt on first access instead of costing a pass over every intersection per call."""
+    reference reads it) is rebuilt on first access instead of costing a pass over every intersection per call.
+    Every way of reading the dict resolves the entry first — ``meta[k]``, ``get``, ``pop``, ``items``, ``values``,
+    ``copy``, ``dict(meta)`` / ``{**meta}`` (``__iter__`` is overridden on purpose: CPython then builds the copy
+    through ``keys()`` + ``__getitem__`` instead of memcpy-ing the raw slots) and pickling / ``torch.save``."""
 
     def _resolve(self, key):
         v = dict.__getitem__(self, key)
@@ -37,17 +40,53 @@ class _LazyMeta(dict):
             dict.__setitem__(self, key, v)
         return v
 
+    def _resolve_all(self):
+        for k in dict.keys(self):
+            self._resolve(k)
+        return self
+
     def __getitem__(self, key):
         return self._resolve(key)
 
+    def __iter__(self):
+        return dict.__iter__(self)
+
     def get(self, key, default=None):
         return self._resolve(key) if key in self else default
+
+    def pop(self, key, *default):
+        if key in self:
+            self._resolve(key)
+        return dict.pop(self, key, *default)
+
+    def popitem(self):
+        self._resolve_all()
+        return dict.popitem(self)
+
+    def setdefault(self, key, default=None):
+        if key in self:
+            return self._resolve(key)
+        return dict.setdefault(self, key, default)
 
     def items(self):
         return [(k, self._resolve(k)) for k in self.keys()]
 
     def values(self):
         return [self._resolve(k) for k in self.keys()]
+
+    def copy(self):
+        return dict(self.items())
+
+    __copy__ = copy
+
+    def __or__(self, other):
+        return {**self.copy(), **other}
+
+    def __ror__(self, other):
+        return {**other, **self.copy()}
+
+    def __reduce__(self):
+        return (dict, (self.copy(),))
 
 
 def _tag_absgrad(target: Tensor, absgrad: Tensor, packed_index: Optional[Tensor]) -> None:
@@ -82,6 +121,11 @@ class _Rasterization(torch.autograd.Function):
     def forward(ctx, means, quats, scales, opacities, colors, viewmats, Ks, backgrounds, cfg):
         width, height, sh_degree = cfg["width"], cfg["height"], cfg["sh_degree"]
         C, N = viewmats.shape[0], means.shape[0]
+        # Dense, 16-byte-aligned copies ONCE (no-ops for the reference's own tensors): the same tensors feed the
+        # forward kernels and are saved for the backward pass, which reads them through raw pointers — a strided
+        # input such as ``viewmats = torch.linalg.inv(camtoworlds)`` must not reach it as is.
+        means, quats, scales, opacities, colors, viewmats, Ks, backgrounds = stages.dense_inputs(
+            means, quats, scales, opacities, colors, viewmats, Ks, backgrounds)
         with stages.nvtx_range("egs.projection_fwd"):
             proj = stages.projection_fwd(means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree,
                                          eps2d=cfg["eps2d"], near_plane=cfg["near_plane"], far_plane=cfg["far_plane"],
@@ -145,6 +189,8 @@ class _RasterizationRaw(torch.autograd.Function):
     def forward(ctx, means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds, cfg):
         width, height, sh_degree = cfg["width"], cfg["height"], cfg["sh_degree"]
         C = viewmats.shape[0]
+        means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds = stages.dense_inputs(
+            means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds)
         with stages.nvtx_range("egs.projection_fwd_raw"):
             proj = stages.projection_fwd_raw(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, width,
                                              height, sh_degree, eps2d=cfg["eps2d"], near_plane=cfg["near_plane"],

@@ -13,6 +13,7 @@ import contextlib
 import ctypes
 import math
 import os
+import threading
 import weakref
 from typing import Dict, Optional, Tuple
 
@@ -45,30 +46,47 @@ def nvtx_range(name: str):
     return _nvtx_on(name) if _NVTX else _NULL_CONTEXT
 
 
-# Caller-owned gradient storage (see distributed.FlatGradBucket.begin_direct): parameter data_ptr -> buffer.  The
-# projection backward writes EVERY element of every parameter gradient exactly once, so it can write straight into a
-# registered buffer — no zero fill, no accumulate pass, and ``param.grad`` becomes a view of the caller's bucket.
-_GRAD_TARGETS: Dict[int, Tuple["weakref.ref", Tensor]] = {}
+# Caller-owned gradient storage (see distributed.FlatGradBucket.begin_direct): (device, parameter data_ptr) -> buffer.
+# The projection backward writes EVERY element of every parameter gradient exactly once, so it can write straight
+# into a registered buffer — no zero fill, no accumulate pass, and ``param.grad`` becomes a view of the caller's bucket.
+# A registration is ONE-SHOT: the backward pass that uses it removes it, so a second backward on the same parameters
+# inside the same begin_direct / end_direct window takes the ordinary allocate-and-accumulate route instead of
+# overwriting the first gradient.  The table is guarded by a lock (a viewer thread may render while the training
+# thread is inside the window; renders under no_grad never touch it).
+_GRAD_TARGETS: Dict[Tuple[int, int], Tuple["weakref.ref", Tensor]] = {}
+_GRAD_TARGETS_LOCK = threading.Lock()
+
+
+def _target_key(t: Tensor) -> Tuple[int, int]:
+    return (t.device.index if t.device.index is not None else -1, t.data_ptr())
 
 
 def register_grad_target(param: Tensor, buffer: Tensor) -> None:
     if buffer.numel() != param.numel() or buffer.dtype != param.dtype or buffer.device != param.device or not buffer.is_contiguous():
         raise ValueError("gradient target must be a contiguous buffer of the parameter's size, dtype and device")
-    _GRAD_TARGETS[param.data_ptr()] = (weakref.ref(param), buffer)
+    with _GRAD_TARGETS_LOCK:
+        _GRAD_TARGETS[_target_key(param)] = (weakref.ref(param), buffer)
 
 
 def clear_grad_targets() -> None:
-    _GRAD_TARGETS.clear()
+    with _GRAD_TARGETS_LOCK:
+        _GRAD_TARGETS.clear()
 
 
 def _grad_buffer(inp: Tensor) -> Tensor:
-    entry = _GRAD_TARGETS.get(inp.data_ptr()) if _GRAD_TARGETS else None
-    if entry is not None:
-        owner, tgt = entry
-        live = owner()  # a registration whose parameter is gone must not capture a new tensor at the same address
-        if live is not None and live.data_ptr() == inp.data_ptr() and live.shape == inp.shape and inp.is_contiguous():
-            return tgt.view(inp.shape)  # a fresh tensor object over the caller's storage: autograd adopts it as .grad
-    return torch.empty_like(inp)
+    """Storage for the gradient of ``inp``: always dense row-major (the kernels write row-major whatever the strides
+    of the input were) and 16-byte aligned (float4 stores)."""
+    if _GRAD_TARGETS:
+        with _GRAD_TARGETS_LOCK:
+            entry = _GRAD_TARGETS.get(_target_key(inp))
+            if entry is not None:
+                owner, tgt = entry
+                live = owner()  # a registration whose parameter is gone must not capture a new tensor at the same address
+                if (live is not None and live.data_ptr() == inp.data_ptr() and live.shape == inp.shape
+                        and inp.is_contiguous() and tgt.data_ptr() % 16 == 0):
+                    del _GRAD_TARGETS[_target_key(inp)]  # one-shot
+                    return tgt.view(inp.shape)  # a fresh tensor object over the caller's storage: autograd adopts it as .grad
+    return torch.empty(inp.shape, dtype=inp.dtype, device=inp.device)
 
 
 def _ptr(t: Optional[Tensor]):
@@ -80,11 +98,32 @@ def _stream(device) -> ctypes.c_void_p:
 
 
 def _f32c(t: Tensor, name: str) -> Tensor:
+    """float32 CUDA tensor -> dense row-major and 16-byte aligned (the kernels use 128-bit loads on quats, SH rows
+    and the packed records); a no-op for tensors that already are, a copy otherwise (e.g. a slice of a flat
+    parameter buffer that starts at an odd element)."""
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor: this rasterizer has no CPU path")
     if t.dtype != torch.float32:
         raise TypeError(f"{name} must be float32, got {t.dtype}")
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def dense_inputs(*tensors: Optional[Tensor]):
+    """The tensors of a rasterization call as dense, aligned fp32 tensors (``None`` stays ``None``).  Identity for
+    tensors that already are — in particular parameter tensors keep their identity, which the gradient-target
+    registry keys on."""
+    out = []
+    for t in tensors:
+        if t is None or (t.is_contiguous() and t.data_ptr() % 16 == 0):
+            out.append(t)
+        else:
+            out.append(t.clone(memory_format=torch.contiguous_format) if t.is_contiguous() else t.contiguous())
+            if out[-1].data_ptr() % 16 != 0:  # cannot happen with the caching allocator; keep the contract explicit
+                raise RuntimeError("allocator returned a tensor that is not 16-byte aligned")
+    return tuple(out)
 
 
 def tile_grid(width: int, height: int, tile_size: int = TILE_SIZE) -> Tuple[int, int]:
@@ -151,6 +190,8 @@ def projection_bwd(means: Tensor, quats: Tensor, scales: Tensor, colors: Tensor,
     opacities: only consulted for a registered gradient buffer (register_grad_target)."""
     lib = _lib.load()
     dev = means.device
+    means, quats, scales, colors, viewmats, Ks = dense_inputs(means, quats, scales, colors, viewmats, Ks)
+    radii, colors_rgb, v_splats = radii.contiguous(), colors_rgb.contiguous(), v_splats.contiguous()
     N, C = means.shape[0], viewmats.shape[0]
     if sh_degree is None:
         K, deg, per_cam = 1, -1, int(colors.dim() == 3)
@@ -223,6 +264,9 @@ def projection_bwd_raw(means: Tensor, quats: Tensor, log_scales: Tensor, logit_o
     """-> v_means, v_quats, v_log_scales, v_logit_opacities, v_sh_0, v_sh_rest (, absgrad)."""
     lib = _lib.load()
     dev = means.device
+    means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks = dense_inputs(
+        means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks)
+    radii, colors_rgb, v_splats = radii.contiguous(), colors_rgb.contiguous(), v_splats.contiguous()
     N, C = means.shape[0], viewmats.shape[0]
     outs = [_grad_buffer(t) for t in (means, quats, log_scales, logit_opacities, sh_0, sh_rest)]
     if v_means2d_extra is not None:

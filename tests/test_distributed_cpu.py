@@ -85,7 +85,8 @@ def test_view_sharded_exchange_matches_single_process():
         _stats_update_cpu(stats, radii, absgrad, W, H)
     for rank, flat, sbuf, aliased in results:
         assert all(aliased), "param.grad must alias the flat bucket (no pack/unpack copies)"
-        assert torch.allclose(flat, bucket.flat, atol=1e-5), f"rank {rank} gradients"
+        n = bucket.flat.numel()  # the 2-rank bucket is padded to whole float4s per rank slice
+        assert torch.allclose(flat[:n], bucket.flat, atol=1e-5), f"rank {rank} gradients"
         assert torch.allclose(sbuf[:2], stats.buf[:2], atol=1e-4), f"rank {rank} SUM statistics"
         assert torch.equal(sbuf[2], stats.buf[2]), f"rank {rank} MAX statistics"
     assert torch.equal(results[0][1], results[1][1]), "replicas must end bit-identical"
@@ -130,19 +131,51 @@ def test_direct_gradient_routes_on_cpu():
     with bucket.direct():
         (params[0] * 1.0).sum().backward()
     assert torch.equal(bucket.views[1], torch.zeros(7)) and torch.equal(bucket.views[0], torch.ones(5, 3))
-    # _grad_buffer: registered target is used while the owner lives, ignored once it is gone
+    # _grad_buffer: a registered target is used ONCE while the owner lives (a second backward on the same parameter
+    # inside the window must not overwrite the first gradient), and is ignored once the owner is gone
     owner = torch.zeros(4, 3)
     target = torch.zeros(12)
     stages.register_grad_target(owner, target)
     out = stages._grad_buffer(owner)
     assert out.data_ptr() == target.data_ptr() and out.shape == owner.shape
-    key = owner.data_ptr()
+    assert stages._grad_buffer(owner).data_ptr() != target.data_ptr(), "registration must be one-shot"
+    assert not stages._GRAD_TARGETS
+    stages.register_grad_target(owner, target)
+    key = stages._target_key(owner)
     del owner, out
     import gc
     gc.collect()
     impostor = torch.zeros(4, 3)
-    stages._GRAD_TARGETS[impostor.data_ptr()] = stages._GRAD_TARGETS.pop(key)  # same address, dead owner
+    stages._GRAD_TARGETS[stages._target_key(impostor)] = stages._GRAD_TARGETS.pop(key)  # same address, dead owner
     assert stages._grad_buffer(impostor).data_ptr() != target.data_ptr()
+    # a target that is not 16-byte aligned is never handed to the kernels (they store float4s)
+    owner2 = torch.zeros(4, 3)
+    store = torch.zeros(16)
+    stages.register_grad_target(owner2, store[1:13])
+    assert stages._grad_buffer(owner2).data_ptr() != store[1:13].data_ptr()
+    # a strided input gets a dense row-major gradient buffer
+    assert stages._grad_buffer(torch.zeros(3, 4).t()).is_contiguous()
     stages.clear_grad_targets()
     with pytest.raises(ValueError):
         stages.register_grad_target(torch.zeros(3), torch.zeros(4))
+
+
+def test_bucket_slices_are_16_byte_aligned_for_any_n():
+    """after densify / prune N is arbitrary; every parameter's slice of the flat bucket must still start on
+    a 16-byte boundary because the fused backward stores float4s into it."""
+    for n in (1, 5, 50, 1001, 4097):
+        params = [torch.zeros(*s, requires_grad=True) for s in ((n, 3), (n, 4), (n, 3), (n,), (n, 1, 3), (n, 15, 3))]
+        bucket = FlatGradBucket(params)
+        base = bucket.flat.data_ptr()
+        for p, v in zip(params, bucket.views):
+            assert (v.data_ptr() - base) % 16 == 0 and v.shape == p.shape and p.grad.data_ptr() == v.data_ptr()
+        assert bucket.flat.numel() % 4 == 0
+
+
+def test_all_reduce_async_contract_without_a_group():
+    params = [torch.zeros(4, 3, requires_grad=True)]
+    bucket = FlatGradBucket(params, symmetric=True)  # no process group: must not try to rendezvous
+    assert bucket.exchange == "NCCL all-reduce"
+    assert bucket.all_reduce() is None
+    work = bucket.all_reduce(async_op=True)
+    assert work.wait() and work.is_completed()

@@ -366,3 +366,93 @@ def test_direct_gradient_bucket():
     run(params)
     for p, r, k in zip(params, ref, PARAMS):
         assert rel_err(p.grad.cpu(), 2 * r.grad.cpu()) <= 1e-5, k
+
+
+def test_non_contiguous_inputs_give_the_same_gradients():
+    """`viewmats = torch.linalg.inv(camtoworlds)` has strides (16, 1, 4), and a transposed `means`
+    is column-major; forward AND backward must see dense copies, and gradients come back in the input's shape."""
+    from easy_gaussian_splatting_b200 import rasterization
+    from easy_gaussian_splatting_b200.synthetic import loss_weights
+    sc = make_scene(**CASES[1]).to("cuda")
+    C = sc.viewmats.shape[0]
+    Wc, Wa = (t.cuda() for t in loss_weights(sc.seed, C, sc.height, sc.width))
+    bg = sc.background[None].expand(C, 3)  # stride-0 expand, not made contiguous on purpose
+
+    def run(params, viewmats, Ks):
+        rc, ra, meta = rasterization(*params, viewmats, Ks, sc.width, sc.height, sh_degree=3, packed=False, absgrad=True,
+                                     backgrounds=bg)
+        ((rc * Wc).sum() + (ra * Wa).sum()).backward()
+        return rc.detach(), meta
+
+    ref = [getattr(sc, k).clone().requires_grad_(True) for k in PARAMS]
+    rc_ref, meta_ref = run(ref, sc.viewmats, sc.Ks)
+    c2w = torch.linalg.inv(sc.viewmats)
+    viewmats = torch.linalg.inv(c2w)  # the gsplat idiom; batch-of-column-major on CUDA
+    odd = []
+    for k in PARAMS:
+        t = getattr(sc, k)
+        if t.dim() >= 2:
+            perm = list(range(t.dim()))[::-1]
+            t2 = t.permute(*perm).contiguous().permute(*perm)  # same values, reversed strides
+            assert not t2.is_contiguous()
+        else:
+            t2 = torch.stack([t, t], 1)[:, 0]  # stride 2
+        odd.append(t2.detach().requires_grad_(True))
+    Ks = torch.stack([sc.Ks, sc.Ks], 1)[:, 0]
+    rc, meta = run(odd, viewmats, Ks)
+    assert (viewmats - sc.viewmats).abs().max() < 1e-5
+    assert torch.equal(meta["radii"], meta_ref["radii"]) or (meta["radii"] != meta_ref["radii"]).float().mean() < 1e-3
+    for p, r, k in zip(odd, ref, PARAMS):
+        assert p.grad.shape == r.grad.shape
+        assert rel_err(p.grad.cpu(), r.grad.cpu()) <= 2e-3, k  # inv(inv(V)) differs from V in the last bits
+    # exactly the same camera, strided: bit-identical forward, gradients to reduction-order noise
+    vm_strided = torch.stack([sc.viewmats, sc.viewmats], 1)[:, 0]
+    odd2 = [t.detach().clone(memory_format=torch.preserve_format).requires_grad_(True) for t in odd]
+    rc2, _ = run(odd2, vm_strided, Ks)
+    assert torch.equal(rc2, rc_ref)
+    for p, r, k in zip(odd2, ref, PARAMS):
+        assert rel_err(p.grad.cpu(), r.grad.cpu()) <= 1e-5, k
+
+
+@pytest.mark.parametrize("n", [4001, 4002, 4003])
+def test_direct_gradient_bucket_any_n(n):
+    """N % 4 != 0 (any N after densify / prune) must not misalign the float4 gradient stores of the
+    direct-to-bucket backward, on the activated-tensor path and on the raw-parameter path."""
+    from easy_gaussian_splatting_b200 import rasterization, rasterization_from_parameters
+    from easy_gaussian_splatting_b200.distributed import FlatGradBucket
+    from easy_gaussian_splatting_b200.synthetic import loss_weights
+    sc = make_scene("blob", n, 96, 80, 100.0, 21, n_views=2).to("cuda")
+    C = sc.viewmats.shape[0]
+    Wc, Wa = (t.cuda() for t in loss_weights(sc.seed, C, sc.height, sc.width))
+    bg = sc.background[None].expand(C, 3).contiguous()
+
+    def loss(rc, ra):
+        return (rc * Wc).sum() + (ra * Wa).sum()
+
+    ref = [getattr(sc, k).clone().requires_grad_(True) for k in PARAMS]
+    rc, ra, _ = rasterization(*ref, sc.viewmats, sc.Ks, sc.width, sc.height, sh_degree=3, packed=False, absgrad=True, backgrounds=bg)
+    loss(rc, ra).backward()
+    params = [getattr(sc, k).clone().requires_grad_(True) for k in PARAMS]
+    bucket = FlatGradBucket(params)
+    bucket.flat.fill_(float("nan"))
+    with bucket.direct():
+        rc, ra, _ = rasterization(*params, sc.viewmats, sc.Ks, sc.width, sc.height, sh_degree=3, packed=False, absgrad=True, backgrounds=bg)
+        loss(rc, ra).backward()
+        adopted = [p.grad.data_ptr() for p in params]
+    torch.cuda.synchronize()
+    assert adopted == [v.data_ptr() for v in bucket.views]
+    for p, r, k in zip(params, ref, PARAMS):
+        assert torch.isfinite(p.grad).all() and rel_err(p.grad.cpu(), r.grad.cpu()) <= 1e-5, k
+    # raw-parameter entry point: six tensors, sh_0 [N,1,3] and sh_rest [N,15,3] slices
+    raw_src = [sc.means, sc.quats, torch.log(sc.scales), torch.logit(sc.opacities), sc.colors[:, :1].contiguous(), sc.colors[:, 1:].contiguous()]
+    raw = [t.clone().requires_grad_(True) for t in raw_src]
+    rbucket = FlatGradBucket(raw)
+    rbucket.flat.fill_(float("nan"))
+    with rbucket.direct():
+        rc, ra, _ = rasterization_from_parameters(*raw, sc.viewmats, sc.Ks, sc.width, sc.height, 3, backgrounds=bg, absgrad=True)
+        loss(rc, ra).backward()
+        adopted = [p.grad.data_ptr() for p in raw]
+    torch.cuda.synchronize()
+    assert adopted == [v.data_ptr() for v in rbucket.views]
+    assert rel_err(raw[0].grad.cpu(), ref[0].grad.cpu()) <= 1e-4 and rel_err(raw[1].grad.cpu(), ref[1].grad.cpu()) <= 1e-4
+    assert rel_err(torch.cat([raw[4].grad, raw[5].grad], 1).cpu(), ref[4].grad.cpu()) <= 1e-4

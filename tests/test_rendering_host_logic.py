@@ -251,3 +251,73 @@ def test_raw_parameter_entry_point(fake):
     with pytest.raises(ValueError):
         rendering.rasterization_from_parameters(raw[0], raw[1], raw[2], raw[3], raw[4], raw[5][:, :3], torch.eye(4)[None],
                                                 torch.eye(3)[None], 32, 16, 3)
+
+
+def test_lazy_meta_resolves_on_every_read_path(fake):
+    """`isect_ids` is a thunk inside the dict; no way of reading the dict may hand the thunk out."""
+    import copy
+    import io
+    import pickle
+    p, vm, K = _inputs()
+
+    def fresh():
+        with torch.no_grad():
+            return rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False)[2]
+
+    is_ids = lambda v: isinstance(v, torch.Tensor) and v.dtype == torch.int64
+    assert is_ids(dict(fresh())["isect_ids"])
+    assert is_ids({**fresh()}["isect_ids"])
+    assert is_ids(fresh().copy()["isect_ids"])
+    assert is_ids(copy.copy(fresh())["isect_ids"])
+    assert is_ids(fresh().pop("isect_ids"))
+    assert is_ids(fresh().setdefault("isect_ids", None))
+    assert is_ids(dict(fresh().items())["isect_ids"])
+    assert is_ids((fresh() | {"extra": 1})["isect_ids"])
+    assert is_ids(pickle.loads(pickle.dumps(fresh()))["isect_ids"])
+    buf = io.BytesIO()
+    torch.save(fresh(), buf)
+    buf.seek(0)
+    assert is_ids(torch.load(buf, weights_only=False)["isect_ids"])
+    m = fresh()
+    assert m.get("missing", 7) == 7 and m.pop("missing", 8) == 8 and "isect_ids" in m
+    assert sorted(m) == sorted(m.keys()) and len(list(m.values())) == len(m)
+
+
+def test_strided_inputs_are_densified_once_and_gradients_are_dense(fake):
+    """the tensors saved for the backward pass are the dense copies the forward kernels read; gradients
+    of strided inputs come back dense with the input's shape."""
+    p, vm, K = _inputs(N=8, C=2)
+    means_t = torch.randn(3, 8).t().requires_grad_(True)  # strides (1, 8)
+    vm_inv = torch.linalg.inv(torch.eye(4)[None].repeat(2, 1, 1) + 0.01 * torch.randn(2, 4, 4))
+    seen = {}
+    real_bwd = fake.projection_bwd
+
+    def spy_bwd(means, quats, scales, colors, viewmats, Ks, *a, **k):
+        seen["contig"] = all(t.is_contiguous() for t in (means, quats, scales, colors, viewmats, Ks))
+        return real_bwd(means, quats, scales, colors, viewmats, Ks, *a, **k)
+
+    import easy_gaussian_splatting_b200.stages as st
+    orig = st.projection_bwd
+    st.projection_bwd = spy_bwd
+    try:
+        rc, _, _ = rendering.rasterization(means_t, p[1][:8], p[2][:8], p[3][:8], p[4][:8], vm_inv.transpose(1, 2).transpose(1, 2),
+                                           K, 16, 16, sh_degree=3, packed=False, absgrad=True)
+        rc.sum().backward()
+    finally:
+        st.projection_bwd = orig
+    assert seen["contig"]
+    assert means_t.grad.shape == (8, 3) and torch.equal(means_t.grad, torch.ones(8, 3))
+
+
+def test_second_backward_in_a_direct_window_accumulates(fake):
+    """a registration is one-shot — a second backward on the same parameters inside the same
+    begin_direct / end_direct window must ADD to the first gradient, not overwrite or double it."""
+    p, vm, K = _inputs()
+    bucket = FlatGradBucket(p)
+    with bucket.direct():
+        for _ in range(2):
+            rc, _, _ = rendering.rasterization(*p, vm, K, 16, 16, sh_degree=3, packed=False, absgrad=True)
+            rc.sum().backward()
+    # FakeStages.projection_bwd fills gradient i with the constant i + 1; two backward passes -> 2 * (i + 1)
+    assert [v.flatten()[0].item() for v in bucket.views] == [2.0, 4.0, 6.0, 8.0, 10.0]
+    assert all(t.grad.data_ptr() == v.data_ptr() for t, v in zip(p, bucket.views))
