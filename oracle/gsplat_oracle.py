@@ -436,7 +436,7 @@ def _tile_pixels(ty, tx, tile_size, width, height, dtype):
 class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, colors, opacities, backgrounds, width, height, tile_size,
-                isect_offsets, flatten_ids, absgrad, counters):
+                isect_offsets, flatten_ids, absgrad, counters, tile_window=None):
         C, N = means2d.shape[:2]
         dt = means2d.dtype
         th, tw = isect_offsets.shape[1:]
@@ -451,10 +451,11 @@ class _Rasterize(torch.autograd.Function):
         op = opacities.reshape(C * N)
         p_eval = p_acc = 0
         border = torch.zeros(C, height, width, dtype=torch.bool)
+        ty0, ty1, tx0, tx1 = (0, th, 0, tw) if tile_window is None else tile_window
         for c in range(C):
             bg = backgrounds[c] if backgrounds is not None else None
-            for ty in range(th):
-                for tx in range(tw):
+            for ty in range(ty0, ty1):
+                for tx in range(tx0, tx1):
                     t = (c * th + ty) * tw + tx
                     s, e = offs[t], offs[t + 1]
                     yy, xx, px, py = _tile_pixels(ty, tx, tile_size, width, height, dt)
@@ -471,14 +472,14 @@ class _Rasterize(torch.autograd.Function):
             counters["P_acc"] = counters.get("P_acc", 0) + p_acc
             counters["borderline"] = border
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids)
-        ctx.meta = (width, height, tile_size, absgrad)
+        ctx.meta = (width, height, tile_size, absgrad, (ty0, ty1, tx0, tx1))
         ctx.mark_non_differentiable(last_ids)
         return out_c, out_a, last_ids
 
     @staticmethod
     def backward(ctx, v_c, v_a, _v_last):
         means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids = ctx.saved_tensors
-        width, height, tile_size, absgrad = ctx.meta
+        width, height, tile_size, absgrad, (ty0, ty1, tx0, tx1) = ctx.meta
         C, N = means2d.shape[:2]
         dt = means2d.dtype
         th, tw = isect_offsets.shape[1:]
@@ -495,8 +496,8 @@ class _Rasterize(torch.autograd.Function):
         g_op = torch.zeros_like(op)
         g_bg = torch.zeros_like(backgrounds) if backgrounds is not None else None
         for c in range(C):
-            for ty in range(th):
-                for tx in range(tw):
+            for ty in range(ty0, ty1):
+                for tx in range(tx0, tx1):
                     t = (c * th + ty) * tw + tx
                     s, e = offs[t], offs[t + 1]
                     yy, xx, px, py = _tile_pixels(ty, tx, tile_size, width, height, dt)
@@ -528,14 +529,16 @@ class _Rasterize(torch.autograd.Function):
         if absgrad:
             means2d.absgrad = g_abs.reshape(C, N, 2)
         return (g_m2.reshape(C, N, 2), g_cn.reshape(C, N, 3), g_cl.reshape(C, N, 3), g_op.reshape(C, N),
-                g_bg, None, None, None, None, None, None, None)
+                g_bg, None, None, None, None, None, None, None, None)
 
 
 def rasterize_to_pixels(means2d, conics, colors, opacities, width, height, tile_size, isect_offsets,
-                        flatten_ids, backgrounds=None, absgrad=False, counters=None):
-    """means2d[C,N,2] conics[C,N,3] colors[C,N,3] opacities[C,N] -> colors[C,H,W,3], alphas[C,H,W,1], last_ids."""
+                        flatten_ids, backgrounds=None, absgrad=False, counters=None, tile_window=None):
+    """means2d[C,N,2] conics[C,N,3] colors[C,N,3] opacities[C,N] -> colors[C,H,W,3], alphas[C,H,W,1], last_ids.
+    tile_window = (ty0, ty1, tx0, tx1): blend only the tiles of that window (pixels outside stay 0 and receive no
+    gradient) — bounds the CPU work of full-size parity checks; the arithmetic per tile is unchanged."""
     return _Rasterize.apply(means2d, conics, colors, opacities, backgrounds, width, height, tile_size,
-                            isect_offsets, flatten_ids, absgrad, counters)
+                            isect_offsets, flatten_ids, absgrad, counters, tile_window)
 
 
 # --------------------------------------------------------------------------------------
@@ -551,7 +554,7 @@ def rasterization(
     sh_degree: Optional[int] = None, packed: bool = True, tile_size: int = 16,
     backgrounds: Optional[Tensor] = None, render_mode: str = "RGB", sparse_grad: bool = False,
     absgrad: bool = False, rasterize_mode: str = "classic", channel_chunk: int = 32,
-    counters: Optional[dict] = None,
+    counters: Optional[dict] = None, tile_window: Optional[Tuple[int, int, int, int]] = None,
 ) -> Tuple[Tensor, Tensor, Dict]:
     """Oracle for the whole path.  ``packed`` only changes upstream's memory layout, not
     results, so the oracle computes the dense (packed=False) form for either value."""
@@ -581,7 +584,7 @@ def rasterization(
         counters["n_isects"] = int(flatten_ids.shape[0])
     render_colors, render_alphas, last_ids = rasterize_to_pixels(
         means2d, conics, cols, opac, width, height, tile_size, isect_offsets, flatten_ids,
-        backgrounds=backgrounds, absgrad=absgrad, counters=counters)
+        backgrounds=backgrounds, absgrad=absgrad, counters=counters, tile_window=tile_window)
     meta = {
         "camera_ids": None, "gaussian_ids": None, "radii": radii, "means2d": means2d, "depths": depths,
         "conics": conics, "opacities": opac, "colors": cols, "tile_width": tw, "tile_height": th,

@@ -36,7 +36,7 @@ def ssim(preds: Tensor, target: Tensor, data_range: float = 1.0, sigma: float = 
     channel = preds.shape[1]
     ks = int(3.5 * sigma + 0.5) * 2 + 1  # 11 for sigma 1.5
     pad = (ks - 1) // 2
-    g = gaussian_window(ks, sigma, preds.dtype)
+    g = gaussian_window(ks, sigma, preds.dtype).to(preds.device)
     kernel = (g[:, None] * g[None, :]).expand(channel, 1, ks, ks)
     p = F.pad(preds, (pad, pad, pad, pad), mode="reflect")
     t = F.pad(target, (pad, pad, pad, pad), mode="reflect")

@@ -210,3 +210,44 @@ def test_update_statistics_matches_reference_semantics():
     c[visible] = c[visible] + 1
     O.update_statistics(mr, acc, cnt, radii, absg, W, H)
     assert torch.equal(mr, a) and torch.equal(acc, b) and torch.equal(cnt, c)
+
+
+def test_tile_window_and_subset_reproduce_the_full_render():
+    """The argument behind tests/test_gpu_fullsize.py::test_window_parity_with_the_oracle_at_full_size: blending only a
+    window of tiles, from only the Gaussians that reach those tiles, gives the full render's pixels and — with loss
+    weights that vanish outside the window — the full render's gradients."""
+    import torch
+    from easy_gaussian_splatting_b200.synthetic import loss_weights, make_scene
+    from oracle import gsplat_oracle as O
+    sc = make_scene("blob", 1500, 112, 96, 110.0, 17, n_views=2)
+    C, N, W, H = 2, 1500, sc.width, sc.height
+    names = ("means", "quats", "scales", "opacities", "colors")
+    win = (2, 4, 3, 6)
+    y0, y1, x0, x1 = win[0] * 16, win[1] * 16, win[2] * 16, win[3] * 16
+    Wc, Wa = loss_weights(sc.seed, C, H, W)
+    mask = torch.zeros(1, H, W, 1)
+    mask[:, y0:y1, x0:x1] = 1.0
+    Wc, Wa = Wc * mask, Wa * mask
+    bg = sc.background[None].expand(C, 3).contiguous()
+    full = {k: getattr(sc, k).clone().requires_grad_(True) for k in names}
+    rc, ra, meta = O.rasterization(*[full[k] for k in names], sc.viewmats, sc.Ks, W, H, sh_degree=3, packed=False,
+                                   absgrad=True, backgrounds=bg)
+    ((rc * Wc).sum() + (ra * Wa).sum()).backward()
+    offs = meta["isect_offsets"].reshape(-1).tolist() + [meta["flatten_ids"].numel()]
+    tw, th = meta["tile_width"], meta["tile_height"]
+    members = [meta["flatten_ids"][offs[(c * th + ty) * tw + tx]:offs[(c * th + ty) * tw + tx + 1]].long() % N
+               for c in range(C) for ty in range(win[0], win[1]) for tx in range(win[2], win[3])]
+    sub = torch.unique(torch.cat(members))
+    assert 0 < sub.numel() < N
+    part = {k: getattr(sc, k)[sub].clone().requires_grad_(True) for k in names}
+    rc2, ra2, meta2 = O.rasterization(*[part[k] for k in names], sc.viewmats, sc.Ks, W, H, sh_degree=3, packed=False,
+                                      absgrad=True, backgrounds=bg, tile_window=win)
+    ((rc2 * Wc).sum() + (ra2 * Wa).sum()).backward()
+    assert torch.equal(rc2[:, y0:y1, x0:x1], rc[:, y0:y1, x0:x1]) and torch.equal(ra2[:, y0:y1, x0:x1], ra[:, y0:y1, x0:x1])
+    assert float(rc2[:, :y0].abs().sum()) == 0.0  # outside the window nothing is blended
+    rest = torch.ones(N, dtype=torch.bool)
+    rest[sub] = False
+    for k in names:
+        assert torch.allclose(full[k].grad[sub], part[k].grad, rtol=1e-5, atol=1e-7), k
+        assert float(full[k].grad[rest].abs().sum()) == 0.0, k
+    assert torch.allclose(meta["means2d"].absgrad[:, sub], meta2["means2d"].absgrad, rtol=1e-5, atol=1e-7)
