@@ -63,6 +63,12 @@ def parse_args():
     ap.add_argument("--views-per-call", type=int, default=4,
                     help="views batched into one rasterization() call (viewmats [C,4,4]); 1 = one call per view as in the reference's loop")
     ap.add_argument("--forward-only", action="store_true", help="no_grad forward renders only (cfg5-style latency runs; not the headline metric)")
+    ap.add_argument("--no-call-pattern", action="store_true",
+                    help="skip line['call_pattern']: the reference's own one-view-per-call loop (strictly sequential, one "
+                         "stream) on the metric scene and BASELINE configs 2, 3, 5, and the config-1 CPU timing")
+    ap.add_argument("--no-exchange-check", action="store_true",
+                    help="N > 1: skip the pre-step that checks the view-sharded step against one GPU rendering all views")
+    ap.add_argument("--quick", action="store_true", help="device-timed value only: no e2e, stage timing, sub-runs or CPU leg")
     return ap.parse_args()
 
 
@@ -220,10 +226,12 @@ def ours(args):
     cfg = CONFIGS[args.workload]
     W, H = cfg["width"], cfg["height"]
 
-    # identical replicated scene on every rank; rank r renders views {r*V .. r*V+V-1} of a world*V orbit
+    # identical replicated scene on every rank; rank r renders views {v : v mod R == r} of a world*V orbit
+    # (distributed.shard_views)
+    from easy_gaussian_splatting_b200.distributed import shard_views
     sc_cpu = make_config_scene(args.workload, n_views=world * V, N=args.n_gaussians)
     N = sc_cpu.means.shape[0]
-    my_views = list(range(rank * V, rank * V + V))
+    my_views = shard_views(world * V, rank, world)
     names = ("means", "quats", "scales", "opacities", "colors")
     if args.activations == "pre":
         params = [getattr(sc_cpu, k).to(dev).requires_grad_(True) for k in names]
@@ -232,18 +240,20 @@ def ours(args):
         raw = [sc_cpu.means, sc_cpu.quats, torch.log(sc_cpu.scales), torch.logit(sc_cpu.opacities),
                sc_cpu.colors[:, :1].contiguous(), sc_cpu.colors[:, 1:].contiguous()]
         params = [t.to(dev).requires_grad_(True) for t in raw]
-    bucket = FlatGradBucket(params)
-    stats = DensifyStats(N, dev)
+    # N > 1: the per-step densify-stat deltas live behind the gradients in the same (symmetric) buffer and travel in
+    # the same exchange launch
+    bucket = FlatGradBucket(params, stats_size=N if world > 1 else 0)
+    stats = DensifyStats(N, dev, bucket=bucket if world > 1 else None)
     optimizer = None
     if args.train_step:
         from easy_gaussian_splatting_b200.optim import FusedAdam
-        # configs/*.yaml learning rates x 1e-4: Adam moves every parameter by ~lr per step whatever the gradient, and
-        # the synthetic objective (a random linear functional) has no minimum — at the real rates the splats grow
-        # step after step, n_isects with them, and the "step time" measures how long the run has been diverging
-        # (seen as 113..323 ms for the same command).  Adam's work does not depend on the learning rate.
-        lrs = {k: v * 1e-4 for k, v in dict(means=1e-3, quats=1e-3, scales=1e-2, opacities=5e-2, colors=2.5e-3,
-                                            log_scales=1e-2, logit_opacities=5e-2, sh_0=2.5e-3, sh_rest=1.25e-4).items()}
-        optimizer = FusedAdam([{"params": [p_], "lr": lrs[k], "name": k} for k, p_ in zip(names, params)], eps=1e-15)
+        # the reference's learning rates (configs/*.yaml: means_lr_init 1e-3, log_scales 1e-2, quats 1e-3, sh_0 2.5e-3,
+        # sh_rest 1.25e-4, logit_opacities 5e-2) and Adam's default eps, as build_optimizers sets them
+        # (model/gaussian.py:389-412).  The objective of the training step is the reference's L1 + SSIM loss against
+        # target images (below), which has a minimum, so the scene stays put while it is being timed.
+        lrs = dict(means=1e-3, quats=1e-3, scales=1e-2, opacities=5e-2, colors=2.5e-3,
+                   log_scales=1e-2, logit_opacities=5e-2, sh_0=2.5e-3, sh_rest=1.25e-4)
+        optimizer = FusedAdam([{"params": [p_], "lr": lrs[k], "name": k} for k, p_ in zip(names, params)])
     # The step's V views are rendered by V / C calls of C views each (viewmats [C,4,4], the call's own batching):
     # every kernel of a call then works on C views' worth of tiles, which fills the 148 SMs where one view's
     # longest tiles would leave most of them idle.  C = 1 is the reference's one-view-per-call loop.
@@ -255,7 +265,7 @@ def ours(args):
     Wc_cpu, Wa_cpu = loss_weights(sc_cpu.seed, C, H, W)  # one "target image" worth of loss weights per view
     # pinned host copies of the per-step inputs (cameras + loss weights = the target images of a training step)
     pin = lambda t: t.contiguous().pin_memory()
-    host_views = [(pin(sc_cpu.viewmats[my_views[g * C]:my_views[g * C] + C]), pin(sc_cpu.Ks[my_views[g * C]:my_views[g * C] + C]))
+    host_views = [(pin(sc_cpu.viewmats[my_views[g * C:g * C + C]]), pin(sc_cpu.Ks[my_views[g * C:g * C + C]]))
                   for g in range(n_calls)]
     host_Wc, host_Wa = pin(Wc_cpu), pin(Wa_cpu)
     dev_views = [(a.to(dev), b.to(dev)) for a, b in host_views]
@@ -283,9 +293,32 @@ def ours(args):
             m, q, ls, lo, s0, sr = params
             return rasterization_from_parameters(m, q, ls, lo, s0, sr, viewmat, K, W, H, 3, backgrounds=bg, absgrad=True)
 
+    targets = None
+    if args.train_step:
+        # Target images of the training step: every view's own render of the initial scene, dimmed (0.9 x + 0.05), so
+        # the L1 + SSIM objective has non-zero, coherent gradients and a minimum next to the initial scene.
+        from easy_gaussian_splatting_b200.loss import fused_l1_ssim_loss
+        targets = []
+        with torch.no_grad():
+            for vm, K_ in dev_views:
+                act = params if args.activations == "pre" else None
+                if act is None:
+                    m, q, ls, lo, s0, sr = params
+                    act = [m, q, torch.exp(ls), torch.sigmoid(lo), torch.cat([s0, sr], dim=1)]
+                rc0 = rasterization(*[a.detach() for a in act], vm, K_, W, H, sh_degree=3, packed=False, backgrounds=bg)[0]
+                targets.append(rc0.clamp_(0.0, 1.0).mul_(0.9).add_(0.05))
+        inv_views = 1.0 / float(world * V)
+
+    def loss_of(slot, Wc, Wa):
+        if targets is None:
+            return lambda rc, ra: (rc * Wc).sum() + (ra * Wa).sum()
+        tgt = targets[slot % n_calls]
+        # gaussian.py:368 clamp, :422-445 LossComputer (fused kernels, csrc/loss.cu); mean over the step's views
+        return lambda rc, ra: fused_l1_ssim_loss(torch.clamp(rc, 0.0, 1.0), tgt, None, 0.2)[0].sum() * inv_views
+
     def one_view(viewmat, K, Wc, Wa, want_loss, slot=0):
         if not args.forward_only:
-            loss = pipe.render_backward(slot, params, viewmat, K, W, H, lambda rc, ra: (rc * Wc).sum() + (ra * Wa).sum(),
+            loss = pipe.render_backward(slot, params, viewmat, K, W, H, loss_of(slot, Wc, Wa),
                                         sh_degree=3, backgrounds=bg, absgrad=True, render=render,
                                         after_backward=lambda meta: stats.update_local(meta["radii"], meta["means2d"].absgrad, W, H))
             return loss if want_loss else None
@@ -305,7 +338,7 @@ def ours(args):
             bucket.begin_direct()
         else:
             bucket.zero_()
-        before = stats.clone() if world > 1 else None
+        stats.begin_step()
         fork_streams()
         for i, (vm, K) in enumerate(dev_views):
             one_view(vm, K, dev_Wc, dev_Wa, False, slot=i)
@@ -314,7 +347,7 @@ def ours(args):
             bucket.end_direct()
         if world > 1:
             bucket.all_reduce()
-            stats.all_reduce_delta(before)
+            stats.all_reduce()
         if optimizer is not None:
             optimizer.step()
 
@@ -344,7 +377,7 @@ def ours(args):
             bucket.begin_direct()
         else:
             bucket.zero_()
-        before = stats.clone() if world > 1 else None
+        stats.begin_step()
         main = torch.cuda.current_stream(dev)
         total = torch.zeros((), device=dev)
         k0 = e2e_state["next"]
@@ -372,7 +405,7 @@ def ours(args):
         e2e_state["next"] = k0 + n_calls
         if world > 1:
             bucket.all_reduce()
-            stats.all_reduce_delta(before)
+            stats.all_reduce()
         if optimizer is not None:
             optimizer.step()
         return total.item()  # device -> host read of the step's result (train.py:107-108 reads the loss)
@@ -411,6 +444,13 @@ def ours(args):
     ms0 = torch.cuda.memory_stats(dev)
     ms_total, clocks = timed(step_resident, args.steps, W_, sample_clocks=True)
     ms1 = torch.cuda.memory_stats(dev)
+    # kernels of this library per step: counted at the launch sites (egs_kernel_launch_count) over `steps` more
+    # steps of the same function, outside the timed region so that reading the counter cannot perturb it
+    lc0 = lib.egs_kernel_launch_count()
+    for _ in range(args.steps):
+        step_resident()
+    torch.cuda.synchronize()
+    own_launches = int(lib.egs_kernel_launch_count() - lc0)
     alloc_stats = {"cudaMalloc_calls_in_timed_region": ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0),
                    "cudaFree_calls_in_timed_region": ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0),
                    "alloc_retries": ms1.get("num_alloc_retries", 0),
@@ -418,8 +458,11 @@ def ours(args):
     ms_step = ms_total / args.steps
     pixels_per_step = world * V * W * H
     value = pixels_per_step / (ms_step * 1e-3) / 1e6
-    ms_e2e_total, _ = timed(step_e2e, args.steps, 2)
-    e2e_value = pixels_per_step / (ms_e2e_total / args.steps * 1e-3) / 1e6
+    if args.quick:
+        ms_e2e_total, e2e_value = float("nan"), None
+    else:
+        ms_e2e_total, _ = timed(step_e2e, args.steps, 2)
+        e2e_value = pixels_per_step / (ms_e2e_total / args.steps * 1e-3) / 1e6
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
@@ -429,7 +472,7 @@ def ours(args):
                    "view_pipelining": pipelined, "activations": args.activations,
                    "l2": "inputs larger than L2 (236 MB parameters + 96 MB splat/gradient records per view vs 126 MB L2)",
                    "gradients": "written straight into the flat bucket by the fused backward (one backward per step)" if direct else "accumulated into the flat bucket by autograd",
-                   "exchange": "none (1 GPU)" if world == 1 else f"{bucket.exchange} of the flat 236 B/Gaussian gradient bucket + NCCL all-reduce of 12 B/Gaussian densify stats each step"},
+                   "exchange": "none (1 GPU)" if world == 1 else f"{bucket.exchange} of the flat 236 B/Gaussian gradient bucket + {stats.exchange} of the 12 B/Gaussian densify stats each step"},
         "clocks": clocks, "allocator": alloc_stats,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e_total / args.steps,
@@ -437,44 +480,232 @@ def ours(args):
                         "from pinned host memory inside the timed region (double buffered on a copy stream) and the step's loss "
                         "read back with .item(); Gaussian parameters stay resident (they are the model, "
                         "/root/reference/train.py:97-108)"},
-        "gpu_launches": (launches_per_call(stages, C, W, H, backward=not args.forward_only) * n_calls
-                         + (1 if args.train_step else 0)) * args.steps,
+        "gpu_launches": own_launches,
+        "gpu_launches_what": f"this library's kernels enqueued by {args.steps} steps, counted at the launch sites "
+                             "(egs_kernel_launch_count); torch's own elementwise kernels of the loss functional are not included",
     }
+    if args.quick:
+        line.pop("e2e")
     if args.n_gaussians:
         line["invalid"] = "N overridden (debug run)"
     if args.train_step:
         line["scaling"] = "strong"
-        line["train_step"] = {"it_per_s": 1e3 / ms_step, "views_per_step": world * V, "optimizer": "fused Adam (csrc/adam.cu)",
-                              "what": "fwd+bwd of every view, gradient + densify-stat all-reduce, Adam step"}
+        line["train_step"] = {"it_per_s": 1e3 / ms_step, "views_per_step": world * V,
+                              "optimizer": "fused Adam (csrc/adam.cu), the reference's learning rates and eps",
+                              "loss": "the reference's L1 + SSIM (lambda 0.2) against per-view target images, fused kernels (csrc/loss.cu)",
+                              "what": "fwd, clamp, L1+SSIM loss, bwd of every view, densify-stat update, gradient + densify-stat exchange, Adam step"}
     if args.forward_only:
         line["invalid"] = "forward-only latency run, not the fwd+bwd metric"
         line["config"]["mode"] = "no_grad forward only"
 
-    if rank == 0 and not args.no_stage_timing and args.activations == "pre":
+    if rank == 0 and not args.no_stage_timing and not args.quick and args.activations == "pre":
         line.update(stage_rooflines(lib, stages, params, dev_views[0], bg, dev_Wc, dev_Wa, W, H, dev))
     return line
 
 
 def add_cpu_baseline(args, line):
     """rank 0, N = 1: the oracle on a bounded crop of the same workload, all host cores (run last: it leaves the
-    host's thread pool busy, which slows the launch-bound parts of whatever is timed after it)."""
+    host's thread pool busy, which slows the launch-bound parts of whatever is timed after it).  The crop the oracle
+    renders is rendered by the CUDA path too and compared — `parity` in the line comes from this very run."""
+    from easy_gaussian_splatting_b200 import rasterization
+    from easy_gaussian_splatting_b200.synthetic import loss_weights
+    from oracle import gsplat_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sc, sample = cpu_sample_scene(args.workload, args.ref_crop, args.n_gaussians)
     med, mpix, _ = run_cpu_oracle(sc, 3, 1)
     line["cpu_baseline"] = {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                             "ms_per_sample": med * 1e3}
+    # parity of the CUDA path with the oracle on that sample (same inputs, same loss functional)
+    names = ("means", "quats", "scales", "opacities", "colors")
+    Wc, Wa = loss_weights(sc.seed, 1, sc.height, sc.width)
+    counters = {}
+    lo = [getattr(sc, k).detach().clone().requires_grad_(True) for k in names]
+    rc_o, ra_o, meta_o = O.rasterization(*lo, sc.viewmats, sc.Ks, sc.width, sc.height, sh_degree=3, packed=False,
+                                         absgrad=True, backgrounds=sc.background[None], counters=counters)
+    ((rc_o * Wc).sum() + (ra_o * Wa).sum()).backward()
+    lg = [getattr(sc, k).detach().clone().cuda().requires_grad_(True) for k in names]
+    rc, ra, meta = rasterization(*lg, sc.viewmats.cuda(), sc.Ks.cuda(), sc.width, sc.height, sh_degree=3, packed=False,
+                                 absgrad=True, backgrounds=sc.background[None].cuda())
+    ((rc * Wc.cuda()).sum() + (ra * Wa.cuda()).sum()).backward()
+    border = counters["borderline"]
+    err = torch.maximum((rc.detach().cpu() - rc_o.detach()).abs().amax(-1), (ra.detach().cpu() - ra_o.detach()).abs().amax(-1))
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    grad_rel = {k: rel(g.grad.cpu(), o.grad) for k, g, o in zip(names, lg, lo)}
+    grad_rel["absgrad"] = rel(meta["means2d"].absgrad.cpu(), meta_o["means2d"].absgrad)
+    line["parity"] = {
+        "against": "oracle/gsplat_oracle.py (CPU restatement of gsplat 1.0.0; parity UNPINNED: gsplat itself is not installable here)",
+        "sample": sample,
+        "bit_exact": {k: bool(torch.equal(meta[k].cpu(), meta_o[k])) for k in ("radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets")},
+        "max_clean": float(err[~border].max()) if (~border).any() else 0.0,
+        "n_border": int(border.sum()), "max_border": float(err[border].max()) if border.any() else 0.0,
+        "grad_rel": grad_rel, "grad_rel_max": max(grad_rel.values()),
+        "tolerances": {"image_abs": 1e-4, "grad_rel": 1e-3},
+    }
 
 
-def launches_per_call(stages, C, W, H, backward=True):
-    """Our kernels launched by one rasterization() call of C views and its backward pass (checked against the ncu
-    launch lists profiles/r1h_launches.csv, C = 1: 23, and profiles/r1i_launches.csv, C = 4: 24):
-    projection fwd, 3 visible-scan kernels, 2 x (histogram + histogram scan), the onesweep passes of both sorts,
-    3 tile-count scan kernels, emit, finalize, blend fwd | blend bwd, projection bwd, densify-stat update."""
-    tw, th = stages.tile_grid(W, H)
-    p64 = math.ceil((32 + stages.camera_n_bits(C)) / 8)
-    p32 = math.ceil(max(1, int(C * tw * th - 1).bit_length()) / 8)
-    return 14 + p64 + p32 + (3 if backward else 0)
+def cfg1_cpu_timing():
+    """BASELINE config 1: 10 k Gaussians, one 256 x 256 camera, SH 3, fwd + bwd through the CPU
+    oracle, 8 threads (or all cores if fewer), forward and backward timed separately, median of 5 after 1 warm-up."""
+    from easy_gaussian_splatting_b200.synthetic import loss_weights, make_config_scene
+    from oracle import gsplat_oracle as O
+    threads = min(8, os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    sc = make_config_scene("cfg1")
+    Wc, Wa = loss_weights(sc.seed, 1, sc.height, sc.width)
+    tf, tb = [], []
+    for it in range(6):
+        leaves = [getattr(sc, k).detach().clone().requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "colors")]
+        t0 = time.perf_counter()
+        rc, ra, _ = O.rasterization(*leaves, sc.viewmats, sc.Ks, sc.width, sc.height, sh_degree=3, packed=False,
+                                    absgrad=True, backgrounds=sc.background[None])
+        t1 = time.perf_counter()
+        ((rc * Wc).sum() + (ra * Wa).sum()).backward()
+        t2 = time.perf_counter()
+        if it >= 1:
+            tf.append(t1 - t0)
+            tb.append(t2 - t1)
+    f, b = statistics.median(tf), statistics.median(tb)
+    return {"workload": "cfg1: 10000 Gaussians (blob, seed 0), 256x256, SH 3, CPU oracle", "threads": threads,
+            "cpu_count": os.cpu_count(), "fwd_ms": f * 1e3, "bwd_ms": b * 1e3,
+            "mpix_per_s": sc.width * sc.height / (f + b) / 1e6,
+            "label": "CPU restatement of gsplat 1.0.0 semantics (gsplat itself unavailable)"}
+
+
+def sequential_views(workload, dev, n_views=4, steps=5, warmup=3, forward_only=False):
+    """The reference's own call pattern (model/gaussian.py:353-367 from train.py:97-104 / eval.py:41): ONE camera per
+    rasterization() call, calls strictly one after the other on one stream — forward, loss functional, backward,
+    densify-stat update, then the next view; fresh gradients per view as after optimizer.zero_grad().  No view
+    batching, no cross-call stream overlap, no direct-to-bucket gradients."""
+    from easy_gaussian_splatting_b200 import rasterization, stages
+    from easy_gaussian_splatting_b200.distributed import DensifyStats
+    from easy_gaussian_splatting_b200.synthetic import CONFIGS, loss_weights, make_config_scene
+    sc = make_config_scene(workload, n_views=n_views)
+    W, H, N = sc.width, sc.height, sc.means.shape[0]
+    params = [getattr(sc, k).to(dev).requires_grad_(not forward_only) for k in ("means", "quats", "scales", "opacities", "colors")]
+    vms, Ks = sc.viewmats.to(dev), sc.Ks.to(dev)
+    bg = sc.background[None].to(dev)
+    Wc, Wa = (t.to(dev) for t in loss_weights(sc.seed, 1, H, W))
+    stats = DensifyStats(N, dev)
+    frame_ms = []
+
+    def view(v, timed_frames=False):
+        if forward_only:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.no_grad():
+                rc, _, _ = rasterization(*params, vms[v:v + 1], Ks[v:v + 1], W, H, sh_degree=3, packed=False, backgrounds=bg)
+            e1.record()
+            if timed_frames:
+                frame_ms.append((e0, e1))
+            return
+        for p_ in params:
+            p_.grad = None
+        rc, ra, meta = rasterization(*params, vms[v:v + 1], Ks[v:v + 1], W, H, sh_degree=3, packed=False, absgrad=True, backgrounds=bg)
+        ((rc * Wc).sum() + (ra * Wa).sum()).backward()
+        stats.update_local(meta["radii"], meta["means2d"].absgrad, W, H)
+
+    for _ in range(warmup):
+        for v in range(n_views):
+            view(v)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        for v in range(n_views):
+            view(v, timed_frames=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_view = e0.elapsed_time(e1) / (steps * n_views)
+    c = CONFIGS[workload]
+    out = {"workload": f"{workload}: {N} Gaussians ({c['kind']}), {W}x{H}", "views_per_call": 1, "views_timed": steps * n_views,
+           "mode": "no_grad forward" if forward_only else "fwd+bwd+stats", "ms_per_view": ms_view,
+           "mpix_per_s": W * H / (ms_view * 1e-3) / 1e6}
+    if forward_only:
+        lat = sorted(a.elapsed_time(b) for a, b in frame_ms)
+        out["p50_frame_ms"] = lat[len(lat) // 2]
+        out["p90_frame_ms"] = lat[(len(lat) * 9) // 10]
+    del params, stats
+    torch.cuda.empty_cache()
+    return out
+
+
+def call_pattern_runs(dev):
+    """line['call_pattern']: BASELINE.json's configurations the way the reference calls the rasterizer."""
+    out = {"what": "one camera per call, calls strictly sequential on one stream (the reference's loop); device-timed with "
+                   "CUDA events over all timed views, inputs resident"}
+    out["metric_c1"] = sequential_views("metric", dev)
+    out["cfg2_c1"] = sequential_views("cfg2", dev, n_views=4, steps=8)
+    out["cfg3_c1"] = sequential_views("cfg3", dev, n_views=2, steps=5)
+    out["cfg5_fwd"] = sequential_views("cfg5", dev, n_views=6, steps=5, forward_only=True)
+    return out
+
+
+def exchange_check(dev, rank, world):
+    """N > 1 pre-step (SURVEY.md section 4 '2-process NCCL test', B-3): the view-sharded step — real kernels, gradients
+    written straight into the symmetric-memory bucket, our all-reduce kernels, densify-stat exchange, fused Adam — must
+    give every rank the gradients and statistics of ONE GPU rendering all views, and leave the replicas bit-identical."""
+    import torch.distributed as dist
+    from easy_gaussian_splatting_b200 import rasterization
+    from easy_gaussian_splatting_b200.distributed import DensifyStats, FlatGradBucket, shard_views
+    from easy_gaussian_splatting_b200.optim import FusedAdam
+    from easy_gaussian_splatting_b200.synthetic import loss_weights, make_scene
+    N, W, H, per_rank = 120_001, 640, 368, 2
+    V = per_rank * world
+    sc = make_scene("outdoor", N, W, H, 554.0, 77, n_views=V)
+    names = ("means", "quats", "scales", "opacities", "colors")
+    lrs = dict(means=1e-3, quats=1e-3, scales=1e-2, opacities=5e-2, colors=2.5e-3)
+    Wc, Wa = (t.to(dev) for t in loss_weights(sc.seed, V, H, W))
+    vms, Ks = sc.viewmats.to(dev), sc.Ks.to(dev)
+
+    def run(view_ids, distributed):
+        params = [getattr(sc, k).to(dev).requires_grad_(True) for k in names]
+        bucket = FlatGradBucket(params, symmetric=None if distributed else False, stats_size=N if distributed else 0)
+        stats = DensifyStats(N, dev, bucket=bucket if distributed else None, distributed=distributed)
+        opt = FusedAdam([{"params": [p_], "lr": lrs[k], "name": k} for k, p_ in zip(names, params)])
+        idx = torch.tensor(view_ids, device=dev)
+        bg = sc.background[None].expand(len(view_ids), 3).contiguous().to(dev)
+        stats.begin_step()
+        with bucket.direct():
+            rc, ra, meta = rasterization(*params, vms[idx], Ks[idx], W, H, sh_degree=3, packed=False, absgrad=True, backgrounds=bg)
+            ((rc * Wc[idx]).sum() + (ra * Wa[idx]).sum()).backward()
+        stats.update_local(meta["radii"], meta["means2d"].absgrad, W, H)
+        if distributed:
+            bucket.all_reduce()
+            stats.all_reduce()
+        grads = [p_.grad.detach().clone() for p_ in params]
+        opt.step()
+        torch.cuda.synchronize()
+        return grads, stats.buf.clone(), [p_.detach().clone() for p_ in params], bucket.exchange, stats.exchange
+
+    g_d, s_d, p_d, ex_g, ex_s = run(shard_views(V, rank, world), True)
+    g_1, s_1, p_1, _, _ = run(list(range(V)), False)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    grad_rel = {k: rel(a, b) for k, a, b in zip(names, g_d, g_1)}
+    res = {
+        "grad_rel_max": max(grad_rel.values()),
+        "accum_rel": rel(s_d[0], s_1[0]),
+        "counts_equal": float(torch.equal(s_d[1], s_1[1])),
+        "max_radii_equal": float(torch.equal(s_d[2], s_1[2])),
+        "param_rel_after_adam": max(rel(a, b) for a, b in zip(p_d, p_1)),
+    }
+    # replicas bit-identical after the step: compare every rank's parameter bits with rank 0's
+    same = 1.0
+    for p_ in p_d + [s_d]:
+        ref = p_.clone()
+        dist.broadcast(ref, src=0)
+        same = min(same, float(torch.equal(ref, p_)))
+    res["replicas_bit_identical"] = same
+    # worst case over ranks
+    keys = sorted(res)
+    t = torch.tensor([res[k] if k.endswith(("equal", "identical")) else -res[k] for k in keys], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    out = {k: (bool(v) if k.endswith(("equal", "identical")) else -v) for k, v in zip(keys, t.tolist())}
+    out.update({"scene": f"{N} Gaussians (outdoor), {W}x{H}, {V} views = {per_rank} per rank", "grad_exchange": ex_g, "stat_exchange": ex_s,
+                "tolerances": {"grad_rel": 1e-5, "accum_rel": 1e-5}, "per_tensor_rank0": grad_rel})
+    out["ok"] = bool(out["grad_rel_max"] <= 1e-5 and out["accum_rel"] <= 1e-5 and out["counts_equal"] and out["max_radii_equal"]
+                     and out["replicas_bit_identical"])
+    return out
 
 
 def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
@@ -562,9 +793,22 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
         u["l1_ssim_loss_bwd"] = tm(lambda: torch.autograd.grad(tot, img, retain_graph=True))
     passes = math.ceil((32 + nbits) / 8)
     sort_bytes = (8 + 24 * passes) * n_isects
+    # The two-level route the product runs (stages.isect_sorted), stage by stage, per launch of Cn views:
+    #   visible scan  : tiles_per_gauss read twice (8 B) per (camera, Gaussian); depth read (4) + level-1 pair written
+    #                   per visible Gaussian
+    #   level-1 sort  : histogram read + p1 passes of read + write over the level-1 pairs
+    #   tile-count scan in depth order: order (4) + gathered count (4), twice, + 8 B offset written, per visible Gaussian
+    #   emission      : order 4 + offset 8 + means2d 8 + radius 4 read per visible Gaussian, 8 B pair written per intersection
+    #   level-2 sort  : 4 B histogram read + p2 passes of 16 B per intersection
+    #   tile offsets  : 4 B key read per intersection + 4 B per tile
+    key1 = stages.LEVEL1_KEY_BYTES
+    p1 = math.ceil(stages.level1_end_bit(Cn) / 8)
+    p2 = math.ceil(max(1, int(Cn * tw * th - 1).bit_length()) / 8)
+    two_level_bytes = (8 * N + (4 + key1 + 4) * n_vis + (key1 + 2 * (key1 + 4) * p1) * n_vis + 24 * n_vis + 24 * n_vis
+                       + 8 * n_isects + (4 + 16 * p2) * n_isects + 4 * n_isects + 4 * Cn * tw * th)
     work = {  # algorithmic bytes (HBM-bound stages) or flops (blend) per launch, BASELINE.md section 4 (frozen)
         "projection_sh_fwd": ("hbm", 68 * N + 204 * n_vis),
-        "binning_fast_path": ("hbm", 44 * N + 12 * n_isects + sort_bytes + 8 * n_isects + 4 * Cn * tw * th),
+        "binning_fast_path": ("hbm", two_level_bytes),
         "rasterize_fwd": ("fp32", 16 * p_eval + 10 * p_acc),
         "rasterize_bwd": ("fp32", 16 * p_eval + 54 * p_acc),
         "projection_sh_bwd": ("hbm", 108 * N + 12 * N + 408 * n_vis + 192 * (N - n_vis)),
@@ -590,8 +834,13 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
                 "frac": ach / fp32_peak, "algorithmic_flops": w}
 
     stages_out = {k: line(t[k], *work[k]) for k in work}
-    stages_out["binning_fast_path"]["note"] = ("algorithmic bytes are the frozen figure of the classic route (emit 64-bit keys, "
-                                               "6-pass LSD sort, offset encode = 172 B/isect); the two-level route moves ~3x less")
+    classic_bytes = 44 * N + 12 * n_isects + sort_bytes + 8 * n_isects + 4 * Cn * tw * th
+    stages_out["binning_fast_path"]["note"] = ("algorithmic bytes of the two-level route the product runs (level-1 sort of the visible "
+                                               f"Gaussians on depth, {p1} passes; emission; level-2 sort on the (camera, tile) index, {p2} passes; "
+                                               "offsets) — includes the route's one host sync when it has one")
+    stages_out["binning_fast_path"]["classic_route"] = {
+        "algorithmic_bytes": classic_bytes, "frac_if_it_were_the_work": classic_bytes / (max(t["binning_fast_path"], 1e-6) * 1e-3) / 1e9 / pk["hbm_gbs"],
+        "what": "SURVEY.md section 8d's frozen figure for gsplat's route (emit 64-bit keys, 6-pass LSD sort, offset encode = 172 B/isect), for comparison only"}
     standalone = {k: line(u[k], *work_u[k]) for k in work_u if k in u}
     dominant = max(t, key=lambda k: t[k])
     roof = dict(stages_out[dominant])
@@ -619,22 +868,32 @@ def main():
         return
     import copy
     import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
     line = ours(args)
-    if args.workload == "metric" and not (args.train_step or args.forward_only or args.no_train_step or args.n_gaussians):
+    extras = args.workload == "metric" and not (args.train_step or args.forward_only or args.n_gaussians or args.quick)
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1 and extras and not args.no_exchange_check:
+        # the view-sharded step against one GPU rendering every view (real kernels, real exchange)
+        line["exchange_check"] = exchange_check(dev, rank, world)
+    if extras and not args.no_train_step:
         # second half of BASELINE.json's metric ("train it/s at 1/2/4/8 GPU"): BASELINE config 4, the view-sharded
         # training step — 3 M Gaussians, 1920x1080, 64 views per step split across the ranks (strong scaling),
-        # fwd+bwd of every view, NCCL all-reduce of gradients and densify statistics, fused Adam
+        # fwd + L1/SSIM loss + bwd of every view, gradient + densify-stat exchange, fused Adam at the reference's rates
         a2 = copy.copy(args)
         a2.train_step, a2.workload, a2.total_views, a2.views_per_call = True, "cfg4", 64, 8
-        a2.steps, a2.warmup, a2.no_stage_timing, a2.no_cpu_baseline, a2.activations = 5, 5, True, True, "pre"
+        a2.steps, a2.warmup, a2.no_stage_timing, a2.no_cpu_baseline, a2.activations, a2.quick = 5, 5, True, True, "pre", True
         l2 = ours(a2)
         line["train_step"] = dict(l2["train_step"], ms_per_step=l2["ms_per_step"], mpix_per_s=l2["value"], scaling="strong",
                                   steps=a2.steps, workload=l2["config"]["workload"], views_per_call=l2["config"]["views_per_call"],
-                                  exchange=l2["config"]["exchange"], allocator=l2["allocator"])
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if int(os.environ.get("RANK", "0")) == 0:
-        if world == 1 and not args.no_cpu_baseline:
+                                  exchange=l2["config"]["exchange"], allocator=l2["allocator"], gpu_launches=l2["gpu_launches"])
+    if rank == 0:
+        if world == 1 and extras and not args.no_call_pattern:
+            line["call_pattern"] = call_pattern_runs(dev)
+        if world == 1 and not args.no_cpu_baseline and not args.quick:
             add_cpu_baseline(args, line)
+            if extras and not args.no_call_pattern:
+                line["call_pattern"]["cfg1_cpu"] = cfg1_cpu_timing()
         print(json.dumps(line), flush=True)
     if dist.is_available() and dist.is_initialized():
         dist.barrier()

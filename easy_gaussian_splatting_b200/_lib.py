@@ -20,6 +20,7 @@ I32, I64, F32 = c_int32, c_int64, c_float
 _SIGNATURES = {
     "egs_abi_version": (c_int32, []),
     "egs_last_error_string": (c_char_p, []),
+    "egs_kernel_launch_count": (c_int64, []),
     "egs_projection_fwd": (c_int32, [I32, I32, P, P, P, P, P, I32, I32, I32, P, P, I32, I32, F32, F32, F32, F32,
                                      I32, I32, I32, P, P, P, P, P, P, P, P]),
     "egs_projection_bwd": (c_int32, [I32, I32, P, P, P, P, I32, I32, I32, P, P, I32, I32, F32, P, P, P, P,
@@ -55,6 +56,8 @@ _SIGNATURES = {
     "egs_l1_ssim_bwd": (c_int32, [I32, I32, I32, P, P, P, P, F32, P, P, P]),
     "egs_allreduce_sum_f32_peer": (c_int32, [I32, I32, P, I64, P]),
     "egs_allreduce_sum_f32_multimem": (c_int32, [I32, I32, P, I64, P]),
+    "egs_allreduce_f32_peer": (c_int32, [I32, I32, P, I64, I64, P]),
+    "egs_allreduce_f32_multimem": (c_int32, [I32, I32, P, I64, I64, P]),
     "egs_fused_adam": (c_int32, [I32, P, P, P, P, P, P, F32, F32, F32, I64, P]),
     "egs_probe_fp32_fma": (c_int32, [I32, I32, P, POINTER(ctypes.c_double), P]),
 }

@@ -408,7 +408,7 @@ extern "C" int egs_exclusive_scan(int64_t n, const int32_t* in, int64_t* out, in
   scan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(in, n, block_sums);
   scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, total);
   scan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(in, n, block_sums, out);
-  return check_launch("exclusive_scan");
+  return check_launch("exclusive_scan", 3);
 }
 
 extern "C" int egs_isect_emit(int32_t C, int32_t N, const float* means2d, const int32_t* radii, const float* depths,
@@ -466,7 +466,7 @@ extern "C" int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles
   visible_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, sums_tiles);
   visible_spine_kernel<<<1, kScanThreads, 0, stream>>>(sums_vis, sums_tiles, nblocks, totals);
   visible_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, N, sums_vis, depths, keys1, vals1);
-  return check_launch("isect_visible_keys");
+  return check_launch("isect_visible_keys", 3);
 }
 
 extern "C" int egs_exclusive_scan_gather(int64_t n, const int32_t* src, const uint32_t* gather, int64_t* out,
@@ -485,7 +485,7 @@ extern "C" int egs_exclusive_scan_gather(int64_t n, const int32_t* src, const ui
   gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, block_sums);
   scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, total);
   gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, block_sums, out);
-  return check_launch("exclusive_scan_gather");
+  return check_launch("exclusive_scan_gather", 3);
 }
 
 extern "C" int egs_isect_emit_sorted(int32_t C, int32_t N, int64_t n_vis, const uint32_t* order,

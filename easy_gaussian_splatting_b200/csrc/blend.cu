@@ -830,7 +830,7 @@ static int launch_fwd(int32_t C, int64_t n_isects, const float* splats, const in
     rasterize_fwd_kernel<1, 1, COUNT><<<grid, Geo<1, 1>::kThreads, 0, st>>>(
         n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, thr,
         0x7fffffff, render_colors, render_alphas, last_ids, pc, nullptr, 0);
-  return check_launch("rasterize_fwd_kernel");
+  return check_launch("rasterize_fwd_kernel", n_isects >= thr ? 2 : 1);
 }
 
 extern "C" int egs_rasterize_fwd(int32_t C, int32_t N, int64_t n_isects, const float* splats,
@@ -909,7 +909,7 @@ static int launch_bwd(int32_t C, int64_t n_isects, const float* splats, const in
     rasterize_bwd_kernel<1, 1><<<grid, Geo<1, 1>::kThreads, 0, st>>>(
         n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, thr,
         0x7fffffff, render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, nullptr, nullptr, 0, 0);
-  return check_launch("rasterize_bwd_kernel");
+  return check_launch("rasterize_bwd_kernel", 1 + (n_slots > 0 ? 1 : 0) + (n_isects >= thr ? 1 : 0));
 }
 
 extern "C" int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const float* splats,

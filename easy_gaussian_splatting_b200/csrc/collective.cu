@@ -14,7 +14,7 @@ constexpr int kArMaxWorld = 16;
 
 template <int WORLD>
 __global__ void __launch_bounds__(kArThreads) allreduce_two_shot_kernel(float* const* __restrict__ bufs, int rank,
-                                                                        int64_t n4) {
+                                                                        int64_t n4, int64_t n4_sum) {
   float4* b[WORLD];
 #pragma unroll
   for (int p = 0; p < WORLD; ++p) b[p] = reinterpret_cast<float4*>(bufs[p]);
@@ -31,10 +31,14 @@ __global__ void __launch_bounds__(kArThreads) allreduce_two_shot_kernel(float* c
       v1[p] = two ? b[p][i1] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float4 a0 = v0[0], a1 = v1[0];
+    // float4s [0, n4_sum) are summed, [n4_sum, n4) take the maximum (the max_radii row of the densify statistics)
+    const bool sum0 = i < n4_sum, sum1 = i1 < n4_sum;
 #pragma unroll
     for (int p = 1; p < WORLD; ++p) {  // fixed rank order: deterministic, identical on every replica
-      a0.x += v0[p].x; a0.y += v0[p].y; a0.z += v0[p].z; a0.w += v0[p].w;
-      a1.x += v1[p].x; a1.y += v1[p].y; a1.z += v1[p].z; a1.w += v1[p].w;
+      a0.x = sum0 ? a0.x + v0[p].x : fmaxf(a0.x, v0[p].x); a0.y = sum0 ? a0.y + v0[p].y : fmaxf(a0.y, v0[p].y);
+      a0.z = sum0 ? a0.z + v0[p].z : fmaxf(a0.z, v0[p].z); a0.w = sum0 ? a0.w + v0[p].w : fmaxf(a0.w, v0[p].w);
+      a1.x = sum1 ? a1.x + v1[p].x : fmaxf(a1.x, v1[p].x); a1.y = sum1 ? a1.y + v1[p].y : fmaxf(a1.y, v1[p].y);
+      a1.z = sum1 ? a1.z + v1[p].z : fmaxf(a1.z, v1[p].z); a1.w = sum1 ? a1.w + v1[p].w : fmaxf(a1.w, v1[p].w);
     }
 #pragma unroll
     for (int p = 0; p < WORLD; ++p) {
@@ -47,8 +51,26 @@ __global__ void __launch_bounds__(kArThreads) allreduce_two_shot_kernel(float* c
 // Same exchange through the NVSwitch's multicast / in-switch reduction (NVLS): one multimem.ld_reduce pulls the SUM
 // of an element over all replicas (the switch reads every GPU's copy and adds in flight), one multimem.st pushes it
 // back to all of them.  Per GPU only 1/R of the bucket crosses its own link in each direction.
+// MAX of non-negative floats == MAX of their bit patterns as unsigned integers, which is what the switch offers
+// (multimem.ld_reduce has .add for f32 but .min/.max only for integer and 16-bit float types).
+__device__ __forceinline__ void multimem_max_u32x4(uint32_t* p) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.max.u32 %0, [%1];" : "=r"(v) : "l"(p + k) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p + k), "r"(v) : "memory");
+  }
+}
+
 __global__ void __launch_bounds__(kArThreads) allreduce_multimem_kernel(float* __restrict__ mc, int world, int rank,
-                                                                        int64_t n4) {
+                                                                        int64_t n4, int64_t n4_sum) {
+  if (n4 > n4_sum) {  // the MAX tail (n_max floats, a few MB at most): rank-sliced like the rest, scalar u32 ops
+    const int64_t nm = n4 - n4_sum, perm = (nm + world - 1) / world;
+    const int64_t lo = n4_sum + (int64_t)rank * perm, hi = min(n4, lo + perm);
+    for (int64_t i = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < hi; i += (int64_t)gridDim.x * kArThreads)
+      multimem_max_u32x4(reinterpret_cast<uint32_t*>(mc) + 4 * i);
+    n4 = n4_sum;
+  }
   const int64_t per = (n4 + world - 1) / world;
   const int64_t lo = (int64_t)rank * per, hi = min(n4, lo + per);
   const int64_t stride = (int64_t)gridDim.x * kArThreads;
@@ -72,28 +94,37 @@ __global__ void __launch_bounds__(kArThreads) allreduce_multimem_kernel(float* _
 
 using namespace egs;
 
-extern "C" int egs_allreduce_sum_f32_multimem(int32_t world, int32_t rank, void* multicast_ptr, int64_t n_floats,
-                                              egs_stream_t stream) {
+extern "C" int egs_allreduce_f32_multimem(int32_t world, int32_t rank, void* multicast_ptr, int64_t n_sum_floats,
+                                          int64_t n_max_floats, egs_stream_t stream) {
   EGS_REQUIRE(world >= 1 && rank >= 0 && rank < world, "allreduce_multimem: bad world=%d rank=%d", world, rank);
-  EGS_REQUIRE(n_floats >= 0 && n_floats % 4 == 0, "allreduce_multimem: n_floats=%lld must be a multiple of 4", (long long)n_floats);
+  EGS_REQUIRE(n_sum_floats >= 0 && n_sum_floats % 4 == 0 && n_max_floats >= 0 && n_max_floats % 4 == 0,
+              "allreduce_multimem: n_sum_floats=%lld and n_max_floats=%lld must be multiples of 4", (long long)n_sum_floats,
+              (long long)n_max_floats);
   EGS_REQUIRE(multicast_ptr != nullptr, "allreduce_multimem: multicast pointer is required");
-  if (n_floats == 0 || world == 1) return 0;
-  const int64_t n4 = n_floats / 4;
+  if (n_sum_floats + n_max_floats == 0 || world == 1) return 0;
+  const int64_t n4_sum = n_sum_floats / 4, n4 = n4_sum + n_max_floats / 4;
   int64_t blocks = ceil_div(ceil_div(n4, world), 2 * kArThreads);
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  allreduce_multimem_kernel<<<(unsigned)blocks, kArThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<float*>(multicast_ptr), world, rank, n4);
+  allreduce_multimem_kernel<<<(unsigned)blocks, kArThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<float*>(multicast_ptr), world, rank, n4, n4_sum);
   return check_launch("allreduce_multimem_kernel");
 }
 
-extern "C" int egs_allreduce_sum_f32_peer(int32_t world, int32_t rank, const void* peer_buffers_dev, int64_t n_floats,
-                                          egs_stream_t stream) {
+extern "C" int egs_allreduce_sum_f32_multimem(int32_t world, int32_t rank, void* multicast_ptr, int64_t n_floats,
+                                              egs_stream_t stream) {
+  return egs_allreduce_f32_multimem(world, rank, multicast_ptr, n_floats, 0, stream);
+}
+
+extern "C" int egs_allreduce_f32_peer(int32_t world, int32_t rank, const void* peer_buffers_dev, int64_t n_sum_floats,
+                                      int64_t n_max_floats, egs_stream_t stream) {
   EGS_REQUIRE(world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world, "allreduce_peer: bad world=%d rank=%d", world, rank);
-  EGS_REQUIRE(n_floats >= 0 && n_floats % 4 == 0, "allreduce_peer: n_floats=%lld must be a multiple of 4", (long long)n_floats);
+  EGS_REQUIRE(n_sum_floats >= 0 && n_sum_floats % 4 == 0 && n_max_floats >= 0 && n_max_floats % 4 == 0,
+              "allreduce_peer: n_sum_floats=%lld and n_max_floats=%lld must be multiples of 4", (long long)n_sum_floats,
+              (long long)n_max_floats);
   EGS_REQUIRE(peer_buffers_dev != nullptr, "allreduce_peer: peer buffer table is required");
-  if (n_floats == 0 || world == 1) return 0;
+  if (n_sum_floats + n_max_floats == 0 || world == 1) return 0;
   float* const* bufs = reinterpret_cast<float* const*>(peer_buffers_dev);
-  const int64_t n4 = n_floats / 4;
+  const int64_t n4_sum = n_sum_floats / 4, n4 = n4_sum + n_max_floats / 4;
   const int64_t per = (n4 + world - 1) / world;
   int64_t blocks = ceil_div(per, 2 * kArThreads);
   if (blocks < 1) blocks = 1;
@@ -101,14 +132,19 @@ extern "C" int egs_allreduce_sum_f32_peer(int32_t world, int32_t rank, const voi
   const unsigned grid = (unsigned)blocks;
   cudaStream_t st = (cudaStream_t)stream;
   switch (world) {
-    case 2: allreduce_two_shot_kernel<2><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
-    case 3: allreduce_two_shot_kernel<3><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
-    case 4: allreduce_two_shot_kernel<4><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
-    case 5: allreduce_two_shot_kernel<5><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
-    case 6: allreduce_two_shot_kernel<6><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
-    case 7: allreduce_two_shot_kernel<7><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
-    case 8: allreduce_two_shot_kernel<8><<<grid, kArThreads, 0, st>>>(bufs, rank, n4); break;
+    case 2: allreduce_two_shot_kernel<2><<<grid, kArThreads, 0, st>>>(bufs, rank, n4, n4_sum); break;
+    case 3: allreduce_two_shot_kernel<3><<<grid, kArThreads, 0, st>>>(bufs, rank, n4, n4_sum); break;
+    case 4: allreduce_two_shot_kernel<4><<<grid, kArThreads, 0, st>>>(bufs, rank, n4, n4_sum); break;
+    case 5: allreduce_two_shot_kernel<5><<<grid, kArThreads, 0, st>>>(bufs, rank, n4, n4_sum); break;
+    case 6: allreduce_two_shot_kernel<6><<<grid, kArThreads, 0, st>>>(bufs, rank, n4, n4_sum); break;
+    case 7: allreduce_two_shot_kernel<7><<<grid, kArThreads, 0, st>>>(bufs, rank, n4, n4_sum); break;
+    case 8: allreduce_two_shot_kernel<8><<<grid, kArThreads, 0, st>>>(bufs, rank, n4, n4_sum); break;
     default: return fail(EGS_ERR_UNSUPPORTED, "allreduce_peer: world=%d is not instantiated (2..8)", world);
   }
   return check_launch("allreduce_two_shot_kernel");
+}
+
+extern "C" int egs_allreduce_sum_f32_peer(int32_t world, int32_t rank, const void* peer_buffers_dev, int64_t n_floats,
+                                          egs_stream_t stream) {
+  return egs_allreduce_f32_peer(world, rank, peer_buffers_dev, n_floats, 0, stream);
 }

@@ -13,9 +13,14 @@ namespace egs {
 char* error_buffer();
 int fail(int code, const char* fmt, ...);
 
-inline int check_launch(const char* what) {
+// Adds to the process-wide count of kernels this library has launched (egs_kernel_launch_count()).
+void note_kernel_launches(int n);
+
+// n_kernels = how many kernels the caller enqueued since its last check (counted only when they were accepted).
+inline int check_launch(const char* what, int n_kernels = 1) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+  note_kernel_launches(n_kernels);
   return 0;
 }
 

@@ -388,7 +388,7 @@ static int run_passes(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, u
     KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
-  return check_launch("radix_sort_pairs");
+  return check_launch("radix_sort_pairs", passes + 2);  // + histogram + histogram scan
 }
 
 extern "C" int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,

@@ -9,8 +9,12 @@ camera views, and then two collectives make the replicas agree again:
   into it and no pack / unpack copy exists;
 * densification statistics (/root/reference/model/gaussian.py:56-64,188-197): SUM for
   ``grad_norm_accum`` and ``collecting_counts``, MAX for ``max_radii`` (12 B per Gaussian).  Each
-  rank first applies the per-view update for its own views (``stages.densify_stats_update``), so the
-  reduced result equals what one GPU would have accumulated over all views.
+  rank applies the per-view update for its own views to a per-step DELTA (``stages.densify_stats_update``
+  on three zeroed rows), the deltas are reduced, and every rank folds the reduced delta into its persistent
+  statistics — which equals what one GPU would have accumulated over all views.  When the statistics are
+  attached to the gradient bucket (``DensifyStats(n, device, bucket=bucket)``) the delta rows live in the
+  same symmetric buffer behind the gradients and travel in the SAME kernel launch (SUM rows with the
+  gradients, the MAX row through the kernel's max tail): no NCCL call, no clone, no subtraction.
 
 Works with any torch.distributed backend (NCCL over NVLink on the B200 box, gloo in CPU tests).
 """
@@ -41,14 +45,22 @@ class FlatGradBucket:
     ranks, falls back to ``dist.all_reduce`` if symmetric memory is unavailable or the check fails
     (EGS_PEER_ALLREDUCE=0 forces the fallback)."""
 
-    def __init__(self, params: Sequence[Tensor], symmetric: Optional[bool] = None):
+    def __init__(self, params: Sequence[Tensor], symmetric: Optional[bool] = None, stats_size: int = 0):
+        """``stats_size`` = N reserves three more rows of N floats behind the gradients for the per-step densify-stat
+        deltas (two SUM rows, one MAX row) so that they ride in the gradient exchange; see ``DensifyStats``."""
         self.params = list(params)
         # every parameter's slice starts on a 16-byte boundary (4 floats): the fused backward stores float4s into
         # it, and N is arbitrary after the first densify / prune
         total = sum(-(-p.numel() // 4) * 4 for p in self.params)
         ref = self.params[0]
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        padded = -(-total // (4 * max(world, 1))) * (4 * max(world, 1))  # whole float4s per rank slice
+        self.grad_floats = -(-total // (4 * max(world, 1))) * (4 * max(world, 1))  # whole float4s per rank slice
+        self.stats_size = int(stats_size)
+        self.stats_row = -(-self.stats_size // 4) * 4  # each row starts on a 16-byte boundary
+        self.n_sum_floats = self.grad_floats + 2 * self.stats_row
+        self.n_max_floats = self.stats_row
+        padded = self.n_sum_floats + self.n_max_floats
+        self.epoch = 0  # number of completed exchanges
         self._symm = None
         self._mode = "nccl"
         if symmetric is None:
@@ -88,7 +100,9 @@ class FlatGradBucket:
                 pattern = torch.arange(n, dtype=torch.float32, device=ref.device).remainder_(977.0).add_(1.0)
                 buf.copy_(pattern * float(dist.get_rank() + 1))
                 expect = buf.clone()
-                dist.all_reduce(expect)
+                dist.all_reduce(expect[:self.n_sum_floats])
+                if self.n_max_floats:
+                    dist.all_reduce(expect[self.n_sum_floats:], op=dist.ReduceOp.MAX)
                 self._peer_all_reduce(buf)
                 ok = int(torch.equal(buf, expect))
         except Exception:
@@ -109,10 +123,12 @@ class FlatGradBucket:
         stream = ctypes.c_void_p(torch.cuda.current_stream(buf.device).cuda_stream)
         hdl.barrier(channel=0)  # every bucket is complete
         if self._mode == "two_shot":
-            rc = lib.egs_allreduce_sum_f32_peer(world, rank, ctypes.c_void_p(hdl.buffer_ptrs_dev), buf.numel(), stream)
+            rc = lib.egs_allreduce_f32_peer(world, rank, ctypes.c_void_p(hdl.buffer_ptrs_dev), self.n_sum_floats,
+                                            self.n_max_floats, stream)
         else:
-            rc = lib.egs_allreduce_sum_f32_multimem(world, rank, ctypes.c_void_p(hdl.multicast_ptr), buf.numel(), stream)
-        _lib.check(rc, "egs_allreduce_sum_f32")
+            rc = lib.egs_allreduce_f32_multimem(world, rank, ctypes.c_void_p(hdl.multicast_ptr), self.n_sum_floats,
+                                                self.n_max_floats, stream)
+        _lib.check(rc, "egs_allreduce_f32")
         hdl.barrier(channel=1)  # every slice has landed everywhere
 
     @property
@@ -120,8 +136,15 @@ class FlatGradBucket:
         return {"nccl": "NCCL all-reduce", "two_shot": "hand-written two-shot all-reduce over NVLink peer memory",
                 "multimem": "hand-written NVLS (multimem.ld_reduce / multimem.st) all-reduce"}[self._mode]
 
+    @property
+    def stats_delta(self) -> Optional[Tensor]:
+        """[3, stats_size] view of the statistics rows behind the gradients (SUM, SUM, MAX), or None."""
+        if not self.stats_size:
+            return None
+        return self.flat[self.grad_floats:].view(3, self.stats_row)[:, :self.stats_size]
+
     def zero_(self) -> None:
-        self.flat.zero_()
+        self.flat[:self.grad_floats].zero_()
         for p, v in zip(self.params, self.views):  # an optimizer may have detached .grad
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                 p.grad = v
@@ -165,9 +188,13 @@ class FlatGradBucket:
                 raise ValueError("the symmetric-memory bucket was rendezvoused on the WORLD group; build the bucket with "
                                  "symmetric=False to all-reduce over another group")
             self._peer_all_reduce(self.flat)
+            self.epoch += 1
             return _CompletedWork() if async_op else None
+        self.epoch += 1
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            if self.n_max_floats:  # the MAX row cannot share a SUM collective: reduce it first, synchronously
+                dist.all_reduce(self.flat[self.n_sum_floats:], op=dist.ReduceOp.MAX, group=group)
+            return dist.all_reduce(self.flat[:self.n_sum_floats], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         return _CompletedWork() if async_op else None
 
     @property
@@ -187,11 +214,29 @@ class _CompletedWork:
 
 
 class DensifyStats:
-    """max_radii / grad_norm_accum / collecting_counts with the reference's semantics, kept as three
-    rows of one [3,N] buffer so the SUM rows travel in one collective."""
+    """``grad_norm_accum`` / ``collecting_counts`` / ``max_radii`` with the reference's semantics
+    (/root/reference/model/gaussian.py:56-64, 188-197), kept as the three rows of one ``[3, N]`` buffer.
 
-    def __init__(self, n: int, device):
+    One process: ``update_local`` applies every view's contribution to the persistent rows directly.
+    View-sharded (``distributed=True``, the default whenever a process group with more than one rank exists): the
+    views of a step go to a per-step DELTA — ``begin_step()`` clears it, ``update_local`` accumulates into it,
+    ``all_reduce()`` reduces it over the ranks (SUM, SUM, MAX) and folds it into the persistent rows.  With
+    ``bucket=`` (a ``FlatGradBucket`` built with ``stats_size=N``) the delta rows ARE the tail of the gradient bucket
+    and have already been reduced by ``bucket.all_reduce()`` — call that first; ``all_reduce()`` here then only folds."""
+
+    def __init__(self, n: int, device, bucket: Optional["FlatGradBucket"] = None, distributed: Optional[bool] = None):
         self.buf = torch.zeros(3, n, dtype=torch.float32, device=device)
+        if distributed is None:
+            distributed = bucket is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        self.bucket = bucket
+        self.delta: Optional[Tensor] = None
+        self._epoch = 0
+        if bucket is not None:
+            if bucket.stats_size != n:
+                raise ValueError(f"the bucket reserves {bucket.stats_size} statistics slots, need {n}")
+            self.delta = bucket.stats_delta
+        elif distributed:
+            self.delta = torch.zeros(3, n, dtype=torch.float32, device=device)
 
     @property
     def grad_norm_accum(self) -> Tensor:
@@ -205,25 +250,42 @@ class DensifyStats:
     def max_radii(self) -> Tensor:
         return self.buf[2]
 
+    @property
+    def step_buf(self) -> Tensor:
+        """Where the views of the current step accumulate: the delta rows when view-sharded, else the persistent rows."""
+        return self.buf if self.delta is None else self.delta
+
+    @property
+    def exchange(self) -> str:
+        if self.delta is None:
+            return "none (one process)"
+        if self.bucket is not None:
+            return "rides in the gradient exchange (SUM rows + MAX row of the same launch)"
+        return "NCCL all-reduce (SUM of the two accumulator deltas, MAX of the max_radii delta)"
+
+    def begin_step(self) -> None:
+        if self.delta is not None:
+            self.delta.zero_()
+            if self.bucket is not None:
+                self._epoch = self.bucket.epoch
+
     def update_local(self, radii: Tensor, absgrad: Tensor, width: int, height: int) -> None:
         """Per-view update for the views this rank rendered (CUDA kernel; no host sync)."""
         from . import stages
-        stages.densify_stats_update(self.max_radii, self.grad_norm_accum, self.collecting_counts, radii, absgrad,
-                                    width, height)
+        t = self.step_buf
+        stages.densify_stats_update(t[2], t[0], t[1], radii, absgrad, width, height)
 
-    def all_reduce_delta(self, before: "DensifyStats", group=None) -> None:
-        """Replicas start a step with identical stats; each adds its own views' contribution.  The
-        globally consistent result is before + SUM(delta) for the two accumulators and MAX for radii."""
-        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+    def all_reduce(self, group=None) -> None:
+        if self.delta is None:
             return
-        delta = self.buf[:2] - before.buf[:2]
-        dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
-        self.buf[:2] = before.buf[:2] + delta
-        mr = self.buf[2].contiguous()
-        dist.all_reduce(mr, op=dist.ReduceOp.MAX, group=group)
-        self.buf[2] = mr
-
-    def clone(self) -> "DensifyStats":
-        c = DensifyStats.__new__(DensifyStats)
-        c.buf = self.buf.clone()
-        return c
+        if self.bucket is not None:
+            if self.bucket.epoch == self._epoch:
+                raise RuntimeError("statistics attached to a gradient bucket are reduced by bucket.all_reduce(): call it "
+                                   "before DensifyStats.all_reduce()")
+        elif dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.delta[:2], op=dist.ReduceOp.SUM, group=group)
+            mr = self.delta[2].contiguous()
+            dist.all_reduce(mr, op=dist.ReduceOp.MAX, group=group)
+            self.delta[2].copy_(mr)
+        self.buf[:2] += self.delta[:2]
+        torch.maximum(self.buf[2], self.delta[2], out=self.buf[2])

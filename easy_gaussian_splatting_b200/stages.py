@@ -138,6 +138,14 @@ def camera_n_bits(C: int) -> int:
     return int(math.floor(math.log2(C))) + 1 if C > 1 else 0
 
 
+# Level 1 of the two-level binning route sorts the visible Gaussians of all cameras on these key bits
+LEVEL1_KEY_BYTES = 8
+
+
+def level1_end_bit(C: int) -> int:
+    return 32 + camera_n_bits(C)
+
+
 def projection_fwd(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, colors: Tensor,
                    viewmats: Tensor, Ks: Tensor, width: int, height: int, sh_degree: Optional[int],
                    eps2d: float = 0.3, near_plane: float = 0.01, far_plane: float = 1e10,
@@ -402,7 +410,7 @@ def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss
     if n_isects >= 2 ** 31 - 1:
         raise RuntimeError(f"{n_isects} tile intersections do not fit int32 offsets; render fewer cameras per call")
     # level 1: visible Gaussians in (camera, depth, index) order
-    k1, order = radix_sort_pairs(keys1[:n_vis], vals1[:n_vis], 32 + camera_n_bits(C))
+    k1, order = radix_sort_pairs(keys1[:n_vis], vals1[:n_vis], level1_end_bit(C))
     # tile counts in that order -> write offsets
     cum = torch.empty(n_vis, dtype=torch.int64, device=dev)
     total2 = torch.empty(1, dtype=torch.int64, device=dev)

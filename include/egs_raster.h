@@ -47,6 +47,10 @@ enum egs_status {
 
 int egs_abi_version(void);
 const char* egs_last_error_string(void);
+/* Kernels this library has enqueued since it was loaded (process-wide, monotonically increasing, counted at the
+ * launch sites): the difference over a region is the number of the library's own kernel launches in it.  Used by
+ * bench.py for `gpu_launches`; not part of the reference's interface (the reference has no such counter). */
+int64_t egs_kernel_launch_count(void);
 
 /* ---- g1 + g2 (+ the count half of g3): fused projection, SH colour, tile count ---------------
  * Replaces gsplat `fully_fused_projection` fwd, `spherical_harmonics` fwd, the Python glue
@@ -263,6 +267,15 @@ int egs_allreduce_sum_f32_peer(int32_t world, int32_t rank, const void* peer_buf
  * rank r pulls the in-switch SUM of slice r (multimem.ld_reduce) and broadcasts it back (multimem.st). */
 int egs_allreduce_sum_f32_multimem(int32_t world, int32_t rank, void* multicast_ptr, int64_t n_floats,
                                    egs_stream_t stream);
+/* Both exchanges of the view-sharded step in ONE launch: the first n_sum_floats of the symmetric
+ * buffer are SUMmed over the ranks (parameter gradients, then the grad_norm_accum / collecting_counts rows of the
+ * step's densify statistics, model/gaussian.py:196-197), the n_max_floats behind them take the MAXimum (the max_radii
+ * row, gaussian.py:194; values must be >= 0: the NVLS variant compares their bit patterns as unsigned integers).
+ * Same slicing, same guarantees (one owner GPU per element => bit-identical replicas), same caller-side barriers. */
+int egs_allreduce_f32_peer(int32_t world, int32_t rank, const void* peer_buffers_dev, int64_t n_sum_floats,
+                           int64_t n_max_floats, egs_stream_t stream);
+int egs_allreduce_f32_multimem(int32_t world, int32_t rank, void* multicast_ptr, int64_t n_sum_floats,
+                               int64_t n_max_floats, egs_stream_t stream);
 
 /* ---- measurement utility (bench.py only) -----------------------------------------------------------------
  * Dependent-FMA throughput probe: the FP32-SIMT roofline denominator for the blending kernels

@@ -31,42 +31,49 @@ def _stats_update_cpu(stats, radii, absgrad, W, H):
     max_hw = max(W, H)
     r = radii[0].float() / max_hw
     vis = r > 0
-    stats.max_radii[vis] = torch.max(stats.max_radii[vis], r[vis])
-    stats.grad_norm_accum[vis] += absgrad[0].norm(dim=-1)[vis] * max_hw
-    stats.collecting_counts[vis] += 1
+    t = stats.step_buf  # rows: grad_norm_accum, collecting_counts, max_radii (the step's delta when view-sharded)
+    t[2][vis] = torch.max(t[2][vis], r[vis])
+    t[0][vis] += absgrad[0].norm(dim=-1)[vis] * max_hw
+    t[1][vis] += 1
 
 
 SHAPES = [(50, 3), (50, 4), (50, 3), (50,), (50, 16, 3)]
 N_VIEWS, N, W, H = 6, 50, 640, 480
 
 
-def _worker(rank, world, port, out_q):
+def _worker(rank, world, port, out_q, rank_attach=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     params = [torch.zeros(*s, requires_grad=True) for s in SHAPES]
-    bucket = FlatGradBucket(params)
-    stats = DensifyStats(N, "cpu")
+    attach = rank_attach  # statistics riding in the gradient bucket, or exchanged on their own
+    bucket = FlatGradBucket(params, stats_size=N if attach else 0)
+    stats = DensifyStats(N, "cpu", bucket=bucket if attach else None)
     stats.buf[0] = 1.0  # pre-existing accumulations, identical on all replicas
-    before = stats.clone()
+    stats.buf[2] = 0.004
     bucket.zero_()
+    stats.begin_step()
     for v in shard_views(N_VIEWS, rank, world):
         grads, radii, absgrad = _fake_view(v, SHAPES, N)
         for p, g in zip(params, grads):
             p.grad += g  # autograd accumulates in place into the bucket views
         _stats_update_cpu(stats, radii, absgrad, W, H)
+    if attach:
+        with pytest.raises(RuntimeError):
+            stats.all_reduce()  # the bucket has not been reduced yet
     bucket.all_reduce()
-    stats.all_reduce_delta(before)
+    stats.all_reduce()
     out_q.put((rank, bucket.flat.clone(), stats.buf.clone(), [p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, bucket.views)]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_view_sharded_exchange_matches_single_process():
+@pytest.mark.parametrize("attach", [True, False])
+def test_view_sharded_exchange_matches_single_process(attach):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, attach)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]
@@ -77,7 +84,9 @@ def test_view_sharded_exchange_matches_single_process():
     params = [torch.zeros(*s, requires_grad=True) for s in SHAPES]
     bucket = FlatGradBucket(params)
     stats = DensifyStats(N, "cpu")
+    assert stats.delta is None and stats.exchange.startswith("none")
     stats.buf[0] = 1.0
+    stats.buf[2] = 0.004
     for v in range(N_VIEWS):
         grads, radii, absgrad = _fake_view(v, SHAPES, N)
         for p, g in zip(params, grads):
@@ -85,8 +94,8 @@ def test_view_sharded_exchange_matches_single_process():
         _stats_update_cpu(stats, radii, absgrad, W, H)
     for rank, flat, sbuf, aliased in results:
         assert all(aliased), "param.grad must alias the flat bucket (no pack/unpack copies)"
-        n = bucket.flat.numel()  # the 2-rank bucket is padded to whole float4s per rank slice
-        assert torch.allclose(flat[:n], bucket.flat, atol=1e-5), f"rank {rank} gradients"
+        n = sum(-(-p.numel() // 4) * 4 for p in params)  # gradient part (the 2-rank bucket is padded and may carry stats rows)
+        assert torch.allclose(flat[:n], bucket.flat[:n], atol=1e-5), f"rank {rank} gradients"
         assert torch.allclose(sbuf[:2], stats.buf[:2], atol=1e-4), f"rank {rank} SUM statistics"
         assert torch.equal(sbuf[2], stats.buf[2]), f"rank {rank} MAX statistics"
     assert torch.equal(results[0][1], results[1][1]), "replicas must end bit-identical"
