@@ -7,6 +7,15 @@ for f in sys.argv[1:]:
     except Exception as e:
         print(f, "parse failed:", e); print(open(f).read()[-1500:]); continue
     ts = d.get("train_step", {}).get("it_per_s")
-    print(f"{f}: value {d['value']:.1f} ms/step {d['ms_per_step']:.3f} e2e {d['e2e']['value']:.1f}" + (f" it/s {ts:.2f}" if ts else ""))
+    e2e = d.get("e2e", {}).get("value")
+    print(f"{f}: value {d['value']:.1f} ms/step {d['ms_per_step']:.3f} e2e {e2e if e2e is None else round(e2e, 1)} launches {d.get('gpu_launches')}"
+          + (f" it/s {ts:.2f}" if ts else ""))
     if "stages" in d:
         print("   " + "  ".join(f"{k}={s['ms']:.3f}({s['frac']:.2f})" for k, s in d["stages"].items()))
+        print("   standalone " + "  ".join(f"{k}={s['ms']:.3f}({s['frac']:.2f})" for k, s in d.get("stages_standalone", {}).items()))
+    for k, v in d.get("call_pattern", {}).items():
+        if isinstance(v, dict):
+            print(f"   {k}: " + "  ".join(f"{a}={round(b, 3) if isinstance(b, float) else b}" for a, b in v.items() if a not in ("workload", "label", "mode")))
+    for k in ("parity", "exchange_check", "cpu_baseline", "clocks", "roofline"):
+        if k in d:
+            print(f"   {k}: {json.dumps(d[k])[:600]}")

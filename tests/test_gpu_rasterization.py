@@ -245,14 +245,15 @@ def _pile_scene(n=6000, seed=5):
     return sc
 
 
-def test_long_tile_launch_parity(monkeypatch):
-    monkeypatch.setenv("EGS_LONG_TILE_THRESHOLD", "2048")  # the 8-warps-per-tile launch is opt-in (csrc/blend.cu)
+def test_long_tile_parity():
+    """A pile of faint Gaussians behind one another: tiles with thousands of entries of which almost every one is
+    blended (no early termination) — the long-list case of the blend kernels, default settings."""
     sc = _pile_scene()
     ref = oracle_run(sc)
     offs = ref["meta"]["isect_offsets"].reshape(-1).long()
     n = ref["meta"]["flatten_ids"].numel()
     lens = torch.diff(torch.cat([offs, torch.tensor([n])]))
-    assert int(lens.max()) > 2048, "scene must trigger the long-tile launch"
+    assert int(lens.max()) > 2048, "scene must contain long tile lists"
     out = cuda_run(sc)
     assert torch.equal(out["meta"]["flatten_ids"].cpu(), ref["meta"]["flatten_ids"])
     border = ref["counters"]["borderline"]
