@@ -206,11 +206,14 @@ __global__ void __launch_bounds__(kScanThreads) visible_spine_kernel(int64_t* __
   if (threadIdx.x == 0) { totals[0] = carry; totals[1] = tiles_total; }
 }
 
-// also writes the level-1 sort input: key = cam << 32 | bits(depth), value = flat index, compacted
-__global__ void __launch_bounds__(kScanThreads) visible_apply_kernel(const int32_t* __restrict__ tiles, int64_t n, int N,
+// also writes the level-1 sort input: key = bits(depth), value = flat index (camera * N + Gaussian), compacted.
+// The camera needs no key bits: level 2 sorts stably on the (camera, tile) index, so sorting the visible entries of
+// ALL cameras on depth alone (ties keep the flat-index order they are written in here) leaves every (camera, tile)
+// bucket in (depth, flat index) order — the order of a sort on cam | tile | depth.
+__global__ void __launch_bounds__(kScanThreads) visible_apply_kernel(const int32_t* __restrict__ tiles, int64_t n,
                                                                       const int64_t* __restrict__ sums_vis,
                                                                       const float* __restrict__ depths,
-                                                                      uint64_t* __restrict__ keys1,
+                                                                      uint32_t* __restrict__ keys1,
                                                                       uint32_t* __restrict__ vals1) {
   __shared__ int64_t smem[33];
   const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
@@ -228,8 +231,7 @@ __global__ void __launch_bounds__(kScanThreads) visible_apply_kernel(const int32
   for (int i = 0; i < kScanItems; ++i) {
     if (v[i] > 0) {
       const int64_t idx = base + i;
-      const uint64_t cam = (uint64_t)(idx / N);
-      keys1[run] = (cam << 32) | (uint64_t)__float_as_uint(depths[idx]);
+      keys1[run] = __float_as_uint(depths[idx]);
       vals1[run] = (uint32_t)idx;
       ++run;
     }
@@ -296,6 +298,10 @@ __global__ void __launch_bounds__(kEmitThreads) isect_emit_sorted_kernel(
     cnt = (x1 - x0) * (y1 - y0);
     excl = cum_excl[i];
   }
+  // j / w for every tile j of the rectangle without a division per pair: one reciprocal per Gaussian,
+  // floor(j * ceil(2^32 / w) / 2^32) == j / w exactly while j * w < 2^32 (j < tile_w * tile_h < 2^31 / ... holds: the
+  // entry point refuses grids of 2^16 tiles or more per side product, see EGS_REQUIRE below)
+  const uint32_t wmagic = w > 1 ? (uint32_t)((0x100000000ull + (uint32_t)w - 1u) / (uint32_t)w) : 0u;
   const int64_t warp_base = __shfl_sync(0xffffffffu, excl, 0);
   const int32_t lexcl = (int32_t)(excl - warp_base);
   const int32_t total = __shfl_sync(0xffffffffu, lexcl + cnt, 31);
@@ -311,12 +317,13 @@ __global__ void __launch_bounds__(kEmitThreads) isect_emit_sorted_kernel(
     }
     const int32_t j = k - __shfl_sync(0xffffffffu, lexcl, o);
     const int32_t ow = __shfl_sync(0xffffffffu, w, o);
+    const uint32_t omagic = __shfl_sync(0xffffffffu, wmagic, o);
     const int32_t ox0 = __shfl_sync(0xffffffffu, x0, o);
     const int32_t oy0 = __shfl_sync(0xffffffffu, y0, o);
     const uint32_t okb = __shfl_sync(0xffffffffu, key_base, o);
     const uint32_t og = __shfl_sync(0xffffffffu, g, o);
     if (k < total) {
-      const int32_t ty = j / ow, tx = j - ty * ow;
+      const int32_t ty = ow > 1 ? (int32_t)__umulhi((uint32_t)j, omagic) : j, tx = j - ty * ow;
       const int64_t dst = warp_base + k;
       if (dst < n_isects) {
         tile_keys[dst] = okb + (uint32_t)((oy0 + ty) * tile_w + ox0 + tx);
@@ -448,7 +455,7 @@ extern "C" int64_t egs_isect_scan_workspace_bytes(int64_t n) {
 }
 
 extern "C" int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths,
-                                      uint64_t* keys1, uint32_t* vals1, int64_t* totals, void* workspace,
+                                      uint32_t* keys1, uint32_t* vals1, int64_t* totals, void* workspace,
                                       int64_t workspace_bytes, egs_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EGS_REQUIRE(C >= 0 && N >= 0, "isect_visible_keys: negative sizes");
@@ -465,7 +472,7 @@ extern "C" int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles
   int64_t* sums_tiles = sums_vis + nblocks + 1;
   visible_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, sums_tiles);
   visible_spine_kernel<<<1, kScanThreads, 0, stream>>>(sums_vis, sums_tiles, nblocks, totals);
-  visible_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, N, sums_vis, depths, keys1, vals1);
+  visible_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, depths, keys1, vals1);
   return check_launch("isect_visible_keys", 3);
 }
 
@@ -494,6 +501,8 @@ extern "C" int egs_isect_emit_sorted(int32_t C, int32_t N, int64_t n_vis, const 
                                      uint32_t* tile_keys, uint32_t* flat_vals, egs_stream_t stream) {
   EGS_REQUIRE(C >= 0 && N >= 0 && n_vis >= 0, "isect_emit_sorted: negative sizes");
   EGS_REQUIRE((int64_t)C * tile_width * tile_height < 0x7fffffffLL, "isect_emit_sorted: too many tiles");
+  EGS_REQUIRE((int64_t)tile_width * tile_height * tile_width < 0x100000000LL,
+              "isect_emit_sorted: tile grid %dx%d too large for the reciprocal row split", tile_width, tile_height);
   if (n_vis == 0 || n_isects == 0) return 0;
   isect_emit_sorted_kernel<<<(unsigned)ceil_div(n_vis, kEmitThreads), kEmitThreads, 0, (cudaStream_t)stream>>>(
       N, n_vis, order, cum_excl, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width,

@@ -3,30 +3,24 @@
 // no tensor cores.
 //
 // Work decomposition.  One CTA (2 warps) per 16x16 pixel tile; each WARP owns a 16x8 pixel half of
-// the tile and runs on its own (there is no block-level barrier in either kernel).  A warp is four
-// QUARTERS of 8 lanes; a quarter owns an 8x4 pixel block and each of its lanes a 2x2 pixel block, so
-// shared-memory reads, loop overhead, the separable parts of the quadratic form and — in the backward
-// pass — the gradient reduction are amortised over 4 pixels.
+// the tile and runs on its own (there is no block-level barrier in either kernel); each lane owns a
+// 2x2 pixel block, so shared-memory reads, loop overhead, the separable parts of the quadratic form
+// and — in the backward pass — the warp reduction are amortised over 4 pixels.
 //
 // Staging + exact culling.  A warp walks the tile's depth-sorted intersection list in batches of 64
 // packed 48-byte splat records, copied with cp.async (LDGSTS.128 x3 per record, double buffered, the
 // flatten ids of the batch after next prefetched into registers).  The binning that produced the list
 // is deliberately coarse (3-sigma bounding SQUARE of the major axis vs 16x16 tiles — it has to be, to
 // stay bit-identical with gsplat's lists), so before a batch is blended every lane tests its two records
-// against the four quarters' pixel rectangles: the minimum of sigma over a rectangle (closed form: centre
+// against the warp's pixel rectangle: the minimum of sigma over the rectangle (closed form: centre
 // inside, else the best point of the four edges) is compared with sigma_cut = ln(255 o), beyond which
-// alpha < 1/255 for every pixel of the rectangle.  Survivors are compacted, in order, into one slot list PER
-// QUARTER (ballot + popc); in the blend loop every quarter walks its own list, so in one trip of the loop the
-// four quarters work on (up to) four different Gaussians.  The loop runs max(list lengths) trips instead of
-// (survivors of the whole 16x8 block) trips: on the 1 M-Gaussian benchmark scene 43 % of a tile's entries reach the
-// 16x8 block of a warp, and the longest quarter list is 0.72 of that (scripts/analysis/subwarp_survivors.py) —
-// the kernels are bound by issue slots, and a lane whose pixels a Gaussian cannot reach used to ride along.
-// Results are unchanged: a culled Gaussian contributes to no pixel of the quarter, and every pixel still
-// meets the Gaussians that reach it in list order.
+// alpha < 1/255 for every pixel of the warp.  Survivors are compacted, in order, into a slot list
+// (ballot + popc); the blend loop only visits survivors.  On the 1M-Gaussian benchmark scene ~47 % of the
+// (tile, Gaussian) pairs fail this test.  Results are unchanged: a culled Gaussian contributes to no pixel.
 //
-// Loops over a batch are WARP-UNIFORM (finished pixels and exhausted quarters are predicated off, a vote at
-// the top of the body is the reconvergence point).  A per-lane break/continue lets the lanes of a warp drift
-// apart under independent thread scheduling: measured with ncu on the first version of the forward kernel,
+// Loops over a batch are WARP-UNIFORM (finished pixels are predicated off, a vote at the top of the
+// body is the reconvergence point).  A per-lane break/continue lets the lanes of a warp drift apart
+// under independent thread scheduling: measured with ncu on the first version of the forward kernel,
 // 1.9 active threads per instruction and a 20x slowdown (profiles/r1a_*).
 //
 // Packed fp32.  Both kernels are issue bound (ncu: 80 % issue-active, FMA pipe 40 % before this change), so in
@@ -34,10 +28,9 @@
 // updates are branch free: a pixel that does not take part blends with weight 0.
 //
 // Backward: per-pixel back-to-front replay from the warp's own last blended index; the 11 per-Gaussian
-// partial gradients are summed over the lane's 4 pixels in registers, then over the QUARTER through a 1.6 KB
-// shared-memory scratch (11 conflict-free row stores; 44 (value, quarter) sums of 8 floats each = 2 LDS.128 + a
-// packed add tree, done by the 32 lanes in two rounds), and each round issues one RED.ADD.F32 per lane into the
-// packed 48-byte gradient record of the quarter's Gaussian.
+// partial gradients are summed over the lane's 4 pixels in registers, then over the warp through a 1.6 KB
+// shared-memory scratch (11 conflict-free row stores, 4 LDS.128 + a packed add tree per lane, one shuffle), and
+// 11 lanes issue one coalesced RED.ADD.F32 into the packed 48-byte gradient record of the Gaussian.
 #include <stdlib.h>
 
 #include "egs_common.cuh"
@@ -48,31 +41,37 @@ constexpr int kTileSize = 16;
 // Resident CTAs per SM the compiler must leave room for (register cap = 65536 / (threads * this)); tuning knobs,
 // overridable at build time for A/B runs (scripts/build_variant.py).
 #ifdef EGS_FWD_MIN_CTAS
-#define EGS_FWD_BOUNDS(T) __launch_bounds__(T, EGS_FWD_MIN_CTAS)
+#define EGS_FWD_BOUNDS(T, PX) __launch_bounds__(T, (PX) == 2 ? EGS_FWD_MIN_CTAS : 1)
 #else
-#define EGS_FWD_BOUNDS(T) __launch_bounds__(T)
+#define EGS_FWD_BOUNDS(T, PX) __launch_bounds__(T)
 #endif
 #ifdef EGS_BWD_MIN_CTAS
-#define EGS_BWD_BOUNDS(T) __launch_bounds__(T, EGS_BWD_MIN_CTAS)
+#define EGS_BWD_BOUNDS(T, PX) __launch_bounds__(T, (PX) == 2 ? EGS_BWD_MIN_CTAS : 1)
 #else
-#define EGS_BWD_BOUNDS(T) __launch_bounds__(T)
+#define EGS_BWD_BOUNDS(T, PX) __launch_bounds__(T)
 #endif
-// Geometry: a lane owns 2x2 pixels, a quarter (8 lanes = 4x2 lane blocks) 8x4 pixels, a warp (2x2 quarters) 16x8
-// pixels, a tile two warps.
-constexpr int NP = 4;                    // pixels per lane
-constexpr int kWarpW = 16, kWarpH = 8;   // pixels per warp
-constexpr int kQuarterW = 8, kQuarterH = 4;
-constexpr int kQuarters = 4;
-constexpr int kWarps = kTileSize / kWarpH;  // 2 per tile
-constexpr int kThreads = 32 * kWarps;
-constexpr int RPL = 2;                   // records staged per lane per batch
-constexpr int kBatch = 32 * RPL;
+// A lane owns PX x PY pixels, a warp 8 x 4 lanes = (8 PX) x (4 PY) pixels.  <2,2>: 2 warps of 16x8 pixels per
+// tile — the throughput configuration.  <1,1>: 8 warps of 8x4 pixels per tile — more warps, smaller culling
+// rectangles and a shorter per-entry chain; used only for tiles whose list is so long that the serial walk of
+// one warp would become the tail of the whole launch.
+template <int PX, int PY>
+struct Geo {
+  static constexpr int NP = PX * PY;
+  static constexpr int kWarpW = 8 * PX, kWarpH = 4 * PY;
+  static constexpr int kWarpsX = kTileSize / kWarpW, kWarpsY = kTileSize / kWarpH;
+  static constexpr int kWarps = kWarpsX * kWarpsY;
+  static constexpr int kThreads = 32 * kWarps;
+  // records staged per warp per batch: 2 per lane for the 2-warp layout, 1 per lane for the 8-warp layout
+  // (keeps the CTA's static shared memory under 48 KB)
+  static constexpr int RPL = kWarps <= 2 ? 2 : 1;
+  static constexpr int kBatch = 32 * RPL;
+};
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.999f;
 constexpr float kTMin = 1e-4f;
 constexpr float kNegLog2e = -1.4426950408889634f;
 constexpr int kGradValues = 11;  // floats of the packed gradient record that the backward blend produces
-constexpr int kRedStride = 36;   // words per row of the backward kernel's sum scratch (32 lanes + 4: conflict-free LDS.128)
+constexpr int kRedStride = 36;   // words per row of the backward kernel's warp-sum scratch (32 lanes + 4: conflict-free LDS.128)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -109,21 +108,23 @@ __device__ __forceinline__ float opaque(float x) {
   return x;
 }
 
-// Per-warp shared memory: raw double-buffered batches, their flatten ids, and the four quarters' survivor lists.
+// Per-warp shared memory: raw double-buffered batches, their flatten ids, and the survivor slot list.
+template <int kBatch>
 struct WarpStage {
   float4 rec[2][kBatch * 3];
   int id[2][kBatch];
-  unsigned char qlist[kQuarters][kBatch];
+  int list[kBatch];
 };
 
 struct WarpView {
   int cam, x0, y0;               // first pixel of this lane's 2x2 block
   int range_start, range_end;    // the tile's slice of the sorted intersection list
-  float rx_lo, ry_lo;            // centre of the first pixel of the warp's 16x8 block
+  float rx_lo, rx_hi, ry_lo, ry_hi;  // pixel-centre rectangle of the warp (16 x 8 pixels)
 };
 
 // tile_id < 0: the tile is the block's position in the (tile_w, tile_h, C) grid; otherwise the given flat tile index
 // (cam * tile_h + ty) * tile_w + tx (the segment launch of the backward pass maps blocks to list segments).
+template <class G>
 __device__ __forceinline__ WarpView warp_setup(int tile_w, int tile_h, int64_t n_isects,
                                                const int32_t* __restrict__ tile_offsets, int n_tiles_total,
                                                int tile_id = -1) {
@@ -139,23 +140,28 @@ __device__ __forceinline__ WarpView warp_setup(int tile_w, int tile_h, int64_t n
     bx = rem - by * tile_w;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = lane >> 3, l = lane & 7;  // quarter (qx = q & 1, qy = q >> 1), lane inside it (4 x 2 blocks of 2x2 pixels)
-  const int wx0 = bx * kTileSize, wy0 = by * kTileSize + warp * kWarpH;
-  v.x0 = wx0 + (q & 1) * kQuarterW + (l & 3) * 2;
-  v.y0 = wy0 + (q >> 1) * kQuarterH + (l >> 2) * 2;
+  const int wx = warp % G::kWarpsX, wy = warp / G::kWarpsX;
+  const int wx0 = bx * kTileSize + wx * G::kWarpW, wy0 = by * kTileSize + wy * G::kWarpH;
+  v.x0 = wx0 + (lane & 7) * (G::kWarpW / 8);
+  v.y0 = wy0 + (lane >> 3) * (G::kWarpH / 4);
   v.range_start = tile_offsets[tile_id];
   v.range_end = (tile_id == n_tiles_total - 1) ? (int)n_isects : tile_offsets[tile_id + 1];
   v.rx_lo = (float)wx0 + 0.5f;
+  v.rx_hi = v.rx_lo + (float)(G::kWarpW - 1);
   v.ry_lo = (float)wy0 + 0.5f;
+  v.ry_hi = v.ry_lo + (float)(G::kWarpH - 1);
   return v;
 }
 
-// Can alpha reach 1/255 anywhere in the rectangle of pixel centres [dxl, dxh] x [dyl, dyh] (relative to the mean)?
-// min over the rectangle of sigma(d) = 0.5 (a dx^2 + c dy^2) + b dx dy against sigma_cut; nb_c = -b / c and
-// nb_a = -b / a give the unconstrained minimiser along a vertical / horizontal line.
-__device__ __forceinline__ bool rect_reaches(float a, float b, float c, float nb_c, float nb_a, float sigma_cut, float dxl,
-                                             float dxh, float dyl, float dyh) {
+// Can alpha reach 1/255 anywhere in the rectangle?  min over the rectangle of
+// sigma(d) = 0.5 (a dx^2 + c dy^2) + b dx dy  (d = pixel - mean) against sigma_cut.
+__device__ __forceinline__ bool splat_touches_rect(const float4 g0, const float4 g1, float sigma_cut, float rx_lo,
+                                                   float rx_hi, float ry_lo, float ry_hi) {
+  if (!(sigma_cut > 0.f)) return false;
+  const float a = g0.z, b = g0.w, c = g1.x;
+  const float dxl = rx_lo - g0.x, dxh = rx_hi - g0.x, dyl = ry_lo - g0.y, dyh = ry_hi - g0.y;
   if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return true;  // centre inside
+  const float nb_c = -b * fast_rcp(c), nb_a = -b * fast_rcp(a);
   float best;
   {
     const float dy = fminf(fmaxf(nb_c * dxl, dyl), dyh);
@@ -176,87 +182,67 @@ __device__ __forceinline__ bool rect_reaches(float a, float b, float c, float nb
   return best <= sigma_cut;  // NaN (degenerate conic) compares false -> culled; such a splat has NaN alpha anyway
 }
 
-// Bit q of the result: the splat can reach quarter q (qx = q & 1, qy = q >> 1) of the warp's 16x8 pixel block whose
-// first pixel centre is (rx_lo, ry_lo).
-__device__ __forceinline__ uint32_t splat_quarter_mask(const float4 g0, const float4 g1, float sigma_cut, float rx_lo,
-                                                       float ry_lo) {
-  if (!(sigma_cut > 0.f)) return 0u;
-  const float a = g0.z, b = g0.w, c = g1.x;
-  const float nb_c = -b * fast_rcp(c), nb_a = -b * fast_rcp(a);
-  const float dx0 = rx_lo - g0.x, dy0 = ry_lo - g0.y;
-  uint32_t m = 0u;
-#pragma unroll
-  for (int q = 0; q < kQuarters; ++q) {
-    const float dxl = dx0 + (float)((q & 1) * kQuarterW), dyl = dy0 + (float)((q >> 1) * kQuarterH);
-    if (rect_reaches(a, b, c, nb_c, nb_a, sigma_cut, dxl, dxl + (float)(kQuarterW - 1), dyl, dyl + (float)(kQuarterH - 1)))
-      m |= 1u << q;
-  }
-  return m;
-}
-
-// Tests this lane's RPL records of raw batch `buf` (record slots lane, lane+32) against the four quarters, writes
-// every quarter's survivor slots, in order, to st.qlist[q] and returns the four list lengths packed one per byte
-// (warp-uniform).  Entry 0 of every list is always a valid slot (0 when the list is empty), so exhausted quarters can
-// keep reading a record.
-__device__ __forceinline__ uint32_t cull_and_compact(WarpStage& st, int buf, int batch_size, int lane, float rx_lo,
-                                                     float ry_lo) {
-  uint32_t keep[RPL];
+// Tests this lane's RPL records of raw batch `buf` (record slots lane, lane+32, ...), writes the survivor
+// slots, in order, to st.list and returns the number of survivors (warp-uniform).
+template <int RPL>
+__device__ __forceinline__ int cull_and_compact(WarpStage<32 * RPL>& st, int buf, int batch_size, int lane, float rx_lo,
+                                                float rx_hi, float ry_lo, float ry_hi) {
+  bool keep[RPL];
 #pragma unroll
   for (int r = 0; r < RPL; ++r) {
     const int slot = r * 32 + lane;
-    keep[r] = 0u;
+    keep[r] = false;
     if (slot < batch_size) {
       const float4 g0 = st.rec[buf][slot * 3 + 0];
       const float4 g1 = st.rec[buf][slot * 3 + 1];
       const float cut = st.rec[buf][slot * 3 + 2].w;
-      keep[r] = splat_quarter_mask(g0, g1, cut, rx_lo, ry_lo);
+      keep[r] = splat_touches_rect(g0, g1, cut, rx_lo, rx_hi, ry_lo, ry_hi);
     }
   }
-  if (lane < kQuarters) st.qlist[lane][0] = 0;
-  __syncwarp();
   const uint32_t lt = (1u << lane) - 1u;
-  uint32_t counts = 0u;
+  int base = 0;
 #pragma unroll
-  for (int q = 0; q < kQuarters; ++q) {
-    int base = 0;
-#pragma unroll
-    for (int r = 0; r < RPL; ++r) {
-      const bool k = (keep[r] >> q) & 1u;
-      const uint32_t m = __ballot_sync(0xffffffffu, k);
-      if (k) st.qlist[q][base + __popc(m & lt)] = (unsigned char)(r * 32 + lane);
-      base += __popc(m);
-    }
-    counts |= (uint32_t)base << (8 * q);
+  for (int r = 0; r < RPL; ++r) {
+    const uint32_t m = __ballot_sync(0xffffffffu, keep[r]);
+    if (keep[r]) st.list[base + __popc(m & lt)] = r * 32 + lane;
+    base += __popc(m);
   }
   __syncwarp();
-  return counts;
-}
-
-__device__ __forceinline__ int max_count(uint32_t counts) {
-  return max(max((int)(counts & 0xffu), (int)((counts >> 8) & 0xffu)), max((int)((counts >> 16) & 0xffu), (int)(counts >> 24)));
+  return base;
 }
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <bool COUNT>
-__global__ void EGS_FWD_BOUNDS(kThreads) rasterize_fwd_kernel(
+// The CTA handles its tile only when len_lo <= (tile list length) < len_hi: the <2,2> launch takes the
+// ordinary tiles, the <1,1> launch the very long ones (see Geo).
+template <int PX, int PY, bool COUNT>
+__global__ void EGS_FWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_fwd_kernel(
     int64_t n_isects, const float4* __restrict__ splats, const int32_t* __restrict__ tile_offsets,
     const int32_t* __restrict__ flatten_ids, const float* __restrict__ backgrounds, int width, int height, int tile_w,
-    int tile_h, int n_tiles_total, float* __restrict__ render_colors, float* __restrict__ render_alphas,
-    int32_t* __restrict__ last_ids, unsigned long long* __restrict__ pair_counters, float4* __restrict__ ckpt,
-    int ckpt_k) {
-  __shared__ __align__(16) WarpStage stage[kWarps];
+    int tile_h, int n_tiles_total, int len_lo, int len_hi, float* __restrict__ render_colors,
+    float* __restrict__ render_alphas, int32_t* __restrict__ last_ids, unsigned long long* __restrict__ pair_counters,
+    float4* __restrict__ ckpt, int ckpt_k) {
+  using G = Geo<PX, PY>;
+  constexpr int NP = G::NP;
+  constexpr int RPL = G::RPL, kBatch = G::kBatch;
+  __shared__ __align__(16) WarpStage<kBatch> stage[G::kWarps];
   const int lane = threadIdx.x & 31;
-  WarpStage& st = stage[threadIdx.x >> 5];
-  const WarpView wv = warp_setup(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total);
+  WarpStage<kBatch>& st = stage[threadIdx.x >> 5];
+  const WarpView wv = warp_setup<G>(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total);
+  {
+    const int len = wv.range_end - wv.range_start;
+    if (len < len_lo || len >= len_hi) return;  // block-uniform: the other launch owns this tile
+  }
   const int nb = (wv.range_end - wv.range_start + kBatch - 1) / kBatch;
 
-  const float2 npx2 = make_float2(opaque(-((float)wv.x0 + 0.5f)), opaque(-((float)wv.x0 + 1.5f)));
-  const float2 npy2 = make_float2(opaque(-((float)wv.y0 + 0.5f)), opaque(-((float)wv.y0 + 1.5f)));
-  const float rx_lo = opaque(wv.rx_lo), ry_lo = opaque(wv.ry_lo);
-  const int my_shift = (lane >> 3) * 8;  // this lane's quarter: byte of the packed list lengths
-  const unsigned char* ql = st.qlist[lane >> 3];
+  float pxf[PX], pyf[PY];
+#pragma unroll
+  for (int i = 0; i < PX; ++i) pxf[i] = opaque((float)(wv.x0 + i) + 0.5f);
+#pragma unroll
+  for (int i = 0; i < PY; ++i) pyf[i] = opaque((float)(wv.y0 + i) + 0.5f);
+  const float2 npx2 = make_float2(-pxf[0], -pxf[PX - 1]), npy2 = make_float2(-pyf[0], -pyf[PY - 1]);
+  const float rx_lo = opaque(wv.rx_lo), rx_hi = opaque(wv.rx_hi), ry_lo = opaque(wv.ry_lo), ry_hi = opaque(wv.ry_hi);
   // T[j] > 0: transmittance of a live pixel; T[j] < 0: pixel finished, |T[j]| is its final transmittance
   // (the "done" flag lives in the sign bit, so liveness is one more FSETP in the accept test).
   float T[NP], cr[NP], cg[NP], cb[NP];
@@ -264,7 +250,7 @@ __global__ void EGS_FWD_BOUNDS(kThreads) rasterize_fwd_kernel(
   bool all_done = true;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    const bool inside = (wv.x0 + (j & 1)) < width && (wv.y0 + (j >> 1)) < height;
+    const bool inside = (wv.x0 + (j % PX)) < width && (wv.y0 + (j / PX)) < height;
     T[j] = inside ? 1.0f : -1.0f; cr[j] = 0.f; cg[j] = 0.f; cb[j] = 0.f; last[j] = 0; term[j] = -1;
     all_done = all_done && !inside;
   }
@@ -307,78 +293,106 @@ __global__ void EGS_FWD_BOUNDS(kThreads) rasterize_fwd_kernel(
       __syncwarp();  // batch b has landed for every lane of this warp
       const int batch_start = wv.range_start + b * kBatch;
       const int batch_size = min(kBatch, wv.range_end - batch_start);
-      const uint32_t counts = cull_and_compact(st, b & 1, batch_size, lane, rx_lo, ry_lo);
-      const int my_n = (int)((counts >> my_shift) & 0xffu);  // survivors of this lane's quarter
-      const int nt = max_count(counts);                      // trips of the blend loop (warp-uniform)
+      const int ns = cull_and_compact<RPL>(st, b & 1, batch_size, lane, rx_lo, rx_hi, ry_lo, ry_hi);
       const float4* s = st.rec[b & 1];
-      // Two list entries per trip: their alphas do not depend on the running transmittance, so both are evaluated
+      // Two survivors per trip: their alphas do not depend on the running transmittance, so both are evaluated
       // up front (independent LDS / FMA / MUFU chains = twice the ILP for a warp that walks a long list alone),
       // then blended in order.  The vote at the top is the warp-uniform exit and the reconvergence point.
-      for (int t = 0; t < nt; t += 2) {
+      for (int t = 0; t < ns; t += 2) {
         if (__all_sync(0xffffffffu, all_done)) break;
-        const bool has_b = t + 1 < nt;  // warp-uniform
-        bool act[2];
-        act[0] = t < my_n;              // this quarter still has an entry for the trip
-        act[1] = t + 1 < my_n;
-        const int cur_a = ql[act[0] ? t : 0], cur_b = ql[act[1] ? t + 1 : 0];
+        const bool has_b = t + 1 < ns;  // warp-uniform
+        const int cur_a = st.list[t], cur_b = st.list[has_b ? t + 1 : t];
         float4 g0[2], g1[2];
         float cbl[2], alpha[2][NP], q[2][NP];
         g0[0] = s[cur_a * 3 + 0]; g1[0] = s[cur_a * 3 + 1]; cbl[0] = s[cur_a * 3 + 2].x;
         g0[1] = s[cur_b * 3 + 0]; g1[1] = s[cur_b * 3 + 1]; cbl[1] = s[cur_b * 3 + 2].x;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          // q(dx,dy) = -log2(e) * sigma, separable parts shared by the rows / columns of the pixel block.
-          // Packed fp32 (FADD2 / FMUL2 / FFMA2, sm_100): the two pixels of a row share one instruction.  The
-          // kernel is issue bound, not FMA-pipe bound (profiles/r1g), so halving the issue slots of the
-          // arithmetic is what counts.
+          // q(dx,dy) = -log2(e) * sigma, separable parts shared by the rows / columns of the pixel block
           const float la = (0.5f * kNegLog2e) * g0[e].z, lc = (0.5f * kNegLog2e) * g1[e].x, lb = kNegLog2e * g0[e].w;
-          const float2 dx = __fadd2_rn(make_float2(g0[e].x, g0[e].x), npx2);
-          const float2 dyv = __fadd2_rn(make_float2(g0[e].y, g0[e].y), npy2);
-          const float2 qx = __fmul2_rn(__fmul2_rn(dx, make_float2(la, la)), dx);
-          const float2 bx = __fmul2_rn(dx, make_float2(lb, lb));
-          const float2 qy = __fmul2_rn(__fmul2_rn(dyv, make_float2(lc, lc)), dyv);
-          const float2 o2 = make_float2(g1[e].y, g1[e].y);
-          const float2 q0 = __ffma2_rn(bx, make_float2(dyv.x, dyv.x), __fadd2_rn(qx, make_float2(qy.x, qy.x)));
-          const float2 q1 = __ffma2_rn(bx, make_float2(dyv.y, dyv.y), __fadd2_rn(qx, make_float2(qy.y, qy.y)));
-          const float2 a0 = __fmul2_rn(o2, make_float2(fast_ex2(q0.x), fast_ex2(q0.y)));
-          const float2 a1 = __fmul2_rn(o2, make_float2(fast_ex2(q1.x), fast_ex2(q1.y)));
-          q[e][0] = q0.x; q[e][1] = q0.y; q[e][2] = q1.x; q[e][3] = q1.y;
-          alpha[e][0] = fminf(kAlphaMax, a0.x); alpha[e][1] = fminf(kAlphaMax, a0.y);
-          alpha[e][2] = fminf(kAlphaMax, a1.x); alpha[e][3] = fminf(kAlphaMax, a1.y);
+          if constexpr (PX == 2 && PY == 2) {
+            // packed fp32 (FADD2 / FMUL2 / FFMA2, sm_100): the two pixels of a row share one instruction.  The
+            // kernel is issue bound, not FMA-pipe bound (profiles/r1g), so halving the issue slots of the
+            // arithmetic is what counts.
+            const float2 dx = __fadd2_rn(make_float2(g0[e].x, g0[e].x), npx2);
+            const float2 dyv = __fadd2_rn(make_float2(g0[e].y, g0[e].y), npy2);
+            const float2 qx = __fmul2_rn(__fmul2_rn(dx, make_float2(la, la)), dx);
+            const float2 bx = __fmul2_rn(dx, make_float2(lb, lb));
+            const float2 qy = __fmul2_rn(__fmul2_rn(dyv, make_float2(lc, lc)), dyv);
+            const float2 o2 = make_float2(g1[e].y, g1[e].y);
+            const float2 q0 = __ffma2_rn(bx, make_float2(dyv.x, dyv.x), __fadd2_rn(qx, make_float2(qy.x, qy.x)));
+            const float2 q1 = __ffma2_rn(bx, make_float2(dyv.y, dyv.y), __fadd2_rn(qx, make_float2(qy.y, qy.y)));
+            const float2 a0 = __fmul2_rn(o2, make_float2(fast_ex2(q0.x), fast_ex2(q0.y)));
+            const float2 a1 = __fmul2_rn(o2, make_float2(fast_ex2(q1.x), fast_ex2(q1.y)));
+            q[e][0] = q0.x; q[e][1] = q0.y; q[e][2] = q1.x; q[e][3] = q1.y;
+            alpha[e][0] = fminf(kAlphaMax, a0.x); alpha[e][1] = fminf(kAlphaMax, a0.y);
+            alpha[e][2] = fminf(kAlphaMax, a1.x); alpha[e][3] = fminf(kAlphaMax, a1.y);
+          } else {
+            float qx[PX], bx[PX], dy[PY], qy[PY];
+#pragma unroll
+            for (int i = 0; i < PX; ++i) { const float dx = g0[e].x - pxf[i]; qx[i] = la * dx * dx; bx[i] = lb * dx; }
+#pragma unroll
+            for (int i = 0; i < PY; ++i) { dy[i] = g0[e].y - pyf[i]; qy[i] = lc * dy[i] * dy[i]; }
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+              q[e][j] = fmaf(bx[j % PX], dy[j / PX], qx[j % PX] + qy[j / PX]);
+              alpha[e][j] = fminf(kAlphaMax, g1[e].y * fast_ex2(q[e][j]));
+            }
+          }
         }
         float tmax = -1.0f;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           if (e == 0 || has_b) {
             const int cur = e == 0 ? cur_a : cur_b;
-            // branch-free, two pixels (one row of the lane's block) per packed instruction: a rejected or
-            // finished pixel — or any pixel of a quarter whose list is exhausted — blends with weight 0
-            // (exact: c + g * 0 = c) and keeps its T
+            if constexpr (PX == 2 && PY == 2) {
+              // branch-free, two pixels (one row of the lane's block) per packed instruction: a rejected or
+              // finished pixel blends with weight 0 (exact: c + g * 0 = c) and keeps its T
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const int j0 = 2 * r, j1 = 2 * r + 1;
-              const float2 a2 = make_float2(alpha[e][j0], alpha[e][j1]);
-              const float2 T2 = make_float2(T[j0], T[j1]);
-              const float2 nT = __fmul2_rn(T2, __ffma2_rn(a2, make_float2(-1.f, -1.f), make_float2(1.f, 1.f)));
-              float2 w = __fmul2_rn(a2, T2);
-              const bool acc0 = act[e] && T[j0] > 0.f && q[e][j0] <= 0.f && alpha[e][j0] >= kAlphaMin;  // sigma >= 0 <=> q <= 0
-              const bool acc1 = act[e] && T[j1] > 0.f && q[e][j1] <= 0.f && alpha[e][j1] >= kAlphaMin;
-              const bool bl0 = acc0 && nT.x > kTMin, bl1 = acc1 && nT.y > kTMin;
-              w.x = bl0 ? w.x : 0.f;
-              w.y = bl1 ? w.y : 0.f;
-              if (acc0) T[j0] = bl0 ? nT.x : -T[j0];  // not blended: finished, sign flags it
-              if (acc1) T[j1] = bl1 ? nT.y : -T[j1];
-              if (bl0) last[j0] = batch_start + cur;
-              if (bl1) last[j1] = batch_start + cur;
-              if (COUNT) {
-                if (acc0 && !bl0) term[j0] = batch_start + cur;
-                if (acc1 && !bl1) term[j1] = batch_start + cur;
-                n_acc += (bl0 ? 1u : 0u) + (bl1 ? 1u : 0u);
+              for (int r = 0; r < 2; ++r) {
+                const int j0 = 2 * r, j1 = 2 * r + 1;
+                const float2 a2 = make_float2(alpha[e][j0], alpha[e][j1]);
+                const float2 T2 = make_float2(T[j0], T[j1]);
+                const float2 nT = __fmul2_rn(T2, __ffma2_rn(a2, make_float2(-1.f, -1.f), make_float2(1.f, 1.f)));
+                float2 w = __fmul2_rn(a2, T2);
+                const bool acc0 = T[j0] > 0.f && q[e][j0] <= 0.f && alpha[e][j0] >= kAlphaMin;
+                const bool acc1 = T[j1] > 0.f && q[e][j1] <= 0.f && alpha[e][j1] >= kAlphaMin;
+                const bool bl0 = acc0 && nT.x > kTMin, bl1 = acc1 && nT.y > kTMin;
+                w.x = bl0 ? w.x : 0.f;
+                w.y = bl1 ? w.y : 0.f;
+                if (acc0) T[j0] = bl0 ? nT.x : -T[j0];  // not blended: finished, sign flags it
+                if (acc1) T[j1] = bl1 ? nT.y : -T[j1];
+                if (bl0) last[j0] = batch_start + cur;
+                if (bl1) last[j1] = batch_start + cur;
+                if (COUNT) {
+                  if (acc0 && !bl0) term[j0] = batch_start + cur;
+                  if (acc1 && !bl1) term[j1] = batch_start + cur;
+                  n_acc += (bl0 ? 1u : 0u) + (bl1 ? 1u : 0u);
+                }
+                const float2 c_r = __ffma2_rn(make_float2(g1[e].z, g1[e].z), w, make_float2(cr[j0], cr[j1]));
+                const float2 c_g = __ffma2_rn(make_float2(g1[e].w, g1[e].w), w, make_float2(cg[j0], cg[j1]));
+                const float2 c_b = __ffma2_rn(make_float2(cbl[e], cbl[e]), w, make_float2(cb[j0], cb[j1]));
+                cr[j0] = c_r.x; cr[j1] = c_r.y; cg[j0] = c_g.x; cg[j1] = c_g.y; cb[j0] = c_b.x; cb[j1] = c_b.y;
               }
-              const float2 c_r = __ffma2_rn(make_float2(g1[e].z, g1[e].z), w, make_float2(cr[j0], cr[j1]));
-              const float2 c_g = __ffma2_rn(make_float2(g1[e].w, g1[e].w), w, make_float2(cg[j0], cg[j1]));
-              const float2 c_b = __ffma2_rn(make_float2(cbl[e], cbl[e]), w, make_float2(cb[j0], cb[j1]));
-              cr[j0] = c_r.x; cr[j1] = c_r.y; cg[j0] = c_g.x; cg[j1] = c_g.y; cb[j0] = c_b.x; cb[j1] = c_b.y;
+            } else {
+#pragma unroll
+              for (int j = 0; j < NP; ++j) {
+                if (T[j] > 0.f && q[e][j] <= 0.f && alpha[e][j] >= kAlphaMin) {  // sigma >= 0  <=>  q <= 0
+                  const float next_T = T[j] * (1.0f - alpha[e][j]);
+                  if (next_T <= kTMin) {
+                    T[j] = -T[j];  // finished: this Gaussian is not blended
+                    if (COUNT) term[j] = batch_start + cur;
+                  } else {
+                    const float w = alpha[e][j] * T[j];
+                    cr[j] = fmaf(g1[e].z, w, cr[j]);
+                    cg[j] = fmaf(g1[e].w, w, cg[j]);
+                    cb[j] = fmaf(cbl[e], w, cb[j]);
+                    last[j] = batch_start + cur;
+                    T[j] = next_T;
+                    if (COUNT) ++n_acc;
+                  }
+                }
+              }
             }
           }
         }
@@ -387,17 +401,19 @@ __global__ void EGS_FWD_BOUNDS(kThreads) rasterize_fwd_kernel(
         all_done = !(tmax > 0.f);
       }
       if (__all_sync(0xffffffffu, all_done)) break;  // this warp needs nothing further down the list
-      // Per-pixel state after every ckpt_k entries of a long list: lets the backward pass start its back-to-front
-      // replay at any of these boundaries, one warp per segment (see rasterize_bwd_kernel).  Slot numbering
-      // floor(start / K) + k is collision free across tiles because their list ranges are disjoint and ordered.
-      const int done_local = (b + 1) * kBatch;
-      if (ckpt != nullptr && done_local % ckpt_k == 0 && done_local < wv.range_end - wv.range_start) {
-        const size_t slot = (size_t)(wv.range_start / ckpt_k + done_local / ckpt_k);
-        float4* dst = ckpt + ((slot * kWarps + (threadIdx.x >> 5)) * NP) * 32 + lane;
+      if constexpr (PX == 2 && PY == 2) {
+        // Per-pixel state after every ckpt_k entries of a long list: lets the backward pass start its back-to-front
+        // replay at any of these boundaries, one warp per segment (see rasterize_bwd_kernel).  Slot numbering
+        // floor(start / K) + k is collision free across tiles because their list ranges are disjoint and ordered.
+        const int done_local = (b + 1) * kBatch;
+        if (ckpt != nullptr && done_local % ckpt_k == 0 && done_local < wv.range_end - wv.range_start) {
+          const size_t slot = (size_t)(wv.range_start / ckpt_k + done_local / ckpt_k);
+          float4* dst = ckpt + ((slot * G::kWarps + (threadIdx.x >> 5)) * NP) * 32 + lane;
 #pragma unroll
-        for (int j = 0; j < NP; ++j) dst[j * 32] = make_float4(T[j], cr[j], cg[j], cb[j]);
+          for (int j = 0; j < NP; ++j) dst[j * 32] = make_float4(T[j], cr[j], cg[j], cb[j]);
+        }
       }
-      __syncwarp();  // every lane is done with buffer b&1 and the lists before they are overwritten
+      __syncwarp();  // every lane is done with buffer b&1 and the list before they are overwritten
     }
     cp_async_wait<0>();
   }
@@ -409,7 +425,7 @@ __global__ void EGS_FWD_BOUNDS(kThreads) rasterize_fwd_kernel(
   unsigned int n_eval = 0;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    const int x = wv.x0 + (j & 1), y = wv.y0 + (j >> 1);
+    const int x = wv.x0 + (j % PX), y = wv.y0 + (j / PX);
     if (x < width && y < height) {
       const size_t pix = ((size_t)wv.cam * height + y) * width + x;
       const float Tf = fabsf(T[j]);
@@ -437,10 +453,12 @@ __global__ void EGS_FWD_BOUNDS(kThreads) rasterize_fwd_kernel(
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-__global__ void EGS_BWD_BOUNDS(kThreads) rasterize_bwd_kernel(
+
+template <int PX, int PY>
+__global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel(
     int64_t n_isects, const float4* __restrict__ splats, const int32_t* __restrict__ tile_offsets,
     const int32_t* __restrict__ flatten_ids, const float* __restrict__ backgrounds, int width, int height, int tile_w,
-    int tile_h, int n_tiles_total, const float* __restrict__ render_alphas,
+    int tile_h, int n_tiles_total, int len_lo, int len_hi, const float* __restrict__ render_alphas,
     const int32_t* __restrict__ last_ids, const float* __restrict__ v_render_colors,
     const float* __restrict__ v_render_alphas, float* __restrict__ v_splats,
     // Segmented replay of long lists (ckpt != nullptr): the forward pass left the per-pixel state after every ckpt_k
@@ -449,10 +467,13 @@ __global__ void EGS_BWD_BOUNDS(kThreads) rasterize_bwd_kernel(
     // entry down to the segment boundary below it, initial state = the final image, as without segments);
     // seg_launch = 1: blocks are checkpoint slots and replay the full segment that ends at their checkpoint.
     const float* __restrict__ render_colors, const float4* __restrict__ ckpt, int ckpt_k, int seg_launch) {
-  __shared__ __align__(16) WarpStage stage[kWarps];
-  __shared__ __align__(16) float red_all[kWarps][kGradValues * kRedStride];
+  using G = Geo<PX, PY>;
+  constexpr int NP = G::NP;
+  constexpr int RPL = G::RPL, kBatch = G::kBatch;
+  __shared__ __align__(16) WarpStage<kBatch> stage[G::kWarps];
+  __shared__ __align__(16) float red_all[G::kWarps][kGradValues * kRedStride];
   const int lane = threadIdx.x & 31;
-  WarpStage& st = stage[threadIdx.x >> 5];
+  WarpStage<kBatch>& st = stage[threadIdx.x >> 5];
   float* red = red_all[threadIdx.x >> 5];
   int seg_tile = -1, seg_k = 0;
   if (seg_launch) {
@@ -467,16 +488,20 @@ __global__ void EGS_BWD_BOUNDS(kThreads) rasterize_bwd_kernel(
     seg_tile = lo_t;
     seg_k = (int)(blockIdx.x + 1) - tile_offsets[seg_tile] / ckpt_k;
   }
-  const WarpView wv = warp_setup(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total, seg_tile);
+  const WarpView wv = warp_setup<G>(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total, seg_tile);
   {
     const int len = wv.range_end - wv.range_start;
-    if (len <= 0) return;  // block-uniform: empty tile
+    if (len <= 0 || len < len_lo || len >= len_hi) return;  // block-uniform: empty, or owned by the other launch
     if (seg_launch && (seg_k < 1 || (int64_t)seg_k * ckpt_k >= len)) return;  // block-uniform: slot not in use
   }
 
-  const float2 npx2 = make_float2(opaque(-((float)wv.x0 + 0.5f)), opaque(-((float)wv.x0 + 1.5f)));
-  const float2 npy2 = make_float2(opaque(-((float)wv.y0 + 0.5f)), opaque(-((float)wv.y0 + 1.5f)));
-  const float rx_lo = opaque(wv.rx_lo), ry_lo = opaque(wv.ry_lo);
+  float pxf[PX], pyf[PY];
+#pragma unroll
+  for (int i = 0; i < PX; ++i) pxf[i] = opaque((float)(wv.x0 + i) + 0.5f);
+#pragma unroll
+  for (int i = 0; i < PY; ++i) pyf[i] = opaque((float)(wv.y0 + i) + 0.5f);
+  const float2 npx2 = make_float2(-pxf[0], -pxf[PX - 1]), npy2 = make_float2(-pyf[0], -pyf[PY - 1]);
+  const float rx_lo = opaque(wv.rx_lo), rx_hi = opaque(wv.rx_hi), ry_lo = opaque(wv.ry_lo), ry_hi = opaque(wv.ry_hi);
 
   // per-pixel replay state.  nbt_ = tfv - bdot with bdot = sum over the Gaussians behind of fac * (rgb . v_colour),
   // which is all the backward pass needs of the colour accumulated behind, and
@@ -490,7 +515,7 @@ __global__ void EGS_BWD_BOUNDS(kThreads) rasterize_bwd_kernel(
   }
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    const int x = wv.x0 + (j & 1), y = wv.y0 + (j >> 1);
+    const int x = wv.x0 + (j % PX), y = wv.y0 + (j / PX);
     T[j] = 1.f; nbt_[j] = 0.f; vcr[j] = 0.f; vcg[j] = 0.f; vcb[j] = 0.f;
     bin_final[j] = -1;  // pixels outside the image never match any index
     if (x < width && y < height) {
@@ -510,35 +535,37 @@ __global__ void EGS_BWD_BOUNDS(kThreads) rasterize_bwd_kernel(
   int end_idx = min(wv.range_end - 1, warp_last);
   if (end_idx < wv.range_start) return;  // warp-uniform
   int lo_idx = wv.range_start;  // the replay walks end_idx, end_idx - 1, ..., lo_idx
-  if (ckpt != nullptr && wv.range_end - wv.range_start > ckpt_k) {
-    const int last_seg = (end_idx - wv.range_start) / ckpt_k;  // segment that holds the warp's last blended entry
-    if (!seg_launch) {
-      lo_idx = wv.range_start + last_seg * ckpt_k;
-    } else {
-      if (seg_k > last_seg) return;  // warp-uniform: nothing of this warp reaches into or beyond this segment
-      end_idx = wv.range_start + seg_k * ckpt_k - 1;
-      lo_idx = end_idx + 1 - ckpt_k;
-      // state after entry end_idx: transmittance and colour accumulated in front of the boundary (the forward
-      // checkpoint); what lies behind it is the final colour minus that
-      const size_t slot = (size_t)(wv.range_start / ckpt_k + seg_k);
-      const float4* src = ckpt + ((slot * kWarps + (threadIdx.x >> 5)) * NP) * 32 + lane;
+  if constexpr (PX == 2 && PY == 2) {
+    if (ckpt != nullptr && wv.range_end - wv.range_start > ckpt_k) {
+      const int last_seg = (end_idx - wv.range_start) / ckpt_k;  // segment that holds the warp's last blended entry
+      if (!seg_launch) {
+        lo_idx = wv.range_start + last_seg * ckpt_k;
+      } else {
+        if (seg_k > last_seg) return;  // warp-uniform: nothing of this warp reaches into or beyond this segment
+        end_idx = wv.range_start + seg_k * ckpt_k - 1;
+        lo_idx = end_idx + 1 - ckpt_k;
+        // state after entry end_idx: transmittance and colour accumulated in front of the boundary (the forward
+        // checkpoint); what lies behind it is the final colour minus that
+        const size_t slot = (size_t)(wv.range_start / ckpt_k + seg_k);
+        const float4* src = ckpt + ((slot * G::kWarps + (threadIdx.x >> 5)) * NP) * 32 + lane;
 #pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        const int x = wv.x0 + (j & 1), y = wv.y0 + (j >> 1);
-        if (x < width && y < height) {
-          const size_t pix = ((size_t)wv.cam * height + y) * width + x;
-          const float4 ck = src[j * 32];
-          const float T_final = T[j];
-          const float br = render_colors[pix * 3 + 0] - T_final * bgr - ck.y;
-          const float bgn = render_colors[pix * 3 + 1] - T_final * bgg - ck.z;
-          const float bb = render_colors[pix * 3 + 2] - T_final * bgb - ck.w;
-          nbt_[j] -= br * vcr[j] + bgn * vcg[j] + bb * vcb[j];
-          T[j] = fabsf(ck.x);
+        for (int j = 0; j < NP; ++j) {
+          const int x = wv.x0 + (j % PX), y = wv.y0 + (j / PX);
+          if (x < width && y < height) {
+            const size_t pix = ((size_t)wv.cam * height + y) * width + x;
+            const float4 ck = src[j * 32];
+            const float T_final = T[j];
+            const float br = render_colors[pix * 3 + 0] - T_final * bgr - ck.y;
+            const float bgn = render_colors[pix * 3 + 1] - T_final * bgg - ck.z;
+            const float bb = render_colors[pix * 3 + 2] - T_final * bgb - ck.w;
+            nbt_[j] -= br * vcr[j] + bgn * vcg[j] + bb * vcb[j];
+            T[j] = fabsf(ck.x);
+          }
         }
       }
+    } else if (seg_launch) {
+      return;
     }
-  } else if (seg_launch) {
-    return;
   }
   const int nb = (end_idx - lo_idx + 1 + kBatch - 1) / kBatch;
 
@@ -565,23 +592,17 @@ __global__ void EGS_BWD_BOUNDS(kThreads) rasterize_bwd_kernel(
     cp_async_commit();
   };
 
-  // Reduction roles, pinned in registers (ptxas otherwise re-derives them from %tid / the CTA's shared window for
-  // every trip).  The 11 x 4 (value, quarter) sums of a trip are taken in two rounds: lane j sums (value j >> 2,
-  // quarter j & 3) in round 1 — values 0..7 — and, for j < 12, (value 8 + (j >> 2), quarter j & 3) in round 2.
-  const int my_shift = (lane >> 3) * 8;           // this lane's own quarter: byte of the packed list lengths
-  const unsigned char* ql = st.qlist[lane >> 3];
-  const int red_q = lane & 3;                     // quarter whose sums this lane takes
-  const unsigned char* rql = st.qlist[red_q];
-  int red2_flag = lane < 4 * (kGradValues - 8) ? 1 : 0;
-  asm volatile("" : "+r"(red2_flag));
+  // Addresses of the warp-sum scratch and of the gradient slot this lane reduces, pinned in registers: ptxas
+  // otherwise re-derives them from %tid / the CTA's shared window for every survivor (~12 of the loop's ~200
+  // instructions).
+  const int out_slot = lane >> 1;
+  int red_flag = ((lane & 1) == 0 && out_slot < kGradValues) ? 1 : 0;
+  asm volatile("" : "+r"(red_flag));
   uint32_t red_st = (uint32_t)__cvta_generic_to_shared(red + lane);
   asm volatile("" : "+r"(red_st));
-  const float4* row1 = reinterpret_cast<const float4*>(red + (lane >> 2) * kRedStride + red_q * 8);
-  const float4* row2 = reinterpret_cast<const float4*>(red + min(8 + (lane >> 2), kGradValues - 1) * kRedStride + red_q * 8);
-  float* out1 = v_splats + (lane >> 2);
-  float* out2 = v_splats + min(8 + (lane >> 2), kGradValues - 1);
-  asm volatile("" : "+l"(out1));
-  asm volatile("" : "+l"(out2));
+  const float4* row = reinterpret_cast<const float4*>(red + min(out_slot, kGradValues - 1) * kRedStride + (lane & 1) * 16);
+  float* out_base = v_splats + min(out_slot, kGradValues - 1);
+  asm volatile("" : "+l"(out_base));
 
   int ids[RPL];
   load_ids(0, ids);
@@ -598,15 +619,13 @@ __global__ void EGS_BWD_BOUNDS(kThreads) rasterize_bwd_kernel(
     __syncwarp();
     const int batch_end = end_idx - b * kBatch;  // sorted index held in slot 0 (the one furthest back)
     const int batch_size = min(kBatch, batch_end + 1 - lo_idx);
-    const uint32_t counts = cull_and_compact(st, b & 1, batch_size, lane, rx_lo, ry_lo);
-    const int my_n = (int)((counts >> my_shift) & 0xffu);       // survivors of this lane's quarter
-    const int red_n = (int)((counts >> (red_q * 8)) & 0xffu);   // survivors of the quarter this lane reduces for
-    const int nt = max_count(counts);                           // trips (warp-uniform)
+    const int ns = cull_and_compact<RPL>(st, b & 1, batch_size, lane, rx_lo, rx_hi, ry_lo, ry_hi);
     const float4* s = st.rec[b & 1];
     const int* sid = st.id[b & 1];
-    for (int t = 0; t < nt; ++t) {  // warp-uniform bounds
-      const bool act = t < my_n;    // this quarter still has an entry for the trip
-      const int cur = ql[act ? t : 0];
+    int slot = st.list[0];
+    for (int t = 0; t < ns; ++t) {  // warp-uniform bounds
+      const int cur = slot;
+      slot = st.list[min(t + 1, kBatch - 1)];
       const int idx = batch_end - cur;
       const float4 g0 = s[cur * 3 + 0];  // x, y, conic_a, conic_b
       const float4 g1 = s[cur * 3 + 1];  // conic_c, opacity, r, g
@@ -616,106 +635,149 @@ __global__ void EGS_BWD_BOUNDS(kThreads) rasterize_bwd_kernel(
       // v[2], v[3], v[4] accumulate sx*dx, sx*dy, sy*dy (the 0.5 of the conic gradient is applied once, after
       // the per-lane sum); v[5] accumulates ov * v_alpha (the 1/opacity is applied after the per-lane sum).
       float v[kGradValues];
-      // Packed fp32 (FADD2 / FMUL2 / FFMA2): the two pixels of a row of the lane's block share one instruction,
-      // and the replay is branch free — a pixel that does not take part gets alpha = 0 and ov = 0, which makes
-      // every one of its contributions an exact zero and leaves its running state untouched.
-      const float2 dx2 = __fadd2_rn(make_float2(g0.x, g0.x), npx2);
-      const float2 dy2 = __fadd2_rn(make_float2(g0.y, g0.y), npy2);
-      const float2 qx = __fmul2_rn(__fmul2_rn(dx2, make_float2(la, la)), dx2);
-      const float2 bx = __fmul2_rn(dx2, make_float2(lb, lb));
-      const float2 qy = __fmul2_rn(__fmul2_rn(dy2, make_float2(lc, lc)), dy2);
-      const float2 o2 = make_float2(g1.y, g1.y);
-      float2 ov2[2];
-      bool valid[NP];
-      bool any_valid = false;
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const float dyr = r == 0 ? dy2.x : dy2.y, qyr = r == 0 ? qy.x : qy.y;
-        const float2 q = __ffma2_rn(bx, make_float2(dyr, dyr), __fadd2_rn(qx, make_float2(qyr, qyr)));
-        ov2[r] = __fmul2_rn(o2, make_float2(fast_ex2(q.x), fast_ex2(q.y)));
-        valid[2 * r] = act && idx <= bin_final[2 * r] && q.x <= 0.f && ov2[r].x >= kAlphaMin;
-        valid[2 * r + 1] = act && idx <= bin_final[2 * r + 1] && q.y <= 0.f && ov2[r].y >= kAlphaMin;
-        any_valid = any_valid || valid[2 * r] || valid[2 * r + 1];
-      }
-      // lanes with a pixel that takes part; a quarter without any has nothing to add for its Gaussian
-      const uint32_t vmask = __ballot_sync(0xffffffffu, any_valid);
-      if (vmask == 0u) continue;  // warp-uniform
-      float2 s_gx = make_float2(0.f, 0.f), s_gy = s_gx, s_xx = s_gx, s_xy = s_gx, s_yy = s_gx, s_w = s_gx, s_r = s_gx,
-             s_g = s_gx, s_b = s_gx, s_ax = s_gx, s_ay = s_gx;
+      for (int k = 0; k < kGradValues; ++k) v[k] = 0.f;
+      if constexpr (PX == 2 && PY == 2) {
+        // Packed fp32 (FADD2 / FMUL2 / FFMA2): the two pixels of a row of the lane's block share one instruction,
+        // and the replay is branch free — a pixel that does not take part gets alpha = 0 and ov = 0, which makes
+        // every one of its contributions an exact zero and leaves its running state untouched.
+        const float2 dx2 = __fadd2_rn(make_float2(g0.x, g0.x), npx2);
+        const float2 dy2 = __fadd2_rn(make_float2(g0.y, g0.y), npy2);
+        const float2 qx = __fmul2_rn(__fmul2_rn(dx2, make_float2(la, la)), dx2);
+        const float2 bx = __fmul2_rn(dx2, make_float2(lb, lb));
+        const float2 qy = __fmul2_rn(__fmul2_rn(dy2, make_float2(lc, lc)), dy2);
+        const float2 o2 = make_float2(g1.y, g1.y);
+        float2 ov2[2];
+        bool valid[NP];
+        bool any_valid = false;
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int j0 = 2 * r, j1 = 2 * r + 1;
-        const float dyr = r == 0 ? dy2.x : dy2.y;
-        const float2 dyb = make_float2(dyr, dyr);
-        float2 ae, oe;  // alpha and ov of the pixels that take part, 0 for the others
-        // ov of the pixels that take part, 0 for the others; everything downstream is then an exact no-op for
-        // a pixel that does not take part: alpha = 0, 1 - alpha = 1, MUFU.RCP(1) = 1 exactly
-        // (scripts/probes/rcp_one.cu), so T * 1 = T needs no select
-        const float ovx = valid[j0] ? ov2[r].x : 0.f, ovy = valid[j1] ? ov2[r].y : 0.f;
-        ae.x = fminf(kAlphaMax, ovx);
-        ae.y = fminf(kAlphaMax, ovy);
-        oe.x = ovx <= kAlphaMax ? ovx : 0.f;  // clamp inactive: alpha depends on sigma, opacity
-        oe.y = ovy <= kAlphaMax ? ovy : 0.f;
-        const float2 om = __ffma2_rn(ae, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
-        const float2 ra = make_float2(fast_rcp(om.x), fast_rcp(om.y));
-        const float2 Tf = __fmul2_rn(make_float2(T[j0], T[j1]), ra);  // transmittance in front of this Gaussian
-        T[j0] = Tf.x; T[j1] = Tf.y;
-        const float2 fac = __fmul2_rn(ae, Tf);
-        const float2 vr2 = make_float2(vcr[j0], vcr[j1]), vg2 = make_float2(vcg[j0], vcg[j1]), vb2 = make_float2(vcb[j0], vcb[j1]);
-        s_r = __ffma2_rn(fac, vr2, s_r);
-        s_g = __ffma2_rn(fac, vg2, s_g);
-        s_b = __ffma2_rn(fac, vb2, s_b);
-        const float2 cdot = __ffma2_rn(make_float2(cbl, cbl), vb2,
-                                       __ffma2_rn(make_float2(g1.w, g1.w), vg2, __fmul2_rn(make_float2(g1.z, g1.z), vr2)));
-        // nbt = tfv - bdot (kept negated so that v_alpha is one FMUL2 + one FFMA2)
-        const float2 nbt = make_float2(nbt_[j0], nbt_[j1]);
-        const float2 v_alpha = __ffma2_rn(Tf, cdot, __fmul2_rn(ra, nbt));
-        const float2 nfac = make_float2(-fac.x, -fac.y);
-        const float2 nbt_new = __ffma2_rn(cdot, nfac, nbt);
-        nbt_[j0] = nbt_new.x; nbt_[j1] = nbt_new.y;
-        const float2 w = __fmul2_rn(oe, v_alpha);  // = opacity * d(alpha)/d(opacity) * v_alpha = -v_sigma
-        const float2 nw = make_float2(-w.x, -w.y);
-        const float2 sx = __fmul2_rn(nw, dx2), sy = __fmul2_rn(nw, dyb);
-        s_xx = __ffma2_rn(sx, dx2, s_xx);
-        s_xy = __ffma2_rn(sx, dyb, s_xy);
-        s_yy = __ffma2_rn(sy, dyb, s_yy);
-        const float2 gx = __ffma2_rn(make_float2(g0.w, g0.w), sy, __fmul2_rn(make_float2(g0.z, g0.z), sx));
-        const float2 gy = __ffma2_rn(make_float2(g1.x, g1.x), sy, __fmul2_rn(make_float2(g0.w, g0.w), sx));
-        s_gx = __fadd2_rn(s_gx, gx);
-        s_gy = __fadd2_rn(s_gy, gy);
-        s_ax = __fadd2_rn(s_ax, make_float2(fabsf(gx.x), fabsf(gx.y)));
-        s_ay = __fadd2_rn(s_ay, make_float2(fabsf(gy.x), fabsf(gy.y)));
-        s_w = __fadd2_rn(s_w, w);
+        for (int r = 0; r < 2; ++r) {
+          const float dyr = r == 0 ? dy2.x : dy2.y, qyr = r == 0 ? qy.x : qy.y;
+          const float2 q = __ffma2_rn(bx, make_float2(dyr, dyr), __fadd2_rn(qx, make_float2(qyr, qyr)));
+          ov2[r] = __fmul2_rn(o2, make_float2(fast_ex2(q.x), fast_ex2(q.y)));
+          valid[2 * r] = idx <= bin_final[2 * r] && q.x <= 0.f && ov2[r].x >= kAlphaMin;
+          valid[2 * r + 1] = idx <= bin_final[2 * r + 1] && q.y <= 0.f && ov2[r].y >= kAlphaMin;
+          any_valid = any_valid || valid[2 * r] || valid[2 * r + 1];
+        }
+        if (!__any_sync(0xffffffffu, any_valid)) continue;  // warp-uniform
+        float2 s_gx = make_float2(0.f, 0.f), s_gy = s_gx, s_xx = s_gx, s_xy = s_gx, s_yy = s_gx, s_w = s_gx, s_r = s_gx,
+               s_g = s_gx, s_b = s_gx, s_ax = s_gx, s_ay = s_gx;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int j0 = 2 * r, j1 = 2 * r + 1;
+          const float dyr = r == 0 ? dy2.x : dy2.y;
+          const float2 dyb = make_float2(dyr, dyr);
+          float2 ae, oe;  // alpha and ov of the pixels that take part, 0 for the others
+          // ov of the pixels that take part, 0 for the others; everything downstream is then an exact no-op for
+          // a pixel that does not take part: alpha = 0, 1 - alpha = 1, MUFU.RCP(1) = 1 exactly
+          // (scripts/probes/rcp_one.cu), so T * 1 = T needs no select
+          const float ovx = valid[j0] ? ov2[r].x : 0.f, ovy = valid[j1] ? ov2[r].y : 0.f;
+          ae.x = fminf(kAlphaMax, ovx);
+          ae.y = fminf(kAlphaMax, ovy);
+          oe.x = ovx <= kAlphaMax ? ovx : 0.f;  // clamp inactive: alpha depends on sigma, opacity
+          oe.y = ovy <= kAlphaMax ? ovy : 0.f;
+          const float2 om = __ffma2_rn(ae, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+          const float2 ra = make_float2(fast_rcp(om.x), fast_rcp(om.y));
+          const float2 Tf = __fmul2_rn(make_float2(T[j0], T[j1]), ra);  // transmittance in front of this Gaussian
+          T[j0] = Tf.x; T[j1] = Tf.y;
+          const float2 fac = __fmul2_rn(ae, Tf);
+          const float2 vr2 = make_float2(vcr[j0], vcr[j1]), vg2 = make_float2(vcg[j0], vcg[j1]), vb2 = make_float2(vcb[j0], vcb[j1]);
+          s_r = __ffma2_rn(fac, vr2, s_r);
+          s_g = __ffma2_rn(fac, vg2, s_g);
+          s_b = __ffma2_rn(fac, vb2, s_b);
+          const float2 cdot = __ffma2_rn(make_float2(cbl, cbl), vb2,
+                                         __ffma2_rn(make_float2(g1.w, g1.w), vg2, __fmul2_rn(make_float2(g1.z, g1.z), vr2)));
+          // nbt = tfv - bdot (kept negated so that v_alpha is one FMUL2 + one FFMA2)
+          const float2 nbt = make_float2(nbt_[j0], nbt_[j1]);
+          const float2 v_alpha = __ffma2_rn(Tf, cdot, __fmul2_rn(ra, nbt));
+          const float2 nfac = make_float2(-fac.x, -fac.y);
+          const float2 nbt_new = __ffma2_rn(cdot, nfac, nbt);
+          nbt_[j0] = nbt_new.x; nbt_[j1] = nbt_new.y;
+          const float2 w = __fmul2_rn(oe, v_alpha);  // = opacity * d(alpha)/d(opacity) * v_alpha = -v_sigma
+          const float2 nw = make_float2(-w.x, -w.y);
+          const float2 sx = __fmul2_rn(nw, dx2), sy = __fmul2_rn(nw, dyb);
+          s_xx = __ffma2_rn(sx, dx2, s_xx);
+          s_xy = __ffma2_rn(sx, dyb, s_xy);
+          s_yy = __ffma2_rn(sy, dyb, s_yy);
+          const float2 gx = __ffma2_rn(make_float2(g0.w, g0.w), sy, __fmul2_rn(make_float2(g0.z, g0.z), sx));
+          const float2 gy = __ffma2_rn(make_float2(g1.x, g1.x), sy, __fmul2_rn(make_float2(g0.w, g0.w), sx));
+          s_gx = __fadd2_rn(s_gx, gx);
+          s_gy = __fadd2_rn(s_gy, gy);
+          s_ax = __fadd2_rn(s_ax, make_float2(fabsf(gx.x), fabsf(gx.y)));
+          s_ay = __fadd2_rn(s_ay, make_float2(fabsf(gy.x), fabsf(gy.y)));
+          s_w = __fadd2_rn(s_w, w);
+        }
+        v[0] = s_gx.x + s_gx.y; v[1] = s_gy.x + s_gy.y; v[2] = s_xx.x + s_xx.y; v[3] = s_xy.x + s_xy.y;
+        v[4] = s_yy.x + s_yy.y; v[5] = s_w.x + s_w.y; v[6] = s_r.x + s_r.y; v[7] = s_g.x + s_g.y;
+        v[8] = s_b.x + s_b.y; v[9] = s_ax.x + s_ax.y; v[10] = s_ay.x + s_ay.y;
+      } else {
+        float dx[PX], qx[PX], bx[PX], dy[PY], qy[PY];
+#pragma unroll
+        for (int i = 0; i < PX; ++i) { dx[i] = g0.x - pxf[i]; qx[i] = la * dx[i] * dx[i]; bx[i] = lb * dx[i]; }
+#pragma unroll
+        for (int i = 0; i < PY; ++i) { dy[i] = g0.y - pyf[i]; qy[i] = lc * dy[i] * dy[i]; }
+        float ov[NP];  // opacity * exp(-sigma), before the 0.999 clamp
+        bool valid[NP];
+        bool any_valid = false;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const float q = fmaf(bx[j % PX], dy[j / PX], qx[j % PX] + qy[j / PX]);  // -log2(e) * sigma
+          ov[j] = g1.y * fast_ex2(q);
+          valid[j] = idx <= bin_final[j] && q <= 0.f && ov[j] >= kAlphaMin;  // min(.999, ov) >= 1/255 <=> ov >= 1/255
+          any_valid = any_valid || valid[j];
+        }
+        if (!__any_sync(0xffffffffu, any_valid)) continue;  // warp-uniform
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          if (valid[j]) {
+            const float ddx = dx[j % PX], ddy = dy[j / PX];
+            const float alpha = fminf(kAlphaMax, ov[j]);
+            const float ra = fast_rcp(1.0f - alpha);
+            T[j] *= ra;  // transmittance in front of this Gaussian
+            const float fac = alpha * T[j];
+            v[6] = fmaf(fac, vcr[j], v[6]);
+            v[7] = fmaf(fac, vcg[j], v[7]);
+            v[8] = fmaf(fac, vcb[j], v[8]);
+            const float cdot = fmaf(cbl, vcb[j], fmaf(g1.w, vcg[j], g1.z * vcr[j]));
+            const float v_alpha = fmaf(T[j], cdot, ra * nbt_[j]);
+            nbt_[j] = fmaf(cdot, -fac, nbt_[j]);
+            if (ov[j] <= kAlphaMax) {  // the clamp was inactive: alpha depends on sigma and opacity
+              const float w = ov[j] * v_alpha;  // = opacity * d(alpha)/d(opacity) * v_alpha = -v_sigma
+              const float sx = -w * ddx, sy = -w * ddy;
+              v[2] = fmaf(sx, ddx, v[2]);
+              v[3] = fmaf(sx, ddy, v[3]);
+              v[4] = fmaf(sy, ddy, v[4]);
+              const float gx = fmaf(g0.w, sy, g0.z * sx);
+              const float gy = fmaf(g1.x, sy, g0.w * sx);
+              v[0] += gx;
+              v[1] += gy;
+              v[9] += fabsf(gx);
+              v[10] += fabsf(gy);
+              v[5] += w;
+            }
+          }
+        }
       }
-      v[0] = s_gx.x + s_gx.y; v[1] = s_gy.x + s_gy.y; v[2] = s_xx.x + s_xx.y; v[3] = s_xy.x + s_xy.y;
-      v[4] = s_yy.x + s_yy.y; v[5] = s_w.x + s_w.y; v[6] = s_r.x + s_r.y; v[7] = s_g.x + s_g.y;
-      v[8] = s_b.x + s_b.y; v[9] = s_ax.x + s_ax.y; v[10] = s_ay.x + s_ay.y;
       v[2] *= 0.5f; v[4] *= 0.5f; v[5] *= inv_o;
-      // Sum over each quarter's 8 lanes through shared memory: every lane stores its 11 partials (row k = value k,
-      // row stride 36 words: conflict free), then each lane adds the 8 floats of one (value, quarter) cell per round
-      // (2 LDS.128 + a packed add tree) and issues the RED for it — to the gradient record of the Gaussian that
-      // quarter worked on in this trip.  ~35 issue slots per trip, whatever the number of Gaussians (1..4) in it.
-      const int rcur = rql[t < red_n ? t : 0];
-      const int red_flag = (t < red_n && ((vmask >> (red_q * 8)) & 0xffu) != 0u) ? 1 : 0;
-      const size_t rec = (size_t)sid[rcur] * EGS_SPLAT_FLOATS;  // the quarter's gradient record
-      __syncwarp();  // the previous trip's cell reads are complete
+      // Warp sum of the 11 values through shared memory: every lane stores its 11 partials (row k = value k,
+      // row stride 36 words: conflict free), then lane 2k+p adds half p of row k (4 LDS.128, a packed add tree),
+      // one shuffle joins the halves and lane 2k issues the RED.  ~40 issue slots against ~90 for the 16-slot
+      // shuffle reduce-scatter (32 selects + 16 SHFL + 16 FADD) — the kernel is issue bound.
+      __syncwarp();  // the previous survivor's row reads are complete
 #pragma unroll
       for (int k = 0; k < kGradValues; ++k) sts_f32(red_st + k * kRedStride * 4, v[k]);
       __syncwarp();
-      {
-        const float4 r0 = row1[0], r1 = row1[1];
-        const float2 sa = __fadd2_rn(__fadd2_rn(make_float2(r0.x, r0.y), make_float2(r0.z, r0.w)),
-                                     __fadd2_rn(make_float2(r1.x, r1.y), make_float2(r1.z, r1.w)));
-        red_add_f32_if(red_flag, out1 + rec, sa.x + sa.y);
-      }
-      {
-        const float4 r0 = row2[0], r1 = row2[1];
-        const float2 sa = __fadd2_rn(__fadd2_rn(make_float2(r0.x, r0.y), make_float2(r0.z, r0.w)),
-                                     __fadd2_rn(make_float2(r1.x, r1.y), make_float2(r1.z, r1.w)));
-        red_add_f32_if(red_flag & red2_flag, out2 + rec, sa.x + sa.y);
-      }
+      const float4 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3];
+      float2 s0 = __fadd2_rn(make_float2(r0.x, r0.y), make_float2(r0.z, r0.w));
+      float2 s1 = __fadd2_rn(make_float2(r1.x, r1.y), make_float2(r1.z, r1.w));
+      float2 s2 = __fadd2_rn(make_float2(r2.x, r2.y), make_float2(r2.z, r2.w));
+      float2 s3 = __fadd2_rn(make_float2(r3.x, r3.y), make_float2(r3.z, r3.w));
+      s0 = __fadd2_rn(__fadd2_rn(s0, s1), __fadd2_rn(s2, s3));
+      float total = s0.x + s0.y;
+      total += __shfl_xor_sync(0xffffffffu, total, 1);
+      red_add_f32_if(red_flag, out_base + (size_t)sid[cur] * EGS_SPLAT_FLOATS, total);
     }
-    __syncwarp();  // buffer b&1, its ids and the lists are free again
+    __syncwarp();  // buffer b&1, its ids and the list are free again
   }
 }
 
@@ -735,6 +797,19 @@ static int check_raster_args(const char* who, int32_t C, int64_t n_isects, int32
   return 0;
 }
 
+// Optional second launch for very long tiles (8 warps of 8x4 pixels per tile, Geo<1,1>): OFF by default.
+// Measured on the 300k-Gaussian object scene (tiles of up to 6 k entries): forward 0.48 -> 0.42 ms
+// but backward 0.59 -> 0.72 ms, because the two launches serialise on the stream and the finer layout's
+// 32-record batches do not cover the gather latency of a lone warp.  The environment variable
+// EGS_LONG_TILE_THRESHOLD=<entries> turns it on (the parity test does) until that is fixed.
+static int long_tile_threshold(int64_t n_isects, int64_t n_tiles) {
+  (void)n_isects; (void)n_tiles;
+  const char* e = getenv("EGS_LONG_TILE_THRESHOLD");
+  if (e == nullptr) return 0x7fffffff;
+  const long v = atol(e);
+  return v > 0 && v < 0x7fffffff ? (int)v : 0x7fffffff;
+}
+
 template <bool COUNT>
 static int launch_fwd(int32_t C, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
                       const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
@@ -743,12 +818,19 @@ static int launch_fwd(int32_t C, int64_t n_isects, const float* splats, const in
                       int32_t segment = 0) {
   dim3 grid(tile_width, tile_height, C);
   const int n_tiles = C * tile_width * tile_height;
-  float4* ck = segment > 0 ? reinterpret_cast<float4*>(checkpoints) : nullptr;
-  rasterize_fwd_kernel<COUNT><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-      n_isects, reinterpret_cast<const float4*>(splats), tile_offsets, flatten_ids, backgrounds, width, height, tile_width,
-      tile_height, n_tiles, render_colors, render_alphas, last_ids, reinterpret_cast<unsigned long long*>(pair_counters), ck,
-      segment);
-  return check_launch("rasterize_fwd_kernel");
+  const int thr = long_tile_threshold(n_isects, n_tiles);
+  float4* ck = (segment > 0 && thr == 0x7fffffff) ? reinterpret_cast<float4*>(checkpoints) : nullptr;
+  const float4* sp = reinterpret_cast<const float4*>(splats);
+  unsigned long long* pc = reinterpret_cast<unsigned long long*>(pair_counters);
+  cudaStream_t st = (cudaStream_t)stream;
+  rasterize_fwd_kernel<2, 2, COUNT><<<grid, Geo<2, 2>::kThreads, 0, st>>>(
+      n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
+      render_colors, render_alphas, last_ids, pc, ck, segment);
+  if (n_isects >= thr)  // otherwise no tile can be that long
+    rasterize_fwd_kernel<1, 1, COUNT><<<grid, Geo<1, 1>::kThreads, 0, st>>>(
+        n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, thr,
+        0x7fffffff, render_colors, render_alphas, last_ids, pc, nullptr, 0);
+  return check_launch("rasterize_fwd_kernel", n_isects >= thr ? 2 : 1);
 }
 
 extern "C" int egs_rasterize_fwd(int32_t C, int32_t N, int64_t n_isects, const float* splats,
@@ -785,7 +867,7 @@ static int segment_ok(const char* who, int32_t segment) {
 extern "C" int64_t egs_rasterize_checkpoint_bytes(int64_t n_isects, int32_t segment) {
   if (n_isects < 0 || segment <= 0) return 0;
   // slots 0 .. n_isects / segment, each: 2 warps x 4 pixels x 32 lanes x float4
-  return (n_isects / segment + 2) * (int64_t)(kWarps * NP * 32 * sizeof(float4));
+  return (n_isects / segment + 2) * (int64_t)(Geo<2, 2>::kWarps * Geo<2, 2>::NP * 32 * sizeof(float4));
 }
 
 extern "C" int egs_rasterize_fwd_checkpointed(int32_t C, int32_t N, int64_t n_isects, const float* splats,
@@ -810,19 +892,24 @@ static int launch_bwd(int32_t C, int64_t n_isects, const float* splats, const in
                       const float* render_colors, const float* checkpoints, int32_t segment, egs_stream_t stream) {
   dim3 grid(tile_width, tile_height, C);
   const int n_tiles = C * tile_width * tile_height;
+  const int thr = long_tile_threshold(n_isects, n_tiles);
   const float4* sp = reinterpret_cast<const float4*>(splats);
-  const float4* ck = segment > 0 ? reinterpret_cast<const float4*>(checkpoints) : nullptr;
+  const float4* ck = (segment > 0 && thr == 0x7fffffff) ? reinterpret_cast<const float4*>(checkpoints) : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   // the segment launch goes first: its warps all have full segments to replay, the tile launch then fills in
   const int64_t n_slots = ck != nullptr ? n_isects / segment : 0;
   if (n_slots > 0)
-    rasterize_bwd_kernel<<<(unsigned)n_slots, kThreads, 0, st>>>(
-        n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles,
+    rasterize_bwd_kernel<2, 2><<<(unsigned)n_slots, Geo<2, 2>::kThreads, 0, st>>>(
+        n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
         render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, 1);
-  rasterize_bwd_kernel<<<grid, kThreads, 0, st>>>(
-      n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles,
+  rasterize_bwd_kernel<2, 2><<<grid, Geo<2, 2>::kThreads, 0, st>>>(
+      n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
       render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, 0);
-  return check_launch("rasterize_bwd_kernel", n_slots > 0 ? 2 : 1);
+  if (n_isects >= thr)
+    rasterize_bwd_kernel<1, 1><<<grid, Geo<1, 1>::kThreads, 0, st>>>(
+        n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, thr,
+        0x7fffffff, render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, nullptr, nullptr, 0, 0);
+  return check_launch("rasterize_bwd_kernel", 1 + (n_slots > 0 ? 1 : 0) + (n_isects >= thr ? 1 : 0));
 }
 
 extern "C" int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const float* splats,

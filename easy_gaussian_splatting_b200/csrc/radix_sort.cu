@@ -21,6 +21,10 @@ constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
 // pairs per thread is the template parameter ITEMS (8 in production: tile = 4096 pairs; 16 was measured slower)
 
+#ifndef EGS_SORT_ITEMS_U32
+#define EGS_SORT_ITEMS_U32 8
+#endif
+
 constexpr int kLookWindow = 8;
 constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagPrefix = 2u << 30;
@@ -366,7 +370,10 @@ static int radix_sort_pairs_impl(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT
   if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
   radix_histogram_kernel<KeyT><<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, passes, w.hist);
   radix_scan_hist_kernel<<<passes, kRadix, 0, stream>>>(w.hist);
-  return run_passes<KeyT, 8>(n, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
+  // pairs per thread: 8 for 64-bit keys (a 16-item tile would need 2 x the shared memory and drop to one CTA per SM);
+  // EGS_SORT_ITEMS_U32 for 32-bit keys (build-time A/B knob, scripts/build_variant.py)
+  if constexpr (sizeof(KeyT) == 4) return run_passes<KeyT, EGS_SORT_ITEMS_U32>(n, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
+  else return run_passes<KeyT, 8>(n, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
 }
 
 template <typename KeyT, int ITEMS>

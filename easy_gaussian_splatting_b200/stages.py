@@ -139,11 +139,12 @@ def camera_n_bits(C: int) -> int:
 
 
 # Level 1 of the two-level binning route sorts the visible Gaussians of all cameras on these key bits
-LEVEL1_KEY_BYTES = 8
+LEVEL1_KEY_BYTES = 4
 
 
 def level1_end_bit(C: int) -> int:
-    return 32 + camera_n_bits(C)
+    """Depth bits only: level 2 sorts stably on the (camera, tile) index, which also separates the cameras."""
+    return 32
 
 
 def projection_fwd(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, colors: Tensor,
@@ -395,7 +396,7 @@ def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss
     ws_bytes = max(lib.egs_isect_scan_workspace_bytes(max(n, 1)), 16)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     totals = torch.empty(2, dtype=torch.int64, device=dev)
-    keys1 = torch.empty(n, dtype=torch.int64, device=dev)  # upper bound n_vis <= C*N; sliced after the sync
+    keys1 = torch.empty(n, dtype=torch.int32, device=dev)  # upper bound n_vis <= C*N; sliced after the sync
     vals1 = torch.empty(n, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         rc = lib.egs_isect_visible_keys(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(keys1), _ptr(vals1),
@@ -409,8 +410,8 @@ def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss
         return (empty_ids if materialize_ids else (lambda: empty_ids)), torch.empty(0, dtype=torch.int32, device=dev), offsets
     if n_isects >= 2 ** 31 - 1:
         raise RuntimeError(f"{n_isects} tile intersections do not fit int32 offsets; render fewer cameras per call")
-    # level 1: visible Gaussians in (camera, depth, index) order
-    k1, order = radix_sort_pairs(keys1[:n_vis], vals1[:n_vis], level1_end_bit(C))
+    # level 1: visible entries of all cameras in (depth, flat index) order
+    k1, order = radix_sort_pairs_u32(keys1[:n_vis], vals1[:n_vis], level1_end_bit(C))
     # tile counts in that order -> write offsets
     cum = torch.empty(n_vis, dtype=torch.int64, device=dev)
     total2 = torch.empty(1, dtype=torch.int64, device=dev)

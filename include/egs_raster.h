@@ -160,18 +160,19 @@ int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, 
                                  int32_t* host_result_in_b, egs_stream_t stream);
 
 /* ---- g3-g5 fast path: identical sorted (isect_ids, flatten_ids, isect_offsets), ~3x less traffic ----------
- * A stable sort on cam|tile|depth keys equals (1) a stable sort of the VISIBLE Gaussians on cam|depth,
- * (2) emitting their tiles in that order, (3) a stable sort of the emitted pairs on the (cam,tile) index alone.
+ * A stable sort on cam|tile|depth keys equals (1) a stable sort of the VISIBLE entries of all cameras on depth
+ * (ties keep flat-index order), (2) emitting their tiles in that order, (3) a stable sort of the emitted pairs on
+ * the (cam,tile) index alone — which also separates the cameras, so level 1 needs no camera bits.
  *   egs_isect_visible_keys : compacts visible entries (tiles_per_gauss > 0) into level-1 pairs
- *                            keys1 = cam<<32 | bits(depth), vals1 = flat index; totals[2] = {n_vis, n_isects} (device)
- *   (sort keys1/vals1 with egs_radix_sort_pairs_u64_u32 on bits [0, 32 + cam bits))
+ *                            keys1 = bits(depth) (u32), vals1 = flat index; totals[2] = {n_vis, n_isects} (device)
+ *   (sort keys1/vals1 with egs_radix_sort_pairs_u32_u32 on bits [0, 32))
  *   egs_exclusive_scan_gather : out[i] = sum_{j<i} src[gather[j]]  (tile counts in depth order)
  *   egs_isect_emit_sorted  : warp-cooperative emission of tile_keys = cam*n_tiles + tile (u32), flat_vals
  *   (sort tile_keys/flat_vals with egs_radix_sort_pairs_u32_u32 on bits [0, ceil(log2(C*n_tiles))))
  *   egs_isect_finalize     : derives the tile offsets and/or rebuilds the 64-bit isect_ids (either output
  *                            pointer may be NULL: the Python side materialises isect_ids lazily, on first access) */
 int64_t egs_isect_scan_workspace_bytes(int64_t n);
-int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths, uint64_t* keys1,
+int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths, uint32_t* keys1,
                            uint32_t* vals1, int64_t* totals, void* workspace, int64_t workspace_bytes,
                            egs_stream_t stream);
 int egs_exclusive_scan_gather(int64_t n, const int32_t* src, const uint32_t* gather, int64_t* out, int64_t* total,

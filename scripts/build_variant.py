@@ -17,6 +17,12 @@ from easy_gaussian_splatting_b200 import build as B  # noqa: E402
 
 def main():
     name, extra = sys.argv[1], sys.argv[2:]
+    # --replace blend.cu=/path/to/other.cu : compile another file in place of a translation unit (A/B of a rewrite)
+    replace = {}
+    for a in [a for a in extra if a.startswith("--replace=")]:
+        k, v = a[len("--replace="):].split("=", 1)
+        replace[k] = Path(v)
+        extra.remove(a)
     out_dir = B.OUT_DIR / "variants"
     obj_dir = out_dir / f"obj_{name}"
     obj_dir.mkdir(parents=True, exist_ok=True)
@@ -24,7 +30,8 @@ def main():
 
     def one(src):
         obj = obj_dir / (src.stem + ".o")
-        cmd = [nvcc, *B.ARCH, *B.COMMON, *B.FLAGS.get(src.name, []), *extra, "-c", str(src), "-o", str(obj)]
+        real = replace.get(src.name, src)
+        cmd = [nvcc, *B.ARCH, *B.COMMON, f"-I{B.CSRC}", *B.FLAGS.get(src.name, []), *extra, "-c", str(real), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(r.stdout + r.stderr)
@@ -38,7 +45,7 @@ def main():
     for _, t in res:
         lines = t.splitlines()
         for i, ln in enumerate(lines):
-            if "rasterize_" in ln and "Function properties" in ln and "ILi2ELi2" in ln:
+            if "rasterize_" in ln and "Function properties" in ln:
                 print(ln.split("for ")[-1][:60], "|", lines[i + 1].strip(), "|", lines[i + 2].strip())
     print(lib)
 
