@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kScanThreads) visible_spine_kernel(int64_t* __
     carry += total;
     tiles_total += block_reduce_sum((j < nblocks) ? sums_tiles[j] : 0, smem);
   }
-  if (threadIdx.x == 0) { totals[0] = carry; totals[1] = tiles_total; }
+  if (threadIdx.x == 0) { totals[0] = carry; totals[1] = tiles_total; totals[2] = 0; totals[3] = 0; }
 }
 
 // also writes the level-1 sort input: key = bits(depth), value = flat index (camera * N + Gaussian), compacted.
@@ -241,8 +241,10 @@ __global__ void __launch_bounds__(kScanThreads) visible_apply_kernel(const int32
 // ---- exclusive scan of src[gather[i]] (tile counts in depth order) -------------------------------------
 __global__ void __launch_bounds__(kScanThreads) gscan_block_sums_kernel(const int32_t* __restrict__ src,
                                                                          const uint32_t* __restrict__ gather, int64_t n,
+                                                                         const int64_t* __restrict__ n_dev,
                                                                          int64_t* __restrict__ block_sums) {
   __shared__ int64_t smem[33];
+  n = live_count(n, n_dev);
   const int64_t base = (int64_t)blockIdx.x * kScanTile;
   int64_t s = 0;
 #pragma unroll
@@ -257,9 +259,11 @@ __global__ void __launch_bounds__(kScanThreads) gscan_block_sums_kernel(const in
 
 __global__ void __launch_bounds__(kScanThreads) gscan_apply_kernel(const int32_t* __restrict__ src,
                                                                     const uint32_t* __restrict__ gather, int64_t n,
+                                                                    const int64_t* __restrict__ n_dev,
                                                                     const int64_t* __restrict__ block_sums,
                                                                     int64_t* __restrict__ out) {
   __shared__ int64_t smem[33];
+  n = live_count(n, n_dev);
   const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
   int32_t v[kScanItems];
   int64_t s = 0;
@@ -282,7 +286,12 @@ __global__ void __launch_bounds__(kScanThreads) gscan_apply_kernel(const int32_t
 __global__ void __launch_bounds__(kEmitThreads) isect_emit_sorted_kernel(
     int N, int64_t n_vis, const uint32_t* __restrict__ order, const int64_t* __restrict__ cum_excl,
     const float2* __restrict__ means2d, const int32_t* __restrict__ radii, float tile_size, int tile_w, int tile_h,
-    int64_t n_isects, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ flat_vals) {
+    int64_t n_isects, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ flat_vals,
+    const int64_t* __restrict__ counts_dev /* nullable: {n_vis, n_isects} live counts, the arguments are capacities */) {
+  if (counts_dev != nullptr) {
+    n_vis = live_count(n_vis, counts_dev);
+    n_isects = live_count(n_isects, counts_dev + 1);
+  }
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * kEmitThreads + threadIdx.x;  // position in (cam, depth) order
   const bool valid = i < n_vis;
@@ -365,8 +374,17 @@ __global__ void __launch_bounds__(kOffThreads) isect_finalize_kernel(int64_t n_i
 // tile t's offset is written by the thread that sees the first key >= t (runs of empty tiles are filled by it too).
 constexpr int kOff4Threads = 256;
 __global__ void __launch_bounds__(kOff4Threads) isect_offsets4_kernel(int32_t n_isects, const uint32_t* __restrict__ tile_keys,
-                                                                       int32_t n_slots, int32_t* __restrict__ offsets) {
+                                                                       int32_t n_slots, int32_t* __restrict__ offsets,
+                                                                       const int64_t* __restrict__ n_dev, int sentinel) {
+  // n_dev: the live count (the argument is then the capacity the grid was sized for); sentinel: offsets has
+  // n_slots + 1 entries and the last one receives the live count (the blend kernels read it as the end of the last tile)
+  n_isects = (int32_t)live_count(n_isects, n_dev);
   const int32_t i0 = (blockIdx.x * kOff4Threads + threadIdx.x) * 4;
+  if (i0 == 0 && sentinel) offsets[n_slots] = n_isects;
+  if (n_isects == 0) {  // nothing visible: every tile is empty (grid-uniform branch)
+    for (int32_t t = i0 / 4; t < n_slots; t += gridDim.x * kOff4Threads) offsets[t] = 0;
+    return;
+  }
   if (i0 >= n_isects) return;
   uint32_t k[4];
   if (i0 + 4 <= n_isects) {
@@ -462,7 +480,7 @@ extern "C" int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles
   const int64_t n = (int64_t)C * N;
   EGS_REQUIRE(n < 0x7fffffffLL, "isect_visible_keys: C*N=%lld does not fit the int32 flatten id", (long long)n);
   if (n == 0) {
-    EGS_CUDA(cudaMemsetAsync(totals, 0, 2 * sizeof(int64_t), stream));
+    EGS_CUDA(cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), stream));
     return 0;
   }
   if (workspace_bytes < egs_isect_scan_workspace_bytes(n))
@@ -489,9 +507,9 @@ extern "C" int egs_exclusive_scan_gather(int64_t n, const int32_t* src, const ui
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "exclusive_scan_gather: workspace too small");
   const int64_t nblocks = ceil_div(n, kScanTile);
   int64_t* block_sums = reinterpret_cast<int64_t*>(workspace);
-  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, block_sums);
+  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, nullptr, block_sums);
   scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, total);
-  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, block_sums, out);
+  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, nullptr, block_sums, out);
   return check_launch("exclusive_scan_gather", 3);
 }
 
@@ -506,7 +524,7 @@ extern "C" int egs_isect_emit_sorted(int32_t C, int32_t N, int64_t n_vis, const 
   if (n_vis == 0 || n_isects == 0) return 0;
   isect_emit_sorted_kernel<<<(unsigned)ceil_div(n_vis, kEmitThreads), kEmitThreads, 0, (cudaStream_t)stream>>>(
       N, n_vis, order, cum_excl, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width,
-      tile_height, n_isects, tile_keys, flat_vals);
+      tile_height, n_isects, tile_keys, flat_vals, nullptr);
   return check_launch("isect_emit_sorted_kernel");
 }
 
@@ -523,10 +541,119 @@ extern "C" int egs_isect_finalize(int64_t n_isects, const uint32_t* tile_keys_so
   }
   if (isect_ids == nullptr && offsets != nullptr && reinterpret_cast<uintptr_t>(tile_keys_sorted) % 16 == 0) {
     isect_offsets4_kernel<<<(unsigned)ceil_div(n_isects, 4 * kOff4Threads), kOff4Threads, 0, stream>>>(
-        (int32_t)n_isects, tile_keys_sorted, (int32_t)n_slots, offsets);
+        (int32_t)n_isects, tile_keys_sorted, (int32_t)n_slots, offsets, nullptr, 0);
     return check_launch("isect_offsets4_kernel");
   }
   isect_finalize_kernel<<<(unsigned)ceil_div(n_isects, kOffThreads), kOffThreads, 0, stream>>>(
       n_isects, tile_keys_sorted, flat_sorted, depths, n_tiles, tile_n_bits, n_slots, isect_ids, offsets);
   return check_launch("isect_finalize_kernel");
+}
+
+// Longest tile list of the call -> counts[2] (the host reads it one call later and uses it to decide whether long
+// lists are worth replaying in segments; a hint, never needed for correctness).
+__global__ void __launch_bounds__(256) tile_len_max_kernel(const int32_t* __restrict__ offsets, int32_t n_slots,
+                                                            unsigned long long* __restrict__ max_len) {
+  int32_t m = 0;
+  for (int32_t t = blockIdx.x * 256 + threadIdx.x; t < n_slots; t += gridDim.x * 256) m = max(m, offsets[t + 1] - offsets[t]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_len, (unsigned long long)m);
+}
+
+// ---- the whole route behind egs_isect_visible_keys in ONE call, with the two counts read on the device -----------------
+// Workspace layout (all 16-byte aligned): keys1_b | vals1_b | cum | scan block sums | level-1 sort workspace |
+// level-2 ping-pong keys | level-2 ping-pong values | level-2 sort workspace.
+namespace {
+struct SortedLayout {
+  int64_t keys1_b, vals1_b, cum, scan, sort1, keys2, vals2, sort2, total;
+};
+SortedLayout sorted_layout(int64_t n, int64_t capacity, int end_bit2) {
+  SortedLayout L;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { const int64_t at = off; off += egs::align_up(bytes > 0 ? bytes : 16, 256); return at; };
+  L.keys1_b = take(n * 4);
+  L.vals1_b = take(n * 4);
+  L.cum = take(n * 8);
+  L.scan = take(egs_exclusive_scan_workspace_bytes(n));
+  L.sort1 = take(egs::radix_sort_workspace_bytes(n, 32));
+  L.keys2 = take(capacity * 4);
+  L.vals2 = take(capacity * 4);
+  L.sort2 = take(egs::radix_sort_workspace_bytes(capacity, end_bit2));
+  L.total = off;
+  return L;
+}
+int level2_end_bit(int64_t n_slots) {
+  int b = 1;
+  while (b < 31 && (1ll << b) < n_slots) ++b;
+  return b;
+}
+}  // namespace
+
+extern "C" int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_t n_tiles, int64_t capacity) {
+  if (C < 0 || N < 0 || n_tiles < 0 || capacity < 0) return 0;
+  const int64_t n = (int64_t)C * N;
+  return sorted_layout(n > 0 ? n : 1, capacity > 0 ? capacity : 1, level2_end_bit((int64_t)C * n_tiles)).total;
+}
+
+extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* means2d,
+                                const int32_t* radii, uint32_t* keys1, uint32_t* vals1, int64_t* stats,
+                                int32_t tile_size, int32_t tile_width, int32_t tile_height, int64_t capacity,
+                                void* workspace, int64_t workspace_bytes, uint32_t* tile_keys, uint32_t* flatten_ids,
+                                int32_t* offsets, egs_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EGS_REQUIRE(C >= 0 && N >= 0, "isect_sorted: negative sizes");
+  const int64_t n = (int64_t)C * N;
+  const int64_t n_slots = (int64_t)C * tile_width * tile_height;
+  EGS_REQUIRE(n < 0x7fffffffLL, "isect_sorted: C*N=%lld does not fit the int32 flatten id", (long long)n);
+  EGS_REQUIRE(n_slots < 0x7fffffffLL, "isect_sorted: too many tiles");
+  EGS_REQUIRE((int64_t)tile_width * tile_height * tile_width < 0x100000000LL,
+              "isect_sorted: tile grid %dx%d too large for the reciprocal row split", tile_width, tile_height);
+  EGS_REQUIRE(capacity >= 1 && capacity < 0x7fffffffLL, "isect_sorted: capacity=%lld out of int32 range", (long long)capacity);
+  EGS_REQUIRE(stats != nullptr, "isect_sorted: the device counts {n_vis, n_isects, ..} of egs_isect_visible_keys are required");
+  const int64_t* counts = stats;
+  stats += 2;  // slot 2: longest tile list (output)
+  if (n_slots == 0) return 0;
+  if (n == 0) {  // nothing to bin: all offsets (and the sentinel) are zero
+    EGS_CUDA(cudaMemsetAsync(offsets, 0, (n_slots + 1) * sizeof(int32_t), stream));
+    return 0;
+  }
+  const int end_bit2 = level2_end_bit(n_slots);
+  const SortedLayout L = sorted_layout(n, capacity, end_bit2);
+  if (workspace == nullptr || workspace_bytes < L.total)
+    return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "isect_sorted: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)L.total);
+  char* ws = reinterpret_cast<char*>(workspace);
+  uint32_t* keys1_b = reinterpret_cast<uint32_t*>(ws + L.keys1_b);
+  uint32_t* vals1_b = reinterpret_cast<uint32_t*>(ws + L.vals1_b);
+  int64_t* cum = reinterpret_cast<int64_t*>(ws + L.cum);
+  int64_t* block_sums = reinterpret_cast<int64_t*>(ws + L.scan);
+  // level 1: visible entries of all cameras in (depth, flat index) order — 4 passes over n_vis 8-byte pairs
+  int in_b = 0;
+  if (int rc = radix_sort_pairs_u32(n, counts, keys1, vals1, keys1_b, vals1_b, 32, ws + L.sort1, L.keys2 - L.sort1, &in_b, stream))
+    return rc;
+  const uint32_t* order = in_b ? vals1_b : vals1;
+  // tile counts in that order -> write offsets (the grand total is counts[1] already; the spine's copy lands in block_sums' tail)
+  const int64_t nblocks = ceil_div(n, kScanTile);
+  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, order, n, counts, block_sums);
+  scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, block_sums + nblocks);
+  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, order, n, counts, block_sums, cum);
+  // emission into whichever side of the level-2 ping-pong makes the sorted pairs end in the caller's buffers
+  const int passes2 = (end_bit2 + 7) / 8;
+  uint32_t* ka = (passes2 & 1) ? reinterpret_cast<uint32_t*>(ws + L.keys2) : tile_keys;
+  uint32_t* va = (passes2 & 1) ? reinterpret_cast<uint32_t*>(ws + L.vals2) : flatten_ids;
+  uint32_t* kb = (passes2 & 1) ? tile_keys : reinterpret_cast<uint32_t*>(ws + L.keys2);
+  uint32_t* vb = (passes2 & 1) ? flatten_ids : reinterpret_cast<uint32_t*>(ws + L.vals2);
+  isect_emit_sorted_kernel<<<(unsigned)ceil_div(n, kEmitThreads), kEmitThreads, 0, stream>>>(
+      N, n, order, cum, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width, tile_height, capacity,
+      ka, va, counts);
+  if (int rc = check_launch("isect_sorted (scan + emit)", 4)) return rc;
+  // level 2: stable sort on the dense (camera, tile) index
+  if (int rc = radix_sort_pairs_u32(capacity, counts + 1, ka, va, kb, vb, end_bit2, ws + L.sort2, L.total - L.sort2, &in_b, stream))
+    return rc;
+  if ((in_b != 0) != ((passes2 & 1) != 0)) return fail(EGS_ERR_INVALID_ARGUMENT, "isect_sorted: internal ping-pong mismatch");
+  isect_offsets4_kernel<<<(unsigned)ceil_div(capacity, 4 * kOff4Threads), kOff4Threads, 0, stream>>>(
+      (int32_t)capacity, tile_keys, (int32_t)n_slots, offsets, counts + 1, 1);
+  int64_t len_blocks = ceil_div(n_slots, 256);
+  if (len_blocks > 148) len_blocks = 148;
+  tile_len_max_kernel<<<(unsigned)len_blocks, 256, 0, stream>>>(offsets, (int32_t)n_slots,
+                                                                 reinterpret_cast<unsigned long long*>(stats));
+  return check_launch("isect_offsets4_kernel", 2);
 }

@@ -145,7 +145,9 @@ __device__ __forceinline__ WarpView warp_setup(int tile_w, int tile_h, int64_t n
   v.x0 = wx0 + (lane & 7) * (G::kWarpW / 8);
   v.y0 = wy0 + (lane >> 3) * (G::kWarpH / 4);
   v.range_start = tile_offsets[tile_id];
-  v.range_end = (tile_id == n_tiles_total - 1) ? (int)n_isects : tile_offsets[tile_id + 1];
+  // n_isects < 0: the offsets carry a sentinel entry behind the last tile (the live list length, written on the
+  // device by egs_isect_sorted); otherwise the last tile ends at n_isects
+  v.range_end = (tile_id == n_tiles_total - 1 && n_isects >= 0) ? (int)n_isects : tile_offsets[tile_id + 1];
   v.rx_lo = (float)wx0 + 0.5f;
   v.rx_hi = v.rx_lo + (float)(G::kWarpW - 1);
   v.ry_lo = (float)wy0 + 0.5f;
@@ -222,7 +224,7 @@ __global__ void EGS_FWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_fwd_kernel
     const int32_t* __restrict__ flatten_ids, const float* __restrict__ backgrounds, int width, int height, int tile_w,
     int tile_h, int n_tiles_total, int len_lo, int len_hi, float* __restrict__ render_colors,
     float* __restrict__ render_alphas, int32_t* __restrict__ last_ids, unsigned long long* __restrict__ pair_counters,
-    float4* __restrict__ ckpt, int ckpt_k) {
+    float4* __restrict__ ckpt, int ckpt_k, int seg_min_len) {
   using G = Geo<PX, PY>;
   constexpr int NP = G::NP;
   constexpr int RPL = G::RPL, kBatch = G::kBatch;
@@ -406,7 +408,8 @@ __global__ void EGS_FWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_fwd_kernel
         // replay at any of these boundaries, one warp per segment (see rasterize_bwd_kernel).  Slot numbering
         // floor(start / K) + k is collision free across tiles because their list ranges are disjoint and ordered.
         const int done_local = (b + 1) * kBatch;
-        if (ckpt != nullptr && done_local % ckpt_k == 0 && done_local < wv.range_end - wv.range_start) {
+        if (ckpt != nullptr && wv.range_end - wv.range_start >= seg_min_len && done_local % ckpt_k == 0 &&
+            done_local < wv.range_end - wv.range_start) {
           const size_t slot = (size_t)(wv.range_start / ckpt_k + done_local / ckpt_k);
           float4* dst = ckpt + ((slot * G::kWarps + (threadIdx.x >> 5)) * NP) * 32 + lane;
 #pragma unroll
@@ -466,7 +469,8 @@ __global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel
     // seg_launch = 0: blocks are tiles and replay the LAST segment their warp needs (from the warp's last blended
     // entry down to the segment boundary below it, initial state = the final image, as without segments);
     // seg_launch = 1: blocks are checkpoint slots and replay the full segment that ends at their checkpoint.
-    const float* __restrict__ render_colors, const float4* __restrict__ ckpt, int ckpt_k, int seg_launch) {
+    // Only lists of at least seg_min_len (> ckpt_k) entries are replayed in segments; shorter ones as one piece.
+    const float* __restrict__ render_colors, const float4* __restrict__ ckpt, int ckpt_k, int seg_min_len, int seg_launch) {
   using G = Geo<PX, PY>;
   constexpr int NP = G::NP;
   constexpr int RPL = G::RPL, kBatch = G::kBatch;
@@ -492,7 +496,7 @@ __global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel
   {
     const int len = wv.range_end - wv.range_start;
     if (len <= 0 || len < len_lo || len >= len_hi) return;  // block-uniform: empty, or owned by the other launch
-    if (seg_launch && (seg_k < 1 || (int64_t)seg_k * ckpt_k >= len)) return;  // block-uniform: slot not in use
+    if (seg_launch && (len < seg_min_len || seg_k < 1 || (int64_t)seg_k * ckpt_k >= len)) return;  // block-uniform: slot not in use
   }
 
   float pxf[PX], pyf[PY];
@@ -536,7 +540,7 @@ __global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel
   if (end_idx < wv.range_start) return;  // warp-uniform
   int lo_idx = wv.range_start;  // the replay walks end_idx, end_idx - 1, ..., lo_idx
   if constexpr (PX == 2 && PY == 2) {
-    if (ckpt != nullptr && wv.range_end - wv.range_start > ckpt_k) {
+    if (ckpt != nullptr && wv.range_end - wv.range_start >= seg_min_len) {
       const int last_seg = (end_idx - wv.range_start) / ckpt_k;  // segment that holds the warp's last blended entry
       if (!seg_launch) {
         lo_idx = wv.range_start + last_seg * ckpt_k;
@@ -792,45 +796,34 @@ static int check_raster_args(const char* who, int32_t C, int64_t n_isects, int32
   EGS_REQUIRE(tile_width == (width + kTileSize - 1) / kTileSize && tile_height == (height + kTileSize - 1) / kTileSize,
               "%s: tile grid %dx%d does not match %dx%d pixels at tile_size 16", who, tile_width, tile_height, width, height);
   EGS_REQUIRE(tile_height <= 65535, "%s: tile_height=%d exceeds the grid limit", who, tile_height);
-  EGS_REQUIRE(n_isects >= 0 && n_isects < 0x7fffffffLL, "%s: n_isects=%lld out of int32 range", who, (long long)n_isects);
+  EGS_REQUIRE(n_isects > -0x7fffffffLL && n_isects < 0x7fffffffLL, "%s: n_isects=%lld out of int32 range", who, (long long)n_isects);
   EGS_REQUIRE((int64_t)C * tile_width * tile_height < 0x7fffffffLL, "%s: too many tiles", who);
   return 0;
 }
 
-// Optional second launch for very long tiles (8 warps of 8x4 pixels per tile, Geo<1,1>): OFF by default.
-// Measured on the 300k-Gaussian object scene (tiles of up to 6 k entries): forward 0.48 -> 0.42 ms
-// but backward 0.59 -> 0.72 ms, because the two launches serialise on the stream and the finer layout's
-// 32-record batches do not cover the gather latency of a lone warp.  The environment variable
-// EGS_LONG_TILE_THRESHOLD=<entries> turns it on (the parity test does) until that is fixed.
-static int long_tile_threshold(int64_t n_isects, int64_t n_tiles) {
-  (void)n_isects; (void)n_tiles;
-  const char* e = getenv("EGS_LONG_TILE_THRESHOLD");
-  if (e == nullptr) return 0x7fffffff;
-  const long v = atol(e);
-  return v > 0 && v < 0x7fffffff ? (int)v : 0x7fffffff;
-}
+// Every tile is handled by the <2,2> layout.  A second launch with the 8-warps-per-tile <1,1> layout for very long
+// lists was measured twice (round 1: object scene, 4 views per call: forward 0.48 -> 0.42 ms, backward 0.59 -> 0.72 ms;
+// round 2, one view per call: 1.224 -> 1.225 ms per view, gpurun_out/r2c_knobs.log) and is no longer built: the busy
+// tiles of an object scene are bound by their serial walk, and eight warps that each cull the whole list do 1.5 x the
+// instructions of two.
+constexpr int kNoLengthLimit = 0x7fffffff;
 
 template <bool COUNT>
 static int launch_fwd(int32_t C, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
                       const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
                       int32_t tile_width, int32_t tile_height, float* render_colors, float* render_alphas,
                       int32_t* last_ids, uint64_t* pair_counters, egs_stream_t stream, float* checkpoints = nullptr,
-                      int32_t segment = 0) {
+                      int32_t segment = 0, int32_t seg_min_len = 0) {
   dim3 grid(tile_width, tile_height, C);
   const int n_tiles = C * tile_width * tile_height;
-  const int thr = long_tile_threshold(n_isects, n_tiles);
-  float4* ck = (segment > 0 && thr == 0x7fffffff) ? reinterpret_cast<float4*>(checkpoints) : nullptr;
+  float4* ck = segment > 0 ? reinterpret_cast<float4*>(checkpoints) : nullptr;
   const float4* sp = reinterpret_cast<const float4*>(splats);
   unsigned long long* pc = reinterpret_cast<unsigned long long*>(pair_counters);
   cudaStream_t st = (cudaStream_t)stream;
   rasterize_fwd_kernel<2, 2, COUNT><<<grid, Geo<2, 2>::kThreads, 0, st>>>(
-      n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
-      render_colors, render_alphas, last_ids, pc, ck, segment);
-  if (n_isects >= thr)  // otherwise no tile can be that long
-    rasterize_fwd_kernel<1, 1, COUNT><<<grid, Geo<1, 1>::kThreads, 0, st>>>(
-        n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, thr,
-        0x7fffffff, render_colors, render_alphas, last_ids, pc, nullptr, 0);
-  return check_launch("rasterize_fwd_kernel", n_isects >= thr ? 2 : 1);
+      n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0,
+      kNoLengthLimit, render_colors, render_alphas, last_ids, pc, ck, segment, seg_min_len > segment ? seg_min_len : segment + 1);
+  return check_launch("rasterize_fwd_kernel");
 }
 
 extern "C" int egs_rasterize_fwd(int32_t C, int32_t N, int64_t n_isects, const float* splats,
@@ -865,7 +858,8 @@ static int segment_ok(const char* who, int32_t segment) {
 }
 
 extern "C" int64_t egs_rasterize_checkpoint_bytes(int64_t n_isects, int32_t segment) {
-  if (n_isects < 0 || segment <= 0) return 0;
+  if (n_isects < 0) n_isects = -n_isects;  // sentinel mode: the capacity
+  if (segment <= 0) return 0;
   // slots 0 .. n_isects / segment, each: 2 warps x 4 pixels x 32 lanes x float4
   return (n_isects / segment + 2) * (int64_t)(Geo<2, 2>::kWarps * Geo<2, 2>::NP * 32 * sizeof(float4));
 }
@@ -875,41 +869,40 @@ extern "C" int egs_rasterize_fwd_checkpointed(int32_t C, int32_t N, int64_t n_is
                                               const float* backgrounds, int32_t width, int32_t height,
                                               int32_t tile_width, int32_t tile_height, float* render_colors,
                                               float* render_alphas, int32_t* last_ids, float* checkpoints,
-                                              int32_t segment, egs_stream_t stream) {
+                                              int32_t segment, int32_t seg_min_len, egs_stream_t stream) {
   (void)N;
   if (int rc = check_raster_args("rasterize_fwd_checkpointed", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (int rc = segment_ok("rasterize_fwd_checkpointed", segment)) return rc;
   EGS_REQUIRE(segment == 0 || checkpoints != nullptr, "rasterize_fwd_checkpointed: checkpoints buffer is required");
   if (C == 0) return 0;
   return launch_fwd<false>(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width,
-                           tile_height, render_colors, render_alphas, last_ids, nullptr, stream, checkpoints, segment);
+                           tile_height, render_colors, render_alphas, last_ids, nullptr, stream, checkpoints, segment,
+                           seg_min_len);
 }
 
 static int launch_bwd(int32_t C, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
                       const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
                       int32_t tile_width, int32_t tile_height, const float* render_alphas, const int32_t* last_ids,
                       const float* v_render_colors, const float* v_render_alphas, float* v_splats,
-                      const float* render_colors, const float* checkpoints, int32_t segment, egs_stream_t stream) {
+                      const float* render_colors, const float* checkpoints, int32_t segment, int32_t seg_min_len,
+                      egs_stream_t stream) {
+  seg_min_len = seg_min_len > segment ? seg_min_len : segment + 1;
   dim3 grid(tile_width, tile_height, C);
   const int n_tiles = C * tile_width * tile_height;
-  const int thr = long_tile_threshold(n_isects, n_tiles);
+  const int thr = kNoLengthLimit;
   const float4* sp = reinterpret_cast<const float4*>(splats);
-  const float4* ck = (segment > 0 && thr == 0x7fffffff) ? reinterpret_cast<const float4*>(checkpoints) : nullptr;
+  const float4* ck = segment > 0 ? reinterpret_cast<const float4*>(checkpoints) : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   // the segment launch goes first: its warps all have full segments to replay, the tile launch then fills in
-  const int64_t n_slots = ck != nullptr ? n_isects / segment : 0;
+  const int64_t n_slots = ck != nullptr ? (n_isects < 0 ? -n_isects : n_isects) / segment : 0;
   if (n_slots > 0)
     rasterize_bwd_kernel<2, 2><<<(unsigned)n_slots, Geo<2, 2>::kThreads, 0, st>>>(
         n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
-        render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, 1);
+        render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, seg_min_len, 1);
   rasterize_bwd_kernel<2, 2><<<grid, Geo<2, 2>::kThreads, 0, st>>>(
       n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
-      render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, 0);
-  if (n_isects >= thr)
-    rasterize_bwd_kernel<1, 1><<<grid, Geo<1, 1>::kThreads, 0, st>>>(
-        n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, thr,
-        0x7fffffff, render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, nullptr, nullptr, 0, 0);
-  return check_launch("rasterize_bwd_kernel", 1 + (n_slots > 0 ? 1 : 0) + (n_isects >= thr ? 1 : 0));
+      render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, seg_min_len, 0);
+  return check_launch("rasterize_bwd_kernel", 1 + (n_slots > 0 ? 1 : 0));
 }
 
 extern "C" int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const float* splats,
@@ -921,7 +914,7 @@ extern "C" int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const f
   if (int rc = check_raster_args("rasterize_bwd", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (C == 0 || n_isects == 0) return 0;
   return launch_bwd(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height,
-                    render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, nullptr, nullptr, 0, stream);
+                    render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, nullptr, nullptr, 0, 0, stream);
 }
 
 extern "C" int egs_rasterize_bwd_segmented(int32_t C, int32_t N, int64_t n_isects, const float* splats,
@@ -930,7 +923,7 @@ extern "C" int egs_rasterize_bwd_segmented(int32_t C, int32_t N, int64_t n_isect
                                            int32_t tile_height, const float* render_colors, const float* render_alphas,
                                            const int32_t* last_ids, const float* v_render_colors,
                                            const float* v_render_alphas, const float* checkpoints, int32_t segment,
-                                           float* v_splats, egs_stream_t stream) {
+                                           int32_t seg_min_len, float* v_splats, egs_stream_t stream) {
   (void)N;
   if (int rc = check_raster_args("rasterize_bwd_segmented", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (int rc = segment_ok("rasterize_bwd_segmented", segment)) return rc;
@@ -939,5 +932,5 @@ extern "C" int egs_rasterize_bwd_segmented(int32_t C, int32_t N, int64_t n_isect
   if (C == 0 || n_isects == 0) return 0;
   return launch_bwd(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height,
                     render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, checkpoints,
-                    segment, stream);
+                    segment, seg_min_len, stream);
 }

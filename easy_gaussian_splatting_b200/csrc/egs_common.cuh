@@ -25,6 +25,21 @@ inline int check_launch(const char* what, int n_kernels = 1) {
 }
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Element counts that only the device knows (the sync-free binning route): a kernel is launched for a CAPACITY and
+// reads the live count itself.  count_dev == nullptr: the capacity is the count.
+__device__ __forceinline__ int64_t live_count(int64_t capacity, const int64_t* __restrict__ count_dev) {
+  if (count_dev == nullptr) return capacity;
+  const int64_t n = *count_dev;
+  return n < capacity ? n : capacity;
+}
+
+// radix_sort.cu: the onesweep sort of (u32 key, u32 value) pairs on key bits [0, end_bit) for up to `capacity` pairs,
+// min(capacity, *count_dev) of which are live.  *result_in_b (host) = the sorted data ended in the b buffers.
+int64_t radix_sort_workspace_bytes(int64_t capacity, int end_bit);
+int radix_sort_pairs_u32(int64_t capacity, const int64_t* count_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
+                         uint32_t* vals_b, int end_bit, void* workspace, int64_t workspace_bytes, int* result_in_b,
+                         cudaStream_t stream);
 inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 }  // namespace egs

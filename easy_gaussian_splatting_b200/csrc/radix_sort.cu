@@ -53,7 +53,9 @@ constexpr int kHistItems = 16;
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kHistThreads) radix_histogram_kernel(const KeyT* __restrict__ keys, int64_t n,
-                                                                        int passes, uint32_t* __restrict__ hist) {
+                                                                        const int64_t* __restrict__ n_dev, int passes,
+                                                                        uint32_t* __restrict__ hist) {
+  n = live_count(n, n_dev);
   // Each thread walks kHistItems CONSECUTIVE keys and combines runs of equal digits in a register before
   // touching shared memory.  The keys of this path come out of isect_emit in runs that share the depth
   // word and most of the tile id (one Gaussian = one run), so almost every shared-memory atomic
@@ -156,9 +158,11 @@ struct SortSmem {
 template <typename KeyT, int ITEMS>
 __global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 : 2) radix_onesweep_kernel(
     const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
-    uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ digit_base /*[256]*/,
-    uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ status /*[ntiles][256]*/) {
+    uint32_t* __restrict__ vals_out, int64_t n, const int64_t* __restrict__ n_dev, int shift,
+    const uint32_t* __restrict__ digit_base /*[256]*/, uint32_t* __restrict__ tile_counter,
+    uint32_t* __restrict__ status /*[ntiles][256]*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  n = live_count(n, n_dev);  // the grid covers the capacity; tiles past the live count leave at once (below)
   constexpr int kSortItems = ITEMS, kSortTile = kSortThreads * ITEMS, kWarpSpan = 32 * ITEMS;
   SortSmem<KeyT, ITEMS>& sm = *reinterpret_cast<SortSmem<KeyT, ITEMS>*>(smem_raw);
 
@@ -169,6 +173,7 @@ __global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 
   __syncthreads();
   const uint32_t tile = sm.tile;
   const int64_t tile_base = (int64_t)tile * kSortTile;
+  if (tile_base >= n) return;  // block-uniform; no later tile can wait for this one (it is past the data too)
   const int tile_count = (int)min((int64_t)kSortTile, n - tile_base);
 
   // (a) load, warp-striped: item i of lane l in warp w is element w*256 + i*32 + l of the tile
@@ -341,12 +346,12 @@ extern "C" int64_t egs_radix_sort_workspace_bytes(int64_t n, int32_t end_bit) {
 }
 
 template <typename KeyT, int ITEMS>
-static int run_passes(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int passes,
-                      const SortWorkspace& w, cudaStream_t stream);
+static int run_passes(int64_t n, const int64_t* n_dev, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
+                      int passes, const SortWorkspace& w, cudaStream_t stream);
 
 template <typename KeyT>
-static int radix_sort_pairs_impl(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
-                                 int32_t end_bit, void* workspace, int64_t workspace_bytes,
+static int radix_sort_pairs_impl(int64_t n, const int64_t* n_dev, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b,
+                                 uint32_t* vals_b, int32_t end_bit, void* workspace, int64_t workspace_bytes,
                                  int32_t* host_result_in_b, cudaStream_t stream) {
   constexpr int kKeyBits = (int)sizeof(KeyT) * 8;
   EGS_REQUIRE(n >= 0, "radix_sort: n=%lld < 0", (long long)n);
@@ -368,17 +373,17 @@ static int radix_sort_pairs_impl(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT
   EGS_CUDA(cudaMemsetAsync(workspace, 0, clear_bytes, stream));
   int64_t hist_blocks = ceil_div(n, (int64_t)kHistThreads * kHistItems);
   if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-  radix_histogram_kernel<KeyT><<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, passes, w.hist);
+  radix_histogram_kernel<KeyT><<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, n_dev, passes, w.hist);
   radix_scan_hist_kernel<<<passes, kRadix, 0, stream>>>(w.hist);
   // pairs per thread: 8 for 64-bit keys (a 16-item tile would need 2 x the shared memory and drop to one CTA per SM);
   // EGS_SORT_ITEMS_U32 for 32-bit keys (build-time A/B knob, scripts/build_variant.py)
-  if constexpr (sizeof(KeyT) == 4) return run_passes<KeyT, EGS_SORT_ITEMS_U32>(n, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
-  else return run_passes<KeyT, 8>(n, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
+  if constexpr (sizeof(KeyT) == 4) return run_passes<KeyT, EGS_SORT_ITEMS_U32>(n, n_dev, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
+  else return run_passes<KeyT, 8>(n, n_dev, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
 }
 
 template <typename KeyT, int ITEMS>
-static int run_passes(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int passes,
-                      const SortWorkspace& w, cudaStream_t stream) {
+static int run_passes(int64_t n, const int64_t* n_dev, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
+                      int passes, const SortWorkspace& w, cudaStream_t stream) {
   constexpr int kSmem = (int)sizeof(SortSmem<KeyT, ITEMS>);
   const cudaError_t attr_rc =  // per-device attribute: set on every call (cheap), not once per process
       cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
@@ -390,7 +395,7 @@ static int run_passes(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, u
   KeyT* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < passes; ++p) {
     radix_onesweep_kernel<KeyT, ITEMS><<<(unsigned)ntiles, kSortThreads, kSmem, stream>>>(
-        kin, vin, kout, vout, n, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
+        kin, vin, kout, vout, n, n_dev, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
         w.status + (size_t)p * status_stride);
     KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
@@ -398,11 +403,21 @@ static int run_passes(int64_t n, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, u
   return check_launch("radix_sort_pairs", passes + 2);  // + histogram + histogram scan
 }
 
+namespace egs {
+int64_t radix_sort_workspace_bytes(int64_t capacity, int end_bit) { return egs_radix_sort_workspace_bytes(capacity, end_bit); }
+int radix_sort_pairs_u32(int64_t capacity, const int64_t* count_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
+                         uint32_t* vals_b, int end_bit, void* workspace, int64_t workspace_bytes, int* result_in_b,
+                         cudaStream_t stream) {
+  return radix_sort_pairs_impl<uint32_t>(capacity, count_dev, keys_a, vals_a, keys_b, vals_b, end_bit, workspace,
+                                         workspace_bytes, result_in_b, stream);
+}
+}  // namespace egs
+
 extern "C" int egs_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
                                             uint32_t* vals_b, int32_t end_bit, void* workspace,
                                             int64_t workspace_bytes, int32_t* host_result_in_b,
                                             egs_stream_t stream) {
-  return radix_sort_pairs_impl<uint64_t>(n, keys_a, vals_a, keys_b, vals_b, end_bit, workspace, workspace_bytes,
+  return radix_sort_pairs_impl<uint64_t>(n, nullptr, keys_a, vals_a, keys_b, vals_b, end_bit, workspace, workspace_bytes,
                                          host_result_in_b, (cudaStream_t)stream);
 }
 
@@ -410,6 +425,6 @@ extern "C" int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_
                                             uint32_t* vals_b, int32_t end_bit, void* workspace,
                                             int64_t workspace_bytes, int32_t* host_result_in_b,
                                             egs_stream_t stream) {
-  return radix_sort_pairs_impl<uint32_t>(n, keys_a, vals_a, keys_b, vals_b, end_bit, workspace, workspace_bytes,
+  return radix_sort_pairs_impl<uint32_t>(n, nullptr, keys_a, vals_a, keys_b, vals_b, end_bit, workspace, workspace_bytes,
                                          host_result_in_b, (cudaStream_t)stream);
 }

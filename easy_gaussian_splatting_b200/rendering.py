@@ -94,16 +94,39 @@ def _tag_absgrad(target: Tensor, absgrad: Tensor, packed_index: Optional[Tensor]
     target.absgrad = absgrad if packed_index is None else absgrad.reshape(-1, 2)[packed_index]
 
 
-def _blend_forward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width, height, grad_enabled=True):
-    """Blend forward; when a backward pass will follow and long-list segmentation is on, the checkpointed variant.
+def _bin_and_blend(ctx, proj, backgrounds, width, height, grad_enabled=True):
+    """Binning + blend forward, enqueued without waiting for the intersection count (stages.isect_sorted_async): the
+    buffers are sized from the previous call of this shape, the count is looked at only after the blend forward is
+    in the queue, and a guess that turns out too small is repaired by running both again with the exact size.
+    When a backward pass will follow and the previous call saw outlier-long tile lists, the checkpointed forward is
+    used so that the backward pass can replay those lists in segments (stages.segment_policy).
     (grad_enabled is the CALLER's grad mode: inside Function.forward it is always off, and needs_input_grad stays
     true under no_grad.)"""
-    seg = stages.backward_segment() if (grad_enabled and any(ctx.needs_input_grad)) else 0
-    ctx.segment = seg
-    with stages.nvtx_range("egs.rasterize_fwd"):
-        if seg > 0:
-            return stages.rasterize_fwd_checkpointed(splats, isect_offsets, flatten_ids, backgrounds, width, height, seg)
-        return (*stages.rasterize_fwd(splats, isect_offsets, flatten_ids, backgrounds, width, height), None)
+    tw, th = stages.tile_grid(width, height)
+    C = proj["radii"].shape[0]
+    dev = proj["radii"].device
+    seg, seg_min = 0, 0
+    if grad_enabled and any(ctx.needs_input_grad):
+        seg, seg_min = stages.segment_policy(stages.binning_hint(C, tw, th, dev), C * tw * th)
+    capacity = None
+    while True:
+        with stages.nvtx_range("egs.binning"):
+            b = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"],
+                                          stages.TILE_SIZE, tw, th, capacity=capacity)
+        with stages.nvtx_range("egs.rasterize_fwd"):
+            if seg > 0:
+                rc, ra, last, ckpt = stages.rasterize_fwd_checkpointed(proj["splats"], b.offsets, b.flat_cap, backgrounds, width,
+                                                                       height, seg, seg_min_len=seg_min, n_isects=b.raster_n)
+            else:
+                rc, ra, last = stages.rasterize_fwd(proj["splats"], b.offsets, b.flat_cap, backgrounds, width, height,
+                                                    n_isects=b.raster_n)
+                ckpt = None
+        if b.resolve():
+            break
+        capacity = b.n_isects  # the guess was too small (rare): same route again, exactly sized
+    b.note_for_next_call()
+    ctx.segment, ctx.seg_min_len, ctx.raster_n = seg, seg_min, b.raster_n
+    return b, rc, ra, last, ckpt
 
 
 def _blend_backward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_colors, render_alphas,
@@ -111,9 +134,10 @@ def _blend_backward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width,
     with stages.nvtx_range("egs.rasterize_bwd"):
         if ckpt is not None:
             return stages.rasterize_bwd_segmented(splats, isect_offsets, flatten_ids, backgrounds, width, height,
-                                                  render_colors, render_alphas, last_ids, v_colors, v_alphas, ckpt, ctx.segment)
+                                                  render_colors, render_alphas, last_ids, v_colors, v_alphas, ckpt, ctx.segment,
+                                                  seg_min_len=ctx.seg_min_len, n_isects=ctx.raster_n)
         return stages.rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, render_alphas, last_ids,
-                                    v_colors, v_alphas)
+                                    v_colors, v_alphas, n_isects=ctx.raster_n)
 
 
 class _Rasterization(torch.autograd.Function):
@@ -131,21 +155,18 @@ class _Rasterization(torch.autograd.Function):
                                          eps2d=cfg["eps2d"], near_plane=cfg["near_plane"], far_plane=cfg["far_plane"],
                                          radius_clip=cfg["radius_clip"], antialiased=cfg["antialiased"])
         cfg["compensations"] = proj.get("compensations")  # non-differentiable side output, like the thunk below
-        tw, th = stages.tile_grid(width, height)
         tiles_per_gauss = proj["tiles_per_gauss"]
-        with stages.nvtx_range("egs.binning"):
-            isect_ids_thunk, flatten_ids, isect_offsets = stages.isect_sorted(
-                proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th,
-                materialize_ids=False)
-        cfg["isect_ids_thunk"] = isect_ids_thunk  # handed to the wrapper (not a tensor: cannot be an output)
-        render_colors, render_alphas, last_ids, ckpt = _blend_forward(ctx, proj["splats"], isect_offsets, flatten_ids,
-                                                                     backgrounds, width, height, cfg.get("grad_enabled", True))
+        binned, render_colors, render_alphas, last_ids, ckpt = _bin_and_blend(ctx, proj, backgrounds, width, height,
+                                                                             cfg.get("grad_enabled", True))
+        cfg["isect_ids_thunk"] = binned.isect_ids  # handed to the wrapper (not a tensor: cannot be an output)
+        flatten_ids, isect_offsets = binned.flatten_ids, binned.offsets
 
         means2d = proj["means2d"]
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)
+        # the backward pass walks the same (capacity-sized) list buffer the forward kernels used
         ctx.save_for_backward(means, quats, scales, colors, viewmats, Ks, backgrounds, proj["radii"], proj["colors"],
-                              proj["splats"], isect_offsets, flatten_ids, render_alphas, last_ids,
+                              proj["splats"], isect_offsets, binned.flat_cap, render_alphas, last_ids,
                               opacities, ckpt, render_colors if ckpt is not None else None)
         nondiff = (proj["radii"], proj["depths"], proj["conics"], proj["colors"], tiles_per_gauss,
                    flatten_ids, isect_offsets, last_ids)
@@ -195,19 +216,15 @@ class _RasterizationRaw(torch.autograd.Function):
             proj = stages.projection_fwd_raw(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, width,
                                              height, sh_degree, eps2d=cfg["eps2d"], near_plane=cfg["near_plane"],
                                              far_plane=cfg["far_plane"], radius_clip=cfg["radius_clip"])
-        tw, th = stages.tile_grid(width, height)
         tiles_per_gauss = proj["tiles_per_gauss"]
-        with stages.nvtx_range("egs.binning"):
-            isect_ids_thunk, flatten_ids, isect_offsets = stages.isect_sorted(
-                proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss, stages.TILE_SIZE, tw, th,
-                materialize_ids=False)
-        cfg["isect_ids_thunk"] = isect_ids_thunk
-        render_colors, render_alphas, last_ids, ckpt = _blend_forward(ctx, proj["splats"], isect_offsets, flatten_ids,
-                                                                     backgrounds, width, height, cfg.get("grad_enabled", True))
+        binned, render_colors, render_alphas, last_ids, ckpt = _bin_and_blend(ctx, proj, backgrounds, width, height,
+                                                                             cfg.get("grad_enabled", True))
+        cfg["isect_ids_thunk"] = binned.isect_ids
+        flatten_ids, isect_offsets = binned.flatten_ids, binned.offsets
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds,
-                              proj["radii"], proj["colors"], proj["splats"], isect_offsets, flatten_ids, render_alphas,
+                              proj["radii"], proj["colors"], proj["splats"], isect_offsets, binned.flat_cap, render_alphas,
                               last_ids, ckpt, render_colors if ckpt is not None else None)
         nondiff = (proj["radii"], proj["depths"], proj["conics"], proj["colors"], tiles_per_gauss,
                    flatten_ids, isect_offsets, last_ids)

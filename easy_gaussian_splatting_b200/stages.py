@@ -15,7 +15,7 @@ import math
 import os
 import threading
 import weakref
-from typing import Dict, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -377,14 +377,146 @@ def radix_sort_pairs_u32(keys: Tensor, vals: Tensor, end_bit: int) -> Tuple[Tens
     return (keys_b, vals_b) if in_b.value else (keys, vals)
 
 
-def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
-                 tile_width: int, tile_height: int, materialize_ids: bool = True):
-    """g3+g4+g5 fast path -> (isect_ids[n] i64 sorted, flatten_ids[n] i32, isect_offsets[C,th,tw] i32).
+# ---- binning without a host round trip --------------------------------------------------------------------------------
+# The sizes of the intersection buffers depend on a count that only the device knows.  Instead of waiting for it
+# (one blocking read per forward pass, during which nothing new is enqueued), a call sizes its buffers from what the
+# previous call of the same shape needed (+ 25 %), enqueues the whole route — every kernel reads the live counts on
+# the device — plus the blend forward, and only THEN looks at the counts, which were copied to pinned host memory
+# right after the first scan and have long arrived.  If the guess was too small the route is enqueued again with the
+# exact size (rare: the count changes slowly from view to view).  The first call of a shape has no guess and waits.
+_HINT_LOCK = threading.Lock()
+_HINTS: Dict[Tuple[int, int, int, int], Dict[str, int]] = {}
+_PINNED: Dict[int, Tuple[Tensor, List[int]]] = {}
+_PINNED_SLOTS = 256
+_CAPACITY_SLACK = 1.25
 
-    Bit-identical to ``isect_tiles(sort=True)`` + ``isect_offset_encode`` (a stable sort on cam|tile|depth
-    equals a stable depth sort of the visible Gaussians followed by a stable sort on the tile index), but the
-    n_isects-sized passes move 8-byte pairs through 2-3 radix passes instead of 12-byte pairs through 6.
-    With ``materialize_ids=False`` the first element is a zero-argument callable that builds isect_ids on demand."""
+
+def _pinned_slot(dev: torch.device) -> Tensor:
+    """A 4 x int64 slot of a per-device ring of pinned host memory (allocated once: cudaHostAlloc is slow)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    with _HINT_LOCK:
+        ring = _PINNED.get(key)
+        if ring is None:
+            ring = (torch.empty(_PINNED_SLOTS, 4, dtype=torch.int64).pin_memory(), [0])
+            _PINNED[key] = ring
+        buf, nxt = ring
+        i = nxt[0]
+        nxt[0] = (i + 1) % _PINNED_SLOTS
+    return buf[i]
+
+
+def reset_binning_hints() -> None:
+    """Forget what previous calls needed (the next call of every shape sizes its buffers exactly, with one wait)."""
+    with _HINT_LOCK:
+        _HINTS.clear()
+
+
+class SortedIsects:
+    """Result of ``isect_sorted_async``: buffers sized for ``capacity`` intersections and the pending counts."""
+
+    def __init__(self, key, C, n_tiles, capacity, tile_keys, flat, offsets_store, offsets, depths, stats_dev, early, early_event, exact):
+        self.key, self.C, self.n_tiles, self.capacity = key, C, n_tiles, capacity
+        self.tile_keys_cap, self.flat_cap, self.offsets_store, self.offsets = tile_keys, flat, offsets_store, offsets
+        self.depths, self.stats_dev = depths, stats_dev
+        self._early, self._early_event = early, early_event
+        self.n_vis: Optional[int] = None
+        self.n_isects: Optional[int] = None
+        self.exact = exact  # the capacity IS the count (first call of a shape, or the re-run after a wrong guess)
+
+    @property
+    def raster_n(self) -> int:
+        """What the egs_rasterize_* entries take as n_isects: -capacity = 'read the live length behind the offsets'."""
+        return -self.capacity
+
+    def resolve(self) -> bool:
+        """Waits for the counts (normally long there).  False = the guess was too small: the buffers hold a truncated
+        binning and the caller must run the route again with ``capacity=self.n_isects``."""
+        if self.n_isects is None:
+            self._early_event.synchronize()
+            self.n_vis, self.n_isects = int(self._early[0]), int(self._early[1])
+            if self.n_isects >= 2 ** 31 - 1:
+                raise RuntimeError(f"{self.n_isects} tile intersections do not fit int32 offsets; render fewer cameras per call")
+        return self.n_isects <= self.capacity
+
+    def note_for_next_call(self) -> None:
+        """Leaves the hint for the next call of this shape and queues the late statistic (longest tile list) for it."""
+        dev = self.flat_cap.device
+        late = _pinned_slot(dev)
+        late.copy_(self.stats_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        with _HINT_LOCK:
+            _HINTS[self.key] = {"n_isects": self.n_isects, "late": late, "late_event": ev}
+
+    @property
+    def flatten_ids(self) -> Tensor:
+        return self.flat_cap[:self.n_isects]
+
+    def isect_ids(self) -> Tensor:
+        """The 64-bit sorted keys, rebuilt from the 32-bit (camera, tile) keys and the depths (bit-identical)."""
+        lib = _lib.load()
+        dev = self.flat_cap.device
+        n = self.n_isects
+        ids = torch.empty(n, dtype=torch.int64, device=dev)
+        if n == 0:
+            return ids
+        nbits = tile_n_bits_from_count(self.n_tiles)
+        with torch.cuda.device(dev):
+            rc = lib.egs_isect_finalize(n, _ptr(self.tile_keys_cap), _ptr(self.flat_cap), _ptr(self.depths), self.C, self.n_tiles,
+                                        nbits, _ptr(ids), None, _stream(dev))
+        _lib.check(rc, "egs_isect_finalize")
+        return ids
+
+
+class ResolvedIsects:
+    """A binning whose sizes are already known, behind the interface of ``SortedIsects`` (synchronous producers:
+    the classic route, test stand-ins)."""
+
+    exact = True
+    raster_n = None  # the rasterize operators then take len(flatten_ids)
+
+    def __init__(self, isect_ids, flatten_ids: Tensor, offsets: Tensor):
+        self._ids, self.flat_cap, self.offsets = isect_ids, flatten_ids, offsets
+        self.n_isects = flatten_ids.numel()
+        self.capacity = max(self.n_isects, 1)
+
+    def resolve(self) -> bool:
+        return True
+
+    def note_for_next_call(self) -> None:
+        pass
+
+    @property
+    def flatten_ids(self) -> Tensor:
+        return self.flat_cap
+
+    def isect_ids(self) -> Tensor:
+        return self._ids() if callable(self._ids) else self._ids
+
+
+def tile_n_bits_from_count(n_tiles: int) -> int:
+    return int(math.floor(math.log2(n_tiles))) + 1
+
+
+def binning_hint(C: int, tile_width: int, tile_height: int, device) -> Optional[Dict[str, int]]:
+    """What the previous call of this shape on this device needed: {'n_isects', 'max_tile_len' (if it has arrived)}."""
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), C, tile_width, tile_height)
+    with _HINT_LOCK:
+        h = _HINTS.get(key)
+        if h is None:
+            return None
+        out = {"n_isects": h["n_isects"]}
+        if h["late_event"].query():  # never waits: a hint that has not arrived yet is simply not used
+            out["max_tile_len"] = int(h["late"][2])
+        return out
+
+
+def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
+                       tile_width: int, tile_height: int, capacity: Optional[int] = None) -> SortedIsects:
+    """g3+g4+g5, enqueued without waiting for the intersection count (see the block comment above).  ``capacity``:
+    intersections to provide room for; None = from the previous call of this shape, or — first call — wait and size
+    exactly."""
     lib = _lib.load()
     means2d, depths = _f32c(means2d, "means2d"), _f32c(depths, "depths")
     radii, tiles_per_gauss = radii.contiguous(), tiles_per_gauss.contiguous()
@@ -392,55 +524,61 @@ def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss
     dev = radii.device
     n = C * N
     n_tiles = tile_width * tile_height
-    nbits = tile_n_bits(tile_width, tile_height)
-    ws_bytes = max(lib.egs_isect_scan_workspace_bytes(max(n, 1)), 16)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    totals = torch.empty(2, dtype=torch.int64, device=dev)
-    keys1 = torch.empty(n, dtype=torch.int32, device=dev)  # upper bound n_vis <= C*N; sliced after the sync
-    vals1 = torch.empty(n, dtype=torch.int32, device=dev)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), C, tile_width, tile_height)
+    ws_scan = max(lib.egs_isect_scan_workspace_bytes(max(n, 1)), 16)
+    scan_ws = torch.empty(ws_scan, dtype=torch.uint8, device=dev)
+    stats = torch.empty(4, dtype=torch.int64, device=dev)
+    keys1 = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    vals1 = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.egs_isect_visible_keys(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(keys1), _ptr(vals1),
-                                        _ptr(totals), _ptr(ws), ws_bytes, _stream(dev))
+        rc = lib.egs_isect_visible_keys(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(keys1), _ptr(vals1), _ptr(stats),
+                                        _ptr(scan_ws), ws_scan, _stream(dev))
     _lib.check(rc, "egs_isect_visible_keys")
-    n_vis, n_isects = (int(v) for v in totals.tolist())  # the one host sync of the forward pass
-    offsets = torch.empty(C, tile_height, tile_width, dtype=torch.int32, device=dev)
-    if n_isects == 0:
-        offsets.zero_()
-        empty_ids = torch.empty(0, dtype=torch.int64, device=dev)
-        return (empty_ids if materialize_ids else (lambda: empty_ids)), torch.empty(0, dtype=torch.int32, device=dev), offsets
-    if n_isects >= 2 ** 31 - 1:
-        raise RuntimeError(f"{n_isects} tile intersections do not fit int32 offsets; render fewer cameras per call")
-    # level 1: visible entries of all cameras in (depth, flat index) order
-    k1, order = radix_sort_pairs_u32(keys1[:n_vis], vals1[:n_vis], level1_end_bit(C))
-    # tile counts in that order -> write offsets
-    cum = torch.empty(n_vis, dtype=torch.int64, device=dev)
-    total2 = torch.empty(1, dtype=torch.int64, device=dev)
-    tile_keys = torch.empty(n_isects, dtype=torch.int32, device=dev)
-    flat_vals = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    early = _pinned_slot(dev)
+    early.copy_(stats, non_blocking=True)
+    early_event = torch.cuda.Event()
+    early_event.record(torch.cuda.current_stream(dev))
+    exact = False
+    if capacity is None:
+        with _HINT_LOCK:
+            h = _HINTS.get(key)
+        if h is not None:
+            capacity = int(h["n_isects"] * _CAPACITY_SLACK) + 65536
+        else:  # no guess: the one blocking read, as in every call before round 2
+            early_event.synchronize()
+            capacity, exact = int(early[1]), True
+    else:
+        exact = True
+    capacity = max(1, min(int(capacity), 2 ** 31 - 2))
+    tile_keys = torch.empty(capacity, dtype=torch.int32, device=dev)
+    flat = torch.empty(capacity, dtype=torch.int32, device=dev)
+    offsets_store = torch.empty(C * n_tiles + 1, dtype=torch.int32, device=dev)
+    offsets = offsets_store[:C * n_tiles].view(C, tile_height, tile_width)
+    ws_bytes = lib.egs_isect_sorted_workspace_bytes(C, N, n_tiles, capacity)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.egs_exclusive_scan_gather(n_vis, _ptr(tiles_per_gauss), _ptr(order), _ptr(cum), _ptr(total2), _ptr(ws),
-                                           ws_bytes, _stream(dev))
-        _lib.check(rc, "egs_exclusive_scan_gather")
-        rc = lib.egs_isect_emit_sorted(C, N, n_vis, _ptr(order), _ptr(cum), _ptr(means2d), _ptr(radii), int(tile_size),
-                                       tile_width, tile_height, n_isects, _ptr(tile_keys), _ptr(flat_vals), _stream(dev))
-        _lib.check(rc, "egs_isect_emit_sorted")
-    # level 2: stable sort on the dense (camera, tile) index
-    end_bit = max(1, int(C * n_tiles - 1).bit_length())
-    tile_keys, flat_vals = radix_sort_pairs_u32(tile_keys, flat_vals, end_bit)
+        rc = lib.egs_isect_sorted(C, N, _ptr(tiles_per_gauss), _ptr(means2d), _ptr(radii), _ptr(keys1), _ptr(vals1), _ptr(stats),
+                                  int(tile_size), tile_width, tile_height, capacity, _ptr(ws), ws.numel(), _ptr(tile_keys),
+                                  _ptr(flat), _ptr(offsets_store), _stream(dev))
+    _lib.check(rc, "egs_isect_sorted")
+    return SortedIsects(key, C, n_tiles, capacity, tile_keys, flat, offsets_store, offsets, depths, stats, early, early_event, exact)
 
-    def finalize(want_ids: bool, want_offsets: bool):
-        ids = torch.empty(n_isects, dtype=torch.int64, device=dev) if want_ids else None
-        with torch.cuda.device(dev):
-            rc_ = lib.egs_isect_finalize(n_isects, _ptr(tile_keys), _ptr(flat_vals), _ptr(depths), C, n_tiles, nbits,
-                                         _ptr(ids), _ptr(offsets) if want_offsets else None, _stream(dev))
-        _lib.check(rc_, "egs_isect_finalize")
-        return ids
 
-    if materialize_ids:
-        return finalize(True, True), flat_vals, offsets
-    finalize(False, True)
-    # the 64-bit keys are only meta data for the caller: rebuild them (bit-identically) on first access
-    return (lambda: finalize(True, False)), flat_vals, offsets
+def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
+                 tile_width: int, tile_height: int, materialize_ids: bool = True):
+    """g3+g4+g5 fast path -> (isect_ids[n] i64 sorted, flatten_ids[n] i32, isect_offsets[C,th,tw] i32).
+
+    Bit-identical to ``isect_tiles(sort=True)`` + ``isect_offset_encode`` (a stable sort on cam|tile|depth
+    equals a stable depth sort of the visible entries followed by a stable sort on the (camera, tile) index), but the
+    n_isects-sized passes move 8-byte pairs through 2-3 radix passes instead of 12-byte pairs through 6.
+    With ``materialize_ids=False`` the first element is a zero-argument callable that builds isect_ids on demand.
+    This is the synchronous form (exact-length tensors on return); ``rasterization()`` uses ``isect_sorted_async``."""
+    b = isect_sorted_async(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height)
+    if not b.resolve():
+        b = isect_sorted_async(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height, capacity=b.n_isects)
+        b.resolve()
+    b.note_for_next_call()
+    return (b.isect_ids() if materialize_ids else b.isect_ids), b.flatten_ids, b.offsets
 
 
 def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height: int) -> Tensor:
@@ -465,8 +603,10 @@ def pack_splats(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tens
 
 
 def rasterize_fwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],
-                  width: int, height: int, count_pairs: bool = False):
-    """g6 -> render_colors[C,H,W,3], render_alphas[C,H,W,1], last_ids[C,H,W] (, (P_eval, P_acc) tensor)."""
+                  width: int, height: int, count_pairs: bool = False, n_isects: Optional[int] = None):
+    """g6 -> render_colors[C,H,W,3], render_alphas[C,H,W,1], last_ids[C,H,W] (, (P_eval, P_acc) tensor).
+    n_isects: None = len(flatten_ids); negative = -capacity, the live length sits behind the offsets
+    (``SortedIsects.raster_n``; isect_offsets must then be the view ``SortedIsects.offsets``)."""
     lib = _lib.load()
     dev = splats.device
     C, N = splats.shape[:2]
@@ -475,8 +615,8 @@ def rasterize_fwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, ba
     alphas = torch.empty(C, height, width, 1, dtype=torch.float32, device=dev)
     last = torch.empty(C, height, width, dtype=torch.int32, device=dev)
     bg = None if backgrounds is None else _f32c(backgrounds, "backgrounds")
-    args = [C, N, flatten_ids.numel(), _ptr(splats), _ptr(isect_offsets), _ptr(flatten_ids), _ptr(bg), int(width),
-            int(height), tw, th, _ptr(colors), _ptr(alphas), _ptr(last)]
+    args = [C, N, flatten_ids.numel() if n_isects is None else int(n_isects), _ptr(splats), _ptr(isect_offsets),
+            _ptr(flatten_ids), _ptr(bg), int(width), int(height), tw, th, _ptr(colors), _ptr(alphas), _ptr(last)]
     with torch.cuda.device(dev):
         if count_pairs:
             counters = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -487,27 +627,55 @@ def rasterize_fwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, ba
     return (colors, alphas, last, counters) if count_pairs else (colors, alphas, last)
 
 
-def backward_segment() -> int:
-    """List entries per backward-replay segment; 0 (the default) = off.  With EGS_BWD_SEGMENT=<multiple of 64> tile
-    lists longer than that are replayed by one warp per segment instead of one warp per tile half.  Measured
-    (BASELINE.md section 5): object-centric scenes whose few hundred busy tiles hold 5-6 k entries gain 7-14 % at 256-512;
-    scenes with ordinary lists (the 1 M-Gaussian benchmark, ~900 entries per tile) lose 2-5 % to the checkpoint stores
-    and the extra launch, hence opt-in."""
-    v = int(os.environ.get("EGS_BWD_SEGMENT", "0"))
+def backward_segment() -> Optional[int]:
+    """EGS_BWD_SEGMENT=<0 or a multiple of 64>: experiment override of the automatic policy below (0 = never segment,
+    K = replay every list longer than K in K-entry segments).  Unset (the default) = automatic."""
+    v = os.environ.get("EGS_BWD_SEGMENT")
+    if v is None or v == "":
+        return None
+    v = int(v)
     if v < 0 or v % 64 != 0:
         raise ValueError(f"EGS_BWD_SEGMENT={v}: must be 0 or a multiple of 64")
     return v
 
 
+SEGMENT_ENTRIES = 512      # list entries per replay segment
+SEGMENT_MIN_ENTRIES = 1024  # never segment lists shorter than this
+SEGMENT_MIN_RATIO = 3.0    # ... or shorter than this many times the average list
+
+
+def segment_policy(hint: Optional[Dict[str, int]], n_tiles_total: int) -> Tuple[int, int]:
+    """-> (segment, seg_min_len) for a forward pass that will be differentiated; (0, 0) = no segmented replay.
+
+    A tile list that is several times longer than the average makes the backward pass wait for ONE warp per tile half
+    walking it (object scenes rendered one view per call: a few hundred tiles hold 5-6 k entries, the average is ~500).
+    Such lists — and only those — are replayed in 512-entry segments, one warp each (csrc/blend.cu).  Whether a scene
+    has them is taken from the previous call of the same shape (``binning_hint``: intersection count and longest
+    list, read back without waiting): measured on the one-view-per-call pattern, object scene 1.22 -> 1.10 ms per
+    view; a scene without outliers (the 1 M-Gaussian benchmark: longest list 2.2 x the average) is left alone, where
+    segmenting everything longer than 512 entries cost 10 % (gpurun_out/r2c_knobs.log)."""
+    forced = backward_segment()
+    if forced is not None:
+        return (forced, forced + 1) if forced > 0 else (0, 0)
+    if hint is None or "max_tile_len" not in hint:
+        return 0, 0
+    mean = hint["n_isects"] / max(n_tiles_total, 1)
+    min_len = max(SEGMENT_MIN_ENTRIES, int(SEGMENT_MIN_RATIO * mean))
+    if hint["max_tile_len"] >= min_len:
+        return SEGMENT_ENTRIES, min_len
+    return 0, 0
+
+
 def rasterize_fwd_checkpointed(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor,
-                               backgrounds: Optional[Tensor], width: int, height: int, segment: int):
+                               backgrounds: Optional[Tensor], width: int, height: int, segment: int,
+                               seg_min_len: int = 0, n_isects: Optional[int] = None):
     """g6 for a forward that will be differentiated: as rasterize_fwd, plus the per-pixel state after every
     `segment` entries of a tile's list -> render_colors, render_alphas, last_ids, checkpoints."""
     lib = _lib.load()
     dev = splats.device
     C, N = splats.shape[:2]
     th, tw = isect_offsets.shape[1:]
-    n_isects = flatten_ids.numel()
+    n_isects = flatten_ids.numel() if n_isects is None else int(n_isects)
     colors = torch.empty(C, height, width, 3, dtype=torch.float32, device=dev)
     alphas = torch.empty(C, height, width, 1, dtype=torch.float32, device=dev)
     last = torch.empty(C, height, width, dtype=torch.int32, device=dev)
@@ -516,14 +684,15 @@ def rasterize_fwd_checkpointed(splats: Tensor, isect_offsets: Tensor, flatten_id
     with torch.cuda.device(dev):
         rc = lib.egs_rasterize_fwd_checkpointed(C, N, n_isects, _ptr(splats), _ptr(isect_offsets), _ptr(flatten_ids),
                                                 _ptr(bg), int(width), int(height), tw, th, _ptr(colors), _ptr(alphas),
-                                                _ptr(last), _ptr(ckpt), int(segment), _stream(dev))
+                                                _ptr(last), _ptr(ckpt), int(segment), int(seg_min_len), _stream(dev))
     _lib.check(rc, "egs_rasterize_fwd_checkpointed")
     return colors, alphas, last, ckpt
 
 
 def rasterize_bwd_segmented(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],
                             width: int, height: int, render_colors: Tensor, render_alphas: Tensor, last_ids: Tensor,
-                            v_render_colors: Tensor, v_render_alphas: Tensor, checkpoints: Tensor, segment: int) -> Tensor:
+                            v_render_colors: Tensor, v_render_alphas: Tensor, checkpoints: Tensor, segment: int,
+                            seg_min_len: int = 0, n_isects: Optional[int] = None) -> Tensor:
     """g7 with one warp per list segment (see include/egs_raster.h) -> v_splats[C,N,12]."""
     lib = _lib.load()
     dev = splats.device
@@ -533,17 +702,17 @@ def rasterize_bwd_segmented(splats: Tensor, isect_offsets: Tensor, flatten_ids: 
     bg = None if backgrounds is None else _f32c(backgrounds, "backgrounds")
     v_c, v_a = _f32c(v_render_colors, "v_render_colors"), _f32c(v_render_alphas, "v_render_alphas")
     with torch.cuda.device(dev):
-        rc = lib.egs_rasterize_bwd_segmented(C, N, flatten_ids.numel(), _ptr(splats), _ptr(isect_offsets),
-                                             _ptr(flatten_ids), _ptr(bg), int(width), int(height), tw, th,
+        rc = lib.egs_rasterize_bwd_segmented(C, N, flatten_ids.numel() if n_isects is None else int(n_isects), _ptr(splats),
+                                             _ptr(isect_offsets), _ptr(flatten_ids), _ptr(bg), int(width), int(height), tw, th,
                                              _ptr(render_colors), _ptr(render_alphas), _ptr(last_ids), _ptr(v_c), _ptr(v_a),
-                                             _ptr(checkpoints), int(segment), _ptr(v_splats), _stream(dev))
+                                             _ptr(checkpoints), int(segment), int(seg_min_len), _ptr(v_splats), _stream(dev))
     _lib.check(rc, "egs_rasterize_bwd_segmented")
     return v_splats
 
 
 def rasterize_bwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],
                   width: int, height: int, render_alphas: Tensor, last_ids: Tensor, v_render_colors: Tensor,
-                  v_render_alphas: Tensor) -> Tensor:
+                  v_render_alphas: Tensor, n_isects: Optional[int] = None) -> Tensor:
     """g7 -> packed gradient records v_splats[C,N,12] (layout in include/egs_raster.h)."""
     lib = _lib.load()
     dev = splats.device
@@ -553,7 +722,8 @@ def rasterize_bwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, ba
     bg = None if backgrounds is None else _f32c(backgrounds, "backgrounds")
     v_c, v_a = _f32c(v_render_colors, "v_render_colors"), _f32c(v_render_alphas, "v_render_alphas")
     with torch.cuda.device(dev):
-        rc = lib.egs_rasterize_bwd(C, N, flatten_ids.numel(), _ptr(splats), _ptr(isect_offsets), _ptr(flatten_ids),
+        rc = lib.egs_rasterize_bwd(C, N, flatten_ids.numel() if n_isects is None else int(n_isects), _ptr(splats),
+                                   _ptr(isect_offsets), _ptr(flatten_ids),
                                    _ptr(bg), int(width), int(height), tw, th, _ptr(render_alphas), _ptr(last_ids),
                                    _ptr(v_c), _ptr(v_a), _ptr(v_splats), _stream(dev))
     _lib.check(rc, "egs_rasterize_bwd")

@@ -164,13 +164,28 @@ int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, 
  * (ties keep flat-index order), (2) emitting their tiles in that order, (3) a stable sort of the emitted pairs on
  * the (cam,tile) index alone — which also separates the cameras, so level 1 needs no camera bits.
  *   egs_isect_visible_keys : compacts visible entries (tiles_per_gauss > 0) into level-1 pairs
- *                            keys1 = bits(depth) (u32), vals1 = flat index; totals[2] = {n_vis, n_isects} (device)
+ *                            keys1 = bits(depth) (u32), vals1 = flat index; totals[4] = {n_vis, n_isects, 0, 0} (device)
  *   (sort keys1/vals1 with egs_radix_sort_pairs_u32_u32 on bits [0, 32))
  *   egs_exclusive_scan_gather : out[i] = sum_{j<i} src[gather[j]]  (tile counts in depth order)
  *   egs_isect_emit_sorted  : warp-cooperative emission of tile_keys = cam*n_tiles + tile (u32), flat_vals
  *   (sort tile_keys/flat_vals with egs_radix_sort_pairs_u32_u32 on bits [0, ceil(log2(C*n_tiles))))
  *   egs_isect_finalize     : derives the tile offsets and/or rebuilds the 64-bit isect_ids (either output
  *                            pointer may be NULL: the Python side materialises isect_ids lazily, on first access) */
+/* Sync-free form of the route (what rasterization() runs): after egs_isect_visible_keys has left the level-1 pairs
+ * and the counts on the device, ONE call enqueues everything else — level-1 sort, tile-count scan, emission, level-2
+ * sort, tile offsets — for a CAPACITY of intersections chosen by the caller (e.g. from the previous call), every
+ * kernel reading the live counts from `stats` on the device.  No host round trip is needed to size anything.
+ *   stats[4] (device int64): [0] n_vis, [1] n_isects as left by egs_isect_visible_keys (inputs); [2] receives the
+ *            longest tile list.  If n_isects > capacity the outputs hold a truncated, memory-safe but meaningless
+ *            binning: the caller reads stats back, and calls again with a sufficient capacity.
+ *   keys1 / vals1: the level-1 pairs (clobbered).  tile_keys / flatten_ids [capacity]: sorted (camera, tile) keys and
+ *            flat indices, the first n_isects valid.  offsets [C * n_tiles + 1]: tile offsets plus a SENTINEL entry
+ *            holding n_isects, which egs_rasterize_* read when they are given a negative n_isects. */
+int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_t n_tiles, int64_t capacity);
+int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* means2d, const int32_t* radii,
+                     uint32_t* keys1, uint32_t* vals1, int64_t* stats, int32_t tile_size, int32_t tile_width,
+                     int32_t tile_height, int64_t capacity, void* workspace, int64_t workspace_bytes,
+                     uint32_t* tile_keys, uint32_t* flatten_ids, int32_t* offsets, egs_stream_t stream);
 int64_t egs_isect_scan_workspace_bytes(int64_t n);
 int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths, uint32_t* keys1,
                            uint32_t* vals1, int64_t* totals, void* workspace, int64_t workspace_bytes,
@@ -193,7 +208,10 @@ int egs_isect_offset_encode(int64_t n_isects, const int64_t* isect_ids_sorted, i
 /* ---- g6: alpha blending forward ----------------------------------------------------------------------
  * Replaces gsplat `rasterize_to_pixels` fwd (3 colour channels, tile_size 16).
  *   backgrounds[C,3] nullable.  outputs: render_colors[C,H,W,3], render_alphas[C,H,W,1],
- *   last_ids[C,H,W] i32 (index into the sorted intersection list of the last blended Gaussian). */
+ *   last_ids[C,H,W] i32 (index into the sorted intersection list of the last blended Gaussian).
+ *   n_isects (all egs_rasterize_* entries): the list length, or a NEGATIVE number -capacity when only the device
+ *   knows it: tile_offsets then has C * n_tiles + 1 entries, the last one holding the live length (egs_isect_sorted
+ *   writes it), and capacity bounds it (sizes the segment launch / the checkpoint buffer). */
 int egs_rasterize_fwd(int32_t C, int32_t N, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
                       const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
                       int32_t tile_width, int32_t tile_height, float* render_colors, float* render_alphas,
@@ -224,20 +242,22 @@ int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const float* splat
  * {T, r, g, b} after every `segment` entries of a list (segment: a multiple of 64; checkpoints: caller-allocated,
  * egs_rasterize_checkpoint_bytes(n_isects, segment) bytes, need not be cleared); the segmented backward then replays
  * every segment with its own warp (an extra launch over the checkpoint slots), starting from the checkpoint and
- * from "final colour minus colour in front" for what lies behind.  Results equal egs_rasterize_fwd / _bwd up to fp32
- * summation order; segment = 0 is exactly those two calls. */
+ * from "final colour minus colour in front" for what lies behind.  Only lists of at least seg_min_len entries
+ * (raised to segment + 1 if smaller) are treated this way; shorter lists are replayed in one piece as by
+ * egs_rasterize_bwd, so ordinary tiles pay nothing.  Results equal egs_rasterize_fwd / _bwd up to fp32 summation
+ * order; segment = 0 is exactly those two calls. */
 int64_t egs_rasterize_checkpoint_bytes(int64_t n_isects, int32_t segment);
 int egs_rasterize_fwd_checkpointed(int32_t C, int32_t N, int64_t n_isects, const float* splats,
                                    const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
                                    int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
                                    float* render_colors, float* render_alphas, int32_t* last_ids, float* checkpoints,
-                                   int32_t segment, egs_stream_t stream);
+                                   int32_t segment, int32_t seg_min_len, egs_stream_t stream);
 int egs_rasterize_bwd_segmented(int32_t C, int32_t N, int64_t n_isects, const float* splats,
                                 const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
                                 int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
                                 const float* render_colors, const float* render_alphas, const int32_t* last_ids,
                                 const float* v_render_colors, const float* v_render_alphas, const float* checkpoints,
-                                int32_t segment, float* v_splats, egs_stream_t stream);
+                                int32_t segment, int32_t seg_min_len, float* v_splats, egs_stream_t stream);
 
 /* ---- §8f-1: fused, sync-free densification statistics (C-aware) ----------------------------------------
  * Replaces GaussianModel.update_statistics, /root/reference/model/gaussian.py:188-197, applied once

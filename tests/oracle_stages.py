@@ -49,18 +49,18 @@ def projection_fwd(means, quats, scales, opacities, colors, viewmats, Ks, width,
             "colors": cols.contiguous(), "tiles_per_gauss": tpg, "splats": splats.contiguous()}
 
 
-def isect_sorted(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height, materialize_ids=True):
+def isect_sorted_async(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height, capacity=None):
     C = radii.shape[0]
     _, ids, flat = O.isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height, sort=True)
     offsets = O.isect_offset_encode(ids, C, tile_width, tile_height)
-    return (ids if materialize_ids else (lambda: ids)), flat, offsets
+    return stages.ResolvedIsects(ids, flat, offsets)
 
 
 def _unpack(splats):
     return splats[..., 0:2], splats[..., 2:5], splats[..., 6:9], splats[..., 5]
 
 
-def rasterize_fwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, count_pairs=False):
+def rasterize_fwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, count_pairs=False, n_isects=None):
     with torch.no_grad():
         m2, cn, cl, op = _unpack(splats)
         rc, ra, last = O.rasterize_to_pixels(m2, cn, cl, op, width, height, 16, isect_offsets, flatten_ids,
@@ -69,7 +69,7 @@ def rasterize_fwd(splats, isect_offsets, flatten_ids, backgrounds, width, height
 
 
 def rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, render_alphas, last_ids,
-                  v_render_colors, v_render_alphas):
+                  v_render_colors, v_render_alphas, n_isects=None):
     with torch.enable_grad():
         leaves = [t.detach().clone().requires_grad_(True) for t in _unpack(splats)]
         rc, ra, _ = O.rasterize_to_pixels(*leaves, width, height, 16, isect_offsets, flatten_ids,
@@ -122,8 +122,9 @@ def densify_stats_update(max_radii, grad_norm_accum, collecting_counts, radii, a
 def install(monkeypatch) -> None:
     """Route ``stages`` to the emulation and let ``rendering`` accept CPU tensors (its own check refuses them:
     the product has no CPU path)."""
-    for name in ("projection_fwd", "isect_sorted", "rasterize_fwd", "rasterize_bwd", "projection_bwd",
+    for name in ("projection_fwd", "isect_sorted_async", "rasterize_fwd", "rasterize_bwd", "projection_bwd",
                  "densify_stats_update"):
         monkeypatch.setattr(stages, name, globals()[name])
+    monkeypatch.setattr(stages, "binning_hint", lambda *a, **k: None)
     monkeypatch.setattr(rendering, "_check_inputs", lambda *a, **k: None)
     monkeypatch.delenv("EGS_BWD_SEGMENT", raising=False)

@@ -457,3 +457,35 @@ def test_direct_gradient_bucket_any_n(n):
     assert adopted == [v.data_ptr() for v in rbucket.views]
     assert rel_err(raw[0].grad.cpu(), ref[0].grad.cpu()) <= 1e-4 and rel_err(raw[1].grad.cpu(), ref[1].grad.cpu()) <= 1e-4
     assert rel_err(torch.cat([raw[4].grad, raw[5].grad], 1).cpu(), ref[4].grad.cpu()) <= 1e-4
+
+
+def test_automatic_segmentation_from_the_previous_call(monkeypatch):
+    """No environment knob: the second call of a shape knows (from the first) that the scene has outlier-long tile
+    lists and replays them in segments; images, lists and gradients must not change."""
+    from easy_gaussian_splatting_b200 import rendering, stages
+    monkeypatch.delenv("EGS_BWD_SEGMENT", raising=False)
+    sc = _pile_scene()
+    ref = oracle_run(sc)
+    stages.reset_binning_hints()
+    used = []
+    real = stages.segment_policy
+    monkeypatch.setattr(stages, "segment_policy", lambda hint, n: used.append(real(hint, n)) or used[-1])
+    first = cuda_run(sc)
+    torch.cuda.synchronize()
+    second = cuda_run(sc)
+    assert used[0] == (0, 0), "first call of a shape: nothing known yet"
+    assert used[1][0] == stages.SEGMENT_ENTRIES and used[1][1] >= stages.SEGMENT_MIN_ENTRIES, used
+    border = ref["counters"]["borderline"]
+    for out in (first, second):
+        assert torch.equal(out["meta"]["flatten_ids"].cpu(), ref["meta"]["flatten_ids"])
+        assert image_report(out["colors"], ref["colors"], border)["max_clean"] <= 1e-4
+        errs = {k: rel_err(out["grads"][k], ref["grads"][k]) for k in PARAMS}
+        errs["absgrad"] = rel_err(out["absgrad"], ref["absgrad"])
+        assert all(e <= 1e-3 for e in errs.values()), errs
+    assert torch.equal(first["colors"], second["colors"])
+    # an ordinary scene of another shape keeps the plain path on its second call
+    sc2 = make_scene(**CASES[3])
+    cuda_run(sc2)
+    torch.cuda.synchronize()
+    cuda_run(sc2)
+    assert used[-1] == (0, 0), used

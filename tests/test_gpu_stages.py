@@ -273,3 +273,85 @@ def test_fused_adam_matches_torch_adam():
     for k in shapes:
         assert torch.allclose(our_p[k].detach().cpu(), ref_p[k].detach(), rtol=2e-5, atol=1e-7), k
         assert ours.state[our_p[k]]["step"] == int(ref.state[ref_p[k]]["step"])
+
+
+def _classic_lists(proj, tw, th):
+    stages = _stages()
+    """Reference lists from the classic 64-bit route (emit + 6-pass sort + offset encode)."""
+    C = proj["radii"].shape[0]
+    _, ids, flat = stages.isect_tiles(proj["means2d"], proj["radii"], proj["depths"], 16, tw, th, sort=True,
+                                      tiles_per_gauss=proj["tiles_per_gauss"])
+    return ids, flat, stages.isect_offset_encode(ids, C, tw, th)
+
+
+def test_async_binning_guess_too_small_too_large_and_empty():
+    """The sync-free route sizes its buffers from the previous call of the same shape.  A guess that is too small must
+    be detected and repaired, one that is far too large must still give exact-length, bit-identical lists, and a
+    view that sees nothing must give all-zero offsets — each against the classic route."""
+    stages = _stages()
+    W, H = 400, 304
+    tw, th = stages.tile_grid(W, H)
+    small = make_scene("blob", 3_000, W, H, 380.0, 5).to("cuda")
+    big = make_scene("blob", 60_000, W, H, 380.0, 6).to("cuda")
+    stages.reset_binning_hints()
+    seen = []
+    for name, sc in (("small", small), ("big", big), ("big", big), ("small", small), ("none", small), ("small", small)):
+        vm = sc.viewmats.clone()
+        if name == "none":
+            vm[:, 2, 3] -= 100.0  # everything behind the camera
+        proj = stages.projection_fwd(sc.means, sc.quats, sc.scales, sc.opacities, sc.colors, vm, sc.Ks, W, H, 3)
+        b = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th)
+        ok = b.resolve()
+        seen.append((name, b.exact, ok, b.capacity, b.n_isects))
+        if not ok:
+            b = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th,
+                                          capacity=b.n_isects)
+            assert b.resolve() and b.exact
+        b.note_for_next_call()
+        ids, flat, offs = _classic_lists(proj, tw, th)
+        assert b.n_isects == flat.numel() and b.n_vis == int((proj["radii"] > 0).sum())
+        assert torch.equal(b.flatten_ids, flat) and torch.equal(b.offsets, offs) and torch.equal(b.isect_ids(), ids), name
+        assert int(b.offsets_store[-1]) == b.n_isects, "sentinel behind the offsets"
+    print(seen)
+    assert seen[0][1] is True, "first call of a shape has no guess: exact"
+    assert seen[1][2] is False, "3 k -> 60 k Gaussians: the guess must have been too small"
+    assert seen[2][1] is False and seen[2][2] is True, "same scene again: guessed, and the guess held"
+    assert seen[3][2] is True and seen[3][3] > 4 * max(seen[3][4], 1), "a far too large buffer is fine"
+    assert seen[4][4] == 0 and seen[5][2] is True
+    hint = stages.binning_hint(1, tw, th, "cuda")
+    torch.cuda.synchronize()
+    hint = stages.binning_hint(1, tw, th, "cuda")
+    assert hint["n_isects"] == seen[5][4] and hint["max_tile_len"] == int(torch.diff(torch.cat([offs.reshape(-1), offs.new_tensor([flat.numel()])])).max())
+
+
+def test_sentinel_mode_equals_exact_length_mode():
+    """egs_rasterize_* with n_isects = -capacity (length read behind the offsets) == with the exact length."""
+    stages = _stages()
+    sc = make_scene(**SCENES[3]).to("cuda")
+    W, H = sc.width, sc.height
+    tw, th = stages.tile_grid(W, H)
+    proj = stages.projection_fwd(sc.means, sc.quats, sc.scales, sc.opacities, sc.colors, sc.viewmats, sc.Ks, W, H, 3)
+    stages.reset_binning_hints()
+    b = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th,
+                                  capacity=None)
+    b.resolve()
+    b.note_for_next_call()
+    b2 = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th)
+    assert b2.resolve() and not b2.exact and b2.capacity > b2.n_isects
+    bg = sc.background[None]
+    ref = stages.rasterize_fwd(proj["splats"], b.offsets, b.flatten_ids, bg, W, H)
+    out = stages.rasterize_fwd(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, n_isects=b2.raster_n)
+    for a, r in zip(out, ref):
+        assert torch.equal(a, r)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    vc, va = torch.rand(1, H, W, 3, device="cuda", generator=g), torch.rand(1, H, W, 1, device="cuda", generator=g)
+    v_ref = stages.rasterize_bwd(proj["splats"], b.offsets, b.flatten_ids, bg, W, H, ref[1], ref[2], vc, va)
+    v_out = stages.rasterize_bwd(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, out[1], out[2], vc, va, n_isects=b2.raster_n)
+    assert float((v_out - v_ref).norm() / v_ref.norm()) <= 1e-5
+    for seg, seg_min in ((128, 0), (128, 600), (512, 100000)):
+        rc, ra, last, ck = stages.rasterize_fwd_checkpointed(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, seg,
+                                                             seg_min_len=seg_min, n_isects=b2.raster_n)
+        assert torch.equal(rc, ref[0]) and torch.equal(last, ref[2])
+        v_seg = stages.rasterize_bwd_segmented(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, rc, ra, last, vc, va, ck, seg,
+                                               seg_min_len=seg_min, n_isects=b2.raster_n)
+        assert float((v_seg - v_ref).norm() / v_ref.norm()) <= 2e-5, (seg, seg_min)

@@ -35,34 +35,36 @@ class FakeStages:
             out["compensations"] = torch.full((C, N), 0.5) * vis
         return out
 
-    def isect_sorted(self, means2d, radii, depths, tiles_per_gauss, tile_size, tw, th, materialize_ids=False):
+    def isect_sorted_async(self, means2d, radii, depths, tiles_per_gauss, tile_size, tw, th, capacity=None):
         self.calls.append("isect_sorted")
         C, N = radii.shape
         flat = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0].int()
         flatten_ids = flat.repeat_interleave(2)
         offsets = torch.zeros(C, th, tw, dtype=torch.int32)
         thunk = lambda: torch.arange(flatten_ids.numel(), dtype=torch.int64)
-        return thunk, flatten_ids, offsets
+        return stages.ResolvedIsects(thunk, flatten_ids, offsets)
 
     def _images(self, C, width, height):
         return (torch.full((C, height, width, 3), 0.25), torch.full((C, height, width, 1), 0.5),
                 torch.zeros(C, height, width, dtype=torch.int32))
 
-    def rasterize_fwd(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, count_pairs=False):
+    def rasterize_fwd(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, count_pairs=False, n_isects=None):
         self.calls.append("rasterize_fwd")
         return self._images(splats.shape[0], width, height)
 
-    def rasterize_fwd_checkpointed(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, segment):
+    def rasterize_fwd_checkpointed(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, segment,
+                                   seg_min_len=0, n_isects=None):
         self.calls.append(f"rasterize_fwd_checkpointed({segment})")
         return (*self._images(splats.shape[0], width, height), torch.zeros(16))
 
     def rasterize_bwd(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_alphas, last_ids,
-                      v_render_colors, v_render_alphas):
+                      v_render_colors, v_render_alphas, n_isects=None):
         self.calls.append("rasterize_bwd")
         return torch.ones_like(splats)
 
     def rasterize_bwd_segmented(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_colors,
-                                render_alphas, last_ids, v_render_colors, v_render_alphas, checkpoints, segment):
+                                render_alphas, last_ids, v_render_colors, v_render_alphas, checkpoints, segment,
+                                seg_min_len=0, n_isects=None):
         self.calls.append(f"rasterize_bwd_segmented({segment})")
         assert checkpoints.numel() == 16 and render_colors.shape[-1] == 3
         return torch.ones_like(splats)
@@ -101,9 +103,10 @@ FakeStages.projection_bwd_raw = _raw_bwd
 @pytest.fixture()
 def fake(monkeypatch):
     f = FakeStages()
-    for name in ("projection_fwd", "isect_sorted", "rasterize_fwd", "rasterize_fwd_checkpointed", "rasterize_bwd",
+    for name in ("projection_fwd", "isect_sorted_async", "rasterize_fwd", "rasterize_fwd_checkpointed", "rasterize_bwd",
                  "rasterize_bwd_segmented", "projection_bwd", "projection_fwd_raw", "projection_bwd_raw"):
         monkeypatch.setattr(stages, name, getattr(f, name))
+    monkeypatch.setattr(stages, "binning_hint", lambda *a, **k: None)  # CPU tensors: no device, no previous call
     monkeypatch.setattr(rendering, "_check_inputs", lambda *a, **k: None)  # the real one refuses CPU tensors
     monkeypatch.delenv("EGS_BWD_SEGMENT", raising=False)
     return f
