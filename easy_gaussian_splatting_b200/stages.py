@@ -639,9 +639,10 @@ def backward_segment() -> Optional[int]:
     return v
 
 
-SEGMENT_ENTRIES = 512      # list entries per replay segment
-SEGMENT_MIN_ENTRIES = 1024  # never segment lists shorter than this
-SEGMENT_MIN_RATIO = 3.0    # ... or shorter than this many times the average list
+SEGMENT_ENTRIES = 512       # list entries per replay segment
+SEGMENT_MIN_ENTRIES = 1024   # never segment lists shorter than this
+SEGMENT_MIN_RATIO = 3.0      # ... or shorter than this many times the average list
+SEGMENT_TRIGGER_RATIO = 6.0  # and only in scenes whose longest list is at least this many times the average
 
 
 def segment_policy(hint: Optional[Dict[str, int]], n_tiles_total: int) -> Tuple[int, int]:
@@ -661,7 +662,7 @@ def segment_policy(hint: Optional[Dict[str, int]], n_tiles_total: int) -> Tuple[
         return 0, 0
     mean = hint["n_isects"] / max(n_tiles_total, 1)
     min_len = max(SEGMENT_MIN_ENTRIES, int(SEGMENT_MIN_RATIO * mean))
-    if hint["max_tile_len"] >= min_len:
+    if hint["max_tile_len"] >= max(min_len, SEGMENT_TRIGGER_RATIO * mean):
         return SEGMENT_ENTRIES, min_len
     return 0, 0
 

@@ -36,6 +36,7 @@ def test_full_size_invariants(name):
     sc = make_config_scene(name)
     N, W, H = sc.means.shape[0], sc.width, sc.height
     Wc, Wa = (t.cuda() for t in loss_weights(sc.seed, 1, H, W))
+    stages.reset_binning_hints()  # first call of the shape: exact sizes, plain backward
     rc, ra, meta, g = _render(sc, Wc, Wa, backward=True)
     radii, tpg, ids, flat, offs = meta["radii"], meta["tiles_per_gauss"], meta["isect_ids"], meta["flatten_ids"], meta["isect_offsets"]
     n = ids.numel()
@@ -74,14 +75,16 @@ def test_full_size_invariants(name):
     assert float(g["means"][~vis].abs().sum()) == 0.0 and float(g["colors"][~vis].abs().sum()) == 0.0
     assert float(g["absgrad"][0][~vis].abs().sum()) == 0.0 and bool((g["absgrad"] >= 0).all())
     # --- determinism of the forward pass, near-determinism of the backward (reduction order) ---
+    # (the second call of a shape may replay outlier-long lists in segments — stages.segment_policy — which changes the
+    #  summation order of the gradients more than a re-run does: 5e-5 on the object scene; north_star allows 1e-3)
     rc2, ra2, meta2, g2 = _render(sc, Wc, Wa, backward=True)
     assert torch.equal(rc, rc2) and torch.equal(ra, ra2) and torch.equal(meta2["flatten_ids"], flat)
     for k in g:
-        assert float((g[k] - g2[k]).norm() / g[k].norm().clamp_min(1e-30)) <= 1e-5, k
-    # --- linearity of the VJP in the upstream gradient: grad(2 Wc, 2 Wa) = 2 grad(Wc, Wa) ---
+        assert float((g[k] - g2[k]).norm() / g[k].norm().clamp_min(1e-30)) <= 2e-4, k
+    # --- linearity of the VJP in the upstream gradient: grad(2 Wc, 2 Wa) = 2 grad(Wc, Wa), same code path as g2 ---
     _, _, _, g3 = _render(sc, 2.0 * Wc, 2.0 * Wa, backward=True)
     for k in g:
-        assert float((g3[k] - 2.0 * g[k]).norm() / (2.0 * g[k]).norm().clamp_min(1e-30)) <= 1e-5, k
+        assert float((g3[k] - 2.0 * g2[k]).norm() / (2.0 * g2[k]).norm().clamp_min(1e-30)) <= 1e-5, k
 
 
 def test_full_size_permutation_invariance():
