@@ -415,14 +415,38 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    lead = {}
+
+    def lead_in_steps(fn):
+        """Steps that keep the GPU busy for ~0.35 s; the SAME number on every rank (the step contains collectives)."""
+        if fn not in lead:
+            torch.cuda.synchronize()
+            t0 = time.time()
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            n = max(3, int(math.ceil(0.35 / max((time.time() - t0) / 3, 1e-4))))
+            if world > 1:
+                t = torch.tensor([n], dtype=torch.int64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                n = int(t.item())
+            lead[fn] = min(n, 2000)
+        return lead[fn]
+
     def timed(fn, steps, warmup, sample_clocks=False):
         for _ in range(warmup):
             fn()
         barrier()
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
+            # nvidia-smi needs ~0.1 s before its first line and prints one every 100 ms, while the timed region of a
+            # default run lasts ~0.1 s: keep the GPU under the SAME load (untimed steps of the same function) until
+            # the sampler has produced a line, then time; samples taken during the timed region and in the loaded
+            # lead-in both count as "under load"
             sampler.start()
-            time.sleep(0.15)
+            for _ in range(lead_in_steps(fn)):
+                fn()
+            barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -431,6 +455,10 @@ def ours(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        if sampler:
+            for _ in range(lead_in_steps(fn) // 2):  # a short run: keep the load up for one more sample
+                fn()
+            torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
