@@ -69,6 +69,10 @@ def parse_args():
     ap.add_argument("--no-exchange-check", action="store_true",
                     help="N > 1: skip the pre-step that checks the view-sharded step against one GPU rendering all views")
     ap.add_argument("--quick", action="store_true", help="device-timed value only: no e2e, stage timing, sub-runs or CPU leg")
+    ap.add_argument("--shard", default="strided", choices=["strided", "contiguous"],
+                    help="N > 1: rank r renders views {v : v mod R == r} (distributed.shard_views, the default) or the "
+                         "contiguous block r*V .. r*V+V-1 (diagnostic)")
+    ap.add_argument("--no-exchange", action="store_true", help="N > 1 diagnostic: skip the exchange step (marks the line invalid)")
     return ap.parse_args()
 
 
@@ -231,7 +235,7 @@ def ours(args):
     from easy_gaussian_splatting_b200.distributed import shard_views
     sc_cpu = make_config_scene(args.workload, n_views=world * V, N=args.n_gaussians)
     N = sc_cpu.means.shape[0]
-    my_views = shard_views(world * V, rank, world)
+    my_views = shard_views(world * V, rank, world) if args.shard == "strided" else list(range(rank * V, rank * V + V))
     names = ("means", "quats", "scales", "opacities", "colors")
     if args.activations == "pre":
         params = [getattr(sc_cpu, k).to(dev).requires_grad_(True) for k in names]
@@ -345,7 +349,7 @@ def ours(args):
         join_streams()
         if direct:
             bucket.end_direct()
-        if world > 1:
+        if world > 1 and not args.no_exchange:
             bucket.all_reduce()
             stats.all_reduce()
         if optimizer is not None:
@@ -516,6 +520,8 @@ def ours(args):
         line.pop("e2e")
     if args.n_gaussians:
         line["invalid"] = "N overridden (debug run)"
+    if args.no_exchange and world > 1:
+        line["invalid"] = "exchange skipped (diagnostic run)"
     if args.train_step:
         line["scaling"] = "strong"
         line["train_step"] = {"it_per_s": 1e3 / ms_step, "views_per_step": world * V,

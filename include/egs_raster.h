@@ -87,6 +87,24 @@ int egs_projection_bwd(int32_t C, int32_t N, const float* means, const float* qu
                        const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
                        float* v_opacities, float* v_sh_coeffs, float* absgrad, egs_stream_t stream);
 
+/* One chunk of Gaussians [n_begin, n_end) of egs_projection_bwd / egs_projection_bwd_raw (K = 16 layout): the same
+ * kernel on a sub-range.  Chunked launches let the multi-GPU gradient exchange of one chunk run while the backward pass of
+ * the next chunk is still computing (easy_gaussian_splatting_b200/distributed.py, FlatGradBucket.begin_direct(overlap=True)). */
+int egs_projection_bwd_range(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
+                             const float* sh_coeffs, int32_t K, int32_t sh_degree, int32_t colors_per_camera,
+                             const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
+                             const int32_t* radii, const float* colors, const float* v_splats,
+                             const float* v_means2d_extra, float* v_means, float* v_quats, float* v_scales,
+                             float* v_opacities, float* v_sh_coeffs, float* absgrad, int32_t n_begin, int32_t n_end,
+                             egs_stream_t stream);
+int egs_projection_bwd_raw_range(int32_t C, int32_t N, const float* means, const float* quats, const float* log_scales,
+                                 const float* logit_opacities, const float* sh_0, const float* sh_rest, int32_t sh_degree,
+                                 const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
+                                 const int32_t* radii, const float* colors, const float* v_splats,
+                                 const float* v_means2d_extra, float* v_means, float* v_quats, float* v_log_scales,
+                                 float* v_logit_opacities, float* v_sh_0, float* v_sh_rest, float* absgrad,
+                                 int32_t n_begin, int32_t n_end, egs_stream_t stream);
+
 /* ---- §8f-4: rasterize_mode="antialiased" of the same two kernels ---------------------------------------------
  * gsplat 1.0.0 `fully_fused_projection(calc_compensations=True)` + the Python glue `opacities * compensations`
  * (the reference passes the default rasterize_mode="classic", model/gaussian.py:353-367; this is the other value the
@@ -297,6 +315,15 @@ int egs_allreduce_f32_peer(int32_t world, int32_t rank, const void* peer_buffers
                            int64_t n_max_floats, egs_stream_t stream);
 int egs_allreduce_f32_multimem(int32_t world, int32_t rank, void* multicast_ptr, int64_t n_sum_floats,
                                int64_t n_max_floats, egs_stream_t stream);
+/* The same exchange restricted to up to 8 ranges of the symmetric buffer (HOST arrays: offsets and lengths in floats,
+ * multiples of 4; is_max nullable = all SUM).  Used to exchange the gradients of one chunk of Gaussians — one range per
+ * parameter tensor — while the projection backward of the next chunk is still running. */
+int egs_allreduce_ranges_f32_peer(int32_t world, int32_t rank, const void* peer_buffers_dev, int32_t n_ranges,
+                                  const int64_t* offsets_floats, const int64_t* lengths_floats, const int32_t* is_max,
+                                  egs_stream_t stream);
+int egs_allreduce_ranges_f32_multimem(int32_t world, int32_t rank, void* multicast_ptr, int32_t n_ranges,
+                                      const int64_t* offsets_floats, const int64_t* lengths_floats, const int32_t* is_max,
+                                      egs_stream_t stream);
 
 /* ---- measurement utility (bench.py only) -----------------------------------------------------------------
  * Dependent-FMA throughput probe: the FP32-SIMT roofline denominator for the blending kernels
