@@ -518,7 +518,7 @@ def test_chunked_projection_backward_equals_one_launch(raw):
         ((rc * Wc).sum() + (ra * Wa).sum()).backward()
         bucket.end_direct()
         torch.cuda.synchronize()
-        return bucket.flat.clone()
+        return torch.cat([v.reshape(-1) for v in bucket.views])  # (the alignment padding between slices is never written)
 
     pieces = []
     whole = run(None)
