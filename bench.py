@@ -195,6 +195,13 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def linear_functional(rc, ra, Wc, Wa):
+    """L = sum(colors * Wc) + sum(alphas * Wa) as two dot products: one fused read of each pair of
+    tensors forward, one multiply per tensor backward — the benchmark's own scaffolding should not weigh on the
+    rasterizer's timed region more than it has to (the elementwise product + sum form costs two more passes)."""
+    return torch.dot(rc.reshape(-1), Wc.reshape(-1)) + torch.dot(ra.reshape(-1), Wa.reshape(-1))
+
+
 def workload_name(args):
     from easy_gaussian_splatting_b200.synthetic import CONFIGS
     c = dict(CONFIGS[args.workload])
@@ -315,7 +322,7 @@ def ours(args):
 
     def loss_of(slot, Wc, Wa):
         if targets is None:
-            return lambda rc, ra: (rc * Wc).sum() + (ra * Wa).sum()
+            return lambda rc, ra: linear_functional(rc, ra, Wc, Wa)
         tgt = targets[slot % n_calls]
         # gaussian.py:368 clamp, :422-445 LossComputer (fused kernels, csrc/loss.cu); mean over the step's views
         return lambda rc, ra: fused_l1_ssim_loss(torch.clamp(rc, 0.0, 1.0), tgt, None, 0.2)[0].sum() * inv_views
@@ -636,7 +643,7 @@ def sequential_views(workload, dev, n_views=4, steps=5, warmup=3, forward_only=F
         for p_ in params:
             p_.grad = None
         rc, ra, meta = rasterization(*params, vms[v:v + 1], Ks[v:v + 1], W, H, sh_degree=3, packed=False, absgrad=True, backgrounds=bg)
-        ((rc * Wc).sum() + (ra * Wa).sum()).backward()
+        linear_functional(rc, ra, Wc, Wa).backward()
         stats.update_local(meta["radii"], meta["means2d"].absgrad, W, H)
 
     for _ in range(warmup):

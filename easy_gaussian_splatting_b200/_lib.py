@@ -46,17 +46,17 @@ _SIGNATURES = {
     "egs_isect_scan_workspace_bytes": (c_int64, [I64]),
     "egs_isect_visible_keys": (c_int32, [I32, I32, P, P, P, P, P, P, I64, P]),
     "egs_isect_sorted_workspace_bytes": (c_int64, [I32, I32, I32, I64]),
-    "egs_isect_sorted": (c_int32, [I32, I32, P, P, P, P, P, P, I32, I32, I32, I64, P, I64, P, P, P, P]),
+    "egs_isect_sorted": (c_int32, [I32, I32, P, P, P, P, P, P, I32, I32, I32, I64, P, I64, P, P, P, P, P]),
     "egs_exclusive_scan_gather": (c_int32, [I64, P, P, P, P, P, I64, P]),
     "egs_isect_emit_sorted": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I64, P, P, P]),
     "egs_isect_finalize": (c_int32, [I64, P, P, P, I32, I32, I32, P, P, P]),
     "egs_isect_offset_encode": (c_int32, [I64, P, I32, I32, I32, P, P]),
-    "egs_rasterize_fwd": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I32, P, P, P, P]),
+    "egs_rasterize_fwd": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I32, P, P, P, P, P]),
     "egs_rasterize_fwd_count": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I32, P, P, P, P, P]),
-    "egs_rasterize_bwd": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I32, P, P, P, P, P, P]),
+    "egs_rasterize_bwd": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I32, P, P, P, P, P, P, P]),
     "egs_rasterize_checkpoint_bytes": (c_int64, [I64, I32]),
-    "egs_rasterize_fwd_checkpointed": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I32, P, P, P, P, I32, I32, P]),
-    "egs_rasterize_bwd_segmented": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I32, P, P, P, P, P, P, I32, I32, P, P]),
+    "egs_rasterize_fwd_checkpointed": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I32, P, P, P, P, I32, I32, P, P]),
+    "egs_rasterize_bwd_segmented": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I32, P, P, P, P, P, P, I32, I32, P, P, P]),
     "egs_densify_stats_update": (c_int32, [I32, I32, P, P, F32, P, P, P, P]),
     "egs_l1_ssim_fwd": (c_int32, [I32, I32, I32, P, P, P, P, P, P]),
     "egs_l1_ssim_bwd": (c_int32, [I32, I32, I32, P, P, P, P, F32, P, P, P]),

@@ -224,14 +224,18 @@ __global__ void EGS_FWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_fwd_kernel
     const int32_t* __restrict__ flatten_ids, const float* __restrict__ backgrounds, int width, int height, int tile_w,
     int tile_h, int n_tiles_total, int len_lo, int len_hi, float* __restrict__ render_colors,
     float* __restrict__ render_alphas, int32_t* __restrict__ last_ids, unsigned long long* __restrict__ pair_counters,
-    float4* __restrict__ ckpt, int ckpt_k, int seg_min_len) {
+    float4* __restrict__ ckpt, int ckpt_k, int seg_min_len,
+    // nullable: block b handles tile tile_order[b] (longest lists first, egs_isect_sorted) instead of the tile at its grid position
+    const int32_t* __restrict__ tile_order) {
   using G = Geo<PX, PY>;
   constexpr int NP = G::NP;
   constexpr int RPL = G::RPL, kBatch = G::kBatch;
   __shared__ __align__(16) WarpStage<kBatch> stage[G::kWarps];
   const int lane = threadIdx.x & 31;
   WarpStage<kBatch>& st = stage[threadIdx.x >> 5];
-  const WarpView wv = warp_setup<G>(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total);
+  const int ordered_tile =
+      tile_order != nullptr ? tile_order[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] : -1;
+  const WarpView wv = warp_setup<G>(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total, ordered_tile);
   {
     const int len = wv.range_end - wv.range_start;
     if (len < len_lo || len >= len_hi) return;  // block-uniform: the other launch owns this tile
@@ -470,7 +474,8 @@ __global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel
     // entry down to the segment boundary below it, initial state = the final image, as without segments);
     // seg_launch = 1: blocks are checkpoint slots and replay the full segment that ends at their checkpoint.
     // Only lists of at least seg_min_len (> ckpt_k) entries are replayed in segments; shorter ones as one piece.
-    const float* __restrict__ render_colors, const float4* __restrict__ ckpt, int ckpt_k, int seg_min_len, int seg_launch) {
+    const float* __restrict__ render_colors, const float4* __restrict__ ckpt, int ckpt_k, int seg_min_len, int seg_launch,
+    const int32_t* __restrict__ tile_order /* nullable, tile launch only: see the forward kernel */) {
   using G = Geo<PX, PY>;
   constexpr int NP = G::NP;
   constexpr int RPL = G::RPL, kBatch = G::kBatch;
@@ -491,6 +496,8 @@ __global__ void EGS_BWD_BOUNDS((Geo<PX, PY>::kThreads), PX) rasterize_bwd_kernel
     }
     seg_tile = lo_t;
     seg_k = (int)(blockIdx.x + 1) - tile_offsets[seg_tile] / ckpt_k;
+  } else if (tile_order != nullptr) {
+    seg_tile = tile_order[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
   }
   const WarpView wv = warp_setup<G>(tile_w, tile_h, n_isects, tile_offsets, n_tiles_total, seg_tile);
   {
@@ -812,8 +819,8 @@ template <bool COUNT>
 static int launch_fwd(int32_t C, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
                       const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
                       int32_t tile_width, int32_t tile_height, float* render_colors, float* render_alphas,
-                      int32_t* last_ids, uint64_t* pair_counters, egs_stream_t stream, float* checkpoints = nullptr,
-                      int32_t segment = 0, int32_t seg_min_len = 0) {
+                      int32_t* last_ids, uint64_t* pair_counters, const int32_t* tile_order, egs_stream_t stream,
+                      float* checkpoints = nullptr, int32_t segment = 0, int32_t seg_min_len = 0) {
   dim3 grid(tile_width, tile_height, C);
   const int n_tiles = C * tile_width * tile_height;
   float4* ck = segment > 0 ? reinterpret_cast<float4*>(checkpoints) : nullptr;
@@ -822,19 +829,21 @@ static int launch_fwd(int32_t C, int64_t n_isects, const float* splats, const in
   cudaStream_t st = (cudaStream_t)stream;
   rasterize_fwd_kernel<2, 2, COUNT><<<grid, Geo<2, 2>::kThreads, 0, st>>>(
       n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0,
-      kNoLengthLimit, render_colors, render_alphas, last_ids, pc, ck, segment, seg_min_len > segment ? seg_min_len : segment + 1);
+      kNoLengthLimit, render_colors, render_alphas, last_ids, pc, ck, segment, seg_min_len > segment ? seg_min_len : segment + 1,
+      tile_order);
   return check_launch("rasterize_fwd_kernel");
 }
 
 extern "C" int egs_rasterize_fwd(int32_t C, int32_t N, int64_t n_isects, const float* splats,
                                  const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
                                  int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
-                                 float* render_colors, float* render_alphas, int32_t* last_ids, egs_stream_t stream) {
+                                 float* render_colors, float* render_alphas, int32_t* last_ids,
+                                 const int32_t* tile_order, egs_stream_t stream) {
   (void)N;
   if (int rc = check_raster_args("rasterize_fwd", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (C == 0) return 0;
   return launch_fwd<false>(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width,
-                           tile_height, render_colors, render_alphas, last_ids, nullptr, stream);
+                           tile_height, render_colors, render_alphas, last_ids, nullptr, tile_order, stream);
 }
 
 // Instrumented variant for the roofline model: also accumulates P_eval and P_acc (in the
@@ -849,7 +858,7 @@ extern "C" int egs_rasterize_fwd_count(int32_t C, int32_t N, int64_t n_isects, c
   if (int rc = check_raster_args("rasterize_fwd_count", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (C == 0) return 0;
   return launch_fwd<true>(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width,
-                          tile_height, render_colors, render_alphas, last_ids, pair_counters, stream);
+                          tile_height, render_colors, render_alphas, last_ids, pair_counters, nullptr, stream);
 }
 
 static int segment_ok(const char* who, int32_t segment) {
@@ -869,15 +878,16 @@ extern "C" int egs_rasterize_fwd_checkpointed(int32_t C, int32_t N, int64_t n_is
                                               const float* backgrounds, int32_t width, int32_t height,
                                               int32_t tile_width, int32_t tile_height, float* render_colors,
                                               float* render_alphas, int32_t* last_ids, float* checkpoints,
-                                              int32_t segment, int32_t seg_min_len, egs_stream_t stream) {
+                                              int32_t segment, int32_t seg_min_len, const int32_t* tile_order,
+                                              egs_stream_t stream) {
   (void)N;
   if (int rc = check_raster_args("rasterize_fwd_checkpointed", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (int rc = segment_ok("rasterize_fwd_checkpointed", segment)) return rc;
   EGS_REQUIRE(segment == 0 || checkpoints != nullptr, "rasterize_fwd_checkpointed: checkpoints buffer is required");
   if (C == 0) return 0;
   return launch_fwd<false>(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width,
-                           tile_height, render_colors, render_alphas, last_ids, nullptr, stream, checkpoints, segment,
-                           seg_min_len);
+                           tile_height, render_colors, render_alphas, last_ids, nullptr, tile_order, stream, checkpoints,
+                           segment, seg_min_len);
 }
 
 static int launch_bwd(int32_t C, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
@@ -885,7 +895,7 @@ static int launch_bwd(int32_t C, int64_t n_isects, const float* splats, const in
                       int32_t tile_width, int32_t tile_height, const float* render_alphas, const int32_t* last_ids,
                       const float* v_render_colors, const float* v_render_alphas, float* v_splats,
                       const float* render_colors, const float* checkpoints, int32_t segment, int32_t seg_min_len,
-                      egs_stream_t stream) {
+                      const int32_t* tile_order, egs_stream_t stream) {
   seg_min_len = seg_min_len > segment ? seg_min_len : segment + 1;
   dim3 grid(tile_width, tile_height, C);
   const int n_tiles = C * tile_width * tile_height;
@@ -898,10 +908,10 @@ static int launch_bwd(int32_t C, int64_t n_isects, const float* splats, const in
   if (n_slots > 0)
     rasterize_bwd_kernel<2, 2><<<(unsigned)n_slots, Geo<2, 2>::kThreads, 0, st>>>(
         n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
-        render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, seg_min_len, 1);
+        render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, seg_min_len, 1, nullptr);
   rasterize_bwd_kernel<2, 2><<<grid, Geo<2, 2>::kThreads, 0, st>>>(
       n_isects, sp, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height, n_tiles, 0, thr,
-      render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, seg_min_len, 0);
+      render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, ck, segment, seg_min_len, 0, tile_order);
   return check_launch("rasterize_bwd_kernel", 1 + (n_slots > 0 ? 1 : 0));
 }
 
@@ -909,12 +919,14 @@ extern "C" int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const f
                                  const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
                                  int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
                                  const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
-                                 const float* v_render_alphas, float* v_splats, egs_stream_t stream) {
+                                 const float* v_render_alphas, float* v_splats, const int32_t* tile_order,
+                                 egs_stream_t stream) {
   (void)N;
   if (int rc = check_raster_args("rasterize_bwd", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (C == 0 || n_isects == 0) return 0;
   return launch_bwd(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height,
-                    render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, nullptr, nullptr, 0, 0, stream);
+                    render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, nullptr, nullptr, 0, 0, tile_order,
+                    stream);
 }
 
 extern "C" int egs_rasterize_bwd_segmented(int32_t C, int32_t N, int64_t n_isects, const float* splats,
@@ -923,7 +935,8 @@ extern "C" int egs_rasterize_bwd_segmented(int32_t C, int32_t N, int64_t n_isect
                                            int32_t tile_height, const float* render_colors, const float* render_alphas,
                                            const int32_t* last_ids, const float* v_render_colors,
                                            const float* v_render_alphas, const float* checkpoints, int32_t segment,
-                                           int32_t seg_min_len, float* v_splats, egs_stream_t stream) {
+                                           int32_t seg_min_len, float* v_splats, const int32_t* tile_order,
+                                           egs_stream_t stream) {
   (void)N;
   if (int rc = check_raster_args("rasterize_bwd_segmented", C, n_isects, width, height, tile_width, tile_height)) return rc;
   if (int rc = segment_ok("rasterize_bwd_segmented", segment)) return rc;
@@ -932,5 +945,5 @@ extern "C" int egs_rasterize_bwd_segmented(int32_t C, int32_t N, int64_t n_isect
   if (C == 0 || n_isects == 0) return 0;
   return launch_bwd(C, n_isects, splats, tile_offsets, flatten_ids, backgrounds, width, height, tile_width, tile_height,
                     render_alphas, last_ids, v_render_colors, v_render_alphas, v_splats, render_colors, checkpoints,
-                    segment, seg_min_len, stream);
+                    segment, seg_min_len, tile_order, stream);
 }

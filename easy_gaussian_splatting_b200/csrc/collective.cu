@@ -11,6 +11,14 @@ namespace egs {
 
 constexpr int kArThreads = 256;
 constexpr int kArMaxWorld = 16;
+// float4s a thread of the NVLS kernel keeps in flight per trip / resident CTAs per SM the grid is capped at
+// (build-time A/B knobs, scripts/build_variant.py)
+#ifndef EGS_AR_UNROLL
+#define EGS_AR_UNROLL 2
+#endif
+#ifndef EGS_AR_CTAS_PER_SM
+#define EGS_AR_CTAS_PER_SM 8
+#endif
 constexpr int kArMaxRanges = 8;
 
 // The float4 ranges one launch reduces, each cut into `world` slices of which this rank owns one.  SUM ranges carry
@@ -85,18 +93,23 @@ __global__ void __launch_bounds__(kArThreads) allreduce_multimem_kernel(float* _
         multimem_max_u32x4(reinterpret_cast<uint32_t*>(mc) + 4 * i);
       continue;
     }
-    for (int64_t i = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < hi; i += 2 * stride) {
-      const int64_t i1 = i + stride;
-      const bool two = i1 < hi;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                   : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(m4 + i) : "memory");
-      if (two)
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(m4 + i1) : "memory");
-      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(m4 + i), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
-      if (two)
-        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(m4 + i1), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+    constexpr int U = EGS_AR_UNROLL;
+    for (int64_t i = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < hi; i += U * stride) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {  // every in-switch reduction of the trip in flight before the first store
+        const int64_t iu = i + u * stride;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iu < hi)
+          asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(m4 + iu) : "memory");
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t iu = i + u * stride;
+        if (iu < hi)
+          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(m4 + iu), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w) : "memory");
+      }
     }
   }
 }
@@ -123,7 +136,7 @@ static int make_ranges(const char* who, int32_t n_ranges, const int64_t* offsets
 static unsigned ar_blocks(int64_t total4, int world) {
   int64_t blocks = ceil_div(ceil_div(total4, world), 2 * kArThreads);
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * EGS_AR_CTAS_PER_SM) blocks = 148 * EGS_AR_CTAS_PER_SM;
   return (unsigned)blocks;
 }
 

@@ -116,16 +116,17 @@ def _bin_and_blend(ctx, proj, backgrounds, width, height, grad_enabled=True):
         with stages.nvtx_range("egs.rasterize_fwd"):
             if seg > 0:
                 rc, ra, last, ckpt = stages.rasterize_fwd_checkpointed(proj["splats"], b.offsets, b.flat_cap, backgrounds, width,
-                                                                       height, seg, seg_min_len=seg_min, n_isects=b.raster_n)
+                                                                       height, seg, seg_min_len=seg_min, n_isects=b.raster_n,
+                                                                       tile_order=b.tile_order)
             else:
                 rc, ra, last = stages.rasterize_fwd(proj["splats"], b.offsets, b.flat_cap, backgrounds, width, height,
-                                                    n_isects=b.raster_n)
+                                                    n_isects=b.raster_n, tile_order=b.tile_order)
                 ckpt = None
         if b.resolve():
             break
         capacity = b.n_isects  # the guess was too small (rare): same route again, exactly sized
     b.note_for_next_call()
-    ctx.segment, ctx.seg_min_len, ctx.raster_n = seg, seg_min, b.raster_n
+    ctx.segment, ctx.seg_min_len, ctx.raster_n, ctx.tile_order = seg, seg_min, b.raster_n, b.tile_order
     return b, rc, ra, last, ckpt
 
 
@@ -135,9 +136,9 @@ def _blend_backward(ctx, splats, isect_offsets, flatten_ids, backgrounds, width,
         if ckpt is not None:
             return stages.rasterize_bwd_segmented(splats, isect_offsets, flatten_ids, backgrounds, width, height,
                                                   render_colors, render_alphas, last_ids, v_colors, v_alphas, ckpt, ctx.segment,
-                                                  seg_min_len=ctx.seg_min_len, n_isects=ctx.raster_n)
+                                                  seg_min_len=ctx.seg_min_len, n_isects=ctx.raster_n, tile_order=ctx.tile_order)
         return stages.rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, render_alphas, last_ids,
-                                    v_colors, v_alphas, n_isects=ctx.raster_n)
+                                    v_colors, v_alphas, n_isects=ctx.raster_n, tile_order=ctx.tile_order)
 
 
 class _Rasterization(torch.autograd.Function):

@@ -456,9 +456,11 @@ def reset_binning_hints() -> None:
 class SortedIsects:
     """Result of ``isect_sorted_async``: buffers sized for ``capacity`` intersections and the pending counts."""
 
-    def __init__(self, key, C, n_tiles, capacity, tile_keys, flat, offsets_store, offsets, depths, stats_dev, early, early_event, exact):
+    def __init__(self, key, C, n_tiles, capacity, tile_keys, flat, offsets_store, offsets, depths, stats_dev, early, early_event, exact,
+                 tile_order=None):
         self.key, self.C, self.n_tiles, self.capacity = key, C, n_tiles, capacity
         self.tile_keys_cap, self.flat_cap, self.offsets_store, self.offsets = tile_keys, flat, offsets_store, offsets
+        self.tile_order = tile_order  # launch order of the blend kernels: tiles by list length, longest first
         self.depths, self.stats_dev = depths, stats_dev
         self._early, self._early_event = early, early_event
         self.n_vis: Optional[int] = None
@@ -516,6 +518,7 @@ class ResolvedIsects:
 
     exact = True
     raster_n = None  # the rasterize operators then take len(flatten_ids)
+    tile_order = None  # grid order
 
     def __init__(self, isect_ids, flatten_ids: Tensor, offsets: Tensor):
         self._ids, self.flat_cap, self.offsets = isect_ids, flatten_ids, offsets
@@ -596,14 +599,16 @@ def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per
     flat = torch.empty(capacity, dtype=torch.int32, device=dev)
     offsets_store = torch.empty(C * n_tiles + 1, dtype=torch.int32, device=dev)
     offsets = offsets_store[:C * n_tiles].view(C, tile_height, tile_width)
+    tile_order = torch.empty(max(C * n_tiles, 1), dtype=torch.int32, device=dev)
     ws_bytes = lib.egs_isect_sorted_workspace_bytes(C, N, n_tiles, capacity)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.egs_isect_sorted(C, N, _ptr(tiles_per_gauss), _ptr(means2d), _ptr(radii), _ptr(keys1), _ptr(vals1), _ptr(stats),
                                   int(tile_size), tile_width, tile_height, capacity, _ptr(ws), ws.numel(), _ptr(tile_keys),
-                                  _ptr(flat), _ptr(offsets_store), _stream(dev))
+                                  _ptr(flat), _ptr(offsets_store), _ptr(tile_order), _stream(dev))
     _lib.check(rc, "egs_isect_sorted")
-    return SortedIsects(key, C, n_tiles, capacity, tile_keys, flat, offsets_store, offsets, depths, stats, early, early_event, exact)
+    return SortedIsects(key, C, n_tiles, capacity, tile_keys, flat, offsets_store, offsets, depths, stats, early, early_event, exact,
+                        tile_order=tile_order)
 
 
 def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
@@ -645,10 +650,13 @@ def pack_splats(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tens
 
 
 def rasterize_fwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],
-                  width: int, height: int, count_pairs: bool = False, n_isects: Optional[int] = None):
+                  width: int, height: int, count_pairs: bool = False, n_isects: Optional[int] = None,
+                  tile_order: Optional[Tensor] = None):
     """g6 -> render_colors[C,H,W,3], render_alphas[C,H,W,1], last_ids[C,H,W] (, (P_eval, P_acc) tensor).
     n_isects: None = len(flatten_ids); negative = -capacity, the live length sits behind the offsets
-    (``SortedIsects.raster_n``; isect_offsets must then be the view ``SortedIsects.offsets``)."""
+    (``SortedIsects.raster_n``; isect_offsets must then be the view ``SortedIsects.offsets``).
+    tile_order: int32 permutation of the C * tiles flat tile indices = the order thread blocks take them in
+    (``SortedIsects.tile_order``: longest lists first); None = grid order.  Results do not depend on it."""
     lib = _lib.load()
     dev = splats.device
     C, N = splats.shape[:2]
@@ -664,7 +672,7 @@ def rasterize_fwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, ba
             counters = torch.zeros(2, dtype=torch.int64, device=dev)
             rc = lib.egs_rasterize_fwd_count(*args, _ptr(counters), _stream(dev))
         else:
-            rc = lib.egs_rasterize_fwd(*args, _stream(dev))
+            rc = lib.egs_rasterize_fwd(*args, _ptr(tile_order), _stream(dev))
     _lib.check(rc, "egs_rasterize_fwd")
     return (colors, alphas, last, counters) if count_pairs else (colors, alphas, last)
 
@@ -711,7 +719,7 @@ def segment_policy(hint: Optional[Dict[str, int]], n_tiles_total: int) -> Tuple[
 
 def rasterize_fwd_checkpointed(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor,
                                backgrounds: Optional[Tensor], width: int, height: int, segment: int,
-                               seg_min_len: int = 0, n_isects: Optional[int] = None):
+                               seg_min_len: int = 0, n_isects: Optional[int] = None, tile_order: Optional[Tensor] = None):
     """g6 for a forward that will be differentiated: as rasterize_fwd, plus the per-pixel state after every
     `segment` entries of a tile's list -> render_colors, render_alphas, last_ids, checkpoints."""
     lib = _lib.load()
@@ -727,7 +735,8 @@ def rasterize_fwd_checkpointed(splats: Tensor, isect_offsets: Tensor, flatten_id
     with torch.cuda.device(dev):
         rc = lib.egs_rasterize_fwd_checkpointed(C, N, n_isects, _ptr(splats), _ptr(isect_offsets), _ptr(flatten_ids),
                                                 _ptr(bg), int(width), int(height), tw, th, _ptr(colors), _ptr(alphas),
-                                                _ptr(last), _ptr(ckpt), int(segment), int(seg_min_len), _stream(dev))
+                                                _ptr(last), _ptr(ckpt), int(segment), int(seg_min_len), _ptr(tile_order),
+                                                _stream(dev))
     _lib.check(rc, "egs_rasterize_fwd_checkpointed")
     return colors, alphas, last, ckpt
 
@@ -735,7 +744,7 @@ def rasterize_fwd_checkpointed(splats: Tensor, isect_offsets: Tensor, flatten_id
 def rasterize_bwd_segmented(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],
                             width: int, height: int, render_colors: Tensor, render_alphas: Tensor, last_ids: Tensor,
                             v_render_colors: Tensor, v_render_alphas: Tensor, checkpoints: Tensor, segment: int,
-                            seg_min_len: int = 0, n_isects: Optional[int] = None) -> Tensor:
+                            seg_min_len: int = 0, n_isects: Optional[int] = None, tile_order: Optional[Tensor] = None) -> Tensor:
     """g7 with one warp per list segment (see include/egs_raster.h) -> v_splats[C,N,12]."""
     lib = _lib.load()
     dev = splats.device
@@ -748,14 +757,15 @@ def rasterize_bwd_segmented(splats: Tensor, isect_offsets: Tensor, flatten_ids: 
         rc = lib.egs_rasterize_bwd_segmented(C, N, flatten_ids.numel() if n_isects is None else int(n_isects), _ptr(splats),
                                              _ptr(isect_offsets), _ptr(flatten_ids), _ptr(bg), int(width), int(height), tw, th,
                                              _ptr(render_colors), _ptr(render_alphas), _ptr(last_ids), _ptr(v_c), _ptr(v_a),
-                                             _ptr(checkpoints), int(segment), int(seg_min_len), _ptr(v_splats), _stream(dev))
+                                             _ptr(checkpoints), int(segment), int(seg_min_len), _ptr(v_splats), _ptr(tile_order),
+                                             _stream(dev))
     _lib.check(rc, "egs_rasterize_bwd_segmented")
     return v_splats
 
 
 def rasterize_bwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor],
                   width: int, height: int, render_alphas: Tensor, last_ids: Tensor, v_render_colors: Tensor,
-                  v_render_alphas: Tensor, n_isects: Optional[int] = None) -> Tensor:
+                  v_render_alphas: Tensor, n_isects: Optional[int] = None, tile_order: Optional[Tensor] = None) -> Tensor:
     """g7 -> packed gradient records v_splats[C,N,12] (layout in include/egs_raster.h)."""
     lib = _lib.load()
     dev = splats.device
@@ -768,7 +778,7 @@ def rasterize_bwd(splats: Tensor, isect_offsets: Tensor, flatten_ids: Tensor, ba
         rc = lib.egs_rasterize_bwd(C, N, flatten_ids.numel() if n_isects is None else int(n_isects), _ptr(splats),
                                    _ptr(isect_offsets), _ptr(flatten_ids),
                                    _ptr(bg), int(width), int(height), tw, th, _ptr(render_alphas), _ptr(last_ids),
-                                   _ptr(v_c), _ptr(v_a), _ptr(v_splats), _stream(dev))
+                                   _ptr(v_c), _ptr(v_a), _ptr(v_splats), _ptr(tile_order), _stream(dev))
     _lib.check(rc, "egs_rasterize_bwd")
     return v_splats
 

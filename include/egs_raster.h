@@ -198,12 +198,15 @@ int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, 
  *            binning: the caller reads stats back, and calls again with a sufficient capacity.
  *   keys1 / vals1: the level-1 pairs (clobbered).  tile_keys / flatten_ids [capacity]: sorted (camera, tile) keys and
  *            flat indices, the first n_isects valid.  offsets [C * n_tiles + 1]: tile offsets plus a SENTINEL entry
- *            holding n_isects, which egs_rasterize_* read when they are given a negative n_isects. */
+ *            holding n_isects, which egs_rasterize_* read when they are given a negative n_isects.
+ *   tile_order [C * n_tiles] (nullable): the flat tile indices sorted by list length, longest first — the launch
+ *            order for egs_rasterize_* (their tile_order argument). */
 int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_t n_tiles, int64_t capacity);
 int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* means2d, const int32_t* radii,
                      uint32_t* keys1, uint32_t* vals1, int64_t* stats, int32_t tile_size, int32_t tile_width,
                      int32_t tile_height, int64_t capacity, void* workspace, int64_t workspace_bytes,
-                     uint32_t* tile_keys, uint32_t* flatten_ids, int32_t* offsets, egs_stream_t stream);
+                     uint32_t* tile_keys, uint32_t* flatten_ids, int32_t* offsets, int32_t* tile_order,
+                     egs_stream_t stream);
 int64_t egs_isect_scan_workspace_bytes(int64_t n);
 int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths, uint32_t* keys1,
                            uint32_t* vals1, int64_t* totals, void* workspace, int64_t workspace_bytes,
@@ -229,11 +232,15 @@ int egs_isect_offset_encode(int64_t n_isects, const int64_t* isect_ids_sorted, i
  *   last_ids[C,H,W] i32 (index into the sorted intersection list of the last blended Gaussian).
  *   n_isects (all egs_rasterize_* entries): the list length, or a NEGATIVE number -capacity when only the device
  *   knows it: tile_offsets then has C * n_tiles + 1 entries, the last one holding the live length (egs_isect_sorted
- *   writes it), and capacity bounds it (sizes the segment launch / the checkpoint buffer). */
+ *   writes it), and capacity bounds it (sizes the segment launch / the checkpoint buffer).
+ *   tile_order (nullable, egs_rasterize_fwd / _fwd_checkpointed / _bwd / _bwd_segmented): a permutation of the
+ *   C * n_tiles flat tile indices; thread block b works on tile tile_order[b].  egs_isect_sorted emits one that puts
+ *   the longest lists first, so that the end of a launch is made of the cheapest tiles (the GPU runs thread blocks
+ *   roughly in index order).  Results do not depend on it. */
 int egs_rasterize_fwd(int32_t C, int32_t N, int64_t n_isects, const float* splats, const int32_t* tile_offsets,
                       const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
                       int32_t tile_width, int32_t tile_height, float* render_colors, float* render_alphas,
-                      int32_t* last_ids, egs_stream_t stream);
+                      int32_t* last_ids, const int32_t* tile_order, egs_stream_t stream);
 
 /* Instrumented variant used only by bench.py / tests for the roofline model: additionally adds the
  * number of evaluated and accepted (pixel, Gaussian) pairs (P_eval, P_acc of SURVEY.md §8d) to
@@ -252,7 +259,7 @@ int egs_rasterize_bwd(int32_t C, int32_t N, int64_t n_isects, const float* splat
                       const int32_t* flatten_ids, const float* backgrounds, int32_t width, int32_t height,
                       int32_t tile_width, int32_t tile_height, const float* render_alphas,
                       const int32_t* last_ids, const float* v_render_colors, const float* v_render_alphas,
-                      float* v_splats, egs_stream_t stream);
+                      float* v_splats, const int32_t* tile_order, egs_stream_t stream);
 
 /* ---- g7 on long lists: segmented replay ---------------------------------------------------------------------------
  * A tile whose list has thousands of entries (object-centric scenes: a few hundred tiles hold the whole object) makes
@@ -269,13 +276,14 @@ int egs_rasterize_fwd_checkpointed(int32_t C, int32_t N, int64_t n_isects, const
                                    const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
                                    int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
                                    float* render_colors, float* render_alphas, int32_t* last_ids, float* checkpoints,
-                                   int32_t segment, int32_t seg_min_len, egs_stream_t stream);
+                                   int32_t segment, int32_t seg_min_len, const int32_t* tile_order, egs_stream_t stream);
 int egs_rasterize_bwd_segmented(int32_t C, int32_t N, int64_t n_isects, const float* splats,
                                 const int32_t* tile_offsets, const int32_t* flatten_ids, const float* backgrounds,
                                 int32_t width, int32_t height, int32_t tile_width, int32_t tile_height,
                                 const float* render_colors, const float* render_alphas, const int32_t* last_ids,
                                 const float* v_render_colors, const float* v_render_alphas, const float* checkpoints,
-                                int32_t segment, int32_t seg_min_len, float* v_splats, egs_stream_t stream);
+                                int32_t segment, int32_t seg_min_len, float* v_splats, const int32_t* tile_order,
+                                egs_stream_t stream);
 
 /* ---- §8f-1: fused, sync-free densification statistics (C-aware) ----------------------------------------
  * Replaces GaussianModel.update_statistics, /root/reference/model/gaussian.py:188-197, applied once

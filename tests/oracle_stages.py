@@ -60,7 +60,7 @@ def _unpack(splats):
     return splats[..., 0:2], splats[..., 2:5], splats[..., 6:9], splats[..., 5]
 
 
-def rasterize_fwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, count_pairs=False, n_isects=None):
+def rasterize_fwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, count_pairs=False, n_isects=None, tile_order=None):
     with torch.no_grad():
         m2, cn, cl, op = _unpack(splats)
         rc, ra, last = O.rasterize_to_pixels(m2, cn, cl, op, width, height, 16, isect_offsets, flatten_ids,
@@ -69,7 +69,7 @@ def rasterize_fwd(splats, isect_offsets, flatten_ids, backgrounds, width, height
 
 
 def rasterize_bwd(splats, isect_offsets, flatten_ids, backgrounds, width, height, render_alphas, last_ids,
-                  v_render_colors, v_render_alphas, n_isects=None):
+                  v_render_colors, v_render_alphas, n_isects=None, tile_order=None):
     with torch.enable_grad():
         leaves = [t.detach().clone().requires_grad_(True) for t in _unpack(splats)]
         rc, ra, _ = O.rasterize_to_pixels(*leaves, width, height, 16, isect_offsets, flatten_ids,

@@ -37,7 +37,7 @@ def test_workspace_queries_and_argument_errors_without_gpu():
     # invalid arguments are rejected before any launch (works without a device)
     rc = lib.egs_radix_sort_pairs_u64_u32(-1, None, None, None, None, 45, None, 0, None, None)
     assert rc == -1 and b"n=-1" in lib.egs_last_error_string()
-    rc = lib.egs_rasterize_fwd(1, 0, 0, None, None, None, None, 100, 100, 3, 3, None, None, None, None)
+    rc = lib.egs_rasterize_fwd(1, 0, 0, None, None, None, None, 100, 100, 3, 3, None, None, None, None, None)
     assert rc == -1 and b"tile grid" in lib.egs_last_error_string()
     rc = lib.egs_projection_fwd(1, 10, None, None, None, None, None, 16, 5, 0, None, None, 64, 64, 0.3, 0.01, 1e10, 0.0,
                                 16, 4, 4, None, None, None, None, None, None, None, None)

@@ -349,9 +349,26 @@ def test_sentinel_mode_equals_exact_length_mode():
     v_out = stages.rasterize_bwd(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, out[1], out[2], vc, va, n_isects=b2.raster_n)
     assert float((v_out - v_ref).norm() / v_ref.norm()) <= 1e-5
     for seg, seg_min in ((128, 0), (128, 600), (512, 100000)):
-        rc, ra, last, ck = stages.rasterize_fwd_checkpointed(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, seg,
-                                                             seg_min_len=seg_min, n_isects=b2.raster_n)
-        assert torch.equal(rc, ref[0]) and torch.equal(last, ref[2])
-        v_seg = stages.rasterize_bwd_segmented(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, rc, ra, last, vc, va, ck, seg,
-                                               seg_min_len=seg_min, n_isects=b2.raster_n)
-        assert float((v_seg - v_ref).norm() / v_ref.norm()) <= 2e-5, (seg, seg_min)
+        for order in (None, b2.tile_order):
+            rc, ra, last, ck = stages.rasterize_fwd_checkpointed(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, seg,
+                                                                 seg_min_len=seg_min, n_isects=b2.raster_n, tile_order=order)
+            assert torch.equal(rc, ref[0]) and torch.equal(last, ref[2])
+            v_seg = stages.rasterize_bwd_segmented(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, rc, ra, last, vc, va, ck, seg,
+                                                   seg_min_len=seg_min, n_isects=b2.raster_n, tile_order=order)
+            assert float((v_seg - v_ref).norm() / v_ref.norm()) <= 2e-5, (seg, seg_min)
+    # the launch order egs_isect_sorted emits: a permutation of the tiles, longest lists first (16 length classes,
+    # grid order inside a class); rendering in that order changes nothing
+    order = b2.tile_order.long()
+    n_tiles = tw * th
+    assert torch.equal(torch.sort(order).values, torch.arange(n_tiles, device="cuda"))
+    lens = torch.diff(torch.cat([b2.offsets.reshape(-1), b2.offsets_store[-1:]])).long()
+    cls = 15 - (lens * 16) // (int(lens.max()) + 1)
+    assert bool((cls[order][1:] >= cls[order][:-1]).all()), "classes in descending length order"
+    same = cls[order][1:] == cls[order][:-1]
+    assert bool((order[1:][same] > order[:-1][same]).all()), "grid order inside a class"
+    out_o = stages.rasterize_fwd(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, n_isects=b2.raster_n, tile_order=b2.tile_order)
+    for a, r in zip(out_o, ref):
+        assert torch.equal(a, r)
+    v_o = stages.rasterize_bwd(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, out_o[1], out_o[2], vc, va, n_isects=b2.raster_n,
+                               tile_order=b2.tile_order)
+    assert float((v_o - v_ref).norm() / v_ref.norm()) <= 1e-5

@@ -48,23 +48,23 @@ class FakeStages:
         return (torch.full((C, height, width, 3), 0.25), torch.full((C, height, width, 1), 0.5),
                 torch.zeros(C, height, width, dtype=torch.int32))
 
-    def rasterize_fwd(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, count_pairs=False, n_isects=None):
+    def rasterize_fwd(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, count_pairs=False, n_isects=None, tile_order=None):
         self.calls.append("rasterize_fwd")
         return self._images(splats.shape[0], width, height)
 
     def rasterize_fwd_checkpointed(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, segment,
-                                   seg_min_len=0, n_isects=None):
+                                   seg_min_len=0, n_isects=None, tile_order=None):
         self.calls.append(f"rasterize_fwd_checkpointed({segment})")
         return (*self._images(splats.shape[0], width, height), torch.zeros(16))
 
     def rasterize_bwd(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_alphas, last_ids,
-                      v_render_colors, v_render_alphas, n_isects=None):
+                      v_render_colors, v_render_alphas, n_isects=None, tile_order=None):
         self.calls.append("rasterize_bwd")
         return torch.ones_like(splats)
 
     def rasterize_bwd_segmented(self, splats, isect_offsets, flatten_ids, backgrounds, width, height, render_colors,
                                 render_alphas, last_ids, v_render_colors, v_render_alphas, checkpoints, segment,
-                                seg_min_len=0, n_isects=None):
+                                seg_min_len=0, n_isects=None, tile_order=None):
         self.calls.append(f"rasterize_bwd_segmented({segment})")
         assert checkpoints.numel() == 16 and render_colors.shape[-1] == 3
         return torch.ones_like(splats)
