@@ -798,15 +798,32 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     rc, ra, last, pairs = stages.rasterize_fwd(proj["splats"], offs, flat, bg, W, H, count_pairs=True)
     p_eval, p_acc = int(pairs[0]), int(pairs[1])
     v_splats = stages.rasterize_bwd(proj["splats"], offs, flat, bg, W, H, ra, last, Wc, Wa)
+    del ids_u, flat_u
+
+    # what rasterization() runs: the tight lists (a Gaussian only in the tiles it can reach with alpha >= 1/255), sized
+    # from the previous call, tiles taken longest list first
+    def product_binning():
+        b_ = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th,
+                                       splats=proj["splats"])
+        if not b_.resolve():
+            b_ = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th,
+                                           capacity=b_.n_isects, splats=proj["splats"])
+            b_.resolve()
+        b_.note_for_next_call()
+        return b_
+    pb = product_binning()
+    n_isects_tight = pb.n_isects
+    _, ra_p, last_p = stages.rasterize_fwd(proj["splats"], pb.offsets, pb.flat_cap, bg, W, H, n_isects=pb.raster_n, tile_order=pb.tile_order)
 
     t = {}
     t["projection_sh_fwd"] = tm(lambda: stages.projection_fwd(means, quats, scales, opac, colors, vm, K, W, H, 3))
-    # product path of g3-g5: two-level route (includes its one host sync)
-    t["binning_fast_path"] = tm(lambda: stages.isect_sorted(proj["means2d"], proj["radii"], proj["depths"],
-                                                            proj["tiles_per_gauss"], 16, tw, th, materialize_ids=False))
-    t["rasterize_fwd"] = tm(lambda: stages.rasterize_fwd(proj["splats"], offs, flat, bg, W, H))
+    # product path of g3-g5: two-level route on tight rectangles (its time includes reading the count back)
+    t["binning_fast_path"] = tm(product_binning)
+    t["rasterize_fwd"] = tm(lambda: stages.rasterize_fwd(proj["splats"], pb.offsets, pb.flat_cap, bg, W, H, n_isects=pb.raster_n,
+                                                         tile_order=pb.tile_order))
     zero_ms = tm(lambda: torch.zeros_like(v_splats))
-    t["rasterize_bwd"] = tm(lambda: stages.rasterize_bwd(proj["splats"], offs, flat, bg, W, H, ra, last, Wc, Wa)) - zero_ms
+    t["rasterize_bwd"] = tm(lambda: stages.rasterize_bwd(proj["splats"], pb.offsets, pb.flat_cap, bg, W, H, ra_p, last_p, Wc, Wa,
+                                                         n_isects=pb.raster_n, tile_order=pb.tile_order)) - zero_ms
     t["projection_sh_bwd"] = tm(lambda: stages.projection_bwd(means, quats, scales, colors, vm, K, W, H, 3, 0.3,
                                                                proj["radii"], proj["colors"], v_splats))
     # standalone C-ABI operators of the classic route (64-bit keys), not on the product path any more
@@ -842,11 +859,13 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     #   emission      : order 4 + offset 8 + means2d 8 + radius 4 read per visible Gaussian, 8 B pair written per intersection
     #   level-2 sort  : 4 B histogram read + p2 passes of 16 B per intersection
     #   tile offsets  : 4 B key read per intersection + 4 B per tile
+    #   ("intersection" = an entry of the TIGHT lists the blend kernels work from; n_isects stays gsplat's count)
     key1 = stages.LEVEL1_KEY_BYTES
     p1 = math.ceil(stages.level1_end_bit(Cn) / 8)
     p2 = math.ceil(max(1, int(Cn * tw * th - 1).bit_length()) / 8)
-    two_level_bytes = (8 * N + (4 + key1 + 4) * n_vis + (key1 + 2 * (key1 + 4) * p1) * n_vis + 24 * n_vis + 24 * n_vis
-                       + 8 * n_isects + (4 + 16 * p2) * n_isects + 4 * n_isects + 4 * Cn * tw * th)
+    #   (+ 52 B per visible Gaussian for the tight rectangle: the 48-byte record read, the count written)
+    two_level_bytes = (8 * N + (4 + key1 + 4 + 52) * n_vis + (key1 + 2 * (key1 + 4) * p1) * n_vis + 24 * n_vis + (24 + 48) * n_vis
+                       + 8 * n_isects_tight + (4 + 16 * p2) * n_isects_tight + 4 * n_isects_tight + 4 * Cn * tw * th)
     work = {  # algorithmic bytes (HBM-bound stages) or flops (blend) per launch, BASELINE.md section 4 (frozen)
         "projection_sh_fwd": ("hbm", 68 * N + 204 * n_vis),
         "binning_fast_path": ("hbm", two_level_bytes),
@@ -898,6 +917,7 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
         f"measured live: dependent-FMA probe kernel, {fp32_peak:.1f} TFLOP/s (theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)"
     return {"roofline": roof, "stages": stages_out, "stages_standalone": standalone,
             "scene_stats": {"views_per_launch": Cn, "N": N // Cn, "N_vis": n_vis, "n_isects": n_isects, "isects_per_visible": n_isects / max(n_vis, 1),
+                            "n_isects_tight": n_isects_tight,
                             "P_eval": p_eval, "P_acc": p_acc, "fp32_peak_tflops_measured": fp32_peak,
                             "sum_stage_ms": sum(t.values())}}
 

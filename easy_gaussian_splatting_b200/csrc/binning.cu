@@ -206,15 +206,49 @@ __global__ void __launch_bounds__(kScanThreads) visible_spine_kernel(int64_t* __
   if (threadIdx.x == 0) { totals[0] = carry; totals[1] = tiles_total; totals[2] = 0; totals[3] = 0; }
 }
 
+// Tight tile rectangle of a visible Gaussian for the BLEND kernels' lists: the classic rectangle (3-sigma square of the
+// major axis, gsplat's rule, which the meta lists must reproduce bit for bit) intersected with the axis-aligned extent
+// of {alpha >= 1/255} = {sigma <= sigma_cut}: |dx| <= sqrt(2 sigma_cut cov_xx), cov = conic^-1.  Tiles outside it hold
+// no pixel the Gaussian can reach (the blend kernels would cull the entry for both warps of such a tile), so they need
+// not be listed: 36 % fewer entries on the 1 M-Gaussian benchmark scene (scripts/analysis/tight_rects.py), which is
+// 36 % less to sort, stage and cull.  Margins: sigma_cut itself is ln(255 o) * 1.001 + 2e-3 (egs_math.cuh), the
+// extents get another 0.1 % + 0.05 px, and an ill-conditioned conic (det lost to cancellation) keeps the classic
+// rectangle.  In: the classic rectangle; out: the tight one (empty when the Gaussian can never reach 1/255).
+__device__ __forceinline__ void tighten_tile_rect(const float4 g0, const float4 g1, float sigma_cut, float tile_size,
+                                                  int32_t& x0, int32_t& y0, int32_t& x1, int32_t& y1) {
+  if (!(sigma_cut > 0.f)) { x1 = x0; y1 = y0; return; }
+  const float a = g0.z, b = g0.w, c = g1.x;
+  const float det = a * c - b * b;
+  if (!(det > 1e-4f * a * c) || !(det > 0.f)) return;
+  const float k = 2.0f * sigma_cut / det;
+  const float hx = sqrtf(k * c) * 1.001f + 0.05f, hy = sqrtf(k * a) * 1.001f + 0.05f;
+  if (!(hx < 1e8f) || !(hy < 1e8f)) return;
+  // pixel centres p + 0.5 within [m - h, m + h]  ->  tiles floor(p / tile_size), max exclusive
+  const float inv = 1.0f / tile_size;
+  const float tx0 = floorf(ceilf(g0.x - hx - 0.5f) * inv), tx1 = floorf(floorf(g0.x + hx - 0.5f) * inv) + 1.0f;
+  const float ty0 = floorf(ceilf(g0.y - hy - 0.5f) * inv), ty1 = floorf(floorf(g0.y + hy - 0.5f) * inv) + 1.0f;
+  x0 = max(x0, (int32_t)fminf(fmaxf(tx0, -1e9f), 1e9f));
+  x1 = min(x1, (int32_t)fminf(fmaxf(tx1, -1e9f), 1e9f));
+  y0 = max(y0, (int32_t)fminf(fmaxf(ty0, -1e9f), 1e9f));
+  y1 = min(y1, (int32_t)fminf(fmaxf(ty1, -1e9f), 1e9f));
+  if (x1 < x0) x1 = x0;
+  if (y1 < y0) y1 = y0;
+}
+
 // also writes the level-1 sort input: key = bits(depth), value = flat index (camera * N + Gaussian), compacted.
 // The camera needs no key bits: level 2 sorts stably on the (camera, tile) index, so sorting the visible entries of
 // ALL cameras on depth alone (ties keep the flat-index order they are written in here) leaves every (camera, tile)
 // bucket in (depth, flat index) order — the order of a sort on cam | tile | depth.
+// With splats != nullptr it also writes tight_counts[flat index] = tiles of the TIGHT rectangle for every visible entry.
 __global__ void __launch_bounds__(kScanThreads) visible_apply_kernel(const int32_t* __restrict__ tiles, int64_t n,
                                                                       const int64_t* __restrict__ sums_vis,
                                                                       const float* __restrict__ depths,
                                                                       uint32_t* __restrict__ keys1,
-                                                                      uint32_t* __restrict__ vals1) {
+                                                                      uint32_t* __restrict__ vals1,
+                                                                      const float4* __restrict__ splats,
+                                                                      const int32_t* __restrict__ radii, float tile_size,
+                                                                      int tile_w, int tile_h,
+                                                                      int32_t* __restrict__ tight_counts) {
   __shared__ int64_t smem[33];
   const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
   int32_t v[kScanItems];
@@ -234,6 +268,14 @@ __global__ void __launch_bounds__(kScanThreads) visible_apply_kernel(const int32
       keys1[run] = __float_as_uint(depths[idx]);
       vals1[run] = (uint32_t)idx;
       ++run;
+      if (splats != nullptr) {
+        const float4 g0 = splats[idx * 3 + 0], g1 = splats[idx * 3 + 1];
+        const float cut = splats[idx * 3 + 2].w;
+        int32_t x0, y0, x1, y1;
+        tile_rect(g0.x, g0.y, radii[idx], tile_size, tile_w, tile_h, x0, y0, x1, y1);
+        tighten_tile_rect(g0, g1, cut, tile_size, x0, y0, x1, y1);
+        tight_counts[idx] = (x1 - x0) * (y1 - y0);
+      }
     }
   }
 }
@@ -287,7 +329,8 @@ __global__ void __launch_bounds__(kEmitThreads) isect_emit_sorted_kernel(
     int N, int64_t n_vis, const uint32_t* __restrict__ order, const int64_t* __restrict__ cum_excl,
     const float2* __restrict__ means2d, const int32_t* __restrict__ radii, float tile_size, int tile_w, int tile_h,
     int64_t n_isects, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ flat_vals,
-    const int64_t* __restrict__ counts_dev /* nullable: {n_vis, n_isects} live counts, the arguments are capacities */) {
+    const int64_t* __restrict__ counts_dev /* nullable: {n_vis, n_isects} live counts, the arguments are capacities */,
+    const float4* __restrict__ splats /* nullable: emit the TIGHT rectangles (tighten_tile_rect) */) {
   if (counts_dev != nullptr) {
     n_vis = live_count(n_vis, counts_dev);
     n_isects = live_count(n_isects, counts_dev + 1);
@@ -303,6 +346,8 @@ __global__ void __launch_bounds__(kEmitThreads) isect_emit_sorted_kernel(
     const float2 m = means2d[g];
     int32_t x1, y1;
     tile_rect(m.x, m.y, radii[g], tile_size, tile_w, tile_h, x0, y0, x1, y1);
+    if (splats != nullptr)
+      tighten_tile_rect(splats[(size_t)g * 3 + 0], splats[(size_t)g * 3 + 1], splats[(size_t)g * 3 + 2].w, tile_size, x0, y0, x1, y1);
     w = max(x1 - x0, 1);
     cnt = (x1 - x0) * (y1 - y0);
     excl = cum_excl[i];
@@ -490,8 +535,37 @@ extern "C" int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles
   int64_t* sums_tiles = sums_vis + nblocks + 1;
   visible_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, sums_tiles);
   visible_spine_kernel<<<1, kScanThreads, 0, stream>>>(sums_vis, sums_tiles, nblocks, totals);
-  visible_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, depths, keys1, vals1);
+  visible_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, depths, keys1, vals1,
+                                                                       nullptr, nullptr, 16.f, 0, 0, nullptr);
   return check_launch("isect_visible_keys", 3);
+}
+
+extern "C" int egs_isect_visible_keys_tight(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths,
+                                            const float* splats, const int32_t* radii, int32_t tile_size,
+                                            int32_t tile_width, int32_t tile_height, uint32_t* keys1, uint32_t* vals1,
+                                            int32_t* tight_counts, int64_t* totals, void* workspace,
+                                            int64_t workspace_bytes, egs_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EGS_REQUIRE(C >= 0 && N >= 0, "isect_visible_keys_tight: negative sizes");
+  const int64_t n = (int64_t)C * N;
+  EGS_REQUIRE(n < 0x7fffffffLL, "isect_visible_keys_tight: C*N=%lld does not fit the int32 flatten id", (long long)n);
+  EGS_REQUIRE(splats != nullptr && radii != nullptr && tight_counts != nullptr, "isect_visible_keys_tight: splats, radii and tight_counts are required");
+  EGS_REQUIRE(reinterpret_cast<uintptr_t>(splats) % 16 == 0, "isect_visible_keys_tight: splats must be 16-byte aligned");
+  if (n == 0) {
+    EGS_CUDA(cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), stream));
+    return 0;
+  }
+  if (workspace_bytes < egs_isect_scan_workspace_bytes(n))
+    return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "isect_visible_keys_tight: workspace too small");
+  const int64_t nblocks = ceil_div(n, kScanTile);
+  int64_t* sums_vis = reinterpret_cast<int64_t*>(workspace);
+  int64_t* sums_tiles = sums_vis + nblocks + 1;
+  visible_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, sums_tiles);
+  visible_spine_kernel<<<1, kScanThreads, 0, stream>>>(sums_vis, sums_tiles, nblocks, totals);
+  visible_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(
+      tiles_per_gauss, n, sums_vis, depths, keys1, vals1, reinterpret_cast<const float4*>(splats), radii, (float)tile_size,
+      tile_width, tile_height, tight_counts);
+  return check_launch("isect_visible_keys_tight", 3);
 }
 
 extern "C" int egs_exclusive_scan_gather(int64_t n, const int32_t* src, const uint32_t* gather, int64_t* out,
@@ -524,7 +598,7 @@ extern "C" int egs_isect_emit_sorted(int32_t C, int32_t N, int64_t n_vis, const 
   if (n_vis == 0 || n_isects == 0) return 0;
   isect_emit_sorted_kernel<<<(unsigned)ceil_div(n_vis, kEmitThreads), kEmitThreads, 0, (cudaStream_t)stream>>>(
       N, n_vis, order, cum_excl, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width,
-      tile_height, n_isects, tile_keys, flat_vals, nullptr);
+      tile_height, n_isects, tile_keys, flat_vals, nullptr, nullptr);
   return check_launch("isect_emit_sorted_kernel");
 }
 
@@ -665,7 +739,7 @@ extern "C" int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_
   return sorted_layout(n > 0 ? n : 1, capacity > 0 ? capacity : 1, level2_end_bit((int64_t)C * n_tiles)).total;
 }
 
-extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* means2d,
+extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts, const float* splats, const float* means2d,
                                 const int32_t* radii, uint32_t* keys1, uint32_t* vals1, int64_t* stats,
                                 int32_t tile_size, int32_t tile_width, int32_t tile_height, int64_t capacity,
                                 void* workspace, int64_t workspace_bytes, uint32_t* tile_keys, uint32_t* flatten_ids,
@@ -680,8 +754,9 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_g
               "isect_sorted: tile grid %dx%d too large for the reciprocal row split", tile_width, tile_height);
   EGS_REQUIRE(capacity >= 1 && capacity < 0x7fffffffLL, "isect_sorted: capacity=%lld out of int32 range", (long long)capacity);
   EGS_REQUIRE(stats != nullptr, "isect_sorted: the device counts {n_vis, n_isects, ..} of egs_isect_visible_keys are required");
-  const int64_t* counts = stats;
-  stats += 2;  // slot 2: longest tile list (output)
+  const int64_t* counts = stats;       // [0] n_vis (input), [1] intersection count (rewritten below from tile_counts)
+  int64_t* n_isects_dev = stats + 1;
+  stats += 2;                          // slot 2: longest tile list (output)
   if (n_slots == 0) return 0;
   if (n == 0) {  // nothing to bin: all offsets (and the sentinel) are zero, any launch order will do
     EGS_CUDA(cudaMemsetAsync(offsets, 0, (n_slots + 1) * sizeof(int32_t), stream));
@@ -704,9 +779,11 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_g
   const uint32_t* order = in_b ? vals1_b : vals1;
   // tile counts in that order -> write offsets (the grand total is counts[1] already; the spine's copy lands in block_sums' tail)
   const int64_t nblocks = ceil_div(n, kScanTile);
-  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, order, n, counts, block_sums);
-  scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, block_sums + nblocks);
-  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, order, n, counts, block_sums, cum);
+  // (tile_counts: the classic tiles_per_gauss, or the tight counts of egs_isect_visible_keys_tight; their total over
+  //  the visible entries becomes stats[1], the intersection count every kernel below works with)
+  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tile_counts, order, n, counts, block_sums);
+  scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, n_isects_dev);
+  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tile_counts, order, n, counts, block_sums, cum);
   // emission into whichever side of the level-2 ping-pong makes the sorted pairs end in the caller's buffers
   const int passes2 = (end_bit2 + 7) / 8;
   uint32_t* ka = (passes2 & 1) ? reinterpret_cast<uint32_t*>(ws + L.keys2) : tile_keys;
@@ -715,7 +792,7 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_g
   uint32_t* vb = (passes2 & 1) ? flatten_ids : reinterpret_cast<uint32_t*>(ws + L.vals2);
   isect_emit_sorted_kernel<<<(unsigned)ceil_div(n, kEmitThreads), kEmitThreads, 0, stream>>>(
       N, n, order, cum, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width, tile_height, capacity,
-      ka, va, counts);
+      ka, va, counts, reinterpret_cast<const float4*>(splats));
   if (int rc = check_launch("isect_sorted (scan + emit)", 4)) return rc;
   // level 2: stable sort on the dense (camera, tile) index
   if (int rc = radix_sort_pairs_u32(capacity, counts + 1, ka, va, kb, vb, end_bit2, ws + L.sort2, L.total - L.sort2, &in_b, stream))

@@ -89,6 +89,35 @@ class _LazyMeta(dict):
         return (dict, (self.copy(),))
 
 
+class _ClassicLists:
+    """gsplat's own intersection lists — ``isect_ids``, ``flatten_ids``, ``isect_offsets``: every Gaussian in every
+    tile of its 3-sigma square — computed on first access with the classic route (64-bit keys, 6-pass sort, offset
+    encode; bit-identical to gsplat 1.0.0's ``isect_tiles`` / ``isect_offset_encode``).  The blend kernels work from
+    TIGHT lists (stages.isect_sorted_async(splats=...): a third fewer entries, same pixels and gradients), and nothing
+    downstream of the reference reads these three meta entries, so building them per call would be wasted work."""
+
+    def __init__(self, means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_width: int, tile_height: int):
+        self._args = (means2d.detach(), radii, depths, tiles_per_gauss, tile_width, tile_height)
+        self._lists = None
+
+    def _get(self):
+        if self._lists is None:
+            means2d, radii, depths, tpg, tw, th = self._args
+            _, ids, flat = stages.isect_tiles(means2d, radii, depths, stages.TILE_SIZE, tw, th, sort=True, tiles_per_gauss=tpg)
+            self._lists = (ids, flat, stages.isect_offset_encode(ids, radii.shape[0], tw, th))
+            self._args = None
+        return self._lists
+
+    def isect_ids(self) -> Tensor:
+        return self._get()[0]
+
+    def flatten_ids(self) -> Tensor:
+        return self._get()[1]
+
+    def isect_offsets(self) -> Tensor:
+        return self._get()[2]
+
+
 def _tag_absgrad(target: Tensor, absgrad: Tensor, packed_index: Optional[Tensor]) -> None:
     """``meta["means2d"].absgrad`` in the layout of ``meta["means2d"]``: dense [C,N,2], or [nnz,2] when packed."""
     target.absgrad = absgrad if packed_index is None else absgrad.reshape(-1, 2)[packed_index]
@@ -112,7 +141,7 @@ def _bin_and_blend(ctx, proj, backgrounds, width, height, grad_enabled=True):
     while True:
         with stages.nvtx_range("egs.binning"):
             b = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"],
-                                          stages.TILE_SIZE, tw, th, capacity=capacity)
+                                          stages.TILE_SIZE, tw, th, capacity=capacity, splats=proj["splats"])
         with stages.nvtx_range("egs.rasterize_fwd"):
             if seg > 0:
                 rc, ra, last, ckpt = stages.rasterize_fwd_checkpointed(proj["splats"], b.offsets, b.flat_cap, backgrounds, width,
@@ -159,7 +188,10 @@ class _Rasterization(torch.autograd.Function):
         tiles_per_gauss = proj["tiles_per_gauss"]
         binned, render_colors, render_alphas, last_ids, ckpt = _bin_and_blend(ctx, proj, backgrounds, width, height,
                                                                              cfg.get("grad_enabled", True))
-        cfg["isect_ids_thunk"] = binned.isect_ids  # handed to the wrapper (not a tensor: cannot be an output)
+        # meta's three list entries are gsplat's lists, built on first access (not tensors: cannot be outputs); the
+        # outputs below carry the tight lists the kernels used
+        cfg["classic_lists"] = _ClassicLists(proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss,
+                                             *stages.tile_grid(width, height))
         flatten_ids, isect_offsets = binned.flatten_ids, binned.offsets
 
         means2d = proj["means2d"]
@@ -220,7 +252,8 @@ class _RasterizationRaw(torch.autograd.Function):
         tiles_per_gauss = proj["tiles_per_gauss"]
         binned, render_colors, render_alphas, last_ids, ckpt = _bin_and_blend(ctx, proj, backgrounds, width, height,
                                                                              cfg.get("grad_enabled", True))
-        cfg["isect_ids_thunk"] = binned.isect_ids
+        cfg["classic_lists"] = _ClassicLists(proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss,
+                                             *stages.tile_grid(width, height))
         flatten_ids, isect_offsets = binned.flatten_ids, binned.offsets
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)
@@ -359,8 +392,9 @@ def rasterization(
 
 def _finish(outs, cfg, opacities_cn, width, height, tile_size, C, absgrad, packed=False):
     (render_colors, render_alphas, means2d, radii, depths, conics, colors_rgb, tiles_per_gauss,
-     flatten_ids, isect_offsets, _last_ids) = outs
-    isect_ids = cfg.pop("isect_ids_thunk")
+     _blend_flatten_ids, _blend_offsets, _last_ids) = outs
+    classic = cfg.pop("classic_lists")
+    isect_ids, flatten_ids, isect_offsets = classic.isect_ids, classic.flatten_ids, classic.isect_offsets
     cfg.pop("compensations", None)
     camera_ids = gaussian_ids = None
     node = render_colors.grad_fn
@@ -375,7 +409,8 @@ def _finish(outs, cfg, opacities_cn, width, height, tile_size, C, absgrad, packe
         camera_ids = torch.div(packed_index, N, rounding_mode="floor")
         gaussian_ids = packed_index - camera_ids * N
         rank = torch.cumsum(visible, 0, dtype=torch.int32) - 1  # flat (c,n) index -> row of the packed list
-        flatten_ids = rank[flatten_ids.long()]
+        dense_flatten_ids = flatten_ids
+        flatten_ids = lambda: rank[dense_flatten_ids().long()]  # stays lazy: built from gsplat's list on first access
         means2d = means2d.reshape(-1, 2)[packed_index]  # differentiable gather: gradients on it reach the dense one
         radii, depths, tiles_per_gauss = (t.reshape(-1)[packed_index] for t in (radii, depths, tiles_per_gauss))
         conics, colors_rgb = (t.reshape(-1, 3)[packed_index] for t in (conics, colors_rgb))

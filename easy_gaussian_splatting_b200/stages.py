@@ -460,7 +460,8 @@ class SortedIsects:
                  tile_order=None):
         self.key, self.C, self.n_tiles, self.capacity = key, C, n_tiles, capacity
         self.tile_keys_cap, self.flat_cap, self.offsets_store, self.offsets = tile_keys, flat, offsets_store, offsets
-        self.tile_order = tile_order  # launch order of the blend kernels: tiles by list length, longest first
+        # launch order of the blend kernels: tiles by list length, longest first (EGS_TILE_ORDER=0: grid order, for A/B runs)
+        self.tile_order = tile_order if os.environ.get("EGS_TILE_ORDER", "1") != "0" else None
         self.depths, self.stats_dev = depths, stats_dev
         self._early, self._early_event = early, early_event
         self.n_vis: Optional[int] = None
@@ -543,10 +544,10 @@ def tile_n_bits_from_count(n_tiles: int) -> int:
     return int(math.floor(math.log2(n_tiles))) + 1
 
 
-def binning_hint(C: int, tile_width: int, tile_height: int, device) -> Optional[Dict[str, int]]:
+def binning_hint(C: int, tile_width: int, tile_height: int, device, tight: bool = True) -> Optional[Dict[str, int]]:
     """What the previous call of this shape on this device needed: {'n_isects', 'max_tile_len' (if it has arrived)}."""
     dev = torch.device(device)
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), C, tile_width, tile_height)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), C, tile_width, tile_height, tight)
     with _HINT_LOCK:
         h = _HINTS.get(key)
         if h is None:
@@ -558,10 +559,16 @@ def binning_hint(C: int, tile_width: int, tile_height: int, device) -> Optional[
 
 
 def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
-                       tile_width: int, tile_height: int, capacity: Optional[int] = None) -> SortedIsects:
+                       tile_width: int, tile_height: int, capacity: Optional[int] = None,
+                       splats: Optional[Tensor] = None) -> SortedIsects:
     """g3+g4+g5, enqueued without waiting for the intersection count (see the block comment above).  ``capacity``:
     intersections to provide room for; None = from the previous call of this shape, or — first call — wait and size
-    exactly."""
+    from the classic count (an upper bound).
+
+    ``splats`` (the packed records of ``projection_fwd``): build the TIGHT lists the blend kernels need instead of
+    gsplat's — a Gaussian is listed only in the tiles of its classic rectangle that hold a pixel it can reach with
+    alpha >= 1/255 (include/egs_raster.h, egs_isect_sorted).  Same pixels and gradients, a third fewer entries to
+    sort, stage and cull.  Without it the lists are bit-identical to gsplat's (``isect_tiles`` + offset encode)."""
     lib = _lib.load()
     means2d, depths = _f32c(means2d, "means2d"), _f32c(depths, "depths")
     radii, tiles_per_gauss = radii.contiguous(), tiles_per_gauss.contiguous()
@@ -569,15 +576,24 @@ def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per
     dev = radii.device
     n = C * N
     n_tiles = tile_width * tile_height
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), C, tile_width, tile_height)
+    tight = splats is not None
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), C, tile_width, tile_height, tight)
     ws_scan = max(lib.egs_isect_scan_workspace_bytes(max(n, 1)), 16)
     scan_ws = torch.empty(ws_scan, dtype=torch.uint8, device=dev)
     stats = torch.empty(4, dtype=torch.int64, device=dev)
     keys1 = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     vals1 = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    tile_counts = tiles_per_gauss
     with torch.cuda.device(dev):
-        rc = lib.egs_isect_visible_keys(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(keys1), _ptr(vals1), _ptr(stats),
-                                        _ptr(scan_ws), ws_scan, _stream(dev))
+        if tight:
+            splats = _f32c(splats, "splats")
+            tile_counts = torch.empty(max(n, 1), dtype=torch.int32, device=dev)  # written for visible entries only
+            rc = lib.egs_isect_visible_keys_tight(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(splats), _ptr(radii),
+                                                  int(tile_size), tile_width, tile_height, _ptr(keys1), _ptr(vals1),
+                                                  _ptr(tile_counts), _ptr(stats), _ptr(scan_ws), ws_scan, _stream(dev))
+        else:
+            rc = lib.egs_isect_visible_keys(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(keys1), _ptr(vals1), _ptr(stats),
+                                            _ptr(scan_ws), ws_scan, _stream(dev))
     _lib.check(rc, "egs_isect_visible_keys")
     early = _pinned_slot(dev)
     early.copy_(stats, non_blocking=True)
@@ -589,7 +605,7 @@ def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per
             h = _HINTS.get(key)
         if h is not None:
             capacity = int(h["n_isects"] * _CAPACITY_SLACK) + 65536
-        else:  # no guess: the one blocking read, as in every call before round 2
+        else:  # no guess: the one blocking read, as in every call before round 2 (the classic count bounds the tight one)
             early_event.synchronize()
             capacity, exact = int(early[1]), True
     else:
@@ -603,10 +619,17 @@ def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per
     ws_bytes = lib.egs_isect_sorted_workspace_bytes(C, N, n_tiles, capacity)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.egs_isect_sorted(C, N, _ptr(tiles_per_gauss), _ptr(means2d), _ptr(radii), _ptr(keys1), _ptr(vals1), _ptr(stats),
-                                  int(tile_size), tile_width, tile_height, capacity, _ptr(ws), ws.numel(), _ptr(tile_keys),
-                                  _ptr(flat), _ptr(offsets_store), _ptr(tile_order), _stream(dev))
+        rc = lib.egs_isect_sorted(C, N, _ptr(tile_counts), _ptr(splats) if tight else None, _ptr(means2d), _ptr(radii),
+                                  _ptr(keys1), _ptr(vals1), _ptr(stats), int(tile_size), tile_width, tile_height, capacity,
+                                  _ptr(ws), ws.numel(), _ptr(tile_keys), _ptr(flat), _ptr(offsets_store), _ptr(tile_order),
+                                  _stream(dev))
     _lib.check(rc, "egs_isect_sorted")
+    if tight:
+        # the count that matters is the emitted one (stats[1], rewritten by the route): read it back the same way
+        early = _pinned_slot(dev)
+        early.copy_(stats, non_blocking=True)
+        early_event = torch.cuda.Event()
+        early_event.record(torch.cuda.current_stream(dev))
     return SortedIsects(key, C, n_tiles, capacity, tile_keys, flat, offsets_store, offsets, depths, stats, early, early_event, exact,
                         tile_order=tile_order)
 
@@ -624,6 +647,7 @@ def isect_sorted(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss
     if not b.resolve():
         b = isect_sorted_async(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height, capacity=b.n_isects)
         b.resolve()
+    assert b.exact or b.n_isects <= b.capacity
     b.note_for_next_call()
     return (b.isect_ids() if materialize_ids else b.isect_ids), b.flatten_ids, b.offsets
 

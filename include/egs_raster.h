@@ -200,10 +200,20 @@ int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, 
  *            flat indices, the first n_isects valid.  offsets [C * n_tiles + 1]: tile offsets plus a SENTINEL entry
  *            holding n_isects, which egs_rasterize_* read when they are given a negative n_isects.
  *   tile_order [C * n_tiles] (nullable): the flat tile indices sorted by list length, longest first — the launch
- *            order for egs_rasterize_* (their tile_order argument). */
+ *            order for egs_rasterize_* (their tile_order argument).
+ *   TIGHT lists (splats != NULL, tile_counts = the tight counts of egs_isect_visible_keys_tight): every Gaussian is
+ *            listed only in the tiles of its classic rectangle that hold a pixel it can reach with alpha >= 1/255
+ *            (axis-aligned extent of sigma <= sigma_cut, from the splat records).  The blend kernels produce the same
+ *            pixels and gradients from them (a dropped entry has alpha < 1/255 at every pixel of its tile);
+ *            the lists themselves then differ from gsplat's, which the classic route (tile_counts =
+ *            tiles_per_gauss, splats = NULL) reproduces bit for bit.  stats[1] is rewritten with the emitted total. */
 int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_t n_tiles, int64_t capacity);
-int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* means2d, const int32_t* radii,
-                     uint32_t* keys1, uint32_t* vals1, int64_t* stats, int32_t tile_size, int32_t tile_width,
+int egs_isect_visible_keys_tight(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths,
+                                 const float* splats, const int32_t* radii, int32_t tile_size, int32_t tile_width,
+                                 int32_t tile_height, uint32_t* keys1, uint32_t* vals1, int32_t* tight_counts,
+                                 int64_t* totals, void* workspace, int64_t workspace_bytes, egs_stream_t stream);
+int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts, const float* splats, const float* means2d,
+                     const int32_t* radii, uint32_t* keys1, uint32_t* vals1, int64_t* stats, int32_t tile_size, int32_t tile_width,
                      int32_t tile_height, int64_t capacity, void* workspace, int64_t workspace_bytes,
                      uint32_t* tile_keys, uint32_t* flatten_ids, int32_t* offsets, int32_t* tile_order,
                      egs_stream_t stream);

@@ -49,7 +49,15 @@ def projection_fwd(means, quats, scales, opacities, colors, viewmats, Ks, width,
             "colors": cols.contiguous(), "tiles_per_gauss": tpg, "splats": splats.contiguous()}
 
 
-def isect_sorted_async(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height, capacity=None):
+def isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, tiles_per_gauss=None, n_isects=None):
+    return O.isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height, sort=sort)
+
+
+def isect_offset_encode(isect_ids, C, tile_width, tile_height):
+    return O.isect_offset_encode(isect_ids, C, tile_width, tile_height)
+
+
+def isect_sorted_async(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height, capacity=None, splats=None):
     C = radii.shape[0]
     _, ids, flat = O.isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height, sort=True)
     offsets = O.isect_offset_encode(ids, C, tile_width, tile_height)
@@ -122,8 +130,8 @@ def densify_stats_update(max_radii, grad_norm_accum, collecting_counts, radii, a
 def install(monkeypatch) -> None:
     """Route ``stages`` to the emulation and let ``rendering`` accept CPU tensors (its own check refuses them:
     the product has no CPU path)."""
-    for name in ("projection_fwd", "isect_sorted_async", "rasterize_fwd", "rasterize_bwd", "projection_bwd",
-                 "densify_stats_update"):
+    for name in ("projection_fwd", "isect_sorted_async", "isect_tiles", "isect_offset_encode", "rasterize_fwd", "rasterize_bwd",
+                 "projection_bwd", "densify_stats_update"):
         monkeypatch.setattr(stages, name, globals()[name])
     monkeypatch.setattr(stages, "binning_hint", lambda *a, **k: None)
     monkeypatch.setattr(rendering, "_check_inputs", lambda *a, **k: None)

@@ -372,3 +372,44 @@ def test_sentinel_mode_equals_exact_length_mode():
     v_o = stages.rasterize_bwd(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, out_o[1], out_o[2], vc, va, n_isects=b2.raster_n,
                                tile_order=b2.tile_order)
     assert float((v_o - v_ref).norm() / v_ref.norm()) <= 1e-5
+
+
+@pytest.mark.parametrize("cfg", SCENES)
+def test_tight_lists_hold_a_subset_and_render_identically(cfg):
+    """The blend kernels' own lists (isect_sorted_async(splats=...)): every Gaussian only in the tiles that hold a
+    pixel it can reach.  They must be a sub-list of gsplat's (same order), and forward / backward through them must
+    give the same pixels bit for bit and the same gradients."""
+    stages = _stages()
+    sc = make_scene(**cfg).to("cuda")
+    W, H, C = sc.width, sc.height, sc.viewmats.shape[0]
+    tw, th = stages.tile_grid(W, H)
+    proj = stages.projection_fwd(sc.means, sc.quats, sc.scales, sc.opacities, sc.colors, sc.viewmats, sc.Ks, W, H, 3)
+    args = (proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th)
+    stages.reset_binning_hints()
+    cl = stages.isect_sorted_async(*args)
+    tg = stages.isect_sorted_async(*args, splats=proj["splats"])
+    assert cl.resolve() and tg.resolve()
+    n_t = C * tw * th
+    key = lambda b: (torch.repeat_interleave(torch.arange(n_t, device="cuda"),
+                                             torch.diff(torch.cat([b.offsets.reshape(-1), b.offsets_store[-1:]])).long()) * (C * sc.means.shape[0])
+                     + b.flatten_ids.long())
+    kc, kt = key(cl), key(tg)
+    print(cfg["kind"], "classic", cl.n_isects, "tight", tg.n_isects, round(tg.n_isects / max(cl.n_isects, 1), 3))
+    assert tg.n_isects < cl.n_isects
+    pos = torch.searchsorted(torch.sort(kc).values, kt)
+    assert bool((torch.sort(kc).values[pos.clamp_max(kc.numel() - 1)] == kt).all()), "every tight entry is a classic entry"
+    # same relative order inside every tile: the tight list is the classic list with entries removed
+    keep = torch.isin(kc, kt)
+    assert torch.equal(kc[keep], kt)
+    bg = sc.background[None].expand(C, 3).contiguous()
+    ref = stages.rasterize_fwd(proj["splats"], cl.offsets, cl.flatten_ids, bg, W, H)
+    out = stages.rasterize_fwd(proj["splats"], tg.offsets, tg.flat_cap, bg, W, H, n_isects=tg.raster_n, tile_order=tg.tile_order)
+    assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
+    hit = ref[1][..., 0] > 0
+    assert torch.equal(tg.flat_cap[out[2][hit].long()], cl.flatten_ids[ref[2][hit].long()]), "same last blended Gaussian per pixel"
+    g = torch.Generator(device="cuda").manual_seed(0)
+    vc, va = torch.rand(C, H, W, 3, device="cuda", generator=g), torch.rand(C, H, W, 1, device="cuda", generator=g)
+    v_ref = stages.rasterize_bwd(proj["splats"], cl.offsets, cl.flatten_ids, bg, W, H, ref[1], ref[2], vc, va)
+    v_out = stages.rasterize_bwd(proj["splats"], tg.offsets, tg.flat_cap, bg, W, H, out[1], out[2], vc, va, n_isects=tg.raster_n,
+                                 tile_order=tg.tile_order)
+    assert float((v_out - v_ref).norm() / v_ref.norm()) <= 1e-5

@@ -35,7 +35,15 @@ class FakeStages:
             out["compensations"] = torch.full((C, N), 0.5) * vis
         return out
 
-    def isect_sorted_async(self, means2d, radii, depths, tiles_per_gauss, tile_size, tw, th, capacity=None):
+    def isect_tiles(self, means2d, radii, depths, tile_size, tw, th, sort=True, tiles_per_gauss=None, n_isects=None):
+        """gsplat's lists (meta's lazy entries): same stand-in values as the blend lists below"""
+        flat = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0].int().repeat_interleave(2)
+        return tiles_per_gauss, torch.arange(flat.numel(), dtype=torch.int64), flat
+
+    def isect_offset_encode(self, isect_ids, C, tw, th):
+        return torch.zeros(C, th, tw, dtype=torch.int32)
+
+    def isect_sorted_async(self, means2d, radii, depths, tiles_per_gauss, tile_size, tw, th, capacity=None, splats=None):
         self.calls.append("isect_sorted")
         C, N = radii.shape
         flat = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0].int()
@@ -103,7 +111,8 @@ FakeStages.projection_bwd_raw = _raw_bwd
 @pytest.fixture()
 def fake(monkeypatch):
     f = FakeStages()
-    for name in ("projection_fwd", "isect_sorted_async", "rasterize_fwd", "rasterize_fwd_checkpointed", "rasterize_bwd",
+    for name in ("projection_fwd", "isect_sorted_async", "isect_tiles", "isect_offset_encode", "rasterize_fwd",
+                 "rasterize_fwd_checkpointed", "rasterize_bwd",
                  "rasterize_bwd_segmented", "projection_bwd", "projection_fwd_raw", "projection_bwd_raw"):
         monkeypatch.setattr(stages, name, getattr(f, name))
     monkeypatch.setattr(stages, "binning_hint", lambda *a, **k: None)  # CPU tensors: no device, no previous call
