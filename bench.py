@@ -798,7 +798,6 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     rc, ra, last, pairs = stages.rasterize_fwd(proj["splats"], offs, flat, bg, W, H, count_pairs=True)
     p_eval, p_acc = int(pairs[0]), int(pairs[1])
     v_splats = stages.rasterize_bwd(proj["splats"], offs, flat, bg, W, H, ra, last, Wc, Wa)
-    del ids_u, flat_u
 
     # what rasterization() runs: the tight lists (a Gaussian only in the tiles it can reach with alpha >= 1/255), sized
     # from the previous call, tiles taken longest list first

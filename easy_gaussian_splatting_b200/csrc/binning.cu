@@ -549,12 +549,12 @@ extern "C" int egs_isect_visible_keys_tight(int32_t C, int32_t N, const int32_t*
   EGS_REQUIRE(C >= 0 && N >= 0, "isect_visible_keys_tight: negative sizes");
   const int64_t n = (int64_t)C * N;
   EGS_REQUIRE(n < 0x7fffffffLL, "isect_visible_keys_tight: C*N=%lld does not fit the int32 flatten id", (long long)n);
-  EGS_REQUIRE(splats != nullptr && radii != nullptr && tight_counts != nullptr, "isect_visible_keys_tight: splats, radii and tight_counts are required");
-  EGS_REQUIRE(reinterpret_cast<uintptr_t>(splats) % 16 == 0, "isect_visible_keys_tight: splats must be 16-byte aligned");
   if (n == 0) {
     EGS_CUDA(cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), stream));
     return 0;
   }
+  EGS_REQUIRE(splats != nullptr && radii != nullptr && tight_counts != nullptr, "isect_visible_keys_tight: splats, radii and tight_counts are required");
+  EGS_REQUIRE(reinterpret_cast<uintptr_t>(splats) % 16 == 0, "isect_visible_keys_tight: splats must be 16-byte aligned");
   if (workspace_bytes < egs_isect_scan_workspace_bytes(n))
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "isect_visible_keys_tight: workspace too small");
   const int64_t nblocks = ceil_div(n, kScanTile);

@@ -318,9 +318,8 @@ def test_async_binning_guess_too_small_too_large_and_empty():
     assert seen[2][1] is False and seen[2][2] is True, "same scene again: guessed, and the guess held"
     assert seen[3][2] is True and seen[3][3] > 4 * max(seen[3][4], 1), "a far too large buffer is fine"
     assert seen[4][4] == 0 and seen[5][2] is True
-    hint = stages.binning_hint(1, tw, th, "cuda")
     torch.cuda.synchronize()
-    hint = stages.binning_hint(1, tw, th, "cuda")
+    hint = stages.binning_hint(1, tw, th, "cuda", tight=False)
     assert hint["n_isects"] == seen[5][4] and hint["max_tile_len"] == int(torch.diff(torch.cat([offs.reshape(-1), offs.new_tensor([flat.numel()])])).max())
 
 
