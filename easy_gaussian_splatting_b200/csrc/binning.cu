@@ -206,49 +206,15 @@ __global__ void __launch_bounds__(kScanThreads) visible_spine_kernel(int64_t* __
   if (threadIdx.x == 0) { totals[0] = carry; totals[1] = tiles_total; totals[2] = 0; totals[3] = 0; }
 }
 
-// Tight tile rectangle of a visible Gaussian for the BLEND kernels' lists: the classic rectangle (3-sigma square of the
-// major axis, gsplat's rule, which the meta lists must reproduce bit for bit) intersected with the axis-aligned extent
-// of {alpha >= 1/255} = {sigma <= sigma_cut}: |dx| <= sqrt(2 sigma_cut cov_xx), cov = conic^-1.  Tiles outside it hold
-// no pixel the Gaussian can reach (the blend kernels would cull the entry for both warps of such a tile), so they need
-// not be listed: 36 % fewer entries on the 1 M-Gaussian benchmark scene (scripts/analysis/tight_rects.py), which is
-// 36 % less to sort, stage and cull.  Margins: sigma_cut itself is ln(255 o) * 1.001 + 2e-3 (egs_math.cuh), the
-// extents get another 0.1 % + 0.05 px, and an ill-conditioned conic (det lost to cancellation) keeps the classic
-// rectangle.  In: the classic rectangle; out: the tight one (empty when the Gaussian can never reach 1/255).
-__device__ __forceinline__ void tighten_tile_rect(const float4 g0, const float4 g1, float sigma_cut, float tile_size,
-                                                  int32_t& x0, int32_t& y0, int32_t& x1, int32_t& y1) {
-  if (!(sigma_cut > 0.f)) { x1 = x0; y1 = y0; return; }
-  const float a = g0.z, b = g0.w, c = g1.x;
-  const float det = a * c - b * b;
-  if (!(det > 1e-4f * a * c) || !(det > 0.f)) return;
-  const float k = 2.0f * sigma_cut / det;
-  const float hx = sqrtf(k * c) * 1.001f + 0.05f, hy = sqrtf(k * a) * 1.001f + 0.05f;
-  if (!(hx < 1e8f) || !(hy < 1e8f)) return;
-  // pixel centres p + 0.5 within [m - h, m + h]  ->  tiles floor(p / tile_size), max exclusive
-  const float inv = 1.0f / tile_size;
-  const float tx0 = floorf(ceilf(g0.x - hx - 0.5f) * inv), tx1 = floorf(floorf(g0.x + hx - 0.5f) * inv) + 1.0f;
-  const float ty0 = floorf(ceilf(g0.y - hy - 0.5f) * inv), ty1 = floorf(floorf(g0.y + hy - 0.5f) * inv) + 1.0f;
-  x0 = max(x0, (int32_t)fminf(fmaxf(tx0, -1e9f), 1e9f));
-  x1 = min(x1, (int32_t)fminf(fmaxf(tx1, -1e9f), 1e9f));
-  y0 = max(y0, (int32_t)fminf(fmaxf(ty0, -1e9f), 1e9f));
-  y1 = min(y1, (int32_t)fminf(fmaxf(ty1, -1e9f), 1e9f));
-  if (x1 < x0) x1 = x0;
-  if (y1 < y0) y1 = y0;
-}
-
 // also writes the level-1 sort input: key = bits(depth), value = flat index (camera * N + Gaussian), compacted.
 // The camera needs no key bits: level 2 sorts stably on the (camera, tile) index, so sorting the visible entries of
 // ALL cameras on depth alone (ties keep the flat-index order they are written in here) leaves every (camera, tile)
 // bucket in (depth, flat index) order — the order of a sort on cam | tile | depth.
-// With splats != nullptr it also writes tight_counts[flat index] = tiles of the TIGHT rectangle for every visible entry.
 __global__ void __launch_bounds__(kScanThreads) visible_apply_kernel(const int32_t* __restrict__ tiles, int64_t n,
                                                                       const int64_t* __restrict__ sums_vis,
                                                                       const float* __restrict__ depths,
                                                                       uint32_t* __restrict__ keys1,
-                                                                      uint32_t* __restrict__ vals1,
-                                                                      const float4* __restrict__ splats,
-                                                                      const int32_t* __restrict__ radii, float tile_size,
-                                                                      int tile_w, int tile_h,
-                                                                      int32_t* __restrict__ tight_counts) {
+                                                                      uint32_t* __restrict__ vals1) {
   __shared__ int64_t smem[33];
   const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
   int32_t v[kScanItems];
@@ -268,23 +234,22 @@ __global__ void __launch_bounds__(kScanThreads) visible_apply_kernel(const int32
       keys1[run] = __float_as_uint(depths[idx]);
       vals1[run] = (uint32_t)idx;
       ++run;
-      if (splats != nullptr) {
-        const float4 g0 = splats[idx * 3 + 0], g1 = splats[idx * 3 + 1];
-        const float cut = splats[idx * 3 + 2].w;
-        int32_t x0, y0, x1, y1;
-        tile_rect(g0.x, g0.y, radii[idx], tile_size, tile_w, tile_h, x0, y0, x1, y1);
-        tighten_tile_rect(g0, g1, cut, tile_size, x0, y0, x1, y1);
-        tight_counts[idx] = (x1 - x0) * (y1 - y0);
-      }
     }
   }
 }
 
 // ---- exclusive scan of src[gather[i]] (tile counts in depth order) -------------------------------------
+// The count of entry j is src[gather[j]], or — records != nullptr — the TIGHT tile count the projection kernel left in
+// slot 10 of the packed splat record of gather[j].
+__device__ __forceinline__ int32_t gathered_count(const int32_t* __restrict__ src, const float* __restrict__ records, uint32_t g) {
+  return records != nullptr ? (int32_t)records[(size_t)g * EGS_SPLAT_FLOATS + 10] : src[g];
+}
+
 __global__ void __launch_bounds__(kScanThreads) gscan_block_sums_kernel(const int32_t* __restrict__ src,
                                                                          const uint32_t* __restrict__ gather, int64_t n,
                                                                          const int64_t* __restrict__ n_dev,
-                                                                         int64_t* __restrict__ block_sums) {
+                                                                         int64_t* __restrict__ block_sums,
+                                                                         const float* __restrict__ records) {
   __shared__ int64_t smem[33];
   n = live_count(n, n_dev);
   const int64_t base = (int64_t)blockIdx.x * kScanTile;
@@ -292,7 +257,7 @@ __global__ void __launch_bounds__(kScanThreads) gscan_block_sums_kernel(const in
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
     int64_t j = base + (int64_t)i * kScanThreads + threadIdx.x;
-    if (j < n) s += src[gather[j]];
+    if (j < n) s += gathered_count(src, records, gather[j]);
   }
   int64_t total;
   block_inclusive_scan(s, smem, total);
@@ -303,7 +268,8 @@ __global__ void __launch_bounds__(kScanThreads) gscan_apply_kernel(const int32_t
                                                                     const uint32_t* __restrict__ gather, int64_t n,
                                                                     const int64_t* __restrict__ n_dev,
                                                                     const int64_t* __restrict__ block_sums,
-                                                                    int64_t* __restrict__ out) {
+                                                                    int64_t* __restrict__ out,
+                                                                    const float* __restrict__ records) {
   __shared__ int64_t smem[33];
   n = live_count(n, n_dev);
   const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
@@ -311,7 +277,7 @@ __global__ void __launch_bounds__(kScanThreads) gscan_apply_kernel(const int32_t
   int64_t s = 0;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
-    v[i] = (base + i < n) ? src[gather[base + i]] : 0;
+    v[i] = (base + i < n) ? gathered_count(src, records, gather[base + i]) : 0;
     s += v[i];
   }
   int64_t total;
@@ -346,8 +312,10 @@ __global__ void __launch_bounds__(kEmitThreads) isect_emit_sorted_kernel(
     const float2 m = means2d[g];
     int32_t x1, y1;
     tile_rect(m.x, m.y, radii[g], tile_size, tile_w, tile_h, x0, y0, x1, y1);
-    if (splats != nullptr)
-      tighten_tile_rect(splats[(size_t)g * 3 + 0], splats[(size_t)g * 3 + 1], splats[(size_t)g * 3 + 2].w, tile_size, x0, y0, x1, y1);
+    if (splats != nullptr) {
+      const float4 g0 = splats[(size_t)g * 3 + 0];
+      tighten_tile_rect(g0.x, g0.y, g0.z, g0.w, splats[(size_t)g * 3 + 1].x, splats[(size_t)g * 3 + 2].w, tile_size, x0, y0, x1, y1);
+    }
     w = max(x1 - x0, 1);
     cnt = (x1 - x0) * (y1 - y0);
     excl = cum_excl[i];
@@ -535,37 +503,8 @@ extern "C" int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles
   int64_t* sums_tiles = sums_vis + nblocks + 1;
   visible_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, sums_tiles);
   visible_spine_kernel<<<1, kScanThreads, 0, stream>>>(sums_vis, sums_tiles, nblocks, totals);
-  visible_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, depths, keys1, vals1,
-                                                                       nullptr, nullptr, 16.f, 0, 0, nullptr);
+  visible_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, depths, keys1, vals1);
   return check_launch("isect_visible_keys", 3);
-}
-
-extern "C" int egs_isect_visible_keys_tight(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths,
-                                            const float* splats, const int32_t* radii, int32_t tile_size,
-                                            int32_t tile_width, int32_t tile_height, uint32_t* keys1, uint32_t* vals1,
-                                            int32_t* tight_counts, int64_t* totals, void* workspace,
-                                            int64_t workspace_bytes, egs_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  EGS_REQUIRE(C >= 0 && N >= 0, "isect_visible_keys_tight: negative sizes");
-  const int64_t n = (int64_t)C * N;
-  EGS_REQUIRE(n < 0x7fffffffLL, "isect_visible_keys_tight: C*N=%lld does not fit the int32 flatten id", (long long)n);
-  if (n == 0) {
-    EGS_CUDA(cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), stream));
-    return 0;
-  }
-  EGS_REQUIRE(splats != nullptr && radii != nullptr && tight_counts != nullptr, "isect_visible_keys_tight: splats, radii and tight_counts are required");
-  EGS_REQUIRE(reinterpret_cast<uintptr_t>(splats) % 16 == 0, "isect_visible_keys_tight: splats must be 16-byte aligned");
-  if (workspace_bytes < egs_isect_scan_workspace_bytes(n))
-    return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "isect_visible_keys_tight: workspace too small");
-  const int64_t nblocks = ceil_div(n, kScanTile);
-  int64_t* sums_vis = reinterpret_cast<int64_t*>(workspace);
-  int64_t* sums_tiles = sums_vis + nblocks + 1;
-  visible_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, sums_tiles);
-  visible_spine_kernel<<<1, kScanThreads, 0, stream>>>(sums_vis, sums_tiles, nblocks, totals);
-  visible_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(
-      tiles_per_gauss, n, sums_vis, depths, keys1, vals1, reinterpret_cast<const float4*>(splats), radii, (float)tile_size,
-      tile_width, tile_height, tight_counts);
-  return check_launch("isect_visible_keys_tight", 3);
 }
 
 extern "C" int egs_exclusive_scan_gather(int64_t n, const int32_t* src, const uint32_t* gather, int64_t* out,
@@ -581,9 +520,9 @@ extern "C" int egs_exclusive_scan_gather(int64_t n, const int32_t* src, const ui
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "exclusive_scan_gather: workspace too small");
   const int64_t nblocks = ceil_div(n, kScanTile);
   int64_t* block_sums = reinterpret_cast<int64_t*>(workspace);
-  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, nullptr, block_sums);
+  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, nullptr, block_sums, nullptr);
   scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, total);
-  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, nullptr, block_sums, out);
+  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, nullptr, block_sums, out, nullptr);
   return check_launch("exclusive_scan_gather", 3);
 }
 
@@ -623,84 +562,65 @@ extern "C" int egs_isect_finalize(int64_t n_isects, const uint32_t* tile_keys_so
   return check_launch("isect_finalize_kernel");
 }
 
-// Launch order of the blend kernels: the tiles sorted by list length, longest first (16 length classes of
-// max_len / 16 entries, original order inside a class so that neighbouring tiles — which share Gaussians — still run
-// close together).  The GPU starts thread blocks roughly in index order; in grid order the last blocks to start are
-// the bottom rows of the last view, whatever their length, and the launch ends with a few SMs walking long lists
-// while the rest idle (achieved occupancy of the blend kernels was 88 % of the theoretical one, profiles/r2k).
-// One CTA: the tile count is 8 k - 65 k per view and three passes over it (maximum, class histogram, stable placement)
-// take ~10 us.  Also leaves the longest list in *max_len (the host reads it one call later: segment policy).
+// Launch order of the blend kernels: the tiles sorted by list length, longest first — by length CLASS
+// (class = position of the highest set bit of the length, so a class spans a factor of two), tiles of one class staying
+// roughly in grid order so that neighbouring tiles, which share Gaussians, still run close together.  The GPU starts
+// thread blocks roughly in index order; in grid order the last blocks to start are the bottom rows of the last view,
+// whatever their length, and a launch can end with a few SMs walking long lists while the rest idle.  Measured: one
+// view per call of the object scene 1.117 -> 1.042 ms, batched benchmark step unchanged (gpurun_out/r2l).
+// Three tiny launches (class histogram, bases, placement; warp-aggregated atomics) instead of one single-CTA kernel,
+// which took 93 us for the 32 640 tiles of the benchmark step (profiles/r2n_launches.csv).
 namespace egs {
-constexpr int kSchedThreads = 1024;
-constexpr int kSchedClasses = 16;
-__global__ void __launch_bounds__(kSchedThreads) tile_schedule_kernel(const int32_t* __restrict__ offsets, int32_t n_slots,
-                                                                      unsigned long long* __restrict__ max_len,
-                                                                      int32_t* __restrict__ order) {
-  __shared__ int32_t s_max[kSchedThreads / 32];
-  __shared__ int32_t s_cnt[kSchedClasses];                        // tiles per class, then running placement base
-  __shared__ int32_t s_warp[kSchedThreads / 32][kSchedClasses];   // per-warp counts of the current chunk
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int32_t m = 0;
-  for (int32_t t = tid; t < n_slots; t += kSchedThreads) m = max(m, offsets[t + 1] - offsets[t]);
-  m = __reduce_max_sync(0xffffffffu, m);
-  if (lane == 0) s_max[warp] = m;
-  if (tid < kSchedClasses) s_cnt[tid] = 0;
-  __syncthreads();
-  m = 0;
-  for (int w = 0; w < kSchedThreads / 32; ++w) m = max(m, s_max[w]);
-  if (tid == 0 && max_len != nullptr) *max_len = (unsigned long long)m;
-  if (order == nullptr) return;
-  // class 0 = longest: cls = 15 - floor(16 len / (max + 1)).  Class sizes: warp-private counts from ballots (an atomic
-  // per tile on 16 shared counters would serialise the whole block), summed over the warps afterwards.
-  const int64_t denom = (int64_t)m + 1;
-  if (lane < kSchedClasses) s_warp[warp][lane] = 0;
-  __syncwarp();
-  for (int32_t base = 0; base < n_slots; base += kSchedThreads) {
-    const int32_t t = base + tid;
-    const int cls = t < n_slots ? kSchedClasses - 1 - (int)(((int64_t)(offsets[t + 1] - offsets[t]) * kSchedClasses) / denom) : -1;
+constexpr int kSchedThreads = 256;
+constexpr int kSchedClasses = 32;
+
+__device__ __forceinline__ int length_class(int32_t len) { return len > 0 ? 32 - __clz(len) : 0; }  // 0 .. 31
+
+// hist[c] = tiles of class c (caller-zeroed); *max_len = longest list
+__global__ void __launch_bounds__(kSchedThreads) tile_classes_kernel(const int32_t* __restrict__ offsets, int32_t n_slots,
+                                                                     int32_t* __restrict__ hist,
+                                                                     unsigned long long* __restrict__ max_len) {
+  const int32_t t = blockIdx.x * kSchedThreads + threadIdx.x;
+  const bool valid = t < n_slots;
+  const int32_t len = valid ? offsets[t + 1] - offsets[t] : 0;
+  const int lane = threadIdx.x & 31;
+  const uint32_t active = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    const int cls = length_class(len);
+    const uint32_t group = __match_any_sync(active, cls);
+    if (lane == __ffs(group) - 1) atomicAdd(&hist[cls], __popc(group));
+  }
+  const int32_t m = __reduce_max_sync(0xffffffffu, len);
+  if (lane == 0 && m > 0 && max_len != nullptr) atomicMax(max_len, (unsigned long long)m);
+}
+
+// cursor[c] = first position of class c in the order (longest class first); one warp
+__global__ void tile_class_bases_kernel(const int32_t* __restrict__ hist, int32_t* __restrict__ cursor) {
+  const int c = threadIdx.x;  // 0 .. 31
+  const int32_t n = hist[c];
+  int32_t after = n;  // inclusive suffix sum over classes >= c
 #pragma unroll
-    for (int c = 0; c < kSchedClasses; ++c) {
-      const uint32_t mask = __ballot_sync(0xffffffffu, cls == c);
-      if (lane == 0) s_warp[warp][c] += __popc(mask);
-    }
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t v = __shfl_down_sync(0xffffffffu, after, d);
+    if (c + d < 32) after += v;
   }
-  __syncthreads();
-  if (tid == 0) {  // class totals -> exclusive scan over the 16 classes
-    int32_t run = 0;
-    for (int c = 0; c < kSchedClasses; ++c) {
-      int32_t n = 0;
-      for (int w = 0; w < kSchedThreads / 32; ++w) n += s_warp[w][c];
-      s_cnt[c] = run;
-      run += n;
-    }
-  }
-  __syncthreads();
-  const uint32_t lt = (1u << lane) - 1u;
-  for (int32_t base = 0; base < n_slots; base += kSchedThreads) {
-    const int32_t t = base + tid;
-    const bool valid = t < n_slots;
-    const int cls = valid ? kSchedClasses - 1 - (int)(((int64_t)(offsets[t + 1] - offsets[t]) * kSchedClasses) / denom) : -1;
-    int rank = 0;
-#pragma unroll
-    for (int c = 0; c < kSchedClasses; ++c) {
-      const uint32_t mask = __ballot_sync(0xffffffffu, cls == c);
-      if (cls == c) rank = __popc(mask & lt);
-      if (lane == 0) s_warp[warp][c] = __popc(mask);
-    }
-    __syncthreads();
-    if (valid) {
-      int32_t before = s_cnt[cls];
-      for (int w = 0; w < warp; ++w) before += s_warp[w][cls];
-      order[before + rank] = t;
-    }
-    __syncthreads();
-    if (tid < kSchedClasses) {
-      int32_t add = 0;
-      for (int w = 0; w < kSchedThreads / 32; ++w) add += s_warp[w][tid];
-      s_cnt[tid] += add;
-    }
-    __syncthreads();
-  }
+  cursor[c] = after - n;  // tiles of strictly longer classes come first
+}
+
+__global__ void __launch_bounds__(kSchedThreads) tile_order_kernel(const int32_t* __restrict__ offsets, int32_t n_slots,
+                                                                   int32_t* __restrict__ cursor, int32_t* __restrict__ order) {
+  const int32_t t = blockIdx.x * kSchedThreads + threadIdx.x;
+  const bool valid = t < n_slots;
+  const int lane = threadIdx.x & 31;
+  const uint32_t active = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
+  const int cls = length_class(offsets[t + 1] - offsets[t]);
+  const uint32_t group = __match_any_sync(active, cls);
+  const int leader = __ffs(group) - 1;
+  int32_t base = 0;
+  if (lane == leader) base = atomicAdd(&cursor[cls], __popc(group));
+  base = __shfl_sync(group, base, leader);
+  order[base + __popc(group & ((1u << lane) - 1u))] = t;
 }
 }  // namespace egs
 
@@ -709,7 +629,7 @@ __global__ void __launch_bounds__(kSchedThreads) tile_schedule_kernel(const int3
 // level-2 ping-pong keys | level-2 ping-pong values | level-2 sort workspace.
 namespace {
 struct SortedLayout {
-  int64_t keys1_b, vals1_b, cum, scan, sort1, keys2, vals2, sort2, total;
+  int64_t keys1_b, vals1_b, cum, scan, sort1, keys2, vals2, sort2, sched, total;
 };
 SortedLayout sorted_layout(int64_t n, int64_t capacity, int end_bit2) {
   SortedLayout L;
@@ -723,6 +643,7 @@ SortedLayout sorted_layout(int64_t n, int64_t capacity, int end_bit2) {
   L.keys2 = take(capacity * 4);
   L.vals2 = take(capacity * 4);
   L.sort2 = take(egs::radix_sort_workspace_bytes(capacity, end_bit2));
+  L.sched = take(2 * 32 * 4);  // class histogram + class cursors of the tile schedule
   L.total = off;
   return L;
 }
@@ -733,13 +654,28 @@ int level2_end_bit(int64_t n_slots) {
 }
 }  // namespace
 
+// offsets[n_slots + 1] (with the sentinel) -> *max_len (nullable), order[n_slots] (nullable); scratch: 64 int32
+static int tile_schedule(const int32_t* offsets, int32_t n_slots, unsigned long long* max_len, int32_t* order, int32_t* scratch,
+                         cudaStream_t stream) {
+  if (n_slots <= 0 || (max_len == nullptr && order == nullptr)) return 0;
+  int32_t* hist = scratch;
+  int32_t* cursor = scratch + kSchedClasses;
+  EGS_CUDA(cudaMemsetAsync(hist, 0, kSchedClasses * sizeof(int32_t), stream));
+  const unsigned blocks = (unsigned)ceil_div(n_slots, kSchedThreads);
+  tile_classes_kernel<<<blocks, kSchedThreads, 0, stream>>>(offsets, n_slots, hist, max_len);
+  if (order == nullptr) return check_launch("tile_classes_kernel");
+  tile_class_bases_kernel<<<1, 32, 0, stream>>>(hist, cursor);
+  tile_order_kernel<<<blocks, kSchedThreads, 0, stream>>>(offsets, n_slots, cursor, order);
+  return check_launch("tile_schedule", 3);
+}
+
 extern "C" int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_t n_tiles, int64_t capacity) {
   if (C < 0 || N < 0 || n_tiles < 0 || capacity < 0) return 0;
   const int64_t n = (int64_t)C * N;
   return sorted_layout(n > 0 ? n : 1, capacity > 0 ? capacity : 1, level2_end_bit((int64_t)C * n_tiles)).total;
 }
 
-extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts, const float* splats, const float* means2d,
+extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* splats, const float* means2d,
                                 const int32_t* radii, uint32_t* keys1, uint32_t* vals1, int64_t* stats,
                                 int32_t tile_size, int32_t tile_width, int32_t tile_height, int64_t capacity,
                                 void* workspace, int64_t workspace_bytes, uint32_t* tile_keys, uint32_t* flatten_ids,
@@ -760,8 +696,8 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts
   if (n_slots == 0) return 0;
   if (n == 0) {  // nothing to bin: all offsets (and the sentinel) are zero, any launch order will do
     EGS_CUDA(cudaMemsetAsync(offsets, 0, (n_slots + 1) * sizeof(int32_t), stream));
-    tile_schedule_kernel<<<1, kSchedThreads, 0, stream>>>(offsets, (int32_t)n_slots, nullptr, tile_order);
-    return check_launch("tile_schedule_kernel");
+    EGS_REQUIRE(tile_order == nullptr || (workspace != nullptr && workspace_bytes >= 256), "isect_sorted: workspace too small");
+    return tile_schedule(offsets, (int32_t)n_slots, nullptr, tile_order, reinterpret_cast<int32_t*>(workspace), stream);
   }
   const int end_bit2 = level2_end_bit(n_slots);
   const SortedLayout L = sorted_layout(n, capacity, end_bit2);
@@ -779,11 +715,11 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts
   const uint32_t* order = in_b ? vals1_b : vals1;
   // tile counts in that order -> write offsets (the grand total is counts[1] already; the spine's copy lands in block_sums' tail)
   const int64_t nblocks = ceil_div(n, kScanTile);
-  // (tile_counts: the classic tiles_per_gauss, or the tight counts of egs_isect_visible_keys_tight; their total over
-  //  the visible entries becomes stats[1], the intersection count every kernel below works with)
-  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tile_counts, order, n, counts, block_sums);
+  // (classic lists: the counts are tiles_per_gauss; tight lists: the count the projection kernel left in slot 10 of
+  //  every record.  Their total over the visible entries becomes stats[1], the count every kernel below works with.)
+  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, order, n, counts, block_sums, splats);
   scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, n_isects_dev);
-  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tile_counts, order, n, counts, block_sums, cum);
+  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, order, n, counts, block_sums, cum, splats);
   // emission into whichever side of the level-2 ping-pong makes the sorted pairs end in the caller's buffers
   const int passes2 = (end_bit2 + 7) / 8;
   uint32_t* ka = (passes2 & 1) ? reinterpret_cast<uint32_t*>(ws + L.keys2) : tile_keys;
@@ -795,12 +731,12 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts
       ka, va, counts, reinterpret_cast<const float4*>(splats));
   if (int rc = check_launch("isect_sorted (scan + emit)", 4)) return rc;
   // level 2: stable sort on the dense (camera, tile) index
-  if (int rc = radix_sort_pairs_u32(capacity, counts + 1, ka, va, kb, vb, end_bit2, ws + L.sort2, L.total - L.sort2, &in_b, stream))
+  if (int rc = radix_sort_pairs_u32(capacity, counts + 1, ka, va, kb, vb, end_bit2, ws + L.sort2, L.sched - L.sort2, &in_b, stream))
     return rc;
   if ((in_b != 0) != ((passes2 & 1) != 0)) return fail(EGS_ERR_INVALID_ARGUMENT, "isect_sorted: internal ping-pong mismatch");
   isect_offsets4_kernel<<<(unsigned)ceil_div(capacity, 4 * kOff4Threads), kOff4Threads, 0, stream>>>(
       (int32_t)capacity, tile_keys, (int32_t)n_slots, offsets, counts + 1, 1);
-  tile_schedule_kernel<<<1, kSchedThreads, 0, stream>>>(offsets, (int32_t)n_slots, reinterpret_cast<unsigned long long*>(stats),
-                                                        tile_order);
-  return check_launch("isect_offsets4_kernel", 2);
+  if (int rc = check_launch("isect_offsets4_kernel")) return rc;
+  return tile_schedule(offsets, (int32_t)n_slots, reinterpret_cast<unsigned long long*>(stats), tile_order,
+                       reinterpret_cast<int32_t*>(ws + L.sched), stream);
 }

@@ -204,6 +204,36 @@ EGS_HD void tile_rect(float m2x, float m2y, int32_t radius, float tile_size, int
   ymax = (int32_t)fminf(fmaxf(ceilf(ty + tr), 0.f), fh);
 }
 
+// Tight tile rectangle of a visible Gaussian for the BLEND kernels' lists: the classic rectangle above (3-sigma square
+// of the major axis, gsplat's rule, which the meta lists must reproduce bit for bit) intersected with the axis-aligned
+// extent of {alpha >= 1/255} = {sigma <= sigma_cut}: |dx| <= sqrt(2 sigma_cut cov_xx), cov = conic^-1.  Tiles outside
+// it hold no pixel the Gaussian can reach, so the blend kernels need not see it there: 36 % fewer list entries on the
+// 1 M-Gaussian benchmark scene (scripts/analysis/tight_rects.py), i.e. 36 % less to sort, stage and cull, for the same
+// pixels and gradients.  Margins: sigma_cut itself is ln(255 o) * 1.001 + 2e-3, the extents get another 0.1 % +
+// 0.05 px, and an ill-conditioned conic (determinant lost to cancellation) keeps the classic rectangle.
+// In: the classic rectangle; out: the tight one (empty when the Gaussian can never reach 1/255).
+EGS_HD void tighten_tile_rect(float m2x, float m2y, float ca, float cb, float cc, float sigma_cut, float tile_size,
+                              int32_t& x0, int32_t& y0, int32_t& x1, int32_t& y1) {
+  if (!(sigma_cut > 0.f)) { x1 = x0; y1 = y0; return; }
+  const float det = ca * cc - cb * cb;
+  if (!(det > 1e-4f * ca * cc) || !(det > 0.f)) return;
+  const float k = 2.0f * sigma_cut / det;
+  const float hx = sqrtf(k * cc) * 1.001f + 0.05f, hy = sqrtf(k * ca) * 1.001f + 0.05f;
+  if (!(hx < 1e8f) || !(hy < 1e8f)) return;
+  // pixel centres p + 0.5 within [m - h, m + h]  ->  tiles floor(p / tile_size), max exclusive
+  const float inv = 1.0f / tile_size;
+  const float tx0 = floorf(ceilf(m2x - hx - 0.5f) * inv), tx1 = floorf(floorf(m2x + hx - 0.5f) * inv) + 1.0f;
+  const float ty0 = floorf(ceilf(m2y - hy - 0.5f) * inv), ty1 = floorf(floorf(m2y + hy - 0.5f) * inv) + 1.0f;
+  const int32_t ix0 = (int32_t)fminf(fmaxf(tx0, -1e9f), 1e9f), ix1 = (int32_t)fminf(fmaxf(tx1, -1e9f), 1e9f);
+  const int32_t iy0 = (int32_t)fminf(fmaxf(ty0, -1e9f), 1e9f), iy1 = (int32_t)fminf(fmaxf(ty1, -1e9f), 1e9f);
+  x0 = x0 > ix0 ? x0 : ix0;
+  x1 = x1 < ix1 ? x1 : ix1;
+  y0 = y0 > iy0 ? y0 : iy0;
+  y1 = y1 < iy1 ? y1 : iy1;
+  if (x1 < x0) x1 = x0;
+  if (y1 < y0) y1 = y0;
+}
+
 // VJP of project_fwd for a visible Gaussian.  Accumulates (+=) into
 // v_mean[3], v_quat[4], v_scale[3].
 EGS_HD void project_bwd(const ProjState& st, const float scale[3], const Camera& cam, float v_m2x, float v_m2y,

@@ -99,7 +99,10 @@ __global__ void __launch_bounds__(kProjThreads) projection_fwd_kernel(const Proj
     float4* s = p.splats + idx * 3;
     s[0] = make_float4(o.m2x, o.m2y, o.ca, o.cb);
     s[1] = make_float4(o.cc, opac, rgb[0], rgb[1]);
-    s[2] = make_float4(rgb[2], o.depth, 0.f, sigma_cutoff(opac));
+    // slot 10: tiles of the TIGHT rectangle (tighten_tile_rect) — the per-Gaussian count of the blend kernels' own lists
+    const float cut = sigma_cutoff(opac);
+    tighten_tile_rect(o.m2x, o.m2y, o.ca, o.cb, o.cc, cut, p.tile_size, x0, y0, x1, y1);
+    s[2] = make_float4(rgb[2], o.depth, (float)((x1 - x0) * (y1 - y0)), cut);
   }
   p.radii[idx] = o.radius;
   p.tiles_per_gauss[idx] = ntiles;
@@ -288,7 +291,10 @@ __global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const 
     float4* s = p.splats + idx * 3;
     s[0] = make_float4(o.m2x, o.m2y, o.ca, o.cb);
     s[1] = make_float4(o.cc, opac, rgb[0], rgb[1]);
-    s[2] = make_float4(rgb[2], o.depth, 0.f, sigma_cutoff(opac));
+    // slot 10: tiles of the TIGHT rectangle (tighten_tile_rect) — the per-Gaussian count of the blend kernels' own lists
+    const float cut = sigma_cutoff(opac);
+    tighten_tile_rect(o.m2x, o.m2y, o.ca, o.cb, o.cc, cut, p.tile_size, x0, y0, x1, y1);
+    s[2] = make_float4(rgb[2], o.depth, (float)((x1 - x0) * (y1 - y0)), cut);
   }
   p.radii[idx] = o.radius;
   p.tiles_per_gauss[idx] = ntiles;

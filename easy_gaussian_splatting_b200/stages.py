@@ -583,17 +583,11 @@ def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per
     stats = torch.empty(4, dtype=torch.int64, device=dev)
     keys1 = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     vals1 = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    tile_counts = tiles_per_gauss
+    if tight:
+        splats = _f32c(splats, "splats")
     with torch.cuda.device(dev):
-        if tight:
-            splats = _f32c(splats, "splats")
-            tile_counts = torch.empty(max(n, 1), dtype=torch.int32, device=dev)  # written for visible entries only
-            rc = lib.egs_isect_visible_keys_tight(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(splats), _ptr(radii),
-                                                  int(tile_size), tile_width, tile_height, _ptr(keys1), _ptr(vals1),
-                                                  _ptr(tile_counts), _ptr(stats), _ptr(scan_ws), ws_scan, _stream(dev))
-        else:
-            rc = lib.egs_isect_visible_keys(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(keys1), _ptr(vals1), _ptr(stats),
-                                            _ptr(scan_ws), ws_scan, _stream(dev))
+        rc = lib.egs_isect_visible_keys(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(keys1), _ptr(vals1), _ptr(stats),
+                                        _ptr(scan_ws), ws_scan, _stream(dev))
     _lib.check(rc, "egs_isect_visible_keys")
     early = _pinned_slot(dev)
     early.copy_(stats, non_blocking=True)
@@ -619,7 +613,7 @@ def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per
     ws_bytes = lib.egs_isect_sorted_workspace_bytes(C, N, n_tiles, capacity)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.egs_isect_sorted(C, N, _ptr(tile_counts), _ptr(splats) if tight else None, _ptr(means2d), _ptr(radii),
+        rc = lib.egs_isect_sorted(C, N, _ptr(tiles_per_gauss), _ptr(splats) if tight else None, _ptr(means2d), _ptr(radii),
                                   _ptr(keys1), _ptr(vals1), _ptr(stats), int(tile_size), tile_width, tile_height, capacity,
                                   _ptr(ws), ws.numel(), _ptr(tile_keys), _ptr(flat), _ptr(offsets_store), _ptr(tile_order),
                                   _stream(dev))

@@ -38,7 +38,10 @@ enum egs_status {
 };
 
 /* Number of floats in one packed splat record / one packed gradient record (48 bytes, 16B aligned).
- * splat record : {x, y, conic_a, conic_b | conic_c, opacity, r, g | b, depth, 0, sigma_cut}
+ * splat record : {x, y, conic_a, conic_b | conic_c, opacity, r, g | b, depth, tight_tiles, sigma_cut}
+ *                tight_tiles = number of tiles (as a float) of the Gaussian's TIGHT rectangle: its classic tile
+ *                rectangle intersected with the axis-aligned extent of {sigma <= sigma_cut}; egs_isect_sorted builds
+ *                the blend kernels' lists from it (0 in records that were not produced by egs_projection_fwd*)
  *                sigma_cut = ln(255 * opacity) (+ margin): the largest sigma at which alpha can reach 1/255.  The
  *                blending kernels drop a Gaussian for a warp when min sigma over the warp's pixels exceeds it
  *                (+inf disables that culling; <= 0 = never visible)
@@ -201,18 +204,14 @@ int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, 
  *            holding n_isects, which egs_rasterize_* read when they are given a negative n_isects.
  *   tile_order [C * n_tiles] (nullable): the flat tile indices sorted by list length, longest first — the launch
  *            order for egs_rasterize_* (their tile_order argument).
- *   TIGHT lists (splats != NULL, tile_counts = the tight counts of egs_isect_visible_keys_tight): every Gaussian is
- *            listed only in the tiles of its classic rectangle that hold a pixel it can reach with alpha >= 1/255
- *            (axis-aligned extent of sigma <= sigma_cut, from the splat records).  The blend kernels produce the same
- *            pixels and gradients from them (a dropped entry has alpha < 1/255 at every pixel of its tile);
- *            the lists themselves then differ from gsplat's, which the classic route (tile_counts =
- *            tiles_per_gauss, splats = NULL) reproduces bit for bit.  stats[1] is rewritten with the emitted total. */
+ *   TIGHT lists (splats != NULL: the records of egs_projection_fwd*): every Gaussian is listed only in the tiles of
+ *            its classic rectangle that hold a pixel it can reach with alpha >= 1/255 (the tight rectangle whose
+ *            tile count the projection kernel left in the record).  The blend kernels produce the same pixels and
+ *            gradients from them (a dropped entry has alpha < 1/255 at every pixel of its tile); the lists
+ *            themselves then differ from gsplat's, which splats = NULL reproduces bit for bit.  stats[1] is rewritten
+ *            with the emitted total. */
 int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_t n_tiles, int64_t capacity);
-int egs_isect_visible_keys_tight(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths,
-                                 const float* splats, const int32_t* radii, int32_t tile_size, int32_t tile_width,
-                                 int32_t tile_height, uint32_t* keys1, uint32_t* vals1, int32_t* tight_counts,
-                                 int64_t* totals, void* workspace, int64_t workspace_bytes, egs_stream_t stream);
-int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts, const float* splats, const float* means2d,
+int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* splats, const float* means2d,
                      const int32_t* radii, uint32_t* keys1, uint32_t* vals1, int64_t* stats, int32_t tile_size, int32_t tile_width,
                      int32_t tile_height, int64_t capacity, void* workspace, int64_t workspace_bytes,
                      uint32_t* tile_keys, uint32_t* flatten_ids, int32_t* offsets, int32_t* tile_order,
