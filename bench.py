@@ -803,10 +803,10 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     # from the previous call, tiles taken longest list first
     def product_binning():
         b_ = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th,
-                                       splats=proj["splats"])
+                                       splats=proj["splats"], tight_tiles=proj["tight_tiles"])
         if not b_.resolve():
             b_ = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th,
-                                           capacity=b_.n_isects, splats=proj["splats"])
+                                           capacity=b_.n_isects, splats=proj["splats"], tight_tiles=proj["tight_tiles"])
             b_.resolve()
         b_.note_for_next_call()
         return b_

@@ -22,7 +22,7 @@ _SIGNATURES = {
     "egs_last_error_string": (c_char_p, []),
     "egs_kernel_launch_count": (c_int64, []),
     "egs_projection_fwd": (c_int32, [I32, I32, P, P, P, P, P, I32, I32, I32, P, P, I32, I32, F32, F32, F32, F32,
-                                     I32, I32, I32, P, P, P, P, P, P, P, P]),
+                                     I32, I32, I32, P, P, P, P, P, P, P, P, P]),
     "egs_projection_bwd": (c_int32, [I32, I32, P, P, P, P, I32, I32, I32, P, P, I32, I32, F32, P, P, P, P,
                                      P, P, P, P, P, P, P]),
     "egs_projection_bwd_range": (c_int32, [I32, I32, P, P, P, P, I32, I32, I32, P, P, I32, I32, F32, P, P, P, P,
@@ -30,11 +30,11 @@ _SIGNATURES = {
     "egs_projection_bwd_raw_range": (c_int32, [I32, I32, P, P, P, P, P, P, I32, P, P, I32, I32, F32, P, P, P, P,
                                                P, P, P, P, P, P, P, I32, I32, P]),
     "egs_projection_fwd_antialiased": (c_int32, [I32, I32, P, P, P, P, P, I32, I32, I32, P, P, I32, I32, F32, F32, F32,
-                                                 F32, I32, I32, I32, P, P, P, P, P, P, P, P, P]),
+                                                 F32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P]),
     "egs_projection_bwd_antialiased": (c_int32, [I32, I32, P, P, P, P, P, I32, I32, I32, P, P, I32, I32, F32, P, P, P,
                                                  P, P, P, P, P, P, P, P]),
     "egs_projection_fwd_raw": (c_int32, [I32, I32, P, P, P, P, P, P, I32, P, P, I32, I32, F32, F32, F32, F32,
-                                         I32, I32, I32, P, P, P, P, P, P, P, P]),
+                                         I32, I32, I32, P, P, P, P, P, P, P, P, P]),
     "egs_projection_bwd_raw": (c_int32, [I32, I32, P, P, P, P, P, P, I32, P, P, I32, I32, F32, P, P, P, P,
                                          P, P, P, P, P, P, P, P]),
     "egs_exclusive_scan_workspace_bytes": (c_int64, [I64]),

@@ -239,17 +239,10 @@ __global__ void __launch_bounds__(kScanThreads) visible_apply_kernel(const int32
 }
 
 // ---- exclusive scan of src[gather[i]] (tile counts in depth order) -------------------------------------
-// The count of entry j is src[gather[j]], or — records != nullptr — the TIGHT tile count the projection kernel left in
-// slot 10 of the packed splat record of gather[j].
-__device__ __forceinline__ int32_t gathered_count(const int32_t* __restrict__ src, const float* __restrict__ records, uint32_t g) {
-  return records != nullptr ? (int32_t)records[(size_t)g * EGS_SPLAT_FLOATS + 10] : src[g];
-}
-
 __global__ void __launch_bounds__(kScanThreads) gscan_block_sums_kernel(const int32_t* __restrict__ src,
                                                                          const uint32_t* __restrict__ gather, int64_t n,
                                                                          const int64_t* __restrict__ n_dev,
-                                                                         int64_t* __restrict__ block_sums,
-                                                                         const float* __restrict__ records) {
+                                                                         int64_t* __restrict__ block_sums) {
   __shared__ int64_t smem[33];
   n = live_count(n, n_dev);
   const int64_t base = (int64_t)blockIdx.x * kScanTile;
@@ -257,7 +250,7 @@ __global__ void __launch_bounds__(kScanThreads) gscan_block_sums_kernel(const in
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
     int64_t j = base + (int64_t)i * kScanThreads + threadIdx.x;
-    if (j < n) s += gathered_count(src, records, gather[j]);
+    if (j < n) s += src[gather[j]];
   }
   int64_t total;
   block_inclusive_scan(s, smem, total);
@@ -268,8 +261,7 @@ __global__ void __launch_bounds__(kScanThreads) gscan_apply_kernel(const int32_t
                                                                     const uint32_t* __restrict__ gather, int64_t n,
                                                                     const int64_t* __restrict__ n_dev,
                                                                     const int64_t* __restrict__ block_sums,
-                                                                    int64_t* __restrict__ out,
-                                                                    const float* __restrict__ records) {
+                                                                    int64_t* __restrict__ out) {
   __shared__ int64_t smem[33];
   n = live_count(n, n_dev);
   const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
@@ -277,7 +269,7 @@ __global__ void __launch_bounds__(kScanThreads) gscan_apply_kernel(const int32_t
   int64_t s = 0;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
-    v[i] = (base + i < n) ? gathered_count(src, records, gather[base + i]) : 0;
+    v[i] = (base + i < n) ? src[gather[base + i]] : 0;
     s += v[i];
   }
   int64_t total;
@@ -520,9 +512,9 @@ extern "C" int egs_exclusive_scan_gather(int64_t n, const int32_t* src, const ui
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "exclusive_scan_gather: workspace too small");
   const int64_t nblocks = ceil_div(n, kScanTile);
   int64_t* block_sums = reinterpret_cast<int64_t*>(workspace);
-  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, nullptr, block_sums, nullptr);
+  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, nullptr, block_sums);
   scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, total);
-  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, nullptr, block_sums, out, nullptr);
+  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(src, gather, n, nullptr, block_sums, out);
   return check_launch("exclusive_scan_gather", 3);
 }
 
@@ -675,7 +667,7 @@ extern "C" int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_
   return sorted_layout(n > 0 ? n : 1, capacity > 0 ? capacity : 1, level2_end_bit((int64_t)C * n_tiles)).total;
 }
 
-extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* splats, const float* means2d,
+extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts, const float* splats, const float* means2d,
                                 const int32_t* radii, uint32_t* keys1, uint32_t* vals1, int64_t* stats,
                                 int32_t tile_size, int32_t tile_width, int32_t tile_height, int64_t capacity,
                                 void* workspace, int64_t workspace_bytes, uint32_t* tile_keys, uint32_t* flatten_ids,
@@ -715,11 +707,11 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_g
   const uint32_t* order = in_b ? vals1_b : vals1;
   // tile counts in that order -> write offsets (the grand total is counts[1] already; the spine's copy lands in block_sums' tail)
   const int64_t nblocks = ceil_div(n, kScanTile);
-  // (classic lists: the counts are tiles_per_gauss; tight lists: the count the projection kernel left in slot 10 of
-  //  every record.  Their total over the visible entries becomes stats[1], the count every kernel below works with.)
-  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, order, n, counts, block_sums, splats);
+  // (tile_counts: tiles_per_gauss for gsplat's lists, the projection kernel's tight_tiles for the blend kernels' own.
+  //  Their total over the visible entries becomes stats[1], the count every kernel below works with.)
+  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tile_counts, order, n, counts, block_sums);
   scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, n_isects_dev);
-  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, order, n, counts, block_sums, cum, splats);
+  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tile_counts, order, n, counts, block_sums, cum);
   // emission into whichever side of the level-2 ping-pong makes the sorted pairs end in the caller's buffers
   const int passes2 = (end_bit2 + 7) / 8;
   uint32_t* ka = (passes2 & 1) ? reinterpret_cast<uint32_t*>(ws + L.keys2) : tile_keys;

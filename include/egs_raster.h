@@ -38,10 +38,7 @@ enum egs_status {
 };
 
 /* Number of floats in one packed splat record / one packed gradient record (48 bytes, 16B aligned).
- * splat record : {x, y, conic_a, conic_b | conic_c, opacity, r, g | b, depth, tight_tiles, sigma_cut}
- *                tight_tiles = number of tiles (as a float) of the Gaussian's TIGHT rectangle: its classic tile
- *                rectangle intersected with the axis-aligned extent of {sigma <= sigma_cut}; egs_isect_sorted builds
- *                the blend kernels' lists from it (0 in records that were not produced by egs_projection_fwd*)
+ * splat record : {x, y, conic_a, conic_b | conic_c, opacity, r, g | b, depth, 0, sigma_cut}
  *                sigma_cut = ln(255 * opacity) (+ margin): the largest sigma at which alpha can reach 1/255.  The
  *                blending kernels drop a Gaussian for a warp when min sigma over the warp's pixels exceeds it
  *                (+inf disables that culling; <= 0 = never visible)
@@ -66,14 +63,18 @@ int64_t egs_kernel_launch_count(void);
  *   viewmats[C,4,4] Ks[C,3,3]
  * outputs (culled entries are zero-filled, radii == 0):
  *   radii[C,N] i32, means2d[C,N,2], depths[C,N], conics[C,N,3], colors[C,N,3],
- *   tiles_per_gauss[C,N] i32, splats[C,N,12] packed records (only visible entries are written). */
+ *   tiles_per_gauss[C,N] i32 (gsplat's count: tiles of the 3-sigma square), splats[C,N,12] packed records (only
+ *   visible entries are written),
+ *   tight_tiles[C,N] i32 (nullable; all egs_projection_fwd* entries): tiles of the TIGHT rectangle — the square
+ *   intersected with the axis-aligned extent of {alpha >= 1/255} — the per-Gaussian count of the blend kernels' own
+ *   lists (egs_isect_sorted); 0 for culled entries. */
 int egs_projection_fwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
                        const float* opacities, const float* sh_coeffs, int32_t K, int32_t sh_degree,
                        int32_t colors_per_camera, const float* viewmats, const float* Ks, int32_t width,
                        int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
                        int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii,
                        float* means2d, float* depths, float* conics, float* colors, int32_t* tiles_per_gauss,
-                       float* splats, egs_stream_t stream);
+                       int32_t* tight_tiles, float* splats, egs_stream_t stream);
 
 /* ---- g8 + g9: fused SH backward + projection backward ------------------------------------------
  * Replaces gsplat `spherical_harmonics` bwd and `fully_fused_projection` bwd (summed over cameras).
@@ -121,7 +122,7 @@ int egs_projection_fwd_antialiased(int32_t C, int32_t N, const float* means, con
                                    int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
                                    int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii,
                                    float* means2d, float* depths, float* conics, float* colors,
-                                   int32_t* tiles_per_gauss, float* splats, float* compensations,
+                                   int32_t* tiles_per_gauss, int32_t* tight_tiles, float* splats, float* compensations,
                                    egs_stream_t stream);
 int egs_projection_bwd_antialiased(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
                                    const float* opacities, const float* sh_coeffs, int32_t K, int32_t sh_degree,
@@ -142,7 +143,8 @@ int egs_projection_fwd_raw(int32_t C, int32_t N, const float* means, const float
                            const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
                            float near_plane, float far_plane, float radius_clip, int32_t tile_size,
                            int32_t tile_width, int32_t tile_height, int32_t* radii, float* means2d, float* depths,
-                           float* conics, float* colors, int32_t* tiles_per_gauss, float* splats, egs_stream_t stream);
+                           float* conics, float* colors, int32_t* tiles_per_gauss, int32_t* tight_tiles, float* splats,
+                           egs_stream_t stream);
 int egs_projection_bwd_raw(int32_t C, int32_t N, const float* means, const float* quats, const float* log_scales,
                            const float* logit_opacities, const float* sh_0, const float* sh_rest, int32_t sh_degree,
                            const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
@@ -204,14 +206,14 @@ int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, 
  *            holding n_isects, which egs_rasterize_* read when they are given a negative n_isects.
  *   tile_order [C * n_tiles] (nullable): the flat tile indices sorted by list length, longest first — the launch
  *            order for egs_rasterize_* (their tile_order argument).
- *   TIGHT lists (splats != NULL: the records of egs_projection_fwd*): every Gaussian is listed only in the tiles of
- *            its classic rectangle that hold a pixel it can reach with alpha >= 1/255 (the tight rectangle whose
- *            tile count the projection kernel left in the record).  The blend kernels produce the same pixels and
- *            gradients from them (a dropped entry has alpha < 1/255 at every pixel of its tile); the lists
- *            themselves then differ from gsplat's, which splats = NULL reproduces bit for bit.  stats[1] is rewritten
- *            with the emitted total. */
+ *   tile_counts [C,N]: tiles_per_gauss and splats = NULL give gsplat's lists bit for bit.  TIGHT lists — tile_counts =
+ *            the tight_tiles output of egs_projection_fwd* and splats = its records: every Gaussian is listed only
+ *            in the tiles of its classic rectangle that hold a pixel it can reach with alpha >= 1/255 (the
+ *            rectangle intersected with the axis-aligned extent of sigma <= sigma_cut).  The blend kernels produce
+ *            the same pixels and gradients from them (a dropped entry has alpha < 1/255 at every pixel of its
+ *            tile); a third fewer entries to sort, stage and cull.  stats[1] is rewritten with the emitted total. */
 int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_t n_tiles, int64_t capacity);
-int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* splats, const float* means2d,
+int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts, const float* splats, const float* means2d,
                      const int32_t* radii, uint32_t* keys1, uint32_t* vals1, int64_t* stats, int32_t tile_size, int32_t tile_width,
                      int32_t tile_height, int64_t capacity, void* workspace, int64_t workspace_bytes,
                      uint32_t* tile_keys, uint32_t* flatten_ids, int32_t* offsets, int32_t* tile_order,

@@ -361,7 +361,7 @@ def test_sentinel_mode_equals_exact_length_mode():
     n_tiles = tw * th
     assert torch.equal(torch.sort(order).values, torch.arange(n_tiles, device="cuda"))
     lens = torch.diff(torch.cat([b2.offsets.reshape(-1), b2.offsets_store[-1:]])).long()
-    cls = torch.where(lens > 0, torch.floor(torch.log2(lens.clamp_min(1).double())).long() + 1, torch.zeros_like(lens))
+    cls = ((lens[:, None] >> torch.arange(32, device="cuda")[None, :]) > 0).sum(1)  # bit length: 0 for an empty tile
     assert bool((cls[order][1:] <= cls[order][:-1]).all()), "length classes in descending order"
     out_o = stages.rasterize_fwd(proj["splats"], b2.offsets, b2.flat_cap, bg, W, H, n_isects=b2.raster_n, tile_order=b2.tile_order)
     for a, r in zip(out_o, ref):
@@ -384,7 +384,7 @@ def test_tight_lists_hold_a_subset_and_render_identically(cfg):
     args = (proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th)
     stages.reset_binning_hints()
     cl = stages.isect_sorted_async(*args)
-    tg = stages.isect_sorted_async(*args, splats=proj["splats"])
+    tg = stages.isect_sorted_async(*args, splats=proj["splats"], tight_tiles=proj["tight_tiles"])
     assert cl.resolve() and tg.resolve()
     n_t = C * tw * th
     key = lambda b: (torch.repeat_interleave(torch.arange(n_t, device="cuda"),
