@@ -40,7 +40,7 @@ def test_workspace_queries_and_argument_errors_without_gpu():
     rc = lib.egs_rasterize_fwd(1, 0, 0, None, None, None, None, 100, 100, 3, 3, None, None, None, None, None)
     assert rc == -1 and b"tile grid" in lib.egs_last_error_string()
     rc = lib.egs_projection_fwd(1, 10, None, None, None, None, None, 16, 5, 0, None, None, 64, 64, 0.3, 0.01, 1e10, 0.0,
-                                16, 4, 4, None, None, None, None, None, None, None, None)
+                                16, 4, 4, None, None, None, None, None, None, None, None, None)
     assert rc == -1 and b"sh_degree" in lib.egs_last_error_string()
 
 
