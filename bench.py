@@ -803,10 +803,10 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
     # from the previous call, tiles taken longest list first
     def product_binning():
         b_ = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th,
-                                       splats=proj["splats"], tight_tiles=proj["tight_tiles"])
+                                       tight_rects=proj["tight_rects"])
         if not b_.resolve():
             b_ = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th,
-                                           capacity=b_.n_isects, splats=proj["splats"], tight_tiles=proj["tight_tiles"])
+                                           capacity=b_.n_isects, tight_rects=proj["tight_rects"])
             b_.resolve()
         b_.note_for_next_call()
         return b_
@@ -850,20 +850,19 @@ def stage_rooflines(lib, stages, params, view, bg, Wc, Wa, W, H, dev, reps=10):
         u["l1_ssim_loss_bwd"] = tm(lambda: torch.autograd.grad(tot, img, retain_graph=True))
     passes = math.ceil((32 + nbits) / 8)
     sort_bytes = (8 + 24 * passes) * n_isects
-    # The two-level route the product runs (stages.isect_sorted), stage by stage, per launch of Cn views:
-    #   visible scan  : tiles_per_gauss read twice (8 B) per (camera, Gaussian); depth read (4) + level-1 pair written
-    #                   per visible Gaussian
+    # The two-level route the product runs (stages.isect_sorted_async), stage by stage, per launch of Cn views:
+    #   visible keys  : tiles_per_gauss read (4 B) per (camera, Gaussian); depth read (4) + level-1 pair written (key + 4)
+    #                   per visible Gaussian — one launch, chained with decoupled look-back
     #   level-1 sort  : histogram read + p1 passes of read + write over the level-1 pairs
-    #   tile-count scan in depth order: order (4) + gathered count (4), twice, + 8 B offset written, per visible Gaussian
-    #   emission      : order 4 + offset 8 + means2d 8 + radius 4 read per visible Gaussian, 8 B pair written per intersection
+    #   scan + emit   : order (4) + packed tight rectangle (8) read per visible Gaussian, 8 B pair written per
+    #                   intersection — one launch, the tile-count scan rides in it
     #   level-2 sort  : 4 B histogram read + p2 passes of 16 B per intersection
     #   tile offsets  : 4 B key read per intersection + 4 B per tile
     #   ("intersection" = an entry of the TIGHT lists the blend kernels work from; n_isects stays gsplat's count)
     key1 = stages.LEVEL1_KEY_BYTES
     p1 = math.ceil(stages.level1_end_bit(Cn) / 8)
     p2 = math.ceil(max(1, int(Cn * tw * th - 1).bit_length()) / 8)
-    #   (+ 52 B per visible Gaussian for the tight rectangle: the 48-byte record read, the count written)
-    two_level_bytes = (8 * N + (4 + key1 + 4 + 52) * n_vis + (key1 + 2 * (key1 + 4) * p1) * n_vis + 24 * n_vis + (24 + 48) * n_vis
+    two_level_bytes = (4 * N + (4 + key1 + 4) * n_vis + (key1 + 2 * (key1 + 4) * p1) * n_vis + (4 + 8) * n_vis
                        + 8 * n_isects_tight + (4 + 16 * p2) * n_isects_tight + 4 * n_isects_tight + 4 * Cn * tw * th)
     work = {  # algorithmic bytes (HBM-bound stages) or flops (blend) per launch, BASELINE.md section 4 (frozen)
         "projection_sh_fwd": ("hbm", 68 * N + 204 * n_vis),

@@ -46,7 +46,7 @@ _SIGNATURES = {
     "egs_isect_scan_workspace_bytes": (c_int64, [I64]),
     "egs_isect_visible_keys": (c_int32, [I32, I32, P, P, P, P, P, P, I64, P]),
     "egs_isect_sorted_workspace_bytes": (c_int64, [I32, I32, I32, I64]),
-    "egs_isect_sorted": (c_int32, [I32, I32, P, P, P, P, P, P, P, I32, I32, I32, I64, P, I64, P, P, P, P, P]),
+    "egs_isect_sorted": (c_int32, [I32, I32, P, P, P, P, P, P, I32, I32, I32, I64, P, I64, P, P, P, P, P]),
     "egs_exclusive_scan_gather": (c_int32, [I64, P, P, P, P, P, I64, P]),
     "egs_isect_emit_sorted": (c_int32, [I32, I32, I64, P, P, P, P, I32, I32, I32, I64, P, P, P]),
     "egs_isect_finalize": (c_int32, [I64, P, P, P, I32, I32, I32, P, P, P]),

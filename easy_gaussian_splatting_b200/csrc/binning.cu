@@ -166,67 +166,103 @@ __global__ void __launch_bounds__(kOffThreads) isect_offset_encode_kernel(int64_
 // are rebuilt for `meta["isect_ids"]` in the same kernel that derives the tile offsets.
 // ================================================================================================
 
-// ---- visible compaction: vis_rank[i] = #visible entries before i; totals = {n_vis, n_isects} -------------
 __device__ __forceinline__ int64_t block_reduce_sum(int64_t v, int64_t* smem /*[33]*/) {
   int64_t total;
   block_inclusive_scan(v, smem, total);
   return total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) visible_block_sums_kernel(const int32_t* __restrict__ tiles, int64_t n,
-                                                                           int64_t* __restrict__ sums_vis,
-                                                                           int64_t* __restrict__ sums_tiles) {
-  __shared__ int64_t smem[33];
-  const int64_t base = (int64_t)blockIdx.x * kScanTile;
-  int64_t a = 0, b = 0;
+// ---- decoupled look-back chain shared by the single-launch scans below --------------------------------------------
+constexpr uint64_t kChainAggregate = 1ull << 62, kChainPrefix = 2ull << 62, kChainValue = (1ull << 62) - 1ull;
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Exclusive prefix of `total` over the blocks before `blk` (ticket order).  Called by one full warp; status words
+// start at zero.  Lane l looks at block blk-1-l: everything up to the first block that has not published yet is
+// consumed, the walk ends at the first inclusive prefix.
+__device__ __forceinline__ int64_t chain_lookback(uint64_t* __restrict__ status, uint32_t blk, int64_t total, int lane) {
+  if (lane == 0) st_volatile_u64(status + blk, (blk == 0 ? kChainPrefix : kChainAggregate) | (uint64_t)total);
+  int64_t excl = 0;
+  if (blk > 0) {
+    int64_t j = (int64_t)blk - 1;
+    for (;;) {
+      const int64_t jj = j - lane;
+      const uint64_t v = jj >= 0 ? ld_volatile_u64(status + jj) : kChainPrefix;  // before block 0: an empty prefix
+      const uint32_t flag = (uint32_t)(v >> 62);
+      const uint32_t not_ready = __ballot_sync(0xffffffffu, flag == 0u);
+      const uint32_t is_prefix = __ballot_sync(0xffffffffu, flag == 2u);
+      const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+      const int first_pf = is_prefix ? __ffs(is_prefix) - 1 : 32;
+      const int take = first_pf < first_nr ? first_pf + 1 : first_nr;
+      int64_t c = lane < take ? (int64_t)(v & kChainValue) : 0;
 #pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    int64_t j = base + (int64_t)i * kScanThreads + threadIdx.x;
-    if (j < n) { const int32_t t = tiles[j]; a += (t > 0); b += t; }
+      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+      excl += c;
+      if (first_pf < first_nr) break;
+      j -= take;  // poll again from the first block that had nothing yet
+    }
+    if (lane == 0) st_volatile_u64(status + blk, kChainPrefix | (uint64_t)(excl + total));
   }
-  const int64_t ta = block_reduce_sum(a, smem);
-  const int64_t tb = block_reduce_sum(b, smem);
-  if (threadIdx.x == 0) { sums_vis[blockIdx.x] = ta; sums_tiles[blockIdx.x] = tb; }
+  return excl;
 }
 
-__global__ void __launch_bounds__(kScanThreads) visible_spine_kernel(int64_t* __restrict__ sums_vis,
-                                                                      const int64_t* __restrict__ sums_tiles,
-                                                                      int64_t nblocks, int64_t* __restrict__ totals) {
-  __shared__ int64_t smem[33];
-  int64_t carry = 0, tiles_total = 0;
-  for (int64_t base = 0; base < nblocks; base += kScanThreads) {
-    int64_t j = base + threadIdx.x;
-    int64_t v = (j < nblocks) ? sums_vis[j] : 0;
-    int64_t total;
-    int64_t inc = block_inclusive_scan(v, smem, total);
-    if (j < nblocks) sums_vis[j] = carry + inc - v;
-    carry += total;
-    tiles_total += block_reduce_sum((j < nblocks) ? sums_tiles[j] : 0, smem);
-  }
-  if (threadIdx.x == 0) { totals[0] = carry; totals[1] = tiles_total; totals[2] = 0; totals[3] = 0; }
-}
-
-// also writes the level-1 sort input: key = bits(depth), value = flat index (camera * N + Gaussian), compacted.
+// ---- visible compaction + level-1 sort input in ONE launch --------------------------------------------------------
+// key = bits(depth), value = flat index (camera * N + Gaussian), compacted; totals = {n_vis, sum of tiles, 0, 0}.
 // The camera needs no key bits: level 2 sorts stably on the (camera, tile) index, so sorting the visible entries of
 // ALL cameras on depth alone (ties keep the flat-index order they are written in here) leaves every (camera, tile)
 // bucket in (depth, flat index) order — the order of a sort on cam | tile | depth.
-__global__ void __launch_bounds__(kScanThreads) visible_apply_kernel(const int32_t* __restrict__ tiles, int64_t n,
-                                                                      const int64_t* __restrict__ sums_vis,
-                                                                      const float* __restrict__ depths,
-                                                                      uint32_t* __restrict__ keys1,
-                                                                      uint32_t* __restrict__ vals1) {
+// control: {ticket u32, finished u32, tile sum u64} then one chain status word per block, all zero at launch.
+struct VisibleControl { uint32_t ticket, finished; unsigned long long tile_sum; };
+
+__global__ void __launch_bounds__(kScanThreads) visible_keys_kernel(const int32_t* __restrict__ tiles, int64_t n,
+                                                                     const float* __restrict__ depths,
+                                                                     uint32_t* __restrict__ keys1, uint32_t* __restrict__ vals1,
+                                                                     int64_t* __restrict__ totals, VisibleControl* __restrict__ control,
+                                                                     uint64_t* __restrict__ status) {
   __shared__ int64_t smem[33];
-  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  __shared__ int64_t block_base;
+  __shared__ uint32_t block_ticket;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) block_ticket = atomicAdd(&control->ticket, 1u);
+  __syncthreads();
+  const uint32_t blk = block_ticket;
+  const int64_t base = (int64_t)blk * kScanTile + (int64_t)threadIdx.x * kScanItems;
   int32_t v[kScanItems];
-  int64_t s = 0;
+  if (base + kScanItems <= n) {  // kScanItems = 8 consecutive counts: two 128-bit loads (base is a multiple of 8)
+    const int4 a = __ldg(reinterpret_cast<const int4*>(tiles + base)), b = __ldg(reinterpret_cast<const int4*>(tiles + base) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
 #pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    v[i] = (base + i < n) ? tiles[base + i] : 0;
-    s += (v[i] > 0);
+    for (int i = 0; i < kScanItems; ++i) v[i] = (base + i < n) ? tiles[base + i] : 0;
   }
+  int64_t s = 0, t = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) { s += (v[i] > 0); t += v[i]; }
   int64_t total;
-  int64_t inc = block_inclusive_scan(s, smem, total);
-  int64_t run = sums_vis[blockIdx.x] + inc - s;
+  const int64_t inc = block_inclusive_scan(s, smem, total);
+  const int64_t tile_total = block_reduce_sum(t, smem);
+  if (warp == 0) {
+    const int64_t excl = chain_lookback(status, blk, total, lane);
+    if (lane == 0) {
+      block_base = excl;
+      if ((int64_t)(blk + 1) * kScanTile >= n) totals[0] = excl + total;  // the last block of the chain
+      atomicAdd(&control->tile_sum, (unsigned long long)tile_total);
+      __threadfence();
+      if (atomicAdd(&control->finished, 1u) == gridDim.x - 1) {  // every block's sum has landed
+        totals[1] = (int64_t)atomicAdd(&control->tile_sum, 0ull);
+        totals[2] = 0; totals[3] = 0;
+      }
+    }
+  }
+  __syncthreads();
+  int64_t run = block_base + inc - s;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
     if (v[i] > 0) {
@@ -343,6 +379,106 @@ __global__ void __launch_bounds__(kEmitThreads) isect_emit_sorted_kernel(
         tile_keys[dst] = okb + (uint32_t)((oy0 + ty) * tile_w + ox0 + tx);
         flat_vals[dst] = og;
       }
+    }
+  }
+}
+
+// ---- the same emission with the scan folded in (the product route) --------------------------------------------------
+// One launch instead of four (block sums, spine, apply, emit): a thread block scans the tile counts of its 256
+// Gaussians, chains its total to the blocks before it with decoupled look-back (one 64-bit status word per block:
+// 2 flag bits | running count), and emits.  The tight rectangle arrives packed in 8 bytes from the projection kernel
+// (pack_tile_rect) — one gather per Gaussian instead of the 60 bytes of record, mean and radius the rectangle was
+// recomputed from (that set-up was two thirds of the old kernel's instructions, profiles/r2p).
+__global__ void __launch_bounds__(kEmitThreads) isect_scan_emit_kernel(
+    int N, int64_t n_vis, const int64_t* __restrict__ n_vis_dev, const uint32_t* __restrict__ order,
+    const int2* __restrict__ tight_rects /* nullable: classic rectangles from means2d / radii */,
+    const float2* __restrict__ means2d, const int32_t* __restrict__ radii, float tile_size, int tile_w, int tile_h,
+    int64_t capacity, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ flat_vals,
+    int64_t* __restrict__ n_isects_out, uint32_t* __restrict__ ticket, uint64_t* __restrict__ status) {
+  __shared__ int32_t warp_excl[kEmitThreads / 32];
+  __shared__ int64_t block_base;
+  __shared__ uint32_t block_ticket;
+  n_vis = live_count(n_vis, n_vis_dev);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ticket order = chain order: a block only ever waits for blocks that are already running
+  if (threadIdx.x == 0) block_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t blk = block_ticket;
+  const int64_t first = (int64_t)blk * kEmitThreads;
+  if (first >= n_vis) {  // block-uniform; nothing behind this block has work either
+    if (blk == 0 && threadIdx.x == 0) *n_isects_out = 0;
+    return;
+  }
+  const int64_t i = first + threadIdx.x;  // position in depth order
+  const bool valid = i < n_vis;
+  uint32_t g = 0;
+  int32_t x0 = 0, y0 = 0, w = 1, cnt = 0;
+  if (valid) {
+    g = order[i];
+    if (tight_rects != nullptr) {
+      const int2 r = __ldg(tight_rects + g);
+      x0 = r.x & 0xffff; y0 = (int32_t)((uint32_t)r.x >> 16);
+      w = r.y & 0xffff;
+      cnt = w * (int32_t)((uint32_t)r.y >> 16);
+    } else {
+      const float2 m = means2d[g];
+      int32_t x1, y1;
+      tile_rect(m.x, m.y, radii[g], tile_size, tile_w, tile_h, x0, y0, x1, y1);
+      w = x1 - x0;
+      cnt = w * (y1 - y0);
+    }
+    w = max(w, 1);
+  }
+  // counts of one block stay far below 2^31 (256 rectangles of < 2^23 tiles each: the entry point checks the grid)
+  int32_t inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  const int32_t lexcl = inc - cnt;
+  const int32_t total = __shfl_sync(0xffffffffu, inc, 31);
+  if (lane == 31) warp_excl[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int32_t wt = lane < kEmitThreads / 32 ? warp_excl[lane] : 0;
+    int32_t wi = wt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += t;
+    }
+    const int32_t block_total = __shfl_sync(0xffffffffu, wi, 31);
+    if (lane < kEmitThreads / 32) warp_excl[lane] = wi - wt;
+    const int64_t excl = chain_lookback(status, blk, block_total, lane);
+    if (lane == 0) {
+      block_base = excl;
+      if (first + kEmitThreads >= n_vis) *n_isects_out = excl + block_total;  // the block that holds the last entry
+    }
+  }
+  __syncthreads();
+  const int64_t warp_base = block_base + warp_excl[warp];
+  // j / w for every tile j of the rectangle without a division per pair (see isect_emit_sorted_kernel)
+  const uint32_t wmagic = w > 1 ? (uint32_t)((0x100000000ull + (uint32_t)w - 1u) / (uint32_t)w) : 0u;
+  const uint32_t key_base = (uint32_t)(g / (uint32_t)N) * (uint32_t)(tile_w * tile_h) + (uint32_t)(y0 * tile_w + x0);
+  for (int32_t k0 = 0; k0 < total; k0 += 32) {
+    const int32_t k = k0 + lane;
+    int o = 0;  // owner = last lane whose run starts at or before k
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int32_t e = __shfl_sync(0xffffffffu, lexcl, o + step);
+      if (e <= k) o += step;
+    }
+    const int32_t j = k - __shfl_sync(0xffffffffu, lexcl, o);
+    const int32_t ow = __shfl_sync(0xffffffffu, w, o);
+    const uint32_t omagic = __shfl_sync(0xffffffffu, wmagic, o);
+    const uint32_t okb = __shfl_sync(0xffffffffu, key_base, o);
+    const uint32_t og = __shfl_sync(0xffffffffu, g, o);
+    const int64_t dst = warp_base + k;
+    if (k < total && dst < capacity) {
+      const int32_t ty = ow > 1 ? (int32_t)__umulhi((uint32_t)j, omagic) : j, tx = j - ty * ow;
+      tile_keys[dst] = okb + (uint32_t)(ty * tile_w + tx);
+      flat_vals[dst] = og;
     }
   }
 }
@@ -474,7 +610,7 @@ extern "C" int egs_isect_offset_encode(int64_t n_isects, const int64_t* isect_id
 // ---- fast path entry points (see the block comment above isect_emit_sorted_kernel) -------------------------
 extern "C" int64_t egs_isect_scan_workspace_bytes(int64_t n) {
   if (n < 0) return 0;
-  return 2 * (ceil_div(n > 0 ? n : 1, kScanTile) + 1) * (int64_t)sizeof(int64_t);
+  return 256 + ceil_div(n > 0 ? n : 1, kScanTile) * (int64_t)sizeof(uint64_t);  // control block + chain status words
 }
 
 extern "C" int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths,
@@ -488,15 +624,18 @@ extern "C" int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles
     EGS_CUDA(cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), stream));
     return 0;
   }
-  if (workspace_bytes < egs_isect_scan_workspace_bytes(n))
+  const int64_t need = egs_isect_scan_workspace_bytes(n);
+  if (workspace == nullptr || workspace_bytes < need)
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "isect_visible_keys: workspace too small");
+  EGS_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 16 == 0 && reinterpret_cast<uintptr_t>(tiles_per_gauss) % 16 == 0,
+              "isect_visible_keys: workspace and tiles_per_gauss must be 16-byte aligned");
+  EGS_CUDA(cudaMemsetAsync(workspace, 0, need, stream));
   const int64_t nblocks = ceil_div(n, kScanTile);
-  int64_t* sums_vis = reinterpret_cast<int64_t*>(workspace);
-  int64_t* sums_tiles = sums_vis + nblocks + 1;
-  visible_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, sums_tiles);
-  visible_spine_kernel<<<1, kScanThreads, 0, stream>>>(sums_vis, sums_tiles, nblocks, totals);
-  visible_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, sums_vis, depths, keys1, vals1);
-  return check_launch("isect_visible_keys", 3);
+  char* ws = reinterpret_cast<char*>(workspace);
+  visible_keys_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, depths, keys1, vals1, totals,
+                                                                      reinterpret_cast<VisibleControl*>(ws),
+                                                                      reinterpret_cast<uint64_t*>(ws + 256));
+  return check_launch("visible_keys_kernel");
 }
 
 extern "C" int egs_exclusive_scan_gather(int64_t n, const int32_t* src, const uint32_t* gather, int64_t* out,
@@ -617,11 +756,12 @@ __global__ void __launch_bounds__(kSchedThreads) tile_order_kernel(const int32_t
 }  // namespace egs
 
 // ---- the whole route behind egs_isect_visible_keys in ONE call, with the two counts read on the device -----------------
-// Workspace layout (all 16-byte aligned): keys1_b | vals1_b | cum | scan block sums | level-1 sort workspace |
-// level-2 ping-pong keys | level-2 ping-pong values | level-2 sort workspace.
+// Workspace layout (all 256-byte aligned): keys1_b | vals1_b | level-2 ping-pong keys | level-2 ping-pong values |
+// control block = {level-1 sort workspace | emission chain (ticket + one status word per block) | level-2 sort
+// workspace | tile-schedule histogram}.  The control block is what must start at zero: ONE memset per call.
 namespace {
 struct SortedLayout {
-  int64_t keys1_b, vals1_b, cum, scan, sort1, keys2, vals2, sort2, sched, total;
+  int64_t keys1_b, vals1_b, keys2, vals2, control, sort1, chain, sort2, sched, total;
 };
 SortedLayout sorted_layout(int64_t n, int64_t capacity, int end_bit2) {
   SortedLayout L;
@@ -629,11 +769,11 @@ SortedLayout sorted_layout(int64_t n, int64_t capacity, int end_bit2) {
   auto take = [&](int64_t bytes) { const int64_t at = off; off += egs::align_up(bytes > 0 ? bytes : 16, 256); return at; };
   L.keys1_b = take(n * 4);
   L.vals1_b = take(n * 4);
-  L.cum = take(n * 8);
-  L.scan = take(egs_exclusive_scan_workspace_bytes(n));
-  L.sort1 = take(egs::radix_sort_workspace_bytes(n, 32));
   L.keys2 = take(capacity * 4);
   L.vals2 = take(capacity * 4);
+  L.control = off;
+  L.sort1 = take(egs::radix_sort_workspace_bytes(n, 32));
+  L.chain = take(256 + ceil_div(n, (int64_t)kEmitThreads) * 8);  // ticket (padded) + status words
   L.sort2 = take(egs::radix_sort_workspace_bytes(capacity, end_bit2));
   L.sched = take(2 * 32 * 4);  // class histogram + class cursors of the tile schedule
   L.total = off;
@@ -648,11 +788,11 @@ int level2_end_bit(int64_t n_slots) {
 
 // offsets[n_slots + 1] (with the sentinel) -> *max_len (nullable), order[n_slots] (nullable); scratch: 64 int32
 static int tile_schedule(const int32_t* offsets, int32_t n_slots, unsigned long long* max_len, int32_t* order, int32_t* scratch,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, bool scratch_is_zero = false) {
   if (n_slots <= 0 || (max_len == nullptr && order == nullptr)) return 0;
   int32_t* hist = scratch;
   int32_t* cursor = scratch + kSchedClasses;
-  EGS_CUDA(cudaMemsetAsync(hist, 0, kSchedClasses * sizeof(int32_t), stream));
+  if (!scratch_is_zero) EGS_CUDA(cudaMemsetAsync(hist, 0, kSchedClasses * sizeof(int32_t), stream));
   const unsigned blocks = (unsigned)ceil_div(n_slots, kSchedThreads);
   tile_classes_kernel<<<blocks, kSchedThreads, 0, stream>>>(offsets, n_slots, hist, max_len);
   if (order == nullptr) return check_launch("tile_classes_kernel");
@@ -667,22 +807,24 @@ extern "C" int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_
   return sorted_layout(n > 0 ? n : 1, capacity > 0 ? capacity : 1, level2_end_bit((int64_t)C * n_tiles)).total;
 }
 
-extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts, const float* splats, const float* means2d,
-                                const int32_t* radii, uint32_t* keys1, uint32_t* vals1, int64_t* stats,
-                                int32_t tile_size, int32_t tile_width, int32_t tile_height, int64_t capacity,
-                                void* workspace, int64_t workspace_bytes, uint32_t* tile_keys, uint32_t* flatten_ids,
-                                int32_t* offsets, int32_t* tile_order, egs_stream_t stream_) {
+extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tight_rects, const float* means2d, const int32_t* radii,
+                                uint32_t* keys1, uint32_t* vals1, int64_t* stats, int32_t tile_size, int32_t tile_width,
+                                int32_t tile_height, int64_t capacity, void* workspace, int64_t workspace_bytes,
+                                uint32_t* tile_keys, uint32_t* flatten_ids, int32_t* offsets, int32_t* tile_order,
+                                egs_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EGS_REQUIRE(C >= 0 && N >= 0, "isect_sorted: negative sizes");
   const int64_t n = (int64_t)C * N;
   const int64_t n_slots = (int64_t)C * tile_width * tile_height;
   EGS_REQUIRE(n < 0x7fffffffLL, "isect_sorted: C*N=%lld does not fit the int32 flatten id", (long long)n);
   EGS_REQUIRE(n_slots < 0x7fffffffLL, "isect_sorted: too many tiles");
+  EGS_REQUIRE(tile_width < 65536 && tile_height < 65536 && (int64_t)tile_width * tile_height < (1 << 23),
+              "isect_sorted: tile grid %dx%d too large (packed rectangles, 32-bit block scan)", tile_width, tile_height);
   EGS_REQUIRE((int64_t)tile_width * tile_height * tile_width < 0x100000000LL,
               "isect_sorted: tile grid %dx%d too large for the reciprocal row split", tile_width, tile_height);
   EGS_REQUIRE(capacity >= 1 && capacity < 0x7fffffffLL, "isect_sorted: capacity=%lld out of int32 range", (long long)capacity);
   EGS_REQUIRE(stats != nullptr, "isect_sorted: the device counts {n_vis, n_isects, ..} of egs_isect_visible_keys are required");
-  const int64_t* counts = stats;       // [0] n_vis (input), [1] intersection count (rewritten below from tile_counts)
+  const int64_t* counts = stats;       // [0] n_vis (input), [1] intersection count (rewritten by the emission below)
   int64_t* n_isects_dev = stats + 1;
   stats += 2;                          // slot 2: longest tile list (output)
   if (n_slots == 0) return 0;
@@ -698,37 +840,33 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts
   char* ws = reinterpret_cast<char*>(workspace);
   uint32_t* keys1_b = reinterpret_cast<uint32_t*>(ws + L.keys1_b);
   uint32_t* vals1_b = reinterpret_cast<uint32_t*>(ws + L.vals1_b);
-  int64_t* cum = reinterpret_cast<int64_t*>(ws + L.cum);
-  int64_t* block_sums = reinterpret_cast<int64_t*>(ws + L.scan);
+  EGS_CUDA(cudaMemsetAsync(ws + L.control, 0, L.total - L.control, stream));  // histograms, look-back words, tickets
   // level 1: visible entries of all cameras in (depth, flat index) order — 4 passes over n_vis 8-byte pairs
   int in_b = 0;
-  if (int rc = radix_sort_pairs_u32(n, counts, keys1, vals1, keys1_b, vals1_b, 32, ws + L.sort1, L.keys2 - L.sort1, &in_b, stream))
+  if (int rc = radix_sort_pairs_u32(n, counts, keys1, vals1, keys1_b, vals1_b, 32, ws + L.sort1, L.chain - L.sort1, &in_b, stream, true))
     return rc;
   const uint32_t* order = in_b ? vals1_b : vals1;
-  // tile counts in that order -> write offsets (the grand total is counts[1] already; the spine's copy lands in block_sums' tail)
-  const int64_t nblocks = ceil_div(n, kScanTile);
-  // (tile_counts: tiles_per_gauss for gsplat's lists, the projection kernel's tight_tiles for the blend kernels' own.
-  //  Their total over the visible entries becomes stats[1], the count every kernel below works with.)
-  gscan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tile_counts, order, n, counts, block_sums);
-  scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nblocks, n_isects_dev);
-  gscan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tile_counts, order, n, counts, block_sums, cum);
-  // emission into whichever side of the level-2 ping-pong makes the sorted pairs end in the caller's buffers
+  // scan of the tile counts in that order + emission, one launch; into whichever side of the level-2 ping-pong makes
+  // the sorted pairs end in the caller's buffers.  (tight_rects: the projection kernel's tight rectangles for the blend
+  // kernels' own lists; null: gsplat's rectangles.  The emitted total becomes stats[1], the count every kernel below
+  // works with.)
   const int passes2 = (end_bit2 + 7) / 8;
   uint32_t* ka = (passes2 & 1) ? reinterpret_cast<uint32_t*>(ws + L.keys2) : tile_keys;
   uint32_t* va = (passes2 & 1) ? reinterpret_cast<uint32_t*>(ws + L.vals2) : flatten_ids;
   uint32_t* kb = (passes2 & 1) ? tile_keys : reinterpret_cast<uint32_t*>(ws + L.keys2);
   uint32_t* vb = (passes2 & 1) ? flatten_ids : reinterpret_cast<uint32_t*>(ws + L.vals2);
-  isect_emit_sorted_kernel<<<(unsigned)ceil_div(n, kEmitThreads), kEmitThreads, 0, stream>>>(
-      N, n, order, cum, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width, tile_height, capacity,
-      ka, va, counts, reinterpret_cast<const float4*>(splats));
-  if (int rc = check_launch("isect_sorted (scan + emit)", 4)) return rc;
+  isect_scan_emit_kernel<<<(unsigned)ceil_div(n, kEmitThreads), kEmitThreads, 0, stream>>>(
+      N, n, counts, order, reinterpret_cast<const int2*>(tight_rects), reinterpret_cast<const float2*>(means2d), radii,
+      (float)tile_size, tile_width, tile_height, capacity, ka, va, n_isects_dev, reinterpret_cast<uint32_t*>(ws + L.chain),
+      reinterpret_cast<uint64_t*>(ws + L.chain + 256));
+  if (int rc = check_launch("isect_scan_emit_kernel")) return rc;
   // level 2: stable sort on the dense (camera, tile) index
-  if (int rc = radix_sort_pairs_u32(capacity, counts + 1, ka, va, kb, vb, end_bit2, ws + L.sort2, L.sched - L.sort2, &in_b, stream))
+  if (int rc = radix_sort_pairs_u32(capacity, n_isects_dev, ka, va, kb, vb, end_bit2, ws + L.sort2, L.sched - L.sort2, &in_b, stream, true))
     return rc;
   if ((in_b != 0) != ((passes2 & 1) != 0)) return fail(EGS_ERR_INVALID_ARGUMENT, "isect_sorted: internal ping-pong mismatch");
   isect_offsets4_kernel<<<(unsigned)ceil_div(capacity, 4 * kOff4Threads), kOff4Threads, 0, stream>>>(
-      (int32_t)capacity, tile_keys, (int32_t)n_slots, offsets, counts + 1, 1);
+      (int32_t)capacity, tile_keys, (int32_t)n_slots, offsets, n_isects_dev, 1);
   if (int rc = check_launch("isect_offsets4_kernel")) return rc;
   return tile_schedule(offsets, (int32_t)n_slots, reinterpret_cast<unsigned long long*>(stats), tile_order,
-                       reinterpret_cast<int32_t*>(ws + L.sched), stream);
+                       reinterpret_cast<int32_t*>(ws + L.sched), stream, true);
 }

@@ -234,6 +234,15 @@ EGS_HD void tighten_tile_rect(float m2x, float m2y, float ca, float cb, float cc
   if (y1 < y0) y1 = y0;
 }
 
+// A tile rectangle in 8 bytes, as the projection kernel hands the tight rectangles to the binning route:
+// {x0 | y0 << 16, w | h << 16}; tile grids stay below 65536 tiles per side (the entry points check).
+EGS_HD void pack_tile_rect(int32_t x0, int32_t y0, int32_t x1, int32_t y1, int32_t& origin, int32_t& extent) {
+  const int32_t w = x1 - x0, h = y1 - y0;
+  const bool empty = w <= 0 || h <= 0;
+  origin = empty ? 0 : (x0 | (y0 << 16));
+  extent = empty ? 0 : (w | (h << 16));
+}
+
 // VJP of project_fwd for a visible Gaussian.  Accumulates (+=) into
 // v_mean[3], v_quat[4], v_scale[3].
 EGS_HD void project_bwd(const ProjState& st, const float scale[3], const Camera& cam, float v_m2x, float v_m2y,

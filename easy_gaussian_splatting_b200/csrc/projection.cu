@@ -19,7 +19,8 @@ struct ProjFwdParams {
   int32_t* radii;
   float *means2d, *depths, *conics, *colors;
   int32_t* tiles_per_gauss;
-  int32_t* tight_tiles;  // nullable [C,N]: tiles of the TIGHT rectangle (tighten_tile_rect), the count of the blend kernels' own lists
+  int32_t* tight_rects;  // nullable [C,N,2]: the TIGHT tile rectangle (tighten_tile_rect) of the blend kernels' own lists,
+                         // packed {x0 | y0 << 16, w | h << 16} (w * h = 0 for a Gaussian that reaches no pixel)
   float4* splats;
   // raw-parameter mode (§8f-2): `scales` holds log-scales, `opacities` logits, `sh` the [N,1,3] DC band and
   // `sh_rest` the [N,15,3] remainder — exp / sigmoid / cat are folded into this kernel
@@ -80,7 +81,8 @@ __global__ void __launch_bounds__(kProjThreads) projection_fwd_kernel(const Proj
   ProjOut o;
   const bool vis = project_fwd(mean, quat, scale, cam, p.width, p.height, p.eps2d, p.near_plane, p.far_plane,
                                p.radius_clip, st, o);
-  int32_t ntiles = 0, ntight = 0;
+  int32_t ntiles = 0;
+  int2 tight = make_int2(0, 0);
   float rgb[3] = {0.f, 0.f, 0.f};
   if (vis) {
     int32_t x0, y0, x1, y1;
@@ -102,14 +104,14 @@ __global__ void __launch_bounds__(kProjThreads) projection_fwd_kernel(const Proj
     s[1] = make_float4(o.cc, opac, rgb[0], rgb[1]);
     const float cut = sigma_cutoff(opac);
     s[2] = make_float4(rgb[2], o.depth, 0.f, cut);
-    if (p.tight_tiles != nullptr) {
+    if (p.tight_rects != nullptr) {
       tighten_tile_rect(o.m2x, o.m2y, o.ca, o.cb, o.cc, cut, p.tile_size, x0, y0, x1, y1);
-      ntight = (x1 - x0) * (y1 - y0);
+      pack_tile_rect(x0, y0, x1, y1, tight.x, tight.y);
     }
   }
   p.radii[idx] = o.radius;
   p.tiles_per_gauss[idx] = ntiles;
-  if (p.tight_tiles != nullptr) p.tight_tiles[idx] = ntight;
+  if (p.tight_rects != nullptr) reinterpret_cast<int2*>(p.tight_rects)[idx] = tight;
   reinterpret_cast<float2*>(p.means2d)[idx] = make_float2(o.m2x, o.m2y);
   p.depths[idx] = o.depth;
   p.conics[idx * 3 + 0] = o.ca; p.conics[idx * 3 + 1] = o.cb; p.conics[idx * 3 + 2] = o.cc;
@@ -253,7 +255,8 @@ __global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const 
   }
   __syncwarp();
   if (!in_range) return;
-  int32_t ntiles = 0, ntight = 0;
+  int32_t ntiles = 0;
+  int2 tight = make_int2(0, 0);
   float rgb[3] = {0.f, 0.f, 0.f};
   if (vis) {
     int32_t x0, y0, x1, y1;
@@ -297,14 +300,14 @@ __global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const 
     s[1] = make_float4(o.cc, opac, rgb[0], rgb[1]);
     const float cut = sigma_cutoff(opac);
     s[2] = make_float4(rgb[2], o.depth, 0.f, cut);
-    if (p.tight_tiles != nullptr) {
+    if (p.tight_rects != nullptr) {
       tighten_tile_rect(o.m2x, o.m2y, o.ca, o.cb, o.cc, cut, p.tile_size, x0, y0, x1, y1);
-      ntight = (x1 - x0) * (y1 - y0);
+      pack_tile_rect(x0, y0, x1, y1, tight.x, tight.y);
     }
   }
   p.radii[idx] = o.radius;
   p.tiles_per_gauss[idx] = ntiles;
-  if (p.tight_tiles != nullptr) p.tight_tiles[idx] = ntight;
+  if (p.tight_rects != nullptr) reinterpret_cast<int2*>(p.tight_rects)[idx] = tight;
   reinterpret_cast<float2*>(p.means2d)[idx] = make_float2(o.m2x, o.m2y);
   p.depths[idx] = o.depth;
   p.conics[idx * 3 + 0] = o.ca; p.conics[idx * 3 + 1] = o.cb; p.conics[idx * 3 + 2] = o.cc;
@@ -641,7 +644,7 @@ static int projection_fwd_impl(int32_t C, int32_t N, const float* means, const f
                                int32_t width, int32_t height, float eps2d, float near_plane, float far_plane,
                                float radius_clip, int32_t tile_size, int32_t tile_width, int32_t tile_height,
                                int32_t* radii, float* means2d, float* depths, float* conics, float* colors,
-                               int32_t* tiles_per_gauss, int32_t* tight_tiles, float* splats, egs_stream_t stream,
+                               int32_t* tiles_per_gauss, int32_t* tight_rects, float* splats, egs_stream_t stream,
                                float* compensations = nullptr) {
   const int raw = sh_rest != nullptr;
   EGS_REQUIRE(C >= 0 && N >= 0, "projection_fwd: negative sizes C=%d N=%d", C, N);
@@ -649,6 +652,8 @@ static int projection_fwd_impl(int32_t C, int32_t N, const float* means, const f
   EGS_REQUIRE(width >= 1 && height >= 1, "projection_fwd: width/height must be >= 1 (got %d x %d)", width, height);
   EGS_REQUIRE(tile_size >= 1 && (tile_size & (tile_size - 1)) == 0, "projection_fwd: tile_size must be a power of two");
   EGS_REQUIRE(sh_degree <= 3, "projection_fwd: sh_degree %d > 3 is not supported", sh_degree);
+  EGS_REQUIRE(tight_rects == nullptr || (tile_width < 65536 && tile_height < 65536),
+              "projection_fwd: tile grid %d x %d too large for the packed tight rectangles", tile_width, tile_height);
   EGS_REQUIRE(sh_degree < 0 || K >= (sh_degree + 1) * (sh_degree + 1), "projection_fwd: K=%d too small for sh_degree=%d", K, sh_degree);
   if (C == 0 || N == 0) return 0;
   ProjFwdParams p;
@@ -659,7 +664,7 @@ static int projection_fwd_impl(int32_t C, int32_t N, const float* means, const f
   p.far_plane = far_plane; p.radius_clip = radius_clip; p.tile_size = (float)tile_size;
   p.tile_w = tile_width; p.tile_h = tile_height;
   p.radii = radii; p.means2d = means2d; p.depths = depths; p.conics = conics; p.colors = colors;
-  p.tiles_per_gauss = tiles_per_gauss; p.tight_tiles = tight_tiles; p.splats = reinterpret_cast<float4*>(splats);
+  p.tiles_per_gauss = tiles_per_gauss; p.tight_rects = tight_rects; p.splats = reinterpret_cast<float4*>(splats);
   p.raw = raw; p.sh_rest = sh_rest;
   p.antialiased = compensations != nullptr; p.compensations = compensations;
   dim3 grid((unsigned)ceil_div(N, kProjThreads), (unsigned)C);
@@ -683,10 +688,10 @@ extern "C" int egs_projection_fwd(int32_t C, int32_t N, const float* means, cons
                                   int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
                                   int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii,
                                   float* means2d, float* depths, float* conics, float* colors,
-                                  int32_t* tiles_per_gauss, int32_t* tight_tiles, float* splats, egs_stream_t stream) {
+                                  int32_t* tiles_per_gauss, int32_t* tight_rects, float* splats, egs_stream_t stream) {
   return projection_fwd_impl(C, N, means, quats, scales, opacities, sh_coeffs, nullptr, K, sh_degree, colors_per_camera,
                              viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
-                             tile_width, tile_height, radii, means2d, depths, conics, colors, tiles_per_gauss, tight_tiles,
+                             tile_width, tile_height, radii, means2d, depths, conics, colors, tiles_per_gauss, tight_rects,
                              splats, stream);
 }
 
@@ -695,12 +700,12 @@ extern "C" int egs_projection_fwd_antialiased(
     const float* sh_coeffs, int32_t K, int32_t sh_degree, int32_t colors_per_camera, const float* viewmats,
     const float* Ks, int32_t width, int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
     int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii, float* means2d, float* depths,
-    float* conics, float* colors, int32_t* tiles_per_gauss, int32_t* tight_tiles, float* splats, float* compensations,
+    float* conics, float* colors, int32_t* tiles_per_gauss, int32_t* tight_rects, float* splats, float* compensations,
     egs_stream_t stream) {
   EGS_REQUIRE(compensations != nullptr, "projection_fwd_antialiased: compensations output is required");
   return projection_fwd_impl(C, N, means, quats, scales, opacities, sh_coeffs, nullptr, K, sh_degree, colors_per_camera,
                              viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
-                             tile_width, tile_height, radii, means2d, depths, conics, colors, tiles_per_gauss, tight_tiles,
+                             tile_width, tile_height, radii, means2d, depths, conics, colors, tiles_per_gauss, tight_rects,
                              splats, stream, compensations);
 }
 
@@ -710,13 +715,13 @@ extern "C" int egs_projection_fwd_raw(int32_t C, int32_t N, const float* means, 
                                       int32_t width, int32_t height, float eps2d, float near_plane, float far_plane,
                                       float radius_clip, int32_t tile_size, int32_t tile_width, int32_t tile_height,
                                       int32_t* radii, float* means2d, float* depths, float* conics, float* colors,
-                                      int32_t* tiles_per_gauss, int32_t* tight_tiles, float* splats, egs_stream_t stream) {
+                                      int32_t* tiles_per_gauss, int32_t* tight_rects, float* splats, egs_stream_t stream) {
   EGS_REQUIRE(sh_rest != nullptr && sh_0 != nullptr, "projection_fwd_raw: sh_0 and sh_rest are required");
   EGS_REQUIRE(reinterpret_cast<uintptr_t>(sh_0) % 16 == 0 && reinterpret_cast<uintptr_t>(sh_rest) % 16 == 0,
               "projection_fwd_raw: sh_0 and sh_rest must be 16-byte aligned");
   return projection_fwd_impl(C, N, means, quats, log_scales, logit_opacities, sh_0, sh_rest, 16, sh_degree, 0, viewmats,
                              Ks, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size, tile_width,
-                             tile_height, radii, means2d, depths, conics, colors, tiles_per_gauss, tight_tiles, splats, stream);
+                             tile_height, radii, means2d, depths, conics, colors, tiles_per_gauss, tight_rects, splats, stream);
 }
 
 static int projection_bwd_impl(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,

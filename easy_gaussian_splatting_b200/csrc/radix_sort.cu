@@ -352,7 +352,7 @@ static int run_passes(int64_t n, const int64_t* n_dev, KeyT* keys_a, uint32_t* v
 template <typename KeyT>
 static int radix_sort_pairs_impl(int64_t n, const int64_t* n_dev, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b,
                                  uint32_t* vals_b, int32_t end_bit, void* workspace, int64_t workspace_bytes,
-                                 int32_t* host_result_in_b, cudaStream_t stream) {
+                                 int32_t* host_result_in_b, cudaStream_t stream, bool workspace_is_zero = false) {
   constexpr int kKeyBits = (int)sizeof(KeyT) * 8;
   EGS_REQUIRE(n >= 0, "radix_sort: n=%lld < 0", (long long)n);
   EGS_REQUIRE(n < (1ll << 30), "radix_sort: n=%lld exceeds the 2^30 pairs the look-back words can count", (long long)n);
@@ -370,7 +370,7 @@ static int radix_sort_pairs_impl(int64_t n, const int64_t* n_dev, KeyT* keys_a, 
   if (carve_workspace(workspace, workspace_bytes, n, passes, w, clear_bytes) != 0 || workspace == nullptr)
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "radix_sort: workspace %lld < %lld bytes", (long long)workspace_bytes,
                 (long long)clear_bytes);
-  EGS_CUDA(cudaMemsetAsync(workspace, 0, clear_bytes, stream));
+  if (!workspace_is_zero) EGS_CUDA(cudaMemsetAsync(workspace, 0, clear_bytes, stream));
   int64_t hist_blocks = ceil_div(n, (int64_t)kHistThreads * kHistItems);
   if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
   radix_histogram_kernel<KeyT><<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, n_dev, passes, w.hist);
@@ -407,9 +407,9 @@ namespace egs {
 int64_t radix_sort_workspace_bytes(int64_t capacity, int end_bit) { return egs_radix_sort_workspace_bytes(capacity, end_bit); }
 int radix_sort_pairs_u32(int64_t capacity, const int64_t* count_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
                          uint32_t* vals_b, int end_bit, void* workspace, int64_t workspace_bytes, int* result_in_b,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, bool workspace_is_zero) {
   return radix_sort_pairs_impl<uint32_t>(capacity, count_dev, keys_a, vals_a, keys_b, vals_b, end_bit, workspace,
-                                         workspace_bytes, result_in_b, stream);
+                                         workspace_bytes, result_in_b, stream, workspace_is_zero);
 }
 }  // namespace egs
 

@@ -141,8 +141,7 @@ def _bin_and_blend(ctx, proj, backgrounds, width, height, grad_enabled=True):
     while True:
         with stages.nvtx_range("egs.binning"):
             b = stages.isect_sorted_async(proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"],
-                                          stages.TILE_SIZE, tw, th, capacity=capacity, splats=proj["splats"],
-                                          tight_tiles=proj["tight_tiles"])
+                                          stages.TILE_SIZE, tw, th, capacity=capacity, tight_rects=proj["tight_rects"])
         with stages.nvtx_range("egs.rasterize_fwd"):
             if seg > 0:
                 rc, ra, last, ckpt = stages.rasterize_fwd_checkpointed(proj["splats"], b.offsets, b.flat_cap, backgrounds, width,

@@ -202,13 +202,13 @@ def projection_fwd(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tens
         "conics": torch.empty(C, N, 3, dtype=torch.float32, device=dev),
         "colors": torch.empty(C, N, 3, dtype=torch.float32, device=dev),
         "tiles_per_gauss": torch.empty(C, N, dtype=torch.int32, device=dev),
-        "tight_tiles": torch.empty(C, N, dtype=torch.int32, device=dev),
+        "tight_rects": torch.empty(C, N, 2, dtype=torch.int32, device=dev),
         "splats": torch.empty(C, N, SPLAT_FLOATS, dtype=torch.float32, device=dev),
     }
     args = (C, N, _ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities), _ptr(colors), K, deg, per_cam,
             _ptr(viewmats), _ptr(Ks), int(width), int(height), float(eps2d), float(near_plane), float(far_plane),
             float(radius_clip), int(tile_size), tw, th, _ptr(out["radii"]), _ptr(out["means2d"]), _ptr(out["depths"]),
-            _ptr(out["conics"]), _ptr(out["colors"]), _ptr(out["tiles_per_gauss"]), _ptr(out["tight_tiles"]),
+            _ptr(out["conics"]), _ptr(out["colors"]), _ptr(out["tiles_per_gauss"]), _ptr(out["tight_rects"]),
             _ptr(out["splats"]))
     with torch.cuda.device(dev):
         if antialiased:
@@ -290,7 +290,7 @@ def projection_fwd_raw(means: Tensor, quats: Tensor, log_scales: Tensor, logit_o
         "conics": torch.empty(C, N, 3, dtype=torch.float32, device=dev),
         "colors": torch.empty(C, N, 3, dtype=torch.float32, device=dev),
         "tiles_per_gauss": torch.empty(C, N, dtype=torch.int32, device=dev),
-        "tight_tiles": torch.empty(C, N, dtype=torch.int32, device=dev),
+        "tight_rects": torch.empty(C, N, 2, dtype=torch.int32, device=dev),
         "splats": torch.empty(C, N, SPLAT_FLOATS, dtype=torch.float32, device=dev),
     }
     with torch.cuda.device(dev):
@@ -299,7 +299,7 @@ def projection_fwd_raw(means: Tensor, quats: Tensor, log_scales: Tensor, logit_o
                                         int(width), int(height), float(eps2d), float(near_plane), float(far_plane),
                                         float(radius_clip), int(tile_size), tw, th, _ptr(out["radii"]),
                                         _ptr(out["means2d"]), _ptr(out["depths"]), _ptr(out["conics"]),
-                                        _ptr(out["colors"]), _ptr(out["tiles_per_gauss"]), _ptr(out["tight_tiles"]),
+                                        _ptr(out["colors"]), _ptr(out["tiles_per_gauss"]), _ptr(out["tight_rects"]),
                                         _ptr(out["splats"]), _stream(dev))
     _lib.check(rc, "egs_projection_fwd_raw")
     return out
@@ -563,13 +563,13 @@ def binning_hint(C: int, tile_width: int, tile_height: int, device, tight: bool 
 
 def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
                        tile_width: int, tile_height: int, capacity: Optional[int] = None,
-                       splats: Optional[Tensor] = None, tight_tiles: Optional[Tensor] = None) -> SortedIsects:
+                       tight_rects: Optional[Tensor] = None) -> SortedIsects:
     """g3+g4+g5, enqueued without waiting for the intersection count (see the block comment above).  ``capacity``:
     intersections to provide room for; None = from the previous call of this shape, or — first call — wait and size
     from the classic count (an upper bound).
 
-    ``splats`` + ``tight_tiles`` (both outputs of ``projection_fwd``): build the TIGHT lists the blend kernels need
-    instead of gsplat's — a Gaussian is listed only in the tiles of its classic rectangle that hold a pixel it can reach with
+    ``tight_rects`` (that output of ``projection_fwd``): build the TIGHT lists the blend kernels need instead of
+    gsplat's — a Gaussian is listed only in the tiles of its classic rectangle that hold a pixel it can reach with
     alpha >= 1/255 (include/egs_raster.h, egs_isect_sorted).  Same pixels and gradients, a third fewer entries to
     sort, stage and cull.  Without it the lists are bit-identical to gsplat's (``isect_tiles`` + offset encode)."""
     lib = _lib.load()
@@ -579,18 +579,17 @@ def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per
     dev = radii.device
     n = C * N
     n_tiles = tile_width * tile_height
-    tight = splats is not None
-    if tight and tight_tiles is None:
-        raise ValueError("tight lists need both outputs of projection_fwd: splats and tight_tiles")
+    tight = tight_rects is not None
+    if tight:
+        if tight_rects.shape != (C, N, 2) or tight_rects.dtype != torch.int32:
+            raise ValueError(f"tight_rects must be the int32 [C, N, 2] output of projection_fwd (got {tuple(tight_rects.shape)})")
+        tight_rects = tight_rects.contiguous()
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), C, tile_width, tile_height, tight)
     ws_scan = max(lib.egs_isect_scan_workspace_bytes(max(n, 1)), 16)
     scan_ws = torch.empty(ws_scan, dtype=torch.uint8, device=dev)
     stats = torch.empty(4, dtype=torch.int64, device=dev)
     keys1 = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     vals1 = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    tile_counts = tiles_per_gauss
-    if tight:
-        splats, tile_counts = _f32c(splats, "splats"), tight_tiles.contiguous()
     with torch.cuda.device(dev):
         rc = lib.egs_isect_visible_keys(C, N, _ptr(tiles_per_gauss), _ptr(depths), _ptr(keys1), _ptr(vals1), _ptr(stats),
                                         _ptr(scan_ws), ws_scan, _stream(dev))
@@ -619,7 +618,7 @@ def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per
     ws_bytes = lib.egs_isect_sorted_workspace_bytes(C, N, n_tiles, capacity)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.egs_isect_sorted(C, N, _ptr(tile_counts), _ptr(splats) if tight else None, _ptr(means2d), _ptr(radii),
+        rc = lib.egs_isect_sorted(C, N, _ptr(tight_rects) if tight else None, _ptr(means2d), _ptr(radii),
                                   _ptr(keys1), _ptr(vals1), _ptr(stats), int(tile_size), tile_width, tile_height, capacity,
                                   _ptr(ws), ws.numel(), _ptr(tile_keys), _ptr(flat), _ptr(offsets_store), _ptr(tile_order),
                                   _stream(dev))

@@ -65,16 +65,17 @@ int64_t egs_kernel_launch_count(void);
  *   radii[C,N] i32, means2d[C,N,2], depths[C,N], conics[C,N,3], colors[C,N,3],
  *   tiles_per_gauss[C,N] i32 (gsplat's count: tiles of the 3-sigma square), splats[C,N,12] packed records (only
  *   visible entries are written),
- *   tight_tiles[C,N] i32 (nullable; all egs_projection_fwd* entries): tiles of the TIGHT rectangle — the square
- *   intersected with the axis-aligned extent of {alpha >= 1/255} — the per-Gaussian count of the blend kernels' own
- *   lists (egs_isect_sorted); 0 for culled entries. */
+ *   tight_rects[C,N,2] i32 (nullable; all egs_projection_fwd* entries): the TIGHT tile rectangle — the square
+ *   intersected with the axis-aligned extent of {alpha >= 1/255} — that the blend kernels' own lists are built from
+ *   (egs_isect_sorted), packed {x0 | y0 << 16, w | h << 16} in tiles; {0, 0} for culled entries and for Gaussians
+ *   that reach no pixel.  Needs tile grids below 65536 tiles per side. */
 int egs_projection_fwd(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
                        const float* opacities, const float* sh_coeffs, int32_t K, int32_t sh_degree,
                        int32_t colors_per_camera, const float* viewmats, const float* Ks, int32_t width,
                        int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
                        int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii,
                        float* means2d, float* depths, float* conics, float* colors, int32_t* tiles_per_gauss,
-                       int32_t* tight_tiles, float* splats, egs_stream_t stream);
+                       int32_t* tight_rects, float* splats, egs_stream_t stream);
 
 /* ---- g8 + g9: fused SH backward + projection backward ------------------------------------------
  * Replaces gsplat `spherical_harmonics` bwd and `fully_fused_projection` bwd (summed over cameras).
@@ -122,7 +123,7 @@ int egs_projection_fwd_antialiased(int32_t C, int32_t N, const float* means, con
                                    int32_t height, float eps2d, float near_plane, float far_plane, float radius_clip,
                                    int32_t tile_size, int32_t tile_width, int32_t tile_height, int32_t* radii,
                                    float* means2d, float* depths, float* conics, float* colors,
-                                   int32_t* tiles_per_gauss, int32_t* tight_tiles, float* splats, float* compensations,
+                                   int32_t* tiles_per_gauss, int32_t* tight_rects, float* splats, float* compensations,
                                    egs_stream_t stream);
 int egs_projection_bwd_antialiased(int32_t C, int32_t N, const float* means, const float* quats, const float* scales,
                                    const float* opacities, const float* sh_coeffs, int32_t K, int32_t sh_degree,
@@ -143,7 +144,7 @@ int egs_projection_fwd_raw(int32_t C, int32_t N, const float* means, const float
                            const float* viewmats, const float* Ks, int32_t width, int32_t height, float eps2d,
                            float near_plane, float far_plane, float radius_clip, int32_t tile_size,
                            int32_t tile_width, int32_t tile_height, int32_t* radii, float* means2d, float* depths,
-                           float* conics, float* colors, int32_t* tiles_per_gauss, int32_t* tight_tiles, float* splats,
+                           float* conics, float* colors, int32_t* tiles_per_gauss, int32_t* tight_rects, float* splats,
                            egs_stream_t stream);
 int egs_projection_bwd_raw(int32_t C, int32_t N, const float* means, const float* quats, const float* log_scales,
                            const float* logit_opacities, const float* sh_0, const float* sh_rest, int32_t sh_degree,
@@ -195,8 +196,8 @@ int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, 
  *   egs_isect_finalize     : derives the tile offsets and/or rebuilds the 64-bit isect_ids (either output
  *                            pointer may be NULL: the Python side materialises isect_ids lazily, on first access) */
 /* Sync-free form of the route (what rasterization() runs): after egs_isect_visible_keys has left the level-1 pairs
- * and the counts on the device, ONE call enqueues everything else — level-1 sort, tile-count scan, emission, level-2
- * sort, tile offsets — for a CAPACITY of intersections chosen by the caller (e.g. from the previous call), every
+ * and the counts on the device, ONE call enqueues everything else — level-1 sort, tile-count scan + emission (one
+ * launch, chained across thread blocks by decoupled look-back), level-2 sort, tile offsets — for a CAPACITY of intersections chosen by the caller (e.g. from the previous call), every
  * kernel reading the live counts from `stats` on the device.  No host round trip is needed to size anything.
  *   stats[4] (device int64): [0] n_vis, [1] n_isects as left by egs_isect_visible_keys (inputs); [2] receives the
  *            longest tile list.  If n_isects > capacity the outputs hold a truncated, memory-safe but meaningless
@@ -206,14 +207,14 @@ int egs_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_a, uint32_t* vals_a, 
  *            holding n_isects, which egs_rasterize_* read when they are given a negative n_isects.
  *   tile_order [C * n_tiles] (nullable): the flat tile indices sorted by list length, longest first — the launch
  *            order for egs_rasterize_* (their tile_order argument).
- *   tile_counts [C,N]: tiles_per_gauss and splats = NULL give gsplat's lists bit for bit.  TIGHT lists — tile_counts =
- *            the tight_tiles output of egs_projection_fwd* and splats = its records: every Gaussian is listed only
- *            in the tiles of its classic rectangle that hold a pixel it can reach with alpha >= 1/255 (the
- *            rectangle intersected with the axis-aligned extent of sigma <= sigma_cut).  The blend kernels produce
- *            the same pixels and gradients from them (a dropped entry has alpha < 1/255 at every pixel of its
- *            tile); a third fewer entries to sort, stage and cull.  stats[1] is rewritten with the emitted total. */
+ *   tight_rects: NULL gives gsplat's lists bit for bit (rectangles from means2d / radii).  TIGHT lists —
+ *            tight_rects = that output of egs_projection_fwd*: every Gaussian is listed only in the tiles of its
+ *            classic rectangle that hold a pixel it can reach with alpha >= 1/255 (the rectangle intersected with
+ *            the axis-aligned extent of sigma <= sigma_cut).  The blend kernels produce the same pixels and gradients
+ *            from them (a dropped entry has alpha < 1/255 at every pixel of its tile); a third fewer entries to
+ *            sort, stage and cull.  stats[1] is rewritten with the emitted total. */
 int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_t n_tiles, int64_t capacity);
-int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tile_counts, const float* splats, const float* means2d,
+int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tight_rects, const float* means2d,
                      const int32_t* radii, uint32_t* keys1, uint32_t* vals1, int64_t* stats, int32_t tile_size, int32_t tile_width,
                      int32_t tile_height, int64_t capacity, void* workspace, int64_t workspace_bytes,
                      uint32_t* tile_keys, uint32_t* flatten_ids, int32_t* offsets, int32_t* tile_order,

@@ -46,7 +46,7 @@ def projection_fwd(means, quats, scales, opacities, colors, viewmats, Ks, width,
                               cols[..., 0], cols[..., 1], cols[..., 2], depths, z, cut], -1)
         splats = torch.where((radii > 0)[..., None], splats, torch.zeros(()))
     return {"radii": radii, "means2d": means2d.contiguous(), "depths": depths.contiguous(), "conics": conics.contiguous(),
-            "colors": cols.contiguous(), "tiles_per_gauss": tpg, "tight_tiles": tpg, "splats": splats.contiguous()}
+            "colors": cols.contiguous(), "tiles_per_gauss": tpg, "tight_rects": None, "splats": splats.contiguous()}
 
 
 def isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, tiles_per_gauss=None, n_isects=None):
@@ -57,8 +57,7 @@ def isect_offset_encode(isect_ids, C, tile_width, tile_height):
     return O.isect_offset_encode(isect_ids, C, tile_width, tile_height)
 
 
-def isect_sorted_async(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height, capacity=None, splats=None,
-                       tight_tiles=None):
+def isect_sorted_async(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height, capacity=None, tight_rects=None):
     C = radii.shape[0]
     _, ids, flat = O.isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height, sort=True)
     offsets = O.isect_offset_encode(ids, C, tile_width, tile_height)

@@ -384,7 +384,7 @@ def test_tight_lists_hold_a_subset_and_render_identically(cfg):
     args = (proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th)
     stages.reset_binning_hints()
     cl = stages.isect_sorted_async(*args)
-    tg = stages.isect_sorted_async(*args, splats=proj["splats"], tight_tiles=proj["tight_tiles"])
+    tg = stages.isect_sorted_async(*args, tight_rects=proj["tight_rects"])
     assert cl.resolve() and tg.resolve()
     n_t = C * tw * th
     key = lambda b: (torch.repeat_interleave(torch.arange(n_t, device="cuda"),

@@ -29,7 +29,7 @@ class FakeStages:
             "conics": torch.ones(C, N, 3) * vis[..., None],
             "colors": torch.full((C, N, 3), 0.5) * vis[..., None],
             "tiles_per_gauss": vis.int() * 2,
-            "tight_tiles": vis.int() * 2,
+            "tight_rects": torch.stack([torch.zeros(C, N, dtype=torch.int32), vis.int() * ((1 << 16) | 2)], -1),
             "splats": torch.zeros(C, N, stages.SPLAT_FLOATS),
         }
         if antialiased:
@@ -44,8 +44,7 @@ class FakeStages:
     def isect_offset_encode(self, isect_ids, C, tw, th):
         return torch.zeros(C, th, tw, dtype=torch.int32)
 
-    def isect_sorted_async(self, means2d, radii, depths, tiles_per_gauss, tile_size, tw, th, capacity=None, splats=None,
-                           tight_tiles=None):
+    def isect_sorted_async(self, means2d, radii, depths, tiles_per_gauss, tile_size, tw, th, capacity=None, tight_rects=None):
         self.calls.append("isect_sorted")
         C, N = radii.shape
         flat = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0].int()
