@@ -185,28 +185,39 @@ __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
 }
 
 // Exclusive prefix of `total` over the blocks before `blk` (ticket order).  Called by one full warp; status words
-// start at zero.  Lane l looks at block blk-1-l: everything up to the first block that has not published yet is
-// consumed, the walk ends at the first inclusive prefix.
+// start at zero.  Per trip a lane polls two blocks, blk-1-lane and blk-33-lane (both loads in flight together: the chain
+// advances up to 64 blocks per L2 round trip); everything up to the first block that has not published yet is consumed,
+// the walk ends at the first inclusive prefix.
 __device__ __forceinline__ int64_t chain_lookback(uint64_t* __restrict__ status, uint32_t blk, int64_t total, int lane) {
   if (lane == 0) st_volatile_u64(status + blk, (blk == 0 ? kChainPrefix : kChainAggregate) | (uint64_t)total);
   int64_t excl = 0;
   if (blk > 0) {
     int64_t j = (int64_t)blk - 1;
-    for (;;) {
-      const int64_t jj = j - lane;
-      const uint64_t v = jj >= 0 ? ld_volatile_u64(status + jj) : kChainPrefix;  // before block 0: an empty prefix
-      const uint32_t flag = (uint32_t)(v >> 62);
-      const uint32_t not_ready = __ballot_sync(0xffffffffu, flag == 0u);
-      const uint32_t is_prefix = __ballot_sync(0xffffffffu, flag == 2u);
-      const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
-      const int first_pf = is_prefix ? __ffs(is_prefix) - 1 : 32;
-      const int take = first_pf < first_nr ? first_pf + 1 : first_nr;
-      int64_t c = lane < take ? (int64_t)(v & kChainValue) : 0;
+    bool done = false;
+    while (!done) {
+      uint64_t v[2];
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-      excl += c;
-      if (first_pf < first_nr) break;
-      j -= take;  // poll again from the first block that had nothing yet
+      for (int q = 0; q < 2; ++q) {
+        const int64_t jj = j - 32 * q - lane;
+        v[q] = jj >= 0 ? ld_volatile_u64(status + jj) : kChainPrefix;  // before block 0: an empty prefix
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (done) break;
+        const uint32_t flag = (uint32_t)(v[q] >> 62);
+        const uint32_t not_ready = __ballot_sync(0xffffffffu, flag == 0u);
+        const uint32_t is_prefix = __ballot_sync(0xffffffffu, flag == 2u);
+        const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+        const int first_pf = is_prefix ? __ffs(is_prefix) - 1 : 32;
+        const int take = first_pf < first_nr ? first_pf + 1 : first_nr;
+        int64_t c = lane < take ? (int64_t)(v[q] & kChainValue) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        excl += c;
+        j -= take;
+        if (first_pf < first_nr) done = true;
+        else if (take < 32) break;  // a block in this half has nothing yet: poll again from it
+      }
     }
     if (lane == 0) st_volatile_u64(status + blk, kChainPrefix | (uint64_t)(excl + total));
   }
@@ -219,41 +230,70 @@ __device__ __forceinline__ int64_t chain_lookback(uint64_t* __restrict__ status,
 // ALL cameras on depth alone (ties keep the flat-index order they are written in here) leaves every (camera, tile)
 // bucket in (depth, flat index) order — the order of a sort on cam | tile | depth.
 // control: {ticket u32, finished u32, tile sum u64} then one chain status word per block, all zero at launch.
+// A block takes 8192 entries (warp w: 512 consecutive ones, 32 per round, so loads and the compacted stores are
+// both coalesced; a thread that owns consecutive entries scatters 4-byte stores over 32 sectors per instruction).
 struct VisibleControl { uint32_t ticket, finished; unsigned long long tile_sum; };
+constexpr int kVisThreads = 512;
+constexpr int kVisRounds = 16;
+constexpr int kVisTile = kVisThreads * kVisRounds;
 
-__global__ void __launch_bounds__(kScanThreads) visible_keys_kernel(const int32_t* __restrict__ tiles, int64_t n,
-                                                                     const float* __restrict__ depths,
-                                                                     uint32_t* __restrict__ keys1, uint32_t* __restrict__ vals1,
-                                                                     int64_t* __restrict__ totals, VisibleControl* __restrict__ control,
-                                                                     uint64_t* __restrict__ status) {
-  __shared__ int64_t smem[33];
+__global__ void __launch_bounds__(kVisThreads) visible_keys_kernel(const int32_t* __restrict__ tiles, int64_t n,
+                                                                    const float* __restrict__ depths,
+                                                                    uint32_t* __restrict__ keys1, uint32_t* __restrict__ vals1,
+                                                                    int64_t* __restrict__ totals, VisibleControl* __restrict__ control,
+                                                                    uint64_t* __restrict__ status) {
+  __shared__ int32_t warp_excl[kVisThreads / 32];
+  __shared__ int64_t warp_tiles[kVisThreads / 32];
   __shared__ int64_t block_base;
   __shared__ uint32_t block_ticket;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) block_ticket = atomicAdd(&control->ticket, 1u);
   __syncthreads();
   const uint32_t blk = block_ticket;
-  const int64_t base = (int64_t)blk * kScanTile + (int64_t)threadIdx.x * kScanItems;
-  int32_t v[kScanItems];
-  if (base + kScanItems <= n) {  // kScanItems = 8 consecutive counts: two 128-bit loads (base is a multiple of 8)
-    const int4 a = __ldg(reinterpret_cast<const int4*>(tiles + base)), b = __ldg(reinterpret_cast<const int4*>(tiles + base) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  } else {
+  const int64_t warp_first = (int64_t)blk * kVisTile + (int64_t)warp * (32 * kVisRounds);
+  int32_t v[kVisRounds];
+  float z[kVisRounds];
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) v[i] = (base + i < n) ? tiles[base + i] : 0;
+  for (int r = 0; r < kVisRounds; ++r) {
+    const int64_t i = warp_first + r * 32 + lane;
+    v[r] = i < n ? __ldg(tiles + i) : 0;
   }
-  int64_t s = 0, t = 0;
 #pragma unroll
-  for (int i = 0; i < kScanItems; ++i) { s += (v[i] > 0); t += v[i]; }
-  int64_t total;
-  const int64_t inc = block_inclusive_scan(s, smem, total);
-  const int64_t tile_total = block_reduce_sum(t, smem);
+  for (int r = 0; r < kVisRounds; ++r) {
+    const int64_t i = warp_first + r * 32 + lane;
+    z[r] = i < n ? __ldg(depths + i) : 0.f;  // unconditional: no dependence on the count (culled entries hold 0)
+  }
+  uint32_t mask[kVisRounds];
+  int32_t warp_total = 0;
+  int64_t t = 0;
+#pragma unroll
+  for (int r = 0; r < kVisRounds; ++r) {
+    mask[r] = __ballot_sync(0xffffffffu, v[r] > 0);
+    warp_total += __popc(mask[r]);
+    t += v[r];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  if (lane == 0) { warp_excl[warp] = warp_total; warp_tiles[warp] = t; }
+  __syncthreads();
   if (warp == 0) {
+    const int32_t wt = lane < kVisThreads / 32 ? warp_excl[lane] : 0;
+    int64_t tt = lane < kVisThreads / 32 ? warp_tiles[lane] : 0;
+    int32_t wi = wt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t u = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += u;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tt += __shfl_xor_sync(0xffffffffu, tt, d);
+    const int32_t total = __shfl_sync(0xffffffffu, wi, 31);
+    if (lane < kVisThreads / 32) warp_excl[lane] = wi - wt;
     const int64_t excl = chain_lookback(status, blk, total, lane);
     if (lane == 0) {
       block_base = excl;
-      if ((int64_t)(blk + 1) * kScanTile >= n) totals[0] = excl + total;  // the last block of the chain
-      atomicAdd(&control->tile_sum, (unsigned long long)tile_total);
+      if ((int64_t)(blk + 1) * kVisTile >= n) totals[0] = excl + total;  // the last block of the chain
+      atomicAdd(&control->tile_sum, (unsigned long long)tt);
       __threadfence();
       if (atomicAdd(&control->finished, 1u) == gridDim.x - 1) {  // every block's sum has landed
         totals[1] = (int64_t)atomicAdd(&control->tile_sum, 0ull);
@@ -262,15 +302,16 @@ __global__ void __launch_bounds__(kScanThreads) visible_keys_kernel(const int32_
     }
   }
   __syncthreads();
-  int64_t run = block_base + inc - s;
+  int64_t run = block_base + warp_excl[warp];
+  const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    if (v[i] > 0) {
-      const int64_t idx = base + i;
-      keys1[run] = __float_as_uint(depths[idx]);
-      vals1[run] = (uint32_t)idx;
-      ++run;
+  for (int r = 0; r < kVisRounds; ++r) {
+    if ((mask[r] >> lane) & 1u) {
+      const int64_t dst = run + __popc(mask[r] & lt);
+      keys1[dst] = __float_as_uint(z[r]);
+      vals1[dst] = (uint32_t)(warp_first + r * 32 + lane);
     }
+    run += __popc(mask[r]);
   }
 }
 
@@ -389,6 +430,15 @@ __global__ void __launch_bounds__(kEmitThreads) isect_emit_sorted_kernel(
 // 2 flag bits | running count), and emits.  The tight rectangle arrives packed in 8 bytes from the projection kernel
 // (pack_tile_rect) — one gather per Gaussian instead of the 60 bytes of record, mean and radius the rectangle was
 // recomputed from (that set-up was two thirds of the old kernel's instructions, profiles/r2p).
+// A block takes kEmitRounds x 256 Gaussians (warp w: 128 consecutive ones, 32 per round): the chain advances 32 blocks
+// per L2 round trip, so the Gaussians per block set how fast the prefix can travel (256 per block: 119 us for the
+// 3.3 M visible Gaussians of the benchmark step, chain-bound; gpurun_out/launches_r2r.csv).
+#ifndef EGS_EMIT_ROUNDS
+#define EGS_EMIT_ROUNDS 4
+#endif
+constexpr int kEmitRounds = EGS_EMIT_ROUNDS;
+constexpr int kEmitBlock = kEmitThreads * kEmitRounds;
+
 __global__ void __launch_bounds__(kEmitThreads) isect_scan_emit_kernel(
     int N, int64_t n_vis, const int64_t* __restrict__ n_vis_dev, const uint32_t* __restrict__ order,
     const int2* __restrict__ tight_rects /* nullable: classic rectangles from means2d / radii */,
@@ -398,47 +448,60 @@ __global__ void __launch_bounds__(kEmitThreads) isect_scan_emit_kernel(
   __shared__ int32_t warp_excl[kEmitThreads / 32];
   __shared__ int64_t block_base;
   __shared__ uint32_t block_ticket;
+  __shared__ __align__(16) uint4 run_table[kEmitThreads / 32][32];
+  __shared__ uint32_t run_gauss[kEmitThreads / 32][32];
   n_vis = live_count(n_vis, n_vis_dev);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // ticket order = chain order: a block only ever waits for blocks that are already running
   if (threadIdx.x == 0) block_ticket = atomicAdd(ticket, 1u);
   __syncthreads();
   const uint32_t blk = block_ticket;
-  const int64_t first = (int64_t)blk * kEmitThreads;
+  const int64_t first = (int64_t)blk * kEmitBlock;
   if (first >= n_vis) {  // block-uniform; nothing behind this block has work either
     if (blk == 0 && threadIdx.x == 0) *n_isects_out = 0;
     return;
   }
-  const int64_t i = first + threadIdx.x;  // position in depth order
-  const bool valid = i < n_vis;
-  uint32_t g = 0;
-  int32_t x0 = 0, y0 = 0, w = 1, cnt = 0;
-  if (valid) {
-    g = order[i];
-    if (tight_rects != nullptr) {
-      const int2 r = __ldg(tight_rects + g);
-      x0 = r.x & 0xffff; y0 = (int32_t)((uint32_t)r.x >> 16);
-      w = r.y & 0xffff;
-      cnt = w * (int32_t)((uint32_t)r.y >> 16);
-    } else {
-      const float2 m = means2d[g];
-      int32_t x1, y1;
-      tile_rect(m.x, m.y, radii[g], tile_size, tile_w, tile_h, x0, y0, x1, y1);
-      w = x1 - x0;
-      cnt = w * (y1 - y0);
-    }
-    w = max(w, 1);
-  }
-  // counts of one block stay far below 2^31 (256 rectangles of < 2^23 tiles each: the entry point checks the grid)
-  int32_t inc = cnt;
+  const int64_t warp_first = first + warp * (32 * kEmitRounds);  // position in depth order of this warp's first Gaussian
+  uint32_t g[kEmitRounds];
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += t;
+  for (int r = 0; r < kEmitRounds; ++r) {
+    const int64_t i = warp_first + r * 32 + lane;
+    g[r] = i < n_vis ? order[i] : 0xffffffffu;
   }
-  const int32_t lexcl = inc - cnt;
-  const int32_t total = __shfl_sync(0xffffffffu, inc, 31);
-  if (lane == 31) warp_excl[warp] = inc;
+  int2 rect[kEmitRounds];
+  if (tight_rects != nullptr) {  // all gathers of the block in flight together
+#pragma unroll
+    for (int r = 0; r < kEmitRounds; ++r) rect[r] = g[r] != 0xffffffffu ? __ldg(tight_rects + g[r]) : make_int2(0, 0);
+  } else {
+#pragma unroll
+    for (int r = 0; r < kEmitRounds; ++r) {
+      rect[r] = make_int2(0, 0);
+      if (g[r] != 0xffffffffu) {
+        const float2 m = means2d[g[r]];
+        int32_t x0, y0, x1, y1;
+        tile_rect(m.x, m.y, radii[g[r]], tile_size, tile_w, tile_h, x0, y0, x1, y1);
+        pack_tile_rect(x0, y0, x1, y1, rect[r].x, rect[r].y);
+      }
+    }
+  }
+  int32_t cnt[kEmitRounds], lexcl[kEmitRounds], round_total[kEmitRounds];
+  int32_t warp_total = 0;
+#pragma unroll
+  for (int r = 0; r < kEmitRounds; ++r) {
+    if (g[r] == 0xffffffffu) g[r] = 0;
+    cnt[r] = (rect[r].y & 0xffff) * (int32_t)((uint32_t)rect[r].y >> 16);
+    // counts of one block stay far below 2^31 (1024 rectangles of < 2^21 tiles each: the entry point checks the grid)
+    int32_t inc = cnt[r];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    lexcl[r] = inc - cnt[r];
+    round_total[r] = __shfl_sync(0xffffffffu, inc, 31);
+    warp_total += round_total[r];
+  }
+  if (lane == 0) warp_excl[warp] = warp_total;
   __syncthreads();
   if (warp == 0) {
     const int32_t wt = lane < kEmitThreads / 32 ? warp_excl[lane] : 0;
@@ -453,33 +516,53 @@ __global__ void __launch_bounds__(kEmitThreads) isect_scan_emit_kernel(
     const int64_t excl = chain_lookback(status, blk, block_total, lane);
     if (lane == 0) {
       block_base = excl;
-      if (first + kEmitThreads >= n_vis) *n_isects_out = excl + block_total;  // the block that holds the last entry
+      if (first + kEmitBlock >= n_vis) *n_isects_out = excl + block_total;  // the block that holds the last entry
     }
   }
   __syncthreads();
-  const int64_t warp_base = block_base + warp_excl[warp];
-  // j / w for every tile j of the rectangle without a division per pair (see isect_emit_sorted_kernel)
-  const uint32_t wmagic = w > 1 ? (uint32_t)((0x100000000ull + (uint32_t)w - 1u) / (uint32_t)w) : 0u;
-  const uint32_t key_base = (uint32_t)(g / (uint32_t)N) * (uint32_t)(tile_w * tile_h) + (uint32_t)(y0 * tile_w + x0);
-  for (int32_t k0 = 0; k0 < total; k0 += 32) {
-    const int32_t k = k0 + lane;
-    int o = 0;  // owner = last lane whose run starts at or before k
+  // Emission, 32 consecutive entries per trip.  The non-empty runs of a round are compacted into a per-warp table
+  // {start, row reciprocal, key base - start, row stride} + Gaussian; the owner of entry k is then
+  // (#runs that start before the trip's window) + (#runs that start inside it at or before k) - 1: one ballot, one
+  // warp-wide OR (redux.sync) and two popc instead of a five-step shuffle search, and two shared-memory loads
+  // instead of five shuffles for the owner's data.
+  int64_t round_base = block_base + warp_excl[warp];
+  uint4* tab = run_table[warp];
+  uint32_t* tab_g = run_gauss[warp];
+  const uint32_t le_mask = (2u << lane) - 1u;
 #pragma unroll
-    for (int step = 16; step > 0; step >>= 1) {
-      const int32_t e = __shfl_sync(0xffffffffu, lexcl, o + step);
-      if (e <= k) o += step;
+  for (int r = 0; r < kEmitRounds; ++r) {
+    const int32_t total = round_total[r];
+    const uint32_t nonempty = __ballot_sync(0xffffffffu, cnt[r] > 0);
+    if (cnt[r] > 0) {
+      const int32_t w = rect[r].y & 0xffff;
+      // floor(j * ceil(2^32 / w) / 2^32) == j / w exactly while j * w < 2^32 (the entry point checks the tile grid);
+      // 0 marks w == 1 (the reciprocal would be 2^32)
+      const uint32_t magic = w > 1 ? 0xffffffffu / (uint32_t)w + 1u : 0u;
+      const uint32_t key_base = (g[r] / (uint32_t)N) * (uint32_t)(tile_w * tile_h) +
+                                (uint32_t)((int32_t)((uint32_t)rect[r].x >> 16) * tile_w + (rect[r].x & 0xffff));
+      const int slot = __popc(nonempty & (le_mask >> 1));
+      tab[slot] = make_uint4((uint32_t)lexcl[r], magic, key_base - (uint32_t)lexcl[r], (uint32_t)(tile_w - w));
+      tab_g[slot] = g[r];
     }
-    const int32_t j = k - __shfl_sync(0xffffffffu, lexcl, o);
-    const int32_t ow = __shfl_sync(0xffffffffu, w, o);
-    const uint32_t omagic = __shfl_sync(0xffffffffu, wmagic, o);
-    const uint32_t okb = __shfl_sync(0xffffffffu, key_base, o);
-    const uint32_t og = __shfl_sync(0xffffffffu, g, o);
-    const int64_t dst = warp_base + k;
-    if (k < total && dst < capacity) {
-      const int32_t ty = ow > 1 ? (int32_t)__umulhi((uint32_t)j, omagic) : j, tx = j - ty * ow;
-      tile_keys[dst] = okb + (uint32_t)(ty * tile_w + tx);
-      flat_vals[dst] = og;
+    __syncwarp();
+    const int32_t start = lane < __popc(nonempty) ? (int32_t)tab[lane].x : 0x7fffffff;  // start of the lane-th run
+    for (int32_t k0 = 0; k0 < total; k0 += 32) {
+      const int32_t k = k0 + lane;
+      const uint32_t before = __popc(__ballot_sync(0xffffffffu, start < k0));
+      const uint32_t d = (uint32_t)(start - k0);
+      const uint32_t inside = __reduce_or_sync(0xffffffffu, d < 32u ? 1u << d : 0u);
+      const int o = (int)(before + __popc(inside & le_mask)) - 1;  // >= 0: the first run starts at entry 0
+      const int64_t dst = round_base + k;
+      if (k < total && dst < capacity) {
+        const uint4 run = tab[o];
+        const uint32_t j = (uint32_t)k - run.x;
+        const uint32_t ty = run.y ? __umulhi(j, run.y) : j;
+        tile_keys[dst] = run.z + (uint32_t)k + ty * run.w;  // key base + j + row * (tile_w - w)
+        flat_vals[dst] = tab_g[o];
+      }
     }
+    __syncwarp();  // the table is rewritten by the next round
+    round_base += total;
   }
 }
 
@@ -610,7 +693,7 @@ extern "C" int egs_isect_offset_encode(int64_t n_isects, const int64_t* isect_id
 // ---- fast path entry points (see the block comment above isect_emit_sorted_kernel) -------------------------
 extern "C" int64_t egs_isect_scan_workspace_bytes(int64_t n) {
   if (n < 0) return 0;
-  return 256 + ceil_div(n > 0 ? n : 1, kScanTile) * (int64_t)sizeof(uint64_t);  // control block + chain status words
+  return 256 + ceil_div(n > 0 ? n : 1, kVisTile) * (int64_t)sizeof(uint64_t);  // control block + chain status words
 }
 
 extern "C" int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles_per_gauss, const float* depths,
@@ -627,12 +710,11 @@ extern "C" int egs_isect_visible_keys(int32_t C, int32_t N, const int32_t* tiles
   const int64_t need = egs_isect_scan_workspace_bytes(n);
   if (workspace == nullptr || workspace_bytes < need)
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "isect_visible_keys: workspace too small");
-  EGS_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 16 == 0 && reinterpret_cast<uintptr_t>(tiles_per_gauss) % 16 == 0,
-              "isect_visible_keys: workspace and tiles_per_gauss must be 16-byte aligned");
+  EGS_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "isect_visible_keys: workspace must be 16-byte aligned");
   EGS_CUDA(cudaMemsetAsync(workspace, 0, need, stream));
-  const int64_t nblocks = ceil_div(n, kScanTile);
+  const int64_t nblocks = ceil_div(n, kVisTile);
   char* ws = reinterpret_cast<char*>(workspace);
-  visible_keys_kernel<<<(unsigned)nblocks, kScanThreads, 0, stream>>>(tiles_per_gauss, n, depths, keys1, vals1, totals,
+  visible_keys_kernel<<<(unsigned)nblocks, kVisThreads, 0, stream>>>(tiles_per_gauss, n, depths, keys1, vals1, totals,
                                                                       reinterpret_cast<VisibleControl*>(ws),
                                                                       reinterpret_cast<uint64_t*>(ws + 256));
   return check_launch("visible_keys_kernel");
@@ -773,7 +855,7 @@ SortedLayout sorted_layout(int64_t n, int64_t capacity, int end_bit2) {
   L.vals2 = take(capacity * 4);
   L.control = off;
   L.sort1 = take(egs::radix_sort_workspace_bytes(n, 32));
-  L.chain = take(256 + ceil_div(n, (int64_t)kEmitThreads) * 8);  // ticket (padded) + status words
+  L.chain = take(256 + ceil_div(n, (int64_t)kEmitBlock) * 8);  // ticket (padded) + status words
   L.sort2 = take(egs::radix_sort_workspace_bytes(capacity, end_bit2));
   L.sched = take(2 * 32 * 4);  // class histogram + class cursors of the tile schedule
   L.total = off;
@@ -818,7 +900,7 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tight_rects
   const int64_t n_slots = (int64_t)C * tile_width * tile_height;
   EGS_REQUIRE(n < 0x7fffffffLL, "isect_sorted: C*N=%lld does not fit the int32 flatten id", (long long)n);
   EGS_REQUIRE(n_slots < 0x7fffffffLL, "isect_sorted: too many tiles");
-  EGS_REQUIRE(tile_width < 65536 && tile_height < 65536 && (int64_t)tile_width * tile_height < (1 << 23),
+  EGS_REQUIRE(tile_width < 65536 && tile_height < 65536 && (int64_t)tile_width * tile_height < (1 << 21),
               "isect_sorted: tile grid %dx%d too large (packed rectangles, 32-bit block scan)", tile_width, tile_height);
   EGS_REQUIRE((int64_t)tile_width * tile_height * tile_width < 0x100000000LL,
               "isect_sorted: tile grid %dx%d too large for the reciprocal row split", tile_width, tile_height);
@@ -855,7 +937,7 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tight_rects
   uint32_t* va = (passes2 & 1) ? reinterpret_cast<uint32_t*>(ws + L.vals2) : flatten_ids;
   uint32_t* kb = (passes2 & 1) ? tile_keys : reinterpret_cast<uint32_t*>(ws + L.keys2);
   uint32_t* vb = (passes2 & 1) ? flatten_ids : reinterpret_cast<uint32_t*>(ws + L.vals2);
-  isect_scan_emit_kernel<<<(unsigned)ceil_div(n, kEmitThreads), kEmitThreads, 0, stream>>>(
+  isect_scan_emit_kernel<<<(unsigned)ceil_div(n, kEmitBlock), kEmitThreads, 0, stream>>>(
       N, n, counts, order, reinterpret_cast<const int2*>(tight_rects), reinterpret_cast<const float2*>(means2d), radii,
       (float)tile_size, tile_width, tile_height, capacity, ka, va, n_isects_dev, reinterpret_cast<uint32_t*>(ws + L.chain),
       reinterpret_cast<uint64_t*>(ws + L.chain + 256));

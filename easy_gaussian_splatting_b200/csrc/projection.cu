@@ -60,10 +60,11 @@ __device__ __forceinline__ void load_coeffs(const float* __restrict__ base, int 
 template <bool VEC4>
 __global__ void __launch_bounds__(kProjThreads) projection_fwd_kernel(const ProjFwdParams p) {
   __shared__ Camera cam;
-  const int c = blockIdx.y;
+  // camera fastest: the C blocks that read one chunk of Gaussians run back to back and share it through L2
+  const int c = blockIdx.x % p.C, chunk = blockIdx.x / p.C;
   if (threadIdx.x == 0) load_camera(p.viewmats + (size_t)c * 16, p.Ks + (size_t)c * 9, cam);
   __syncthreads();
-  const int n = blockIdx.x * kProjThreads + threadIdx.x;
+  const int n = chunk * kProjThreads + threadIdx.x;
   if (n >= p.N) return;
   const size_t idx = (size_t)c * p.N + n;
 
@@ -210,11 +211,13 @@ constexpr int kFwdRowStride = 52;  // floats; conflict-free float4 row reads for
 __global__ void __launch_bounds__(kPF2Threads) projection_fwd_sh16_kernel(const ProjFwdParams p) {
   __shared__ Camera cam;
   __shared__ __align__(16) float tile[kPF2Threads / 32][32 * kFwdRowStride];
-  const int c = blockIdx.y;
+  // camera fastest: the C blocks that read one chunk of Gaussians (their 192 B of SH coefficients above all) run back
+  // to back and share it through L2, instead of every camera streaming all Gaussians from HBM again
+  const int c = blockIdx.x % p.C, chunk = blockIdx.x / p.C;
   if (threadIdx.x == 0) load_camera(p.viewmats + (size_t)c * 16, p.Ks + (size_t)c * 9, cam);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_base = blockIdx.x * kPF2Threads + warp * 32;
+  const int n_base = chunk * kPF2Threads + warp * 32;
   const int n = n_base + lane;
   const bool in_range = n < p.N;
   const size_t idx = (size_t)c * p.N + (in_range ? n : 0);
@@ -667,13 +670,13 @@ static int projection_fwd_impl(int32_t C, int32_t N, const float* means, const f
   p.tiles_per_gauss = tiles_per_gauss; p.tight_rects = tight_rects; p.splats = reinterpret_cast<float4*>(splats);
   p.raw = raw; p.sh_rest = sh_rest;
   p.antialiased = compensations != nullptr; p.compensations = compensations;
-  dim3 grid((unsigned)ceil_div(N, kProjThreads), (unsigned)C);
+  const unsigned grid = (unsigned)(ceil_div(N, kProjThreads) * C);
   const bool vec4 = sh_degree >= 0 && (K * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(sh_coeffs) % 16 == 0);
   if (raw) {
     EGS_REQUIRE(K == 16 && sh_degree >= 0, "projection_fwd_raw: needs sh_0 [N,1,3] + sh_rest [N,15,3] and sh_degree >= 0");
   }
   if (raw || (vec4 && K == 16)) {
-    dim3 grid2((unsigned)ceil_div(N, kPF2Threads), (unsigned)C);
+    const unsigned grid2 = (unsigned)(ceil_div(N, kPF2Threads) * C);
     projection_fwd_sh16_kernel<<<grid2, kPF2Threads, 0, (cudaStream_t)stream>>>(p);
     return check_launch("projection_fwd_sh16_kernel");
   }

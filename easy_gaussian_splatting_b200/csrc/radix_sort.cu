@@ -17,15 +17,22 @@ namespace egs {
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
-constexpr int kSortThreads = 512;
-constexpr int kSortWarps = kSortThreads / 32;
-// pairs per thread is the template parameter ITEMS (8 in production: tile = 4096 pairs; 16 was measured slower)
+constexpr int kSortTilePairs = 4096;  // pairs per tile in every configuration: threads x ITEMS
+// threads per block = kSortTilePairs / ITEMS (template parameter ITEMS = pairs per thread):
+//   64-bit keys: ITEMS = 8, 512 threads (16 keys per thread do not fit the registers of two resident blocks)
+//   32-bit keys: EGS_SORT_ITEMS_U32 (build-time A/B knob)
 
 #ifndef EGS_SORT_ITEMS_U32
-#define EGS_SORT_ITEMS_U32 8
+#define EGS_SORT_ITEMS_U32 16
+#endif
+#ifndef EGS_SORT_BLOCKS_16  // resident blocks per SM asked of ptxas for the 256-thread, 16-item form
+#define EGS_SORT_BLOCKS_16 4
 #endif
 
-constexpr int kLookWindow = 8;
+#ifndef EGS_SORT_LOOK_WINDOW
+#define EGS_SORT_LOOK_WINDOW 4
+#endif
+constexpr int kLookWindow = EGS_SORT_LOOK_WINDOW;
 constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagPrefix = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1u;
@@ -36,7 +43,7 @@ struct SortWorkspace {
   uint32_t* status;    // [passes][ntiles][256]
 };
 
-__host__ __device__ inline int64_t sort_ntiles(int64_t n, int items) { const int64_t t = (int64_t)kSortThreads * items; return (n + t - 1) / t; }
+__host__ __device__ inline int64_t sort_ntiles(int64_t n) { return (n + kSortTilePairs - 1) / kSortTilePairs; }
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   uint32_t v;
@@ -140,7 +147,9 @@ __global__ void __launch_bounds__(kRadix) radix_scan_hist_kernel(uint32_t* __res
 // Dynamic shared memory layout of one tile (67.6 KB with 64-bit keys -> 2 resident CTAs of 16 warps per SM):
 template <typename KeyT, int ITEMS>
 struct SortSmem {
-  static constexpr int kSortTile = kSortThreads * ITEMS;
+  static constexpr int kSortThreads = kSortTilePairs / ITEMS, kSortWarps = kSortThreads / 32;
+  static constexpr int kSortTile = kSortTilePairs;
+  static_assert(kSortThreads >= kRadix && kSortThreads % 32 == 0, "one thread per digit owns its look-back");
   KeyT keys[kSortTile];                     // 32 KB (u64) / 16 KB (u32)  tile-sorted keys
   uint32_t vals[kSortTile];                 // 16 KB  tile-sorted values
   uint32_t warp_hist[kSortWarps][kRadix];   // 16 KB  per-warp digit counts, then per-warp exclusive offsets
@@ -155,27 +164,17 @@ struct SortSmem {
 // ranks / slots are packed two per register; the values are loaded after the keys have left, and the
 // global destination of a slot is recomputed from the key's digit instead of being kept.  That keeps
 // the kernel at 64 registers (2 CTAs of 512 threads per SM) with every global load of a phase in flight at once.
-template <typename KeyT, int ITEMS>
-__global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 : 2) radix_onesweep_kernel(
-    const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
-    uint32_t* __restrict__ vals_out, int64_t n, const int64_t* __restrict__ n_dev, int shift,
-    const uint32_t* __restrict__ digit_base /*[256]*/, uint32_t* __restrict__ tile_counter,
-    uint32_t* __restrict__ status /*[ntiles][256]*/) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  n = live_count(n, n_dev);  // the grid covers the capacity; tiles past the live count leave at once (below)
-  constexpr int kSortItems = ITEMS, kSortTile = kSortThreads * ITEMS, kWarpSpan = 32 * ITEMS;
-  SortSmem<KeyT, ITEMS>& sm = *reinterpret_cast<SortSmem<KeyT, ITEMS>*>(smem_raw);
-
+// One tile of a pass (FULL: all kSortTile slots are live — every tile but the last; the ragged form clamps its loads
+// and predicates every shared-memory and global store, ~15 % more instructions).
+template <typename KeyT, int ITEMS, bool FULL>
+__device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, ITEMS>& sm, const KeyT* __restrict__ keys_in,
+                                              const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+                                              uint32_t* __restrict__ vals_out, int shift,
+                                              const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ status,
+                                              uint32_t tile, int64_t tile_base, int tile_count) {
+  constexpr int kSortItems = ITEMS, kSortTile = kSortTilePairs, kWarpSpan = 32 * ITEMS;
+  constexpr int kSortThreads = kSortTilePairs / ITEMS, kSortWarps = kSortThreads / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // dynamic tile id: a tile only waits on tiles that have already started (no look-back deadlock)
-  if (tid == 0) sm.tile = atomicAdd(tile_counter, 1u);
-  for (int i = tid; i < 2 * kSortWarps * kRadix; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;  // warp_hist + match
-  __syncthreads();
-  const uint32_t tile = sm.tile;
-  const int64_t tile_base = (int64_t)tile * kSortTile;
-  if (tile_base >= n) return;  // block-uniform; no later tile can wait for this one (it is past the data too)
-  const int tile_count = (int)min((int64_t)kSortTile, n - tile_base);
-
   // (a) load, warp-striped: item i of lane l in warp w is element w*256 + i*32 + l of the tile
   // (loads are unpredicated — out-of-range items re-read the tile's last element and are masked by `valid`
   //  where it matters — because per-load predicates exhaust the 7 predicate registers and make ptxas
@@ -183,8 +182,14 @@ __global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 
   KeyT key[kSortItems];
   const int warp_off = warp * kWarpSpan + lane;
   const int last_local = tile_count - 1;
+  if constexpr (FULL) {  // every tile but the last: plain strided loads off one pointer
+    const KeyT* kp = keys_in + tile_base + warp_off;
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) key[i] = keys_in[tile_base + min(warp_off + i * 32, last_local)];
+    for (int i = 0; i < kSortItems; ++i) key[i] = kp[i * 32];
+  } else {
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) key[i] = keys_in[tile_base + min(warp_off + i * 32, last_local)];
+  }
 
   // (b) stable rank of every item among the items of its warp with the same digit (two ranks per register)
   uint32_t packed[kSortItems / 2];
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 
   const uint32_t lanemask_lt = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
-    const bool valid = (warp_off + i * 32) < tile_count;
+    const bool valid = FULL || (warp_off + i * 32) < tile_count;
     const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
     // lanes holding the same digit: each lane ORs its bit into a per-warp, per-digit mask word in shared
     // memory (ATOMS.OR), then reads the word back.  ~12 instructions per item; 8 ballots cost ~48 (ALU bound,
@@ -256,15 +261,21 @@ __global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 
     const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
     const uint32_t rank = (i & 1) ? (packed[i / 2] >> 16) : (packed[i / 2] & 0xffffu);
     const uint32_t pos = sm.digit_start[d] + wh[d] + rank;
-    if ((warp_off + i * 32) < tile_count) sm.keys[pos] = key[i];
+    if (FULL || (warp_off + i * 32) < tile_count) sm.keys[pos] = key[i];
     if (i & 1) packed[i / 2] = (packed[i / 2] & 0xffffu) | (pos << 16);
     else packed[i / 2] = (packed[i / 2] & 0xffff0000u) | pos;
   }
 
   // the values can start travelling now (their registers are the ones the keys just released)
   uint32_t val[kSortItems];
+  if constexpr (FULL) {
+    const uint32_t* vp = vals_in + tile_base + warp_off;
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) val[i] = vals_in[tile_base + min(warp_off + i * 32, last_local)];
+    for (int i = 0; i < kSortItems; ++i) val[i] = vp[i * 32];
+  } else {
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) val[i] = vals_in[tile_base + min(warp_off + i * 32, last_local)];
+  }
 
   // (f) decoupled look-back for digit tid.  kLookWindow predecessors are polled with independent loads per
   // round (one L2 latency per round instead of one per predecessor), then consumed in order.
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const uint32_t pos = (i & 1) ? (packed[i / 2] >> 16) : (packed[i / 2] & 0xffffu);
-    if ((warp_off + i * 32) < tile_count) sm.vals[pos] = val[i];
+    if (FULL || (warp_off + i * 32) < tile_count) sm.vals[pos] = val[i];
   }
   __syncthreads();
 
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const int p = tid + i * kSortThreads;
-    if (p < tile_count) {
+    if (FULL || p < tile_count) {
       const KeyT k = sm.keys[p];
       const uint32_t d = (uint32_t)(k >> shift) & (kRadix - 1);
       const uint32_t dst = sm.dst_base[d] + (uint32_t)p;
@@ -316,8 +327,36 @@ __global__ void __launch_bounds__(kSortThreads, (sizeof(KeyT) * ITEMS > 64) ? 1 
   }
 }
 
+template <typename KeyT, int ITEMS>
+__global__ void __launch_bounds__(kSortTilePairs / ITEMS, (ITEMS > 8) ? EGS_SORT_BLOCKS_16 : 2) radix_onesweep_kernel(
+    const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, int64_t n, const int64_t* __restrict__ n_dev, int shift,
+    const uint32_t* __restrict__ digit_base /*[256]*/, uint32_t* __restrict__ tile_counter,
+    uint32_t* __restrict__ status /*[ntiles][256]*/) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  n = live_count(n, n_dev);  // the grid covers the capacity; tiles past the live count leave at once (below)
+  constexpr int kSortItems = ITEMS, kSortTile = kSortTilePairs, kWarpSpan = 32 * ITEMS;
+  constexpr int kSortThreads = kSortTilePairs / ITEMS, kSortWarps = kSortThreads / 32;
+  SortSmem<KeyT, ITEMS>& sm = *reinterpret_cast<SortSmem<KeyT, ITEMS>*>(smem_raw);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // dynamic tile id: a tile only waits on tiles that have already started (no look-back deadlock)
+  if (tid == 0) sm.tile = atomicAdd(tile_counter, 1u);
+  for (int i = tid; i < 2 * kSortWarps * kRadix; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;  // warp_hist + match
+  __syncthreads();
+  const uint32_t tile = sm.tile;
+  const int64_t tile_base = (int64_t)tile * kSortTile;
+  if (tile_base >= n) return;  // block-uniform; no later tile can wait for this one (it is past the data too)
+  const int tile_count = (int)min((int64_t)kSortTile, n - tile_base);
+
+  if (tile_count == kSortTile)
+    onesweep_tile<KeyT, ITEMS, true>(sm, keys_in, vals_in, keys_out, vals_out, shift, digit_base, status, tile, tile_base, tile_count);
+  else
+    onesweep_tile<KeyT, ITEMS, false>(sm, keys_in, vals_in, keys_out, vals_out, shift, digit_base, status, tile, tile_base, tile_count);
+}
+
 static int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, int passes, SortWorkspace& w, int64_t& clear_bytes) {
-  const int64_t ntiles = sort_ntiles(n, 8);  // sized for the smallest tile (most tiles)
+  const int64_t ntiles = sort_ntiles(n);
   const int64_t hist_b = (int64_t)kMaxPasses * kRadix * 4;
   const int64_t cnt_b = 256;  // kMaxPasses counters, padded
   const int64_t status_b = (int64_t)passes * ntiles * kRadix * 4;
@@ -389,12 +428,12 @@ static int run_passes(int64_t n, const int64_t* n_dev, KeyT* keys_a, uint32_t* v
       cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (attr_rc != cudaSuccess)
     return fail((int)attr_rc, "radix_sort: cannot opt in to %d bytes of shared memory: %s", kSmem, cudaGetErrorString(attr_rc));
-  const int64_t ntiles = sort_ntiles(n, ITEMS);
-  const int64_t status_stride = sort_ntiles(n, 8) * kRadix;  // workspace was carved for the smallest tile
+  const int64_t ntiles = sort_ntiles(n);
+  const int64_t status_stride = ntiles * kRadix;
   KeyT* kin = keys_a; uint32_t* vin = vals_a;
   KeyT* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < passes; ++p) {
-    radix_onesweep_kernel<KeyT, ITEMS><<<(unsigned)ntiles, kSortThreads, kSmem, stream>>>(
+    radix_onesweep_kernel<KeyT, ITEMS><<<(unsigned)ntiles, kSortTilePairs / ITEMS, kSmem, stream>>>(
         kin, vin, kout, vout, n, n_dev, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
         w.status + (size_t)p * status_stride);
     KeyT* tk = kin; kin = kout; kout = tk;
