@@ -531,15 +531,31 @@ __global__ void EGS_PB_BOUNDS projection_bwd_sh16_kernel(const ProjBwdParams p) 
     if (p.raw) { scale[0] = act_exp(scale[0]); scale[1] = act_exp(scale[1]); scale[2] = act_exp(scale[2]); }
     const float* co = co_tile + lane * kRowStride;
     float* vc = vc_tile + lane * kRowStride;
+    // The gradient record, stored colour and radius of camera c + 1 are requested before camera c is worked on: the
+    // loop is a chain of dependent global loads otherwise (one exposed latency per camera; long-scoreboard stalls
+    // were the kernel's top stall reason, profiles/r2p).  Records of culled entries are zero, loading them is safe.
+    float4 ng0, ng1, ng2;
+    float ncol[3];
+    int nrad;
+    auto fetch = [&](int c) {
+      const size_t idx = (size_t)c * p.N + n;
+      nrad = p.radii[idx];
+      ng0 = p.v_splats[idx * 3 + 0];
+      ng1 = p.v_splats[idx * 3 + 1];
+      ng2 = p.v_splats[idx * 3 + 2];
+      ncol[0] = p.colors[idx * 3 + 0]; ncol[1] = p.colors[idx * 3 + 1]; ncol[2] = p.colors[idx * 3 + 2];
+    };
+    fetch(0);
     for (int c = 0; c < p.C; ++c) {
       const size_t idx = (size_t)c * p.N + n;
-      if (!(p.radii[idx] > 0)) continue;
+      const int rad = nrad;
+      const float4 g0 = ng0, g1 = ng1, g2 = ng2;
+      const float col[3] = {ncol[0], ncol[1], ncol[2]};
+      if (c + 1 < p.C) fetch(c + 1);
+      if (!(rad > 0)) continue;
       Camera cam_local;
       const Camera* cam = &cams[c < kMaxCamerasSmem ? c : 0];
       if (c >= kMaxCamerasSmem) { load_camera(p.viewmats + (size_t)c * 16, p.Ks + (size_t)c * 9, cam_local); cam = &cam_local; }
-      const float4 g0 = p.v_splats[idx * 3 + 0];
-      const float4 g1 = p.v_splats[idx * 3 + 1];
-      const float4 g2 = p.v_splats[idx * 3 + 2];
       float v_m2x = g0.x, v_m2y = g0.y;
       if (p.v_means2d_extra != nullptr) {
         v_m2x += p.v_means2d_extra[idx * 2 + 0];
@@ -561,7 +577,6 @@ __global__ void EGS_PB_BOUNDS projection_bwd_sh16_kernel(const ProjBwdParams p) 
         }
       }
       // SH: rgb = max(sum + 0.5, 0) -> gradient passes where the stored colour is > 0
-      const float* col = p.colors + idx * 3;
       const float vr = (col[0] > 0.f) ? g1.z : 0.f, vg = (col[1] > 0.f) ? g1.w : 0.f, vb = (col[2] > 0.f) ? g2.x : 0.f;
       const float dx = mean[0] - cam->campos[0], dy = mean[1] - cam->campos[1], dz = mean[2] - cam->campos[2];
       const float inorm = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);

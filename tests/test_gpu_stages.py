@@ -410,3 +410,50 @@ def test_tight_lists_hold_a_subset_and_render_identically(cfg):
     v_out = stages.rasterize_bwd(proj["splats"], tg.offsets, tg.flat_cap, bg, W, H, out[1], out[2], vc, va, n_isects=tg.raster_n,
                                  tile_order=tg.tile_order)
     assert float((v_out - v_ref).norm() / v_ref.norm()) <= 1e-5
+
+
+@pytest.mark.parametrize("C,N,tw,th", [(2, 40_000, 37, 23), (1, 1500, 120, 68), (3, 5000, 1, 1), (1, 70_000, 5, 300)])
+def test_scan_emit_on_arbitrary_packed_rectangles(C, N, tw, th):
+    """The single-launch scan + emission (decoupled look-back over 1024-Gaussian blocks, table / redux owner search)
+    on rectangles no projection would produce together: empty ones between full-grid ones, single columns and rows,
+    visible Gaussians without a tile, depth ties — against a list built with torch sorts from the same rectangles."""
+    st = _stages()
+    g = torch.Generator().manual_seed(C * 1000 + N)
+    n_tiles = tw * th
+    x0 = torch.randint(0, tw, (C, N), generator=g)
+    y0 = torch.randint(0, th, (C, N), generator=g)
+    kind = torch.rand(C, N, generator=g)
+    w = torch.minimum(torch.randint(1, 5, (C, N), generator=g), tw - x0)
+    h = torch.minimum(torch.randint(1, 5, (C, N), generator=g), th - y0)
+    full = kind < 0.03
+    x0, y0 = torch.where(full, 0, x0), torch.where(full, 0, y0)
+    w, h = torch.where(full, tw, w), torch.where(full, th, h)
+    w = torch.where((kind > 0.90) & (kind <= 0.95), 1, w)      # single columns
+    h = torch.where((kind > 0.95), 1, h)                       # single rows
+    visible = torch.rand(C, N, generator=g) < 0.8
+    empty = (torch.rand(C, N, generator=g) < 0.3) | ~visible  # visible, but reaches no pixel
+    w, h = torch.where(empty, 0, w), torch.where(empty, 0, h)
+    rects = torch.stack([torch.where(empty, 0, x0 | (y0 << 16)), torch.where(empty, 0, w | (h << 16))], -1).int().cuda()
+    radii = visible.int().cuda()
+    tpg = torch.where(visible, torch.clamp(w * h, min=1), 0).int().cuda()
+    depths = (torch.randint(1, 50, (C, N), generator=g).float() * 0.25).cuda()  # many ties
+    m2 = torch.zeros(C, N, 2, device="cuda")
+    st.reset_binning_hints()
+    b = st.isect_sorted_async(m2, radii, depths, tpg, 16, tw, th, tight_rects=rects)
+    if not b.resolve():
+        b = st.isect_sorted_async(m2, radii, depths, tpg, 16, tw, th, capacity=b.n_isects, tight_rects=rects)
+        assert b.resolve()
+    # reference: every (Gaussian, tile) entry, ordered by (camera, tile), then depth, then flat index
+    cnt = (w * h).reshape(-1).cuda()
+    flat = torch.repeat_interleave(torch.arange(C * N, device="cuda"), cnt)
+    j = torch.arange(flat.numel(), device="cuda") - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+    ww = w.reshape(-1).cuda()[flat].clamp(min=1)
+    key = (flat // N) * n_tiles + (y0.reshape(-1).cuda()[flat] + j // ww) * tw + x0.reshape(-1).cuda()[flat] + j % ww
+    order = torch.sort(depths.reshape(-1)[flat], stable=True).indices
+    order = order[torch.sort(key[order], stable=True).indices]
+    assert b.n_isects == flat.numel()
+    assert torch.equal(b.flatten_ids.long(), flat[order])
+    counts = torch.bincount(key, minlength=C * n_tiles)
+    offsets = torch.cumsum(counts, 0) - counts
+    assert torch.equal(b.offsets.reshape(-1).long(), offsets)
+    assert int(b.offsets_store[-1]) == flat.numel(), "sentinel behind the offsets"
