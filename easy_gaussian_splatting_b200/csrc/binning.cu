@@ -452,15 +452,17 @@ __global__ void __launch_bounds__(kEmitThreads) isect_scan_emit_kernel(
   __shared__ uint32_t run_gauss[kEmitThreads / 32][32];
   n_vis = live_count(n_vis, n_vis_dev);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the grid covers C * N: blocks past the visible entries leave before they take a ticket, so exactly the live
+  // blocks draw tickets 0 .. live-1 (block 0 is spare only when nothing is visible)
+  if ((int64_t)blockIdx.x * kEmitBlock >= n_vis) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_isects_out = 0;
+    return;
+  }
   // ticket order = chain order: a block only ever waits for blocks that are already running
   if (threadIdx.x == 0) block_ticket = atomicAdd(ticket, 1u);
   __syncthreads();
   const uint32_t blk = block_ticket;
   const int64_t first = (int64_t)blk * kEmitBlock;
-  if (first >= n_vis) {  // block-uniform; nothing behind this block has work either
-    if (blk == 0 && threadIdx.x == 0) *n_isects_out = 0;
-    return;
-  }
   const int64_t warp_first = first + warp * (32 * kEmitRounds);  // position in depth order of this warp's first Gaussian
   uint32_t g[kEmitRounds];
 #pragma unroll

@@ -340,13 +340,15 @@ __global__ void __launch_bounds__(kSortTilePairs / ITEMS, (ITEMS > 8) ? EGS_SORT
   SortSmem<KeyT, ITEMS>& sm = *reinterpret_cast<SortSmem<KeyT, ITEMS>*>(smem_raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // The grid covers the capacity.  Blocks past the live tiles leave before they take a ticket, so exactly the live
+  // tiles' worth of blocks draw tickets 0 .. live-1 (a buffer sized generously costs a load per spare block, not an atomic).
+  if ((int64_t)blockIdx.x * kSortTile >= n) return;
   // dynamic tile id: a tile only waits on tiles that have already started (no look-back deadlock)
   if (tid == 0) sm.tile = atomicAdd(tile_counter, 1u);
   for (int i = tid; i < 2 * kSortWarps * kRadix; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;  // warp_hist + match
   __syncthreads();
   const uint32_t tile = sm.tile;
   const int64_t tile_base = (int64_t)tile * kSortTile;
-  if (tile_base >= n) return;  // block-uniform; no later tile can wait for this one (it is past the data too)
   const int tile_count = (int)min((int64_t)kSortTile, n - tile_base);
 
   if (tile_count == kSortTile)

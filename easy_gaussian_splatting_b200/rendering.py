@@ -192,7 +192,7 @@ class _Rasterization(torch.autograd.Function):
         # outputs below carry the tight lists the kernels used
         cfg["classic_lists"] = _ClassicLists(proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss,
                                              *stages.tile_grid(width, height))
-        flatten_ids, isect_offsets = binned.flatten_ids, binned.offsets
+        flatten_ids, isect_offsets = binned.flat_cap, binned.offsets  # (capacity-sized: the exact length would be a wait)
 
         means2d = proj["means2d"]
         ctx.cfg = cfg
@@ -254,7 +254,7 @@ class _RasterizationRaw(torch.autograd.Function):
                                                                              cfg.get("grad_enabled", True))
         cfg["classic_lists"] = _ClassicLists(proj["means2d"], proj["radii"], proj["depths"], tiles_per_gauss,
                                              *stages.tile_grid(width, height))
-        flatten_ids, isect_offsets = binned.flatten_ids, binned.offsets
+        flatten_ids, isect_offsets = binned.flat_cap, binned.offsets  # (capacity-sized: the exact length would be a wait)
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(means, quats, log_scales, logit_opacities, sh_0, sh_rest, viewmats, Ks, backgrounds,
