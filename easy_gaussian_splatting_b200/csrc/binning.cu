@@ -783,7 +783,7 @@ extern "C" int egs_isect_finalize(int64_t n_isects, const uint32_t* tile_keys_so
 // thread blocks roughly in index order; in grid order the last blocks to start are the bottom rows of the last view,
 // whatever their length, and a launch can end with a few SMs walking long lists while the rest idle.  Measured: one
 // view per call of the object scene 1.117 -> 1.042 ms, batched benchmark step unchanged (gpurun_out/r2l).
-// Three tiny launches (class histogram, bases, placement; warp-aggregated atomics) instead of one single-CTA kernel,
+// Two tiny launches (class histogram; bases + placement; warp-aggregated atomics) instead of one single-CTA kernel,
 // which took 93 us for the 32 640 tiles of the benchmark step (profiles/r2n_launches.csv).
 namespace egs {
 constexpr int kSchedThreads = 256;
@@ -809,31 +809,33 @@ __global__ void __launch_bounds__(kSchedThreads) tile_classes_kernel(const int32
   if (lane == 0 && m > 0 && max_len != nullptr) atomicMax(max_len, (unsigned long long)m);
 }
 
-// cursor[c] = first position of class c in the order (longest class first); one warp
-__global__ void tile_class_bases_kernel(const int32_t* __restrict__ hist, int32_t* __restrict__ cursor) {
-  const int c = threadIdx.x;  // 0 .. 31
-  const int32_t n = hist[c];
-  int32_t after = n;  // inclusive suffix sum over classes >= c
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int32_t v = __shfl_down_sync(0xffffffffu, after, d);
-    if (c + d < 32) after += v;
-  }
-  cursor[c] = after - n;  // tiles of strictly longer classes come first
-}
-
+// Placement: class c starts behind all longer classes (suffix sums of the class histogram, recomputed by every block —
+// 32 values — rather than by a launch of their own); `taken` counts what each class has handed out (zero at launch).
 __global__ void __launch_bounds__(kSchedThreads) tile_order_kernel(const int32_t* __restrict__ offsets, int32_t n_slots,
-                                                                   int32_t* __restrict__ cursor, int32_t* __restrict__ order) {
+                                                                   const int32_t* __restrict__ hist, int32_t* __restrict__ taken,
+                                                                   int32_t* __restrict__ order) {
+  __shared__ int32_t class_base[kSchedClasses];
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    const int32_t n = hist[lane];
+    int32_t after = n;  // inclusive suffix sum over classes >= lane
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t v = __shfl_down_sync(0xffffffffu, after, d);
+      if (lane + d < 32) after += v;
+    }
+    class_base[lane] = after - n;  // tiles of strictly longer classes come first
+  }
+  __syncthreads();
   const int32_t t = blockIdx.x * kSchedThreads + threadIdx.x;
   const bool valid = t < n_slots;
-  const int lane = threadIdx.x & 31;
   const uint32_t active = __ballot_sync(0xffffffffu, valid);
   if (!valid) return;
   const int cls = length_class(offsets[t + 1] - offsets[t]);
   const uint32_t group = __match_any_sync(active, cls);
   const int leader = __ffs(group) - 1;
   int32_t base = 0;
-  if (lane == leader) base = atomicAdd(&cursor[cls], __popc(group));
+  if (lane == leader) base = class_base[cls] + atomicAdd(&taken[cls], __popc(group));
   base = __shfl_sync(group, base, leader);
   order[base + __popc(group & ((1u << lane) - 1u))] = t;
 }
@@ -875,14 +877,13 @@ static int tile_schedule(const int32_t* offsets, int32_t n_slots, unsigned long 
                          cudaStream_t stream, bool scratch_is_zero = false) {
   if (n_slots <= 0 || (max_len == nullptr && order == nullptr)) return 0;
   int32_t* hist = scratch;
-  int32_t* cursor = scratch + kSchedClasses;
-  if (!scratch_is_zero) EGS_CUDA(cudaMemsetAsync(hist, 0, kSchedClasses * sizeof(int32_t), stream));
+  int32_t* taken = scratch + kSchedClasses;
+  if (!scratch_is_zero) EGS_CUDA(cudaMemsetAsync(scratch, 0, 2 * kSchedClasses * sizeof(int32_t), stream));
   const unsigned blocks = (unsigned)ceil_div(n_slots, kSchedThreads);
   tile_classes_kernel<<<blocks, kSchedThreads, 0, stream>>>(offsets, n_slots, hist, max_len);
   if (order == nullptr) return check_launch("tile_classes_kernel");
-  tile_class_bases_kernel<<<1, 32, 0, stream>>>(hist, cursor);
-  tile_order_kernel<<<blocks, kSchedThreads, 0, stream>>>(offsets, n_slots, cursor, order);
-  return check_launch("tile_schedule", 3);
+  tile_order_kernel<<<blocks, kSchedThreads, 0, stream>>>(offsets, n_slots, hist, taken, order);
+  return check_launch("tile_schedule", 2);
 }
 
 extern "C" int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_t n_tiles, int64_t capacity) {

@@ -3,8 +3,8 @@
 //
 // Launch sequence for P = ceil(end_bit / 8) passes over n pairs:
 //   1 memset   : histograms, dynamic tile counters and look-back status words
-//   1 histogram: reads the keys once (8 B/pair) and builds all P digit histograms
-//   1 scan     : exclusive scan of each 256-bin histogram -> global digit bases
+//   1 histogram: reads the keys once (8 B/pair) and builds all P digit histograms; the block that finishes last
+//                turns each 256-bin histogram into exclusive global digit bases
 //   P passes   : each reads 12 B/pair and writes 12 B/pair; a tile of 4096 pairs is ranked in
 //                shared memory (warp-level shared-memory atomicOr multisplit, stable), its per-digit counts are
 //                chained to the preceding tiles with decoupled look-back, and the tile is written
@@ -61,7 +61,8 @@ constexpr int kHistItems = 16;
 template <typename KeyT>
 __global__ void __launch_bounds__(kHistThreads) radix_histogram_kernel(const KeyT* __restrict__ keys, int64_t n,
                                                                         const int64_t* __restrict__ n_dev, int passes,
-                                                                        uint32_t* __restrict__ hist) {
+                                                                        uint32_t* __restrict__ hist,
+                                                                        uint32_t* __restrict__ blocks_done) {
   n = live_count(n, n_dev);
   // Each thread walks kHistItems CONSECUTIVE keys and combines runs of equal digits in a register before
   // touching shared memory.  The keys of this path come out of isect_emit in runs that share the depth
@@ -122,25 +123,33 @@ __global__ void __launch_bounds__(kHistThreads) radix_histogram_kernel(const Key
     const uint32_t v = sh[i];
     if (v) atomicAdd(&hist[i], v);
   }
-}
-
-// one block per pass: counts -> exclusive bases, in place
-__global__ void __launch_bounds__(kRadix) radix_scan_hist_kernel(uint32_t* __restrict__ hist) {
-  __shared__ uint32_t warp_tot[kRadix / 32];
-  uint32_t* h = hist + (size_t)blockIdx.x * kRadix;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t v = h[threadIdx.x];
-  uint32_t inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += t;
-  }
-  if (lane == 31) warp_tot[warp] = inc;
+  // The block that finishes last turns the counts into exclusive digit bases, in place (kHistThreads = 256 = one
+  // thread per digit): the scan needs no launch of its own.
+  __shared__ bool last_block;
+  __threadfence();
   __syncthreads();
-  uint32_t base = 0;
-  for (int w = 0; w < warp; ++w) base += warp_tot[w];
-  h[threadIdx.x] = base + inc - v;
+  if (threadIdx.x == 0) last_block = atomicAdd(blocks_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last_block) return;
+  __threadfence();
+  __shared__ uint32_t warp_tot[kRadix / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int p = 0; p < passes; ++p) {
+    volatile uint32_t* h = hist + (size_t)p * kRadix;
+    const uint32_t v = h[threadIdx.x];
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    h[threadIdx.x] = base + inc - v;
+    __syncthreads();
+  }
 }
 
 // ---- one onesweep pass ------------------------------------------------------------------------------
@@ -414,8 +423,9 @@ static int radix_sort_pairs_impl(int64_t n, const int64_t* n_dev, KeyT* keys_a, 
   if (!workspace_is_zero) EGS_CUDA(cudaMemsetAsync(workspace, 0, clear_bytes, stream));
   int64_t hist_blocks = ceil_div(n, (int64_t)kHistThreads * kHistItems);
   if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-  radix_histogram_kernel<KeyT><<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, n_dev, passes, w.hist);
-  radix_scan_hist_kernel<<<passes, kRadix, 0, stream>>>(w.hist);
+  static_assert(kHistThreads == kRadix, "the last histogram block scans one digit per thread");
+  radix_histogram_kernel<KeyT><<<(unsigned)hist_blocks, kHistThreads, 0, stream>>>(keys_a, n, n_dev, passes, w.hist,
+                                                                                    w.counters + kMaxPasses);
   // pairs per thread: 8 for 64-bit keys (a 16-item tile would need 2 x the shared memory and drop to one CTA per SM);
   // EGS_SORT_ITEMS_U32 for 32-bit keys (build-time A/B knob, scripts/build_variant.py)
   if constexpr (sizeof(KeyT) == 4) return run_passes<KeyT, EGS_SORT_ITEMS_U32>(n, n_dev, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
@@ -441,7 +451,7 @@ static int run_passes(int64_t n, const int64_t* n_dev, KeyT* keys_a, uint32_t* v
     KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
-  return check_launch("radix_sort_pairs", passes + 2);  // + histogram + histogram scan
+  return check_launch("radix_sort_pairs", passes + 1);  // + histogram (its last block scans)
 }
 
 namespace egs {
