@@ -457,3 +457,36 @@ def test_scan_emit_on_arbitrary_packed_rectangles(C, N, tw, th):
     offsets = torch.cumsum(counts, 0) - counts
     assert torch.equal(b.offsets.reshape(-1).long(), offsets)
     assert int(b.offsets_store[-1]) == flat.numel(), "sentinel behind the offsets"
+
+
+def test_capacity_between_the_emitted_count_and_the_bound():
+    """Buffers are checked against the BOUND (gsplat's count, known after the first kernel) first; when the bound does
+    not fit, the count the tight route really emitted decides: room for it is enough, one entry less is not."""
+    st = _stages()
+    sc = make_scene(**SCENES[2]).to("cuda")
+    W, H, C = sc.width, sc.height, sc.viewmats.shape[0]
+    tw, th = st.tile_grid(W, H)
+    proj = st.projection_fwd(sc.means, sc.quats, sc.scales, sc.opacities, sc.colors, sc.viewmats, sc.Ks, W, H, 3)
+    args = (proj["means2d"], proj["radii"], proj["depths"], proj["tiles_per_gauss"], 16, tw, th)
+    st.reset_binning_hints()
+    ref = st.isect_sorted_async(*args, tight_rects=proj["tight_rects"])
+    assert ref.resolve() and ref.exact and ref.n_bound == int(proj["tiles_per_gauss"].sum())
+    n_t = ref.n_isects
+    assert 0 < n_t < ref.n_bound
+    mid = st.isect_sorted_async(*args, capacity=(n_t + ref.n_bound) // 2, tight_rects=proj["tight_rects"])
+    assert mid.resolve() and mid.n_isects == n_t and mid.n_bound == ref.n_bound
+    assert torch.equal(mid.flatten_ids, ref.flatten_ids) and torch.equal(mid.offsets, ref.offsets)
+    assert int(mid.offsets_store[-1]) == n_t
+    exact = st.isect_sorted_async(*args, capacity=n_t, tight_rects=proj["tight_rects"])
+    assert exact.resolve() and torch.equal(exact.flatten_ids, ref.flatten_ids)
+    short = st.isect_sorted_async(*args, capacity=n_t - 1, tight_rects=proj["tight_rects"])
+    assert not short.resolve() and short.n_isects == n_t
+    # the hint a call leaves carries the bound (what the next call sizes its buffers from) and, once it has arrived,
+    # the emitted count
+    ref.note_for_next_call()
+    torch.cuda.synchronize()
+    hint = st.binning_hint(C, tw, th, "cuda")
+    assert hint["n_bound"] == ref.n_bound and hint["n_isects"] == n_t
+    nxt = st.isect_sorted_async(*args, tight_rects=proj["tight_rects"])
+    assert not nxt.exact and nxt.capacity >= ref.n_bound and nxt.resolve()
+    assert torch.equal(nxt.flatten_ids, ref.flatten_ids)
