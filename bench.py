@@ -344,7 +344,14 @@ def ours(args):
     # one backward per step: gradients are written straight into the bucket (FlatGradBucket.begin_direct)
     direct = n_calls == 1 and not args.forward_only
 
-    def step_resident():
+    def step_resident(marks=None):
+        """marks: a list that receives one CUDA event per phase boundary (start, rendered, exchanged, stepped)"""
+        def mark():
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
+        mark()
         if direct:
             bucket.begin_direct()
         else:
@@ -356,11 +363,14 @@ def ours(args):
         join_streams()
         if direct:
             bucket.end_direct()
+        mark()
         if world > 1 and not args.no_exchange:
             bucket.all_reduce()
             stats.all_reduce()
+        mark()
         if optimizer is not None:
             optimizer.step()
+        mark()
 
     # e2e: per-view inputs travel host -> device inside the timed region, double buffered on a copy stream so
     # the copy of view i+1 overlaps the rendering of view i; the step's loss is read back once per step.
@@ -494,6 +504,25 @@ def ours(args):
                    "cudaFree_calls_in_timed_region": ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0),
                    "alloc_retries": ms1.get("num_alloc_retries", 0),
                    "reserved_gb": ms1.get("reserved_bytes.all.peak", 0) / 1e9}
+    # N > 1: where one step spends its time on every rank (CUDA events at the phase boundaries of `steps` more steps).
+    # A rank that finishes rendering early waits for the slowest one INSIDE the exchange kernel, so its "exchange" is
+    # the transfer plus that wait; the transfer itself is what the slowest renderer sees.
+    step_phases = None
+    if world > 1 and not args.no_exchange:
+        acc = [0.0, 0.0, 0.0]
+        for _ in range(args.steps):
+            marks = []
+            step_resident(marks)
+            torch.cuda.synchronize()
+            for i in range(3):
+                acc[i] += marks[i].elapsed_time(marks[i + 1]) / args.steps
+        mine = {"render_ms": acc[0], "exchange_ms": acc[1], "optimizer_ms": acc[2]}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        slowest = max(range(world), key=lambda r: gathered[r]["render_ms"])
+        step_phases = {"per_rank": gathered, "slowest_renderer": slowest,
+                       "transfer_ms_seen_by_the_slowest_renderer": gathered[slowest]["exchange_ms"],
+                       "what": "mean over the steps, each step synchronised at its end (so the phases of one step do not overlap the next)"}
     ms_step = ms_total / args.steps
     pixels_per_step = world * V * W * H
     value = pixels_per_step / (ms_step * 1e-3) / 1e6
@@ -523,6 +552,8 @@ def ours(args):
         "gpu_launches_what": f"this library's kernels enqueued by {args.steps} steps, counted at the launch sites "
                              "(egs_kernel_launch_count); torch's own elementwise kernels of the loss functional are not included",
     }
+    if step_phases is not None:
+        line["step_phases"] = step_phases
     if args.quick:
         line.pop("e2e")
     if args.n_gaussians:
@@ -948,6 +979,8 @@ def main():
         line["train_step"] = dict(l2["train_step"], ms_per_step=l2["ms_per_step"], mpix_per_s=l2["value"], scaling="strong",
                                   steps=a2.steps, workload=l2["config"]["workload"], views_per_call=l2["config"]["views_per_call"],
                                   exchange=l2["config"]["exchange"], allocator=l2["allocator"], gpu_launches=l2["gpu_launches"])
+        if "step_phases" in l2:
+            line["train_step"]["step_phases"] = l2["step_phases"]
     if rank == 0:
         if world == 1 and extras and not args.no_call_pattern:
             line["call_pattern"] = call_pattern_runs(dev)

@@ -19,3 +19,8 @@ for f in sys.argv[1:]:
     for k in ("parity", "exchange_check", "cpu_baseline", "clocks", "roofline"):
         if k in d:
             print(f"   {k}: {json.dumps(d[k])[:600]}")
+    for name, ph in (("step_phases", d.get("step_phases")), ("train_step.step_phases", d.get("train_step", {}).get("step_phases"))):
+        if ph:
+            r = lambda k: " ".join(f"{x[k]:.3f}" for x in ph["per_rank"])
+            print(f"   {name}: render [{r('render_ms')}] exchange [{r('exchange_ms')}] optimizer [{r('optimizer_ms')}] ms; "
+                  f"transfer seen by the slowest renderer (rank {ph['slowest_renderer']}): {ph['transfer_ms_seen_by_the_slowest_renderer']:.3f} ms")

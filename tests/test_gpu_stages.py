@@ -259,6 +259,12 @@ def test_fused_adam_matches_torch_adam():
     init = {k: torch.randn(*s, generator=g) for k, s in shapes.items()}
     ref_p = {k: v.clone().requires_grad_(True) for k, v in init.items()}
     our_p = {k: v.clone().cuda().requires_grad_(True) for k, v in init.items()}
+    # one parameter that is NOT 16-byte aligned (a view one float into a buffer): the kernel's scalar path; the odd N
+    # leaves every other group with a ragged last unit of its 128-bit path
+    off_by_one = torch.empty(N + 1, device="cuda")
+    off_by_one[1:].copy_(init["logit_opacities"])
+    our_p["logit_opacities"] = off_by_one[1:].detach().requires_grad_(True)
+    assert our_p["logit_opacities"].data_ptr() % 16 == 4
     ref = torch.optim.Adam([{"params": [ref_p[k]], "lr": lrs[k], "name": k} for k in shapes], eps=1e-15)
     ours = FusedAdam([{"params": [our_p[k]], "lr": lrs[k], "name": k} for k in shapes], eps=1e-15)
     for it in range(5):
