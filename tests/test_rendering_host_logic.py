@@ -334,3 +334,55 @@ def test_second_backward_in_a_direct_window_accumulates(fake):
     # FakeStages.projection_bwd fills gradient i with the constant i + 1; two backward passes -> 2 * (i + 1)
     assert [v.flatten()[0].item() for v in bucket.views] == [2.0, 4.0, 6.0, 8.0, 10.0]
     assert all(t.grad.data_ptr() == v.data_ptr() for t, v in zip(p, bucket.views))
+
+
+class _FakeEvent:
+    """Stands in for torch.cuda.Event: counts the waits"""
+
+    def __init__(self, done=True):
+        self.done, self.waits = done, 0
+
+    def synchronize(self):
+        self.waits += 1
+        self.done = True
+
+    def query(self):
+        return self.done
+
+
+def _fake_binning(capacity, bound=500, emitted=300):
+    from easy_gaussian_splatting_b200 import stages
+    e_bound, e_emitted = _FakeEvent(), _FakeEvent(done=False)
+    z = torch.zeros(max(capacity, 1), dtype=torch.int32)
+    offs = torch.zeros(5, dtype=torch.int32)
+    b = stages.SortedIsects(("cpu", 1, 2, 2, True), 1, 4, capacity, z, z.clone(), offs, offs[:4].view(1, 2, 2), None, None,
+                            torch.tensor([10, bound, 0, 0]), e_bound, False,
+                            emitted=torch.tensor([10, emitted, 7, 0]), emitted_event=e_emitted)
+    return b, e_bound, e_emitted
+
+
+def test_capacity_check_waits_for_the_route_only_when_the_bound_does_not_fit():
+    """stages.SortedIsects.resolve: the bound (gsplat's count, known after the first kernel of the route) settles the
+    capacity question when it fits; the count the route emits is waited for only otherwise, or when the exact length
+    is asked for."""
+    b, e_bound, e_emitted = _fake_binning(capacity=600)
+    assert b.resolve() and (e_bound.waits, e_emitted.waits) == (1, 0)
+    assert b.n_vis == 10 and b.n_bound == 500
+    assert b.n_isects == 300 and e_emitted.waits == 1 and b.flatten_ids.numel() == 300
+    b, e_bound, e_emitted = _fake_binning(capacity=400)   # bound 500 does not fit, the emitted 300 do
+    assert b.resolve() and e_emitted.waits == 1 and b.n_isects == 300
+    b, e_bound, e_emitted = _fake_binning(capacity=299)
+    assert not b.resolve() and b.n_isects == 300          # what the re-run is sized with
+    assert b.raster_n == -299
+
+
+def test_hint_counts_never_wait():
+    """stages._hint_count: a count that has not arrived is not waited for — the one before it is used."""
+    from easy_gaussian_splatting_b200 import stages
+    late = torch.tensor([10, 320, 9, 0])
+    pending = {"n_isects": None, "known": 280, "n_bound": 500, "late": late, "late_event": _FakeEvent(done=False)}
+    assert stages._hint_count(pending) == 280 and pending["late_event"].waits == 0
+    pending["late_event"].done = True
+    assert stages._hint_count(pending) == 320 and pending["n_isects"] == 320
+    assert stages._hint_count(None) is None
+    assert stages._hint_count({"n_isects": None, "known": None, "n_bound": 5, "late": late, "late_event": _FakeEvent(done=False)}) is None
