@@ -224,6 +224,33 @@ __device__ __forceinline__ int64_t chain_lookback(uint64_t* __restrict__ status,
   return excl;
 }
 
+// The same chain with MIN instead of SUM (value = a 32-bit position; 0xffffffff = nothing): the minimum over the blocks
+// before `blk` in ticket order.
+__device__ __forceinline__ uint32_t chain_lookback_min(uint64_t* __restrict__ status, uint32_t blk, uint32_t own, int lane) {
+  if (lane == 0) st_volatile_u64(status + blk, (blk == 0 ? kChainPrefix : kChainAggregate) | (uint64_t)own);
+  uint32_t excl = 0xffffffffu;
+  if (blk > 0) {
+    int64_t j = (int64_t)blk - 1;
+    bool done = false;
+    while (!done) {
+      const int64_t jj = j - lane;
+      const uint64_t v = jj >= 0 ? ld_volatile_u64(status + jj) : (kChainPrefix | 0xffffffffull);
+      const uint32_t flag = (uint32_t)(v >> 62);
+      const uint32_t not_ready = __ballot_sync(0xffffffffu, flag == 0u);
+      const uint32_t is_prefix = __ballot_sync(0xffffffffu, flag == 2u);
+      const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+      const int first_pf = is_prefix ? __ffs(is_prefix) - 1 : 32;
+      const int take = first_pf < first_nr ? first_pf + 1 : first_nr;
+      const uint32_t c = lane < take ? (uint32_t)(v & 0xffffffffull) : 0xffffffffu;
+      excl = min(excl, __reduce_min_sync(0xffffffffu, c));
+      j -= take;
+      done = first_pf < first_nr;
+    }
+    if (lane == 0) st_volatile_u64(status + blk, kChainPrefix | (uint64_t)min(excl, own));
+  }
+  return excl;
+}
+
 // ---- visible compaction + level-1 sort input in ONE launch --------------------------------------------------------
 // key = bits(depth), value = flat index (camera * N + Gaussian), compacted; totals = {n_vis, sum of tiles, 0, 0}.
 // The camera needs no key bits: level 2 sorts stably on the (camera, tile) index, so sorting the visible entries of
@@ -809,6 +836,80 @@ __global__ void __launch_bounds__(kSchedThreads) tile_classes_kernel(const int32
   if (lane == 0 && m > 0 && max_len != nullptr) atomicMax(max_len, (unsigned long long)m);
 }
 
+// Tile offsets from the first positions the last sort pass left (radix_sort.cu, onesweep_tile (h)), the sentinel, the
+// class histogram of the list lengths and the longest list, in one launch: offsets[t] = the first position of the
+// first non-empty tile at or behind t = a suffix minimum, chained from the LAST chunk of tiles to the first (ticket 0
+// takes the last chunk).  Takes the place of a pass over all sorted keys (isect_offsets4_kernel: 74 MB read for the 18 M
+// entries of the benchmark step) and of tile_classes_kernel.
+constexpr int kFillItems = 8;
+constexpr int kFillChunk = kSchedThreads * kFillItems;  // 2048 tiles per block
+
+__global__ void __launch_bounds__(kSchedThreads) tile_offsets_fill_kernel(int32_t* __restrict__ offsets /* in: first positions */,
+                                                                          int32_t n_slots, int64_t capacity,
+                                                                          const int64_t* __restrict__ n_dev,
+                                                                          int32_t* __restrict__ hist,
+                                                                          unsigned long long* __restrict__ max_len,
+                                                                          uint32_t* __restrict__ ticket, uint64_t* __restrict__ status) {
+  __shared__ uint32_t warp_min[kSchedThreads / 32];
+  __shared__ uint32_t carry_s;
+  __shared__ uint32_t block_ticket;
+  const uint32_t n_live = (uint32_t)live_count(capacity, n_dev);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) block_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t blk = block_ticket;
+  const int32_t chunk = (int32_t)(gridDim.x - 1 - blk);  // chain order: from the last tiles to the first
+  const int32_t base = chunk * kFillChunk + threadIdx.x * kFillItems;
+  uint32_t v[kFillItems];
+#pragma unroll
+  for (int i = 0; i < kFillItems; ++i) v[i] = base + i < n_slots ? (uint32_t)offsets[base + i] : 0xffffffffu;
+  // suffix minimum inside the thread, then across the threads behind it (higher thread index = later tiles)
+#pragma unroll
+  for (int i = kFillItems - 2; i >= 0; --i) v[i] = min(v[i], v[i + 1]);
+  uint32_t suf = v[0];  // inclusive suffix minimum over this thread and the later threads of the warp
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_down_sync(0xffffffffu, suf, d);
+    if (lane + d < 32) suf = min(suf, t);
+  }
+  if (lane == 0) warp_min[warp] = suf;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t block_min = 0xffffffffu;
+#pragma unroll
+    for (int w = 0; w < kSchedThreads / 32; ++w) block_min = min(block_min, warp_min[w]);
+    const uint32_t carry = chain_lookback_min(status, blk, block_min, lane);  // minimum over all later chunks
+    if (lane == 0) carry_s = min(carry, n_live);  // behind the last non-empty tile: the end of the list
+  }
+  __syncthreads();
+  uint32_t behind = carry_s;  // suffix minimum over everything behind this thread's tiles
+#pragma unroll
+  for (int w = kSchedThreads / 32 - 1; w >= 0; --w) behind = w > warp ? min(behind, warp_min[w]) : behind;
+  const uint32_t next_lane = __shfl_down_sync(0xffffffffu, suf, 1);
+  if (lane < 31) behind = min(behind, next_lane);
+  int32_t longest = 0;
+  uint32_t after = behind;  // offsets[t + 1] while walking the thread's tiles backwards
+#pragma unroll
+  for (int i = kFillItems - 1; i >= 0; --i) {
+    const int32_t t = base + i;
+    const bool valid = t < n_slots;
+    const uint32_t active = __ballot_sync(0xffffffffu, valid);
+    const uint32_t mine = min(v[i], behind);
+    if (valid) {
+      offsets[t] = (int32_t)mine;
+      const int32_t len = (int32_t)(after - mine);
+      longest = max(longest, len);
+      const int cls = length_class(len);
+      const uint32_t group = __match_any_sync(active, cls);
+      if (lane == __ffs(group) - 1) atomicAdd(&hist[cls], __popc(group));
+      after = mine;
+    }
+  }
+  if (blk == 0 && threadIdx.x == 0) offsets[n_slots] = (int32_t)n_live;  // the sentinel the blend kernels read
+  const int32_t m = __reduce_max_sync(0xffffffffu, longest);
+  if (lane == 0 && m > 0 && max_len != nullptr) atomicMax(max_len, (unsigned long long)m);
+}
+
 // Placement: class c starts behind all longer classes (suffix sums of the class histogram, recomputed by every block —
 // 32 values — rather than by a launch of their own); `taken` counts what each class has handed out (zero at launch).
 __global__ void __launch_bounds__(kSchedThreads) tile_order_kernel(const int32_t* __restrict__ offsets, int32_t n_slots,
@@ -847,9 +948,9 @@ __global__ void __launch_bounds__(kSchedThreads) tile_order_kernel(const int32_t
 // workspace | tile-schedule histogram}.  The control block is what must start at zero: ONE memset per call.
 namespace {
 struct SortedLayout {
-  int64_t keys1_b, vals1_b, keys2, vals2, control, sort1, chain, sort2, sched, total;
+  int64_t keys1_b, vals1_b, keys2, vals2, control, sort1, chain, sort2, sched, fill, total;
 };
-SortedLayout sorted_layout(int64_t n, int64_t capacity, int end_bit2) {
+SortedLayout sorted_layout(int64_t n, int64_t capacity, int end_bit2, int64_t n_slots) {
   SortedLayout L;
   int64_t off = 0;
   auto take = [&](int64_t bytes) { const int64_t at = off; off += egs::align_up(bytes > 0 ? bytes : 16, 256); return at; };
@@ -862,6 +963,7 @@ SortedLayout sorted_layout(int64_t n, int64_t capacity, int end_bit2) {
   L.chain = take(256 + ceil_div(n, (int64_t)kEmitBlock) * 8);  // ticket (padded) + status words
   L.sort2 = take(egs::radix_sort_workspace_bytes(capacity, end_bit2));
   L.sched = take(2 * 32 * 4);  // class histogram + class cursors of the tile schedule
+  L.fill = take(256 + ceil_div(n_slots > 0 ? n_slots : 1, (int64_t)egs::kFillChunk) * 8);  // offsets chain: ticket + status words
   L.total = off;
   return L;
 }
@@ -889,7 +991,7 @@ static int tile_schedule(const int32_t* offsets, int32_t n_slots, unsigned long 
 extern "C" int64_t egs_isect_sorted_workspace_bytes(int32_t C, int32_t N, int32_t n_tiles, int64_t capacity) {
   if (C < 0 || N < 0 || n_tiles < 0 || capacity < 0) return 0;
   const int64_t n = (int64_t)C * N;
-  return sorted_layout(n > 0 ? n : 1, capacity > 0 ? capacity : 1, level2_end_bit((int64_t)C * n_tiles)).total;
+  return sorted_layout(n > 0 ? n : 1, capacity > 0 ? capacity : 1, level2_end_bit((int64_t)C * n_tiles), (int64_t)C * n_tiles).total;
 }
 
 extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tight_rects, const float* means2d, const int32_t* radii,
@@ -919,7 +1021,7 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tight_rects
     return tile_schedule(offsets, (int32_t)n_slots, nullptr, tile_order, reinterpret_cast<int32_t*>(workspace), stream);
   }
   const int end_bit2 = level2_end_bit(n_slots);
-  const SortedLayout L = sorted_layout(n, capacity, end_bit2);
+  const SortedLayout L = sorted_layout(n, capacity, end_bit2, n_slots);
   if (workspace == nullptr || workspace_bytes < L.total)
     return fail(EGS_ERR_WORKSPACE_TOO_SMALL, "isect_sorted: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)L.total);
   char* ws = reinterpret_cast<char*>(workspace);
@@ -945,13 +1047,21 @@ extern "C" int egs_isect_sorted(int32_t C, int32_t N, const int32_t* tight_rects
       (float)tile_size, tile_width, tile_height, capacity, ka, va, n_isects_dev, reinterpret_cast<uint32_t*>(ws + L.chain),
       reinterpret_cast<uint64_t*>(ws + L.chain + 256));
   if (int rc = check_launch("isect_scan_emit_kernel")) return rc;
-  // level 2: stable sort on the dense (camera, tile) index
-  if (int rc = radix_sort_pairs_u32(capacity, n_isects_dev, ka, va, kb, vb, end_bit2, ws + L.sort2, L.sched - L.sort2, &in_b, stream, true))
+  // level 2: stable sort on the dense (camera, tile) index.  Its last pass leaves every occurring key's first position
+  // in `offsets` (0xffffffff = "no entry"), which one small launch turns into the tile offsets, the sentinel, the class
+  // histogram of the list lengths and the longest list.
+  EGS_CUDA(cudaMemsetAsync(offsets, 0xFF, (n_slots + 1) * sizeof(int32_t), stream));
+  if (int rc = radix_sort_pairs_u32(capacity, n_isects_dev, ka, va, kb, vb, end_bit2, ws + L.sort2, L.sched - L.sort2, &in_b, stream, true,
+                                    reinterpret_cast<uint32_t*>(offsets)))
     return rc;
   if ((in_b != 0) != ((passes2 & 1) != 0)) return fail(EGS_ERR_INVALID_ARGUMENT, "isect_sorted: internal ping-pong mismatch");
-  isect_offsets4_kernel<<<(unsigned)ceil_div(capacity, 4 * kOff4Threads), kOff4Threads, 0, stream>>>(
-      (int32_t)capacity, tile_keys, (int32_t)n_slots, offsets, n_isects_dev, 1);
-  if (int rc = check_launch("isect_offsets4_kernel")) return rc;
-  return tile_schedule(offsets, (int32_t)n_slots, reinterpret_cast<unsigned long long*>(stats), tile_order,
-                       reinterpret_cast<int32_t*>(ws + L.sched), stream, true);
+  int32_t* sched = reinterpret_cast<int32_t*>(ws + L.sched);  // class histogram | handed-out counters (zero: control block)
+  const unsigned fill_blocks = (unsigned)ceil_div(n_slots, (int64_t)kFillChunk);
+  tile_offsets_fill_kernel<<<fill_blocks, kSchedThreads, 0, stream>>>(
+      offsets, (int32_t)n_slots, capacity, n_isects_dev, sched, reinterpret_cast<unsigned long long*>(stats),
+      reinterpret_cast<uint32_t*>(ws + L.fill), reinterpret_cast<uint64_t*>(ws + L.fill + 256));
+  if (tile_order == nullptr) return check_launch("tile_offsets_fill_kernel");
+  tile_order_kernel<<<(unsigned)ceil_div(n_slots, (int64_t)kSchedThreads), kSchedThreads, 0, stream>>>(
+      offsets, (int32_t)n_slots, sched, sched + kSchedClasses, tile_order);
+  return check_launch("tile offsets + schedule", 2);
 }

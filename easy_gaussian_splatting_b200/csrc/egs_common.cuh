@@ -37,10 +37,12 @@ __device__ __forceinline__ int64_t live_count(int64_t capacity, const int64_t* _
 // radix_sort.cu: the onesweep sort of (u32 key, u32 value) pairs on key bits [0, end_bit) for up to `capacity` pairs,
 // min(capacity, *count_dev) of which are live.  *result_in_b (host) = the sorted data ended in the b buffers.
 // workspace_is_zero: the caller has already cleared the workspace (one memset for several stages).
+// first_pos (nullable, [number of distinct keys], filled with 0xffffffff by the caller): receives the position of the
+// first pair of every key that occurs — only meaningful when end_bit covers every set key bit (a complete sort).
 int64_t radix_sort_workspace_bytes(int64_t capacity, int end_bit);
 int radix_sort_pairs_u32(int64_t capacity, const int64_t* count_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
                          uint32_t* vals_b, int end_bit, void* workspace, int64_t workspace_bytes, int* result_in_b,
-                         cudaStream_t stream, bool workspace_is_zero = false);
+                         cudaStream_t stream, bool workspace_is_zero = false, uint32_t* first_pos = nullptr);
 inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 }  // namespace egs

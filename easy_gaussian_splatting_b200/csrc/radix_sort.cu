@@ -175,12 +175,13 @@ struct SortSmem {
 // the kernel at 64 registers (2 CTAs of 512 threads per SM) with every global load of a phase in flight at once.
 // One tile of a pass (FULL: all kSortTile slots are live — every tile but the last; the ragged form clamps its loads
 // and predicates every shared-memory and global store, ~15 % more instructions).
-template <typename KeyT, int ITEMS, bool FULL>
+template <typename KeyT, int ITEMS, bool FULL, bool FIRST_POS>
 __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, ITEMS>& sm, const KeyT* __restrict__ keys_in,
                                               const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                                               uint32_t* __restrict__ vals_out, int shift,
                                               const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ status,
-                                              uint32_t tile, int64_t tile_base, int tile_count) {
+                                              uint32_t tile, int64_t tile_base, int tile_count,
+                                              uint32_t* __restrict__ first_pos) {
   constexpr int kSortItems = ITEMS, kSortTile = kSortTilePairs, kWarpSpan = 32 * ITEMS;
   constexpr int kSortThreads = kSortTilePairs / ITEMS, kSortWarps = kSortThreads / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -332,16 +333,27 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, ITEMS>& sm, const K
       const uint32_t dst = sm.dst_base[d] + (uint32_t)p;
       keys_out[dst] = k;
       vals_out[dst] = sm.vals[p];
+      if constexpr (sizeof(KeyT) == 4 && FIRST_POS) {
+        // LAST pass of a complete sort (first_pos given): the tile is then sorted on the whole key (its input was
+        // sorted on the lower bits, the ranking is stable), so a key's first slot in the tile is a key boundary.  A
+        // boundary INSIDE a digit run is the key's first position in the whole output (an earlier tile cannot hold the
+        // key behind a smaller one of the same digit): plain store.  The first slot of a digit run may continue a key
+        // of an earlier tile: atomicMin.  first_pos starts at 0xffffffff; keys without entries keep it.
+        const KeyT kp = sm.keys[p > 0 ? p - 1 : 0];
+        const bool run_start = p == 0 || ((uint32_t)(kp >> shift) & (kRadix - 1)) != d;
+        if (run_start) atomicMin(first_pos + k, dst);
+        else if (kp != k) first_pos[k] = dst;
+      }
     }
   }
 }
 
-template <typename KeyT, int ITEMS>
+template <typename KeyT, int ITEMS, bool FIRST_POS>
 __global__ void __launch_bounds__(kSortTilePairs / ITEMS, (ITEMS > 8) ? EGS_SORT_BLOCKS_16 : 2) radix_onesweep_kernel(
     const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, int64_t n, const int64_t* __restrict__ n_dev, int shift,
     const uint32_t* __restrict__ digit_base /*[256]*/, uint32_t* __restrict__ tile_counter,
-    uint32_t* __restrict__ status /*[ntiles][256]*/) {
+    uint32_t* __restrict__ status /*[ntiles][256]*/, uint32_t* __restrict__ first_pos /* nullable, see onesweep_tile (h) */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   n = live_count(n, n_dev);  // the grid covers the capacity; tiles past the live count leave at once (below)
   constexpr int kSortItems = ITEMS, kSortTile = kSortTilePairs, kWarpSpan = 32 * ITEMS;
@@ -361,9 +373,9 @@ __global__ void __launch_bounds__(kSortTilePairs / ITEMS, (ITEMS > 8) ? EGS_SORT
   const int tile_count = (int)min((int64_t)kSortTile, n - tile_base);
 
   if (tile_count == kSortTile)
-    onesweep_tile<KeyT, ITEMS, true>(sm, keys_in, vals_in, keys_out, vals_out, shift, digit_base, status, tile, tile_base, tile_count);
+    onesweep_tile<KeyT, ITEMS, true, FIRST_POS>(sm, keys_in, vals_in, keys_out, vals_out, shift, digit_base, status, tile, tile_base, tile_count, first_pos);
   else
-    onesweep_tile<KeyT, ITEMS, false>(sm, keys_in, vals_in, keys_out, vals_out, shift, digit_base, status, tile, tile_base, tile_count);
+    onesweep_tile<KeyT, ITEMS, false, FIRST_POS>(sm, keys_in, vals_in, keys_out, vals_out, shift, digit_base, status, tile, tile_base, tile_count, first_pos);
 }
 
 static int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, int passes, SortWorkspace& w, int64_t& clear_bytes) {
@@ -397,12 +409,13 @@ extern "C" int64_t egs_radix_sort_workspace_bytes(int64_t n, int32_t end_bit) {
 
 template <typename KeyT, int ITEMS>
 static int run_passes(int64_t n, const int64_t* n_dev, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
-                      int passes, const SortWorkspace& w, cudaStream_t stream);
+                      int passes, const SortWorkspace& w, cudaStream_t stream, uint32_t* first_pos);
 
 template <typename KeyT>
 static int radix_sort_pairs_impl(int64_t n, const int64_t* n_dev, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b,
                                  uint32_t* vals_b, int32_t end_bit, void* workspace, int64_t workspace_bytes,
-                                 int32_t* host_result_in_b, cudaStream_t stream, bool workspace_is_zero = false) {
+                                 int32_t* host_result_in_b, cudaStream_t stream, bool workspace_is_zero = false,
+                                 uint32_t* first_pos = nullptr) {
   constexpr int kKeyBits = (int)sizeof(KeyT) * 8;
   EGS_REQUIRE(n >= 0, "radix_sort: n=%lld < 0", (long long)n);
   EGS_REQUIRE(n < (1ll << 30), "radix_sort: n=%lld exceeds the 2^30 pairs the look-back words can count", (long long)n);
@@ -428,26 +441,33 @@ static int radix_sort_pairs_impl(int64_t n, const int64_t* n_dev, KeyT* keys_a, 
                                                                                     w.counters + kMaxPasses);
   // pairs per thread: 8 for 64-bit keys (a 16-item tile would need 2 x the shared memory and drop to one CTA per SM);
   // EGS_SORT_ITEMS_U32 for 32-bit keys (build-time A/B knob, scripts/build_variant.py)
-  if constexpr (sizeof(KeyT) == 4) return run_passes<KeyT, EGS_SORT_ITEMS_U32>(n, n_dev, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
-  else return run_passes<KeyT, 8>(n, n_dev, keys_a, vals_a, keys_b, vals_b, passes, w, stream);
+  if constexpr (sizeof(KeyT) == 4) return run_passes<KeyT, EGS_SORT_ITEMS_U32>(n, n_dev, keys_a, vals_a, keys_b, vals_b, passes, w, stream, first_pos);
+  else return run_passes<KeyT, 8>(n, n_dev, keys_a, vals_a, keys_b, vals_b, passes, w, stream, nullptr);
 }
 
 template <typename KeyT, int ITEMS>
 static int run_passes(int64_t n, const int64_t* n_dev, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
-                      int passes, const SortWorkspace& w, cudaStream_t stream) {
+                      int passes, const SortWorkspace& w, cudaStream_t stream, uint32_t* first_pos) {
   constexpr int kSmem = (int)sizeof(SortSmem<KeyT, ITEMS>);
-  const cudaError_t attr_rc =  // per-device attribute: set on every call (cheap), not once per process
-      cudaFuncSetAttribute(radix_onesweep_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-  if (attr_rc != cudaSuccess)
-    return fail((int)attr_rc, "radix_sort: cannot opt in to %d bytes of shared memory: %s", kSmem, cudaGetErrorString(attr_rc));
+  // the variant that also records every key's first position (last pass of the level-2 sort) is its own kernel:
+  // the plain passes keep their register budget
+  auto plain = radix_onesweep_kernel<KeyT, ITEMS, false>;
+  auto with_first_pos = radix_onesweep_kernel<KeyT, ITEMS, sizeof(KeyT) == 4>;
+  for (auto kernel : {plain, with_first_pos}) {
+    const cudaError_t attr_rc =  // per-device attribute: set on every call (cheap), not once per process
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (attr_rc != cudaSuccess)
+      return fail((int)attr_rc, "radix_sort: cannot opt in to %d bytes of shared memory: %s", kSmem, cudaGetErrorString(attr_rc));
+  }
   const int64_t ntiles = sort_ntiles(n);
   const int64_t status_stride = ntiles * kRadix;
   KeyT* kin = keys_a; uint32_t* vin = vals_a;
   KeyT* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < passes; ++p) {
-    radix_onesweep_kernel<KeyT, ITEMS><<<(unsigned)ntiles, kSortTilePairs / ITEMS, kSmem, stream>>>(
+    auto kernel = (p == passes - 1 && first_pos != nullptr) ? with_first_pos : plain;
+    kernel<<<(unsigned)ntiles, kSortTilePairs / ITEMS, kSmem, stream>>>(
         kin, vin, kout, vout, n, n_dev, p * kRadixBits, w.hist + (size_t)p * kRadix, w.counters + p,
-        w.status + (size_t)p * status_stride);
+        w.status + (size_t)p * status_stride, first_pos);
     KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
@@ -458,9 +478,9 @@ namespace egs {
 int64_t radix_sort_workspace_bytes(int64_t capacity, int end_bit) { return egs_radix_sort_workspace_bytes(capacity, end_bit); }
 int radix_sort_pairs_u32(int64_t capacity, const int64_t* count_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
                          uint32_t* vals_b, int end_bit, void* workspace, int64_t workspace_bytes, int* result_in_b,
-                         cudaStream_t stream, bool workspace_is_zero) {
+                         cudaStream_t stream, bool workspace_is_zero, uint32_t* first_pos) {
   return radix_sort_pairs_impl<uint32_t>(capacity, count_dev, keys_a, vals_a, keys_b, vals_b, end_bit, workspace,
-                                         workspace_bytes, result_in_b, stream, workspace_is_zero);
+                                         workspace_bytes, result_in_b, stream, workspace_is_zero, first_pos);
 }
 }  // namespace egs
 
