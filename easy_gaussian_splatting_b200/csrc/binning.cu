@@ -945,7 +945,8 @@ __global__ void __launch_bounds__(kSchedThreads) tile_order_kernel(const int32_t
 // ---- the whole route behind egs_isect_visible_keys in ONE call, with the two counts read on the device -----------------
 // Workspace layout (all 256-byte aligned): keys1_b | vals1_b | level-2 ping-pong keys | level-2 ping-pong values |
 // control block = {level-1 sort workspace | emission chain (ticket + one status word per block) | level-2 sort
-// workspace | tile-schedule histogram}.  The control block is what must start at zero: ONE memset per call.
+// workspace | tile-schedule histogram | offsets chain}.  The control block is what must start at zero: ONE memset per
+// call (plus one of 0xFF over the tile offsets, which receive the keys' first positions from the last sort pass).
 namespace {
 struct SortedLayout {
   int64_t keys1_b, vals1_b, keys2, vals2, control, sort1, chain, sort2, sched, fill, total;
