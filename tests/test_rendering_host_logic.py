@@ -386,3 +386,15 @@ def test_hint_counts_never_wait():
     assert stages._hint_count(pending) == 320 and pending["n_isects"] == 320
     assert stages._hint_count(None) is None
     assert stages._hint_count({"n_isects": None, "known": None, "n_bound": 5, "late": late, "late_event": _FakeEvent(done=False)}) is None
+
+
+def test_guessed_capacities_take_few_distinct_values():
+    """stages._round_capacity: 8 steps per octave, never below the request, at most 12.5 % above it."""
+    from easy_gaussian_splatting_b200.stages import _round_capacity
+    seen = set()
+    for n in list(range(1, 300_000, 997)) + [18_591_996, 36_038_741, 2 ** 30 + 5]:
+        c = _round_capacity(n)
+        assert c >= n and (c <= 1 << 16 or c <= n * 1.125 + 1)
+        seen.add(c)
+    assert len(seen) < 40
+    assert _round_capacity(131072) == 131072 and _round_capacity(131073) == 147456
