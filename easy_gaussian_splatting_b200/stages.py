@@ -651,7 +651,7 @@ def isect_sorted_async(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per
     if capacity is None:
         with _HINT_LOCK:
             h = _HINTS.get(key)
-        if h is not None:
+        if h is not None and h.get("n_bound") is not None:
             capacity = _round_capacity(int(h["n_bound"] * _CAPACITY_SLACK) + 65536)
         else:  # no guess: the one blocking read, as in every call before round 2 (the classic count bounds the tight one)
             early_event.synchronize()
