@@ -159,11 +159,15 @@ __global__ void __launch_bounds__(kOffThreads) isect_offset_encode_kernel(int64_
 // ================================================================================================
 // Fast path of g3-g5: same sorted (isect_ids, flatten_ids, offsets) as emit + 64-bit sort + offset
 // encode, with ~3x less HBM traffic.  A stable sort on (cam | tile | depth) keys equals
-//   (1) a stable sort of the VISIBLE Gaussians on (cam | depth)        [N_vis pairs, not n_isects]
+//   (1) a stable sort of the VISIBLE Gaussians of all cameras on depth  [N_vis pairs, not n_isects; 32-bit keys]
 //   (2) emitting their tiles in that order, and
 //   (3) a stable sort of the emitted pairs on the 13..19-bit (cam, tile) index alone [2-3 passes of 8 B pairs]
-// because (3) keeps, inside every tile, the (depth, flat index) order that (1) established.  The 64-bit keys
-// are rebuilt for `meta["isect_ids"]` in the same kernel that derives the tile offsets.
+// because (3) keeps, inside every tile, the (depth, flat index) order that (1) established.
+// Launches of the route (egs_isect_visible_keys + egs_isect_sorted): visible keys | histogram + 4 passes | scan + emit |
+// histogram + 2-3 passes (the last one records every key's first position) | tile offsets | tile order = 12-13, with
+// one memset of the control block and one of the offsets.  The separate operators further down (three-launch scans,
+// egs_isect_emit_sorted, egs_isect_finalize with its offsets4 / 64-bit-key kernels) are the same steps as C-ABI
+// entries of their own; isect_finalize also rebuilds the 64-bit keys for `meta["isect_ids"]`.
 // ================================================================================================
 
 __device__ __forceinline__ int64_t block_reduce_sum(int64_t v, int64_t* smem /*[33]*/) {
