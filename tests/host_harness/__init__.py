@@ -59,3 +59,17 @@ def projection_bwd(sc, sh_degree, radii, colors, v_means2d, v_conics, v_colors, 
                           _p(arrs[7]), _p(arrs[8]), _p(arrs[9]), _p(out["v_means"]), _p(out["v_quats"]),
                           _p(out["v_scales"]), _p(out["v_sh"]), None if v_comps is None else _p(vc))
     return out
+
+
+def tight_rects(means2d, radii, conics, opacities, tw, th, tile=16):
+    """-> (classic [n,4] = x0 y0 x1 y1 in tiles, packed [n,2] = the 8 bytes the projection kernel hands to the binning)"""
+    lib = load()
+    n = radii.shape[0]
+    m2 = np.ascontiguousarray(means2d, dtype=np.float32)
+    rd = np.ascontiguousarray(radii, dtype=np.int32)
+    cn = np.ascontiguousarray(conics, dtype=np.float32)
+    op = np.ascontiguousarray(opacities, dtype=np.float32)
+    classic = np.zeros((n, 4), dtype=np.int32)
+    packed = np.zeros((n, 2), dtype=np.int32)
+    lib.hh_tight_rects(n, _p(m2), _p(rd), _p(cn), _p(op), tile, tw, th, _p(classic), _p(packed))
+    return classic, packed

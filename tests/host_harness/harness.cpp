@@ -80,3 +80,18 @@ extern "C" void hh_projection_bwd(int C, int N, const float* means, const float*
     }
   }
 }
+
+// Tight tile rectangles exactly as the projection kernels produce them (tile_rect -> sigma_cutoff ->
+// tighten_tile_rect -> pack_tile_rect), from 2-D means / radii / conics / opacities.
+extern "C" void hh_tight_rects(int n, const float* means2d, const int32_t* radii, const float* conics, const float* opacities,
+                               int tile_size, int tw, int th, int32_t* classic /*[n,4] x0 y0 x1 y1*/, int32_t* packed /*[n,2]*/) {
+  for (int i = 0; i < n; ++i) {
+    int32_t x0, y0, x1, y1;
+    tile_rect(means2d[2 * i], means2d[2 * i + 1], radii[i], (float)tile_size, tw, th, x0, y0, x1, y1);
+    classic[4 * i] = x0; classic[4 * i + 1] = y0; classic[4 * i + 2] = x1; classic[4 * i + 3] = y1;
+    const float cut = sigma_cutoff(opacities[i]);
+    tighten_tile_rect(means2d[2 * i], means2d[2 * i + 1], conics[3 * i], conics[3 * i + 1], conics[3 * i + 2], cut,
+                      (float)tile_size, x0, y0, x1, y1);
+    pack_tile_rect(x0, y0, x1, y1, packed[2 * i], packed[2 * i + 1]);
+  }
+}

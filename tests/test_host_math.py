@@ -96,3 +96,69 @@ def test_compensation_backward_vs_fp64_autograd(cfg):
         a = torch.from_numpy(out[name]).double()
         rel = ((a - ref).norm() / ref.norm().clamp_min(1e-30)).item()
         assert rel <= 5e-5, (name, rel)
+
+
+def test_tight_rectangles_never_drop_a_reachable_pixel():
+    """The tight tile rectangle the projection kernels pack for the blend kernels' lists (egs_math.cuh:
+    tighten_tile_rect / pack_tile_rect, compiled for the host) against brute force over the pixels: every tile of
+    gsplat's rectangle that holds a pixel centre with alpha = o exp(-sigma) >= 1/255 must lie inside the tight
+    rectangle, the tight rectangle must lie inside gsplat's, and it must actually be tighter on anisotropic splats."""
+    from tests import host_harness
+    rng = np.random.default_rng(0)
+    n, W, H, T = 4000, 640, 368, 16
+    tw, th = -(-W // T), -(-H // T)
+    # covariances: random orientation, axis ratios up to 30:1, sizes from sub-pixel to a few tiles
+    ang = rng.uniform(0, np.pi, n)
+    s1 = np.exp(rng.uniform(np.log(0.3), np.log(40.0), n))
+    s2 = s1 / np.exp(rng.uniform(0, np.log(30.0), n))
+    c, s = np.cos(ang), np.sin(ang)
+    cxx = c * c * s1 ** 2 + s * s * s2 ** 2 + 0.3
+    cyy = s * s * s1 ** 2 + c * c * s2 ** 2 + 0.3
+    cxy = c * s * (s1 ** 2 - s2 ** 2)
+    det = cxx * cyy - cxy ** 2
+    conics = np.stack([cyy / det, -cxy / det, cxx / det], -1).astype(np.float32)
+    # gsplat's radius: ceil(3 sqrt(larger eigenvalue))
+    mid = 0.5 * (cxx + cyy)
+    lam = mid + np.sqrt(np.maximum(mid ** 2 - det, 0.01))
+    radii = np.ceil(3.0 * np.sqrt(lam)).astype(np.int32)
+    means2d = np.stack([rng.uniform(-20, W + 20, n), rng.uniform(-20, H + 20, n)], -1).astype(np.float32)
+    opac = np.concatenate([rng.uniform(0.002, 1.0, n - 200), rng.uniform(0.0, 1 / 255.0, 200)]).astype(np.float32)
+    classic, packed = host_harness.tight_rects(means2d, radii, conics, opac, tw, th, T)
+    x0, y0 = packed[:, 0] & 0xffff, (packed[:, 0] >> 16) & 0xffff
+    w, h = packed[:, 1] & 0xffff, (packed[:, 1] >> 16) & 0xffff
+    cw, ch = classic[:, 2] - classic[:, 0], classic[:, 3] - classic[:, 1]
+    nonempty = (w > 0) & (h > 0)
+    # inside gsplat's rectangle
+    assert np.all(x0[nonempty] >= classic[nonempty, 0]) and np.all((x0 + w)[nonempty] <= classic[nonempty, 2])
+    assert np.all(y0[nonempty] >= classic[nonempty, 1]) and np.all((y0 + h)[nonempty] <= classic[nonempty, 3])
+    # brute force: reachable pixels of every tile of gsplat's rectangle, in fp64
+    dropped = 0
+    reach_tiles = 0
+    for i in range(n):
+        if cw[i] <= 0 or ch[i] <= 0:
+            continue
+        px = np.arange(classic[i, 0] * T, min(classic[i, 2] * T, W)) + 0.5
+        py = np.arange(classic[i, 1] * T, min(classic[i, 3] * T, H)) + 0.5
+        if px.size == 0 or py.size == 0:
+            continue
+        dx = px[None, :] - float(means2d[i, 0])
+        dy = py[:, None] - float(means2d[i, 1])
+        a_, b_, c_ = (float(v) for v in conics[i])
+        sigma = 0.5 * (a_ * dx * dx + c_ * dy * dy) + b_ * dx * dy
+        alpha = float(opac[i]) * np.exp(-sigma)
+        hit = (sigma >= 0) & (alpha >= 1.0 / 255.0)
+        ys, xs = np.nonzero(hit)
+        if ys.size == 0:
+            continue
+        tx = (px[xs] // T).astype(np.int64)
+        ty = (py[ys] // T).astype(np.int64)
+        reach_tiles += np.unique(ty * tw + tx).size
+        inside = (tx >= x0[i]) & (tx < x0[i] + w[i]) & (ty >= y0[i]) & (ty < y0[i] + h[i])
+        dropped += int((~inside).sum())
+    assert dropped == 0, f"{dropped} reachable pixels lie outside their Gaussian's tight rectangle"
+    classic_tiles = int((np.maximum(cw, 0) * np.maximum(ch, 0)).sum())
+    tight_tiles = int((w.astype(np.int64) * h).sum())
+    print(f"classic {classic_tiles} tiles, tight {tight_tiles} ({tight_tiles / classic_tiles:.3f}), exactly reachable {reach_tiles}")
+    assert reach_tiles <= tight_tiles < 0.8 * classic_tiles
+    # Gaussians that can never reach 1/255 are listed nowhere
+    assert np.all(w[opac <= 1 / 255.0] == 0)
