@@ -418,7 +418,8 @@ def test_tight_lists_hold_a_subset_and_render_identically(cfg):
     assert float((v_out - v_ref).norm() / v_ref.norm()) <= 1e-5
 
 
-@pytest.mark.parametrize("C,N,tw,th", [(2, 40_000, 37, 23), (1, 1500, 120, 68), (3, 5000, 1, 1), (1, 70_000, 5, 300)])
+@pytest.mark.parametrize("C,N,tw,th", [(2, 40_000, 37, 23), (1, 1500, 120, 68), (3, 5000, 1, 1), (1, 70_000, 5, 300),
+                                        (2, 3000, 300, 200)])  # the last one: 120 000 tile slots = three level-2 passes
 def test_scan_emit_on_arbitrary_packed_rectangles(C, N, tw, th):
     """The single-launch scan + emission (decoupled look-back over 1024-Gaussian blocks, table / redux owner search)
     on rectangles no projection would produce together: empty ones between full-grid ones, single columns and rows,
