@@ -398,3 +398,22 @@ def test_guessed_capacities_take_few_distinct_values():
         seen.add(c)
     assert len(seen) < 40
     assert _round_capacity(131072) == 131072 and _round_capacity(131073) == 147456
+
+
+def test_segment_policy_from_hints(monkeypatch):
+    """stages.segment_policy: segmented replay only for outlier-long lists, and only from a hint whose counts have
+    arrived (a hint that carries just the bound decides nothing)."""
+    from easy_gaussian_splatting_b200 import stages
+    monkeypatch.delenv("EGS_BWD_SEGMENT", raising=False)
+    n_tiles = 1000
+    assert stages.segment_policy(None, n_tiles) == (0, 0)
+    assert stages.segment_policy({"n_bound": 900_000}, n_tiles) == (0, 0)                      # counts still on their way
+    even = {"n_bound": 900_000, "n_isects": 500_000, "max_tile_len": 1100}                      # 2.2 x the average of 500
+    assert stages.segment_policy(even, n_tiles) == (0, 0)
+    outlier = {"n_bound": 900_000, "n_isects": 500_000, "max_tile_len": 6000}                  # 12 x the average
+    seg, min_len = stages.segment_policy(outlier, n_tiles)
+    assert seg == stages.SEGMENT_ENTRIES and min_len == max(stages.SEGMENT_MIN_ENTRIES, int(stages.SEGMENT_MIN_RATIO * 500))
+    monkeypatch.setenv("EGS_BWD_SEGMENT", "64")
+    assert stages.segment_policy(None, n_tiles) == (64, 65)
+    monkeypatch.setenv("EGS_BWD_SEGMENT", "0")
+    assert stages.segment_policy(outlier, n_tiles) == (0, 0)
