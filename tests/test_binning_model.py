@@ -1,0 +1,67 @@
+"""CPU model of one claim the binning route's last sort pass relies on (csrc/radix_sort.cu, onesweep_tile (h), and
+csrc/binning.cu, tile_offsets_fill_kernel): in the LAST pass of a complete LSD radix sort every 4096-pair tile is sorted
+on the whole key, so the first slot of a key inside a digit run of a tile is that key's first position in the whole
+output and may be written with a plain store, while the first slot of a digit run needs an atomicMin — and the result
+does not depend on the order in which the thread blocks' stores and atomics land.  The model replays exactly those
+operations in random order; the suffix minimum over the tiles then has to give the tile offsets."""
+import numpy as np
+import pytest
+
+TILE = 4096
+
+
+def _last_pass_operations(keys, shift):
+    """keys: input of the last pass (sorted on the bits below `shift`).  -> (sorted output, [(op, key, position)])"""
+    n = keys.size
+    digit = (keys >> shift) & 255
+    tiles = [np.arange(s, min(s + TILE, n)) for s in range(0, n, TILE)]
+    # stable partition on the digit: all tiles' digit-0 runs in tile order, then digit 1, ...
+    order = np.argsort(digit, kind="stable")
+    pos_of = np.empty(n, dtype=np.int64)
+    pos_of[order] = np.arange(n)
+    ops = []
+    for idx in tiles:
+        local = idx[np.argsort(digit[idx], kind="stable")]   # the tile in shared memory: digit runs, stable inside
+        k, d, dst = keys[local], digit[local], pos_of[local]
+        for p in range(local.size):
+            run_start = p == 0 or d[p - 1] != d[p]
+            if run_start:
+                ops.append(("min", int(k[p]), int(dst[p])))
+            elif k[p - 1] != k[p]:
+                ops.append(("store", int(k[p]), int(dst[p])))
+    return keys[order], ops
+
+
+@pytest.mark.parametrize("n,n_slots,seed", [(30_000, 3000, 0), (50_000, 40_000, 1), (9000, 70_000, 2), (4096, 300, 3), (1, 10, 4)])
+def test_first_positions_do_not_depend_on_the_order_of_stores_and_atomics(n, n_slots, seed):
+    rng = np.random.default_rng(seed)
+    # many empty slots, a narrow band of busy ones and one very long list that spans several tiles of the pass —
+    # like the (camera, tile) indices of a scene that covers part of the image
+    keys = rng.integers(0, n_slots, size=n, dtype=np.int64)
+    busy = rng.random(n) < 0.35
+    keys[busy] = rng.integers(n_slots // 3, n_slots // 3 + max(n_slots // 50, 1), size=int(busy.sum()))
+    keys[rng.random(n) < 0.3] = n_slots // 2
+    bits = max(1, int(n_slots - 1).bit_length())
+    passes = (bits + 7) // 8
+    cur = keys
+    for p in range(passes - 1):  # all passes but the last: plain stable LSD passes
+        cur = cur[np.argsort((cur >> (8 * p)) & 255, kind="stable")]
+    out, ops = _last_pass_operations(cur, 8 * (passes - 1))
+    assert np.array_equal(out, np.sort(keys, kind="stable"))
+    stores = [k for op, k, _ in ops if op == "store"]
+    assert len(stores) == len(set(stores)), "at most one plain store per key"
+    expected = np.full(n_slots, np.iinfo(np.int64).max)
+    first = np.searchsorted(out, np.arange(n_slots), side="left")
+    present = np.zeros(n_slots, dtype=bool)
+    present[np.unique(keys)] = True
+    expected[present] = first[present]
+    for trial in range(4):
+        order = rng.permutation(len(ops))
+        got = np.full(n_slots, np.iinfo(np.int64).max)
+        for i in order:
+            op, k, dst = ops[i]
+            got[k] = min(got[k], dst) if op == "min" else dst
+        assert np.array_equal(got, expected), f"trial {trial}"
+    # tile_offsets_fill_kernel: offsets[t] = first position of the first non-empty slot at or behind t, n behind the last
+    filled = np.minimum.accumulate(np.minimum(expected, n)[::-1])[::-1]
+    assert np.array_equal(filled, first)
