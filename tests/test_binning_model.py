@@ -65,3 +65,35 @@ def test_first_positions_do_not_depend_on_the_order_of_stores_and_atomics(n, n_s
     # tile_offsets_fill_kernel: offsets[t] = first position of the first non-empty slot at or behind t, n behind the last
     filled = np.minimum.accumulate(np.minimum(expected, n)[::-1])[::-1]
     assert np.array_equal(filled, first)
+
+
+def test_emission_owner_formula():
+    """isect_scan_emit_kernel: the owner of entry k among a warp's (compacted, non-empty) runs is
+    #runs that start before the 32-entry window + #runs that start inside it at or before k, minus one —
+    one ballot, one warp-wide OR and two popcounts in the kernel.  Checked against the plain expansion."""
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        cnt = rng.integers(0, 40, size=32) * (rng.random(32) < 0.7)
+        if trial == 0:
+            cnt = np.zeros(32, dtype=np.int64); cnt[31] = 5          # only the last lane has a run
+        if trial == 1:
+            cnt = np.full(32, 1)                                     # 32 runs of one entry
+        if trial == 2:
+            cnt = np.zeros(32, dtype=np.int64); cnt[0] = 8160        # one run far longer than a window
+        nonempty = np.flatnonzero(cnt > 0)
+        starts_all = np.cumsum(cnt) - cnt
+        start = np.full(32, np.iinfo(np.int32).max, dtype=np.int64)  # what lane l holds after the compaction
+        start[:nonempty.size] = starts_all[nonempty]
+        total = int(cnt.sum())
+        truth = np.repeat(np.arange(nonempty.size), cnt[nonempty])   # owner (compacted index) of every entry
+        for k0 in range(0, total, 32):
+            before = int((start < k0).sum())
+            d = start - k0
+            inside = 0
+            for l in range(32):
+                if 0 <= d[l] < 32:
+                    inside |= 1 << int(d[l])
+            for lane in range(min(32, total - k0)):
+                le_mask = (2 << lane) - 1
+                owner = before + bin(inside & le_mask).count("1") - 1
+                assert owner == truth[k0 + lane], (trial, k0, lane)
