@@ -97,3 +97,65 @@ def test_emission_owner_formula():
                 le_mask = (2 << lane) - 1
                 owner = before + bin(inside & le_mask).count("1") - 1
                 assert owner == truth[k0 + lane], (trial, k0, lane)
+
+
+def _lookback_block(status, blk, total, out):
+    """Generator model of chain_lookback (csrc/binning.cu) for one thread block: yields at every memory operation so a
+    scheduler can interleave the blocks.  status[b] = (flag, value): flag 0 nothing, 1 aggregate, 2 inclusive prefix."""
+    status[blk] = (2 if blk == 0 else 1, total)
+    yield
+    excl = 0
+    if blk > 0:
+        j = blk - 1
+        done = False
+        while not done:
+            words = []
+            for q in range(2):                       # a lane polls blk-1-lane and blk-33-lane: 64 loads, each at its own time
+                chunk = []
+                for lane in range(32):
+                    jj = j - 32 * q - lane
+                    chunk.append(status[jj] if jj >= 0 else (2, 0))   # before block 0: an empty prefix
+                    yield
+                words.append(chunk)
+            for q in range(2):
+                if done:
+                    break
+                flags = [w[0] for w in words[q]]
+                first_nr = flags.index(0) if 0 in flags else 32
+                first_pf = flags.index(2) if 2 in flags else 32
+                take = first_pf + 1 if first_pf < first_nr else first_nr
+                excl += sum(w[1] for w in words[q][:take])
+                j -= take
+                if first_pf < first_nr:
+                    done = True
+                elif take < 32:
+                    break
+        status[blk] = (2, excl + total)
+        yield
+    out[blk] = excl
+
+
+@pytest.mark.parametrize("n_blocks,resident,seed", [(1, 1, 0), (40, 40, 1), (300, 37, 2), (700, 148, 3), (200, 1, 4)])
+def test_decoupled_lookback_under_random_interleaving(n_blocks, resident, seed):
+    """Blocks start in ticket order, at most `resident` at a time, and advance one memory operation at a time in a
+    random order: every block must still come out with the exact exclusive prefix of the blocks before it."""
+    rng = np.random.default_rng(seed)
+    totals = rng.integers(0, 10_000, size=n_blocks).tolist()
+    status = {b: (0, 0) for b in range(n_blocks)}
+    out = {}
+    nxt = 0
+    running = []
+    steps = 0
+    while len(out) < n_blocks:
+        while nxt < n_blocks and len(running) < resident:      # a block slot frees up: the next ticket starts
+            running.append(_lookback_block(status, nxt, totals[nxt], out))
+            nxt += 1
+        i = int(rng.integers(0, len(running)))
+        try:
+            next(running[i])
+        except StopIteration:
+            running.pop(i)
+        steps += 1
+        assert steps < 5_000_000, "the chain does not make progress"
+    prefix = np.cumsum([0] + totals[:-1])
+    assert [out[b] for b in range(n_blocks)] == prefix.tolist()
